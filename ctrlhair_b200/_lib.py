@@ -1,0 +1,111 @@
+"""ctypes binding of include/ctrlhair_b200.h.  The library is built in-tree by ctrlhair_b200/build.py.
+
+There is deliberately no fallback: if the shared library is missing or the device is not sm_100, every
+entry point raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+
+class ChbError(RuntimeError):
+    pass
+
+
+class ConvSeg(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p),
+        ("a_sb", C.c_int64), ("a_sy", C.c_int64), ("a_sx", C.c_int64),
+        ("Ca", C.c_int), ("ch_off", C.c_int), ("C", C.c_int), ("taps", C.c_int),
+        ("w", C.c_void_p),
+        ("per_image", C.c_int),
+        ("w_sb", C.c_int64),
+    ]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("TW", C.c_int), ("TH", C.c_int), ("TB", C.c_int),
+        ("nseg", C.c_int),
+        ("seg", ConvSeg * 3),
+        ("N", C.c_int), ("Nrows", C.c_int), ("BN", C.c_int),
+        ("epi", C.c_int), ("act", C.c_int),
+        ("bias", C.c_void_p), ("bias_per_image", C.c_int),
+        ("out", C.c_void_p), ("out_dtype", C.c_int),
+        ("o_sb", C.c_int64), ("o_sy", C.c_int64), ("o_sx", C.c_int64), ("o_sn", C.c_int64),
+        ("o_ngroup", C.c_int), ("o_sgroup", C.c_int64),
+        ("res", C.c_void_p), ("r_sb", C.c_int64), ("r_sy", C.c_int64), ("r_sx", C.c_int64), ("r_shift", C.c_int),
+        ("x", C.c_void_p), ("x_sb", C.c_int64), ("x_sy", C.c_int64), ("x_sx", C.c_int64), ("x_shift", C.c_int),
+        ("noise", C.c_void_p),
+        ("chan", C.c_void_p),
+    ]
+
+
+class GenConfig(C.Structure):
+    _fields_ = [("ngf", C.c_int), ("label_nc", C.c_int), ("crop", C.c_int), ("style_len", C.c_int),
+                ("max_batch", C.c_int)]
+
+
+EPI_PLAIN, EPI_MODULATE = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+F16, F32 = 0, 1
+IMPL_TCGEN05, IMPL_SIMT_DEBUG = 0, 1
+
+# every symbol include/ctrlhair_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("chb_version", C.c_int, []),
+    ("chb_last_error", C.c_char_p, []),
+    ("chb_check_device", C.c_int, []),
+    ("chb_conv_run", C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
+    ("chb_onehot_pyramid", C.c_int,
+     [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    ("chb_noise_fill", C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    ("chb_f32_to_f16", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("chb_generator_create", C.c_int, [C.POINTER(GenConfig), C.POINTER(C.c_void_p)]),
+    ("chb_generator_destroy", None, [C.c_void_p]),
+    ("chb_generator_num_tensors", C.c_int, [C.c_void_p]),
+    ("chb_generator_tensor_info", C.c_int,
+     [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    ("chb_generator_blob_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_generator_workspace_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_generator_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("chb_generator_forward", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("chb_generator_forward_host", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("chb_generator_noise_floats", C.c_int64, [C.c_void_p, C.c_int]),
+    ("chb_generator_launches", C.c_int, [C.c_void_p]),
+    ("chb_generator_flops", C.c_double, [C.c_void_p, C.c_int]),
+    ("chb_generator_set_step_limit", C.c_int, [C.c_void_p, C.c_int]),
+    ("chb_generator_debug_tensor", C.c_int64,
+     [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+]
+
+
+def load(build_if_missing=True):
+    """Loads (building first if needed) the CUDA library.  Raises if it cannot be had."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.lib_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise ChbError("ctrlhair_b200: %s is missing (run __graft_entry__.build())" % path)
+        _build.build_library()
+    lib = C.CDLL(path)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().chb_last_error()
+        raise ChbError("ctrlhair_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))

@@ -1,0 +1,635 @@
+// Implicit-GEMM 3x3 / 1x1 convolution for sm_100a.
+//
+//   M = 128 output pixels of a TB x TH x TW tile, N = BN output channels, K = sum over segments of taps * C.
+//   A tiles are fetched by TMA straight from the NHWC activation tensor with the tap offset folded into the
+//   box coordinates (out-of-bounds -> zero fill = the conv's zero padding), B tiles by TMA from the K-major
+//   weight matrix (optionally a per-image one: the SEAN region-factored style weights).  One thread issues
+//   tcgen05.mma into a double-buffered fp32 TMEM accumulator, four epilogue warps drain it with tcgen05.ld
+//   and apply the fused epilogue (bias / residual / activation, or the ACE normalise-modulate of
+//   sean_codes/models/networks/normalization.py:111-112,177-187) while the next tile's main loop runs.
+//
+// Reference call sites this operator stands in for: normalization.py:172-173 (conv_gamma/conv_beta),
+// :241-256 (SPADE mlp_shared / mlp_gamma / mlp_beta), architecture.py:75,79,90 (conv_0, conv_1, conv_s),
+// generator.py:76,107 (fc, conv_img).
+#include "conv_igemm.cuh"
+#include "ptx_sm100.cuh"
+
+#include <cuda_fp16.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace chb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error_cstr() { return g_err.c_str(); }
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue math shared by the tcgen05 kernel and the SIMT checker kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case CHB_ACT_RELU: return fmaxf(v, 0.f);
+    case CHB_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
+    case CHB_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ long long out_offset(const EpiK& e, int b, int y, int x, int n) {
+  long long off = (long long)b * e.o_sb + (long long)y * e.o_sy + (long long)x * e.o_sx;
+  if (e.o_ngroup > 0) {
+    off += (long long)(n / e.o_ngroup) * e.o_sgroup + (long long)(n % e.o_ngroup) * e.o_sn;
+  } else {
+    off += (long long)n * e.o_sn;
+  }
+  return off;
+}
+
+__device__ __forceinline__ void plain_store_elem(const EpiK& e, int b, int y, int x, int n, float acc) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + (e.bias_per_image ? (long long)b * e.nrows : 0) + n);
+  if (e.res) {
+    v += __ldg(e.res + (long long)b * e.r_sb + (long long)(y >> e.r_shift) * e.r_sy +
+               (long long)(x >> e.r_shift) * e.r_sx + n);
+  }
+  v = apply_act(v, e.act);
+  const long long off = out_offset(e, b, y, x, n);
+  if (e.out_dtype == CHB_F16) {
+    reinterpret_cast<__half*>(e.out)[off] = __float2half_rn(v);
+  } else {
+    reinterpret_cast<float*>(e.out)[off] = v;
+  }
+}
+
+// xn = (x + noise*noise_var - mean) * rstd  (folded);  out = act(xn * (1 + gamma) + beta)
+__device__ __forceinline__ float modulate_elem(float xv, float nz, float4 ch, float gamma, float beta, int act) {
+  const float xn = fmaf(xv, ch.x, fmaf(nz, ch.z, ch.y));
+  return apply_act(fmaf(xn, 1.f + gamma, beta), act);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nst = p.nstages;
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nst * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      tma_prefetch_desc(&p.tmA[s]);
+      tma_prefetch_desc(&p.tmW[s]);
+    }
+    for (int i = 0; i < nst; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile / p.m_tiles;
+        int m = tile - n_tile * p.m_tiles;
+        const int xt = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int yt = m % p.tiles_y;
+        const int bt = m / p.tiles_y;
+        const int x0 = xt * p.TW, y0 = yt * p.TH, b0 = bt * p.TB, n0 = n_tile * p.BN;
+        for (int s = 0; s < p.nseg; ++s) {
+          const SegK sg = p.seg[s];
+          const uint32_t bytes = (uint32_t)(p.rows + p.BN) * (uint32_t)sg.kc * 2u;
+          for (int tap = 0; tap < sg.taps; ++tap) {
+            const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
+            const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;
+            for (int c = 0; c < sg.nchunk; ++c) {
+              mbar_wait(&empty[stage], phase ^ 1u);
+              uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
+              uint8_t* sb = sa + kATileBytes;
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              tma_load_4d(&p.tmA[s], sa, &full[stage], sg.ch_off + c * sg.kc, x0 + dx, y0 + dy, b0);
+              tma_load_3d(&p.tmW[s], sb, &full[stage], (tap * sg.nchunk + c) * sg.kc, n0, sg.per_image ? b0 : 0);
+              if (++stage == (uint32_t)nst) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16((uint32_t)p.BN);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const SegK sg = p.seg[s];
+          const int chunks = sg.taps * sg.nchunk;
+          const uint32_t row_bytes = (uint32_t)sg.kc * 2u;
+          const int ksteps = sg.kc / 16;
+          for (int c = 0; c < chunks; ++c) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
+            const uint64_t adesc = umma_smem_desc(sa, row_bytes);
+            const uint64_t bdesc = umma_smem_desc(sa + kATileBytes, row_bytes);
+            for (int k = 0; k < ksteps; ++k) {
+              umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == (uint32_t)nst) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tpix = p.TW * p.TH;
+    const int tb = row / tpix;
+    const int rem = row - tb * tpix;
+    const int ty = rem / p.TW;
+    const int tx = rem - ty * p.TW;
+    const EpiK& e = p.e;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      const int n_tile = tile / p.m_tiles;
+      int m = tile - n_tile * p.m_tiles;
+      const int xt = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int yt = m % p.tiles_y;
+      const int bt = m / p.tiles_y;
+      const int x = xt * p.TW + tx, y = yt * p.TH + ty, b = bt * p.TB + tb;
+      const bool valid = (row < p.rows) && (b < p.B) && (y < p.H) && (x < p.W);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+
+      if (EPI == CHB_EPI_PLAIN) {
+        const int n0 = n_tile * p.BN;
+        const bool vec = (e.o_sn == 1);
+        for (int j = 0; j < p.BN; j += 16) {
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)j, v);
+          tmem_ld_wait();
+          const int n = n0 + j;
+          if (!valid || n >= p.N) {
+            // nothing to store for this lane / chunk
+          } else if (vec && n + 16 <= p.N && (e.o_ngroup <= 0 || (e.o_ngroup % 16) == 0)) {
+            if (e.bias) {
+              const float4* bp =
+                  reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)b * e.nrows : 0) + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 t = __ldg(bp + i);
+                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+              }
+            }
+            if (e.res) {
+              const float4* rp = reinterpret_cast<const float4*>(
+                  e.res + (long long)b * e.r_sb + (long long)(y >> e.r_shift) * e.r_sy +
+                  (long long)(x >> e.r_shift) * e.r_sx + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 t = __ldg(rp + i);
+                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], e.act);
+            const long long off = out_offset(e, b, y, x, n);
+            if (e.out_dtype == CHB_F16) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + off);
+              op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (n + i < p.N) plain_store_elem(e, b, y, x, n + i, v[i]);
+          }
+          __syncwarp();
+        }
+      } else {
+        // MODULATE: columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2
+        const int half_n = p.BN >> 1;
+        const int c0 = n_tile * half_n;
+        const int nrow0 = n_tile * p.BN;
+        float nz = 0.f;
+        const float* xp = nullptr;
+        __half* hp = nullptr;
+        if (valid) {
+          if (e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
+          xp = e.x + (long long)b * e.x_sb + (long long)(y >> e.x_shift) * e.x_sy +
+               (long long)(x >> e.x_shift) * e.x_sx + c0;
+          hp = reinterpret_cast<__half*>(e.out) + (long long)b * e.o_sb + (long long)y * e.o_sy +
+               (long long)x * e.o_sx + c0;
+        }
+        for (int j = 0; j < half_n; j += 16) {
+          float g[16], bt16[16];
+          tmem_ld16(taddr + (uint32_t)j, g);
+          tmem_ld16(taddr + (uint32_t)(half_n + j), bt16);
+          tmem_ld_wait();
+          if (valid) {
+          const float4* bg = reinterpret_cast<const float4*>(e.bias + nrow0 + j);
+          const float4* bb = reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + j);
+          const float4* xv4 = reinterpret_cast<const float4*>(xp + j);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 tg = __ldg(bg + i), tb4 = __ldg(bb + i), xv = __ldg(xv4 + i);
+            const float4 ch0 = __ldg(e.chan + c0 + j + 4 * i);
+            const float4 ch1 = __ldg(e.chan + c0 + j + 4 * i + 1);
+            const float4 ch2 = __ldg(e.chan + c0 + j + 4 * i + 2);
+            const float4 ch3 = __ldg(e.chan + c0 + j + 4 * i + 3);
+            const float o0 = modulate_elem(xv.x, nz, ch0, g[4 * i] + tg.x, bt16[4 * i] + tb4.x, e.act);
+            const float o1 = modulate_elem(xv.y, nz, ch1, g[4 * i + 1] + tg.y, bt16[4 * i + 1] + tb4.y, e.act);
+            const float o2 = modulate_elem(xv.z, nz, ch2, g[4 * i + 2] + tg.z, bt16[4 * i + 2] + tb4.z, e.act);
+            const float o3 = modulate_elem(xv.w, nz, ch3, g[4 * i + 3] + tg.w, bt16[4 * i + 3] + tb4.w, e.act);
+            __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
+            pk[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+          uint4* op = reinterpret_cast<uint4*>(hp + j);
+          op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT checker kernel: same contract, one thread per output element, no tensor cores / TMA.
+// Used only by tests (impl = CHB_IMPL_SIMT_DEBUG) to bisect the tcgen05 main loop from the epilogue.
+// ------------------------------------------------------------------------------------------------
+struct SimtSeg {
+  const __half* a;
+  long long a_sb, a_sy, a_sx;
+  int ch_off, C, taps, per_image;
+  const __half* w;
+  long long w_sb;
+};
+struct SimtParams {
+  SimtSeg seg[kMaxSeg];
+  int nseg, B, H, W, N, BN, epi;
+  EpiK e;
+};
+
+__device__ float simt_dot(const SimtParams& p, int b, int y, int x, int nrow) {
+  float acc = 0.f;
+  for (int s = 0; s < p.nseg; ++s) {
+    const SimtSeg& sg = p.seg[s];
+    const int K = sg.taps * sg.C;
+    const __half* wrow = sg.w + (sg.per_image ? (long long)b * (sg.w_sb > 0 ? sg.w_sb : (long long)p.e.nrows * K) : 0) + (long long)nrow * K;
+    for (int tap = 0; tap < sg.taps; ++tap) {
+      const int yy = y + (sg.taps == 9 ? tap / 3 - 1 : 0);
+      const int xx = x + (sg.taps == 9 ? tap % 3 - 1 : 0);
+      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+      const __half* ap = sg.a + (long long)b * sg.a_sb + (long long)yy * sg.a_sy + (long long)xx * sg.a_sx + sg.ch_off;
+      const __half* wp = wrow + tap * sg.C;
+      for (int c = 0; c < sg.C; ++c) acc = fmaf(__half2float(ap[c]), __half2float(wp[c]), acc);
+    }
+  }
+  return acc;
+}
+
+__global__ void conv_simt_kernel(const SimtParams p) {
+  const long long cols = p.epi == CHB_EPI_PLAIN ? p.N : p.N / 2;
+  const long long total = (long long)p.B * p.H * p.W * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % cols);
+    long long pix = i / cols;
+    const int x = (int)(pix % p.W);
+    pix /= p.W;
+    const int y = (int)(pix % p.H);
+    const int b = (int)(pix / p.H);
+    if (p.epi == CHB_EPI_PLAIN) {
+      plain_store_elem(p.e, b, y, x, n, simt_dot(p, b, y, x, n));
+    } else {
+      const int half_n = p.BN / 2;
+      const int t = n / half_n, j = n % half_n;
+      const int grow = t * p.BN + j, brow = grow + half_n;
+      const float g = simt_dot(p, b, y, x, grow) + __ldg(p.e.bias + grow);
+      const float be = simt_dot(p, b, y, x, brow) + __ldg(p.e.bias + brow);
+      const float nz = p.e.noise ? __ldg(p.e.noise + ((long long)b * p.W + x) * p.H + y) : 0.f;
+      const float xv = __ldg(p.e.x + (long long)b * p.e.x_sb + (long long)(y >> p.e.x_shift) * p.e.x_sy +
+                             (long long)(x >> p.e.x_shift) * p.e.x_sx + n);
+      const float o = modulate_elem(xv, nz, __ldg(p.e.chan + n), g, be, p.e.act);
+      reinterpret_cast<__half*>(p.e.out)[(long long)b * p.e.o_sb + (long long)y * p.e.o_sy + (long long)x * p.e.o_sx + n] =
+          __float2half_rn(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor maps, plans, launches
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box, int kc) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return CHB_ERR_CUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u stride0 %llu", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+             (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], box[2], rank > 3 ? box[3] : 0,
+             (unsigned long long)strides_b[0]);
+    set_error(buf);
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+static int validate_desc(const chb_conv_desc& d) {
+  char buf[256];
+#define CHB_REQUIRE(cond, msg)                                      \
+  if (!(cond)) {                                                    \
+    snprintf(buf, sizeof buf, "chb_conv: invalid descriptor: %s", msg); \
+    set_error(buf);                                                 \
+    return CHB_ERR_ARG;                                             \
+  }
+  CHB_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0, "B,H,W must be positive");
+  CHB_REQUIRE(d.TW > 0 && d.TH > 0 && d.TB > 0 && d.TW * d.TH * d.TB <= 128, "tile must have 1..128 rows");
+  CHB_REQUIRE(d.TW <= 256 && d.TH <= 256 && d.TB <= 256, "tile dims <= 256");
+  CHB_REQUIRE(d.nseg >= 1 && d.nseg <= kMaxSeg, "1..3 segments");
+  CHB_REQUIRE(d.BN >= 16 && d.BN <= 256 && d.BN % 16 == 0, "BN in 16..256, multiple of 16");
+  CHB_REQUIRE(d.Nrows > 0 && d.Nrows % d.BN == 0, "Nrows must be a positive multiple of BN");
+  CHB_REQUIRE(d.N > 0 && d.N <= d.Nrows, "0 < N <= Nrows");
+  CHB_REQUIRE(d.epi == CHB_EPI_PLAIN || d.epi == CHB_EPI_MODULATE, "unknown epilogue");
+  CHB_REQUIRE(d.out != nullptr, "out is NULL");
+  for (int s = 0; s < d.nseg; ++s) {
+    const chb_conv_seg& g = d.seg[s];
+    CHB_REQUIRE(g.a && g.w, "segment pointers NULL");
+    CHB_REQUIRE(g.taps == 9 || g.taps == 1, "taps must be 9 or 1");
+    CHB_REQUIRE(g.C == 32 || (g.C > 0 && g.C % 64 == 0), "segment C must be 32 or a multiple of 64");
+    CHB_REQUIRE(g.ch_off >= 0 && g.ch_off + g.C <= g.Ca, "channel window exceeds tensor");
+    CHB_REQUIRE((g.a_sx % 8) == 0 && (g.a_sy % 8) == 0 && (g.a_sb % 8) == 0 && (g.ch_off % 8) == 0,
+                "activation strides must be multiples of 8 elements (16 B)");
+    CHB_REQUIRE(!g.per_image || d.TB == 1, "per-image weights need TB == 1");
+    CHB_REQUIRE((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0,
+                "operands must be 16-byte aligned");
+  }
+  if (d.epi == CHB_EPI_MODULATE) {
+    CHB_REQUIRE(d.x && d.chan && d.bias, "modulate epilogue needs x, chan and bias");
+    CHB_REQUIRE(d.BN % 32 == 0 && d.N == d.Nrows, "modulate epilogue needs BN % 32 == 0 and N == Nrows");
+    CHB_REQUIRE(d.o_sn == 1 || d.o_sn == 0, "modulate output is channels-last");
+  }
+#undef CHB_REQUIRE
+  return CHB_OK;
+}
+
+int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
+  int rc = validate_desc(d);
+  if (rc != CHB_OK) return rc;
+  memset(plan, 0, sizeof(*plan));
+  plan->desc = d;
+  ConvKParams& k = plan->kp;
+  k.nseg = d.nseg;
+  k.B = d.B; k.H = d.H; k.W = d.W;
+  k.TW = d.TW; k.TH = d.TH; k.TB = d.TB;
+  k.rows = d.TW * d.TH * d.TB;
+  k.tiles_x = (d.W + d.TW - 1) / d.TW;
+  k.tiles_y = (d.H + d.TH - 1) / d.TH;
+  const int tiles_b = (d.B + d.TB - 1) / d.TB;
+  k.m_tiles = k.tiles_x * k.tiles_y * tiles_b;
+  k.n_tiles = d.Nrows / d.BN;
+  k.BN = d.BN;
+  k.N = d.N;
+  k.stage_bytes = kATileBytes + ((d.BN * 128 + 1023) / 1024) * 1024;
+  k.nstages = kSmemBudget / k.stage_bytes;
+  if (k.nstages > kMaxStages) k.nstages = kMaxStages;
+  plan->smem_bytes = k.nstages * k.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  long long ktotal = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    const chb_conv_seg& g = d.seg[s];
+    const int kc = g.C == 32 ? 32 : 64;
+    k.seg[s].taps = g.taps;
+    k.seg[s].kc = kc;
+    k.seg[s].nchunk = g.C / kc;
+    k.seg[s].ch_off = g.ch_off;
+    k.seg[s].per_image = g.per_image;
+    ktotal += (long long)g.taps * g.C;
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)g.Ca, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+      cuuint64_t str[3] = {(cuuint64_t)g.a_sx * 2, (cuuint64_t)g.a_sy * 2, (cuuint64_t)g.a_sb * 2};
+      cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)d.TW, (cuuint32_t)d.TH, (cuuint32_t)d.TB};
+      rc = encode_map(&k.tmA[s], g.a, 4, dims, str, box, kc);
+      if (rc != CHB_OK) return rc;
+    }
+    {
+      const cuuint64_t K = (cuuint64_t)g.taps * g.C;
+      cuuint64_t dims[3] = {K, (cuuint64_t)d.Nrows, (cuuint64_t)(g.per_image ? d.B : 1)};
+      const cuuint64_t img_stride = (g.per_image && g.w_sb > 0) ? (cuuint64_t)g.w_sb * 2 : K * 2 * (cuuint64_t)d.Nrows;
+      cuuint64_t str[2] = {K * 2, img_stride};
+      cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)d.BN, 1};
+      rc = encode_map(&k.tmW[s], g.w, 3, dims, str, box, kc);
+      if (rc != CHB_OK) return rc;
+    }
+  }
+  EpiK& e = k.e;
+  e.act = d.act; e.bias = d.bias; e.bias_per_image = d.bias_per_image; e.nrows = d.Nrows;
+  e.out = d.out; e.out_dtype = d.out_dtype;
+  e.o_sb = d.o_sb; e.o_sy = d.o_sy; e.o_sx = d.o_sx; e.o_sn = d.o_sn;
+  e.o_ngroup = d.o_ngroup; e.o_sgroup = d.o_sgroup;
+  e.res = d.res; e.r_sb = d.r_sb; e.r_sy = d.r_sy; e.r_sx = d.r_sx; e.r_shift = d.r_shift;
+  e.x = d.x; e.x_sb = d.x_sb; e.x_sy = d.x_sy; e.x_sx = d.x_sx; e.x_shift = d.x_shift;
+  e.noise = d.noise;
+  e.chan = reinterpret_cast<const float4*>(d.chan);
+  const int total = k.m_tiles * k.n_tiles;
+  const int sms = device_sm_count();
+  plan->grid = total < sms ? total : sms;
+  plan->flops = 2.0 * 128.0 * d.BN * (double)ktotal * (double)total;
+  return CHB_OK;
+}
+
+static int ensure_smem_attr() {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(conv_igemm_kernel<CHB_EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kSmemBudget + 2048);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(conv_igemm_kernel<CHB_EPI_MODULATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemBudget + 2048);
+  });
+  if (err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
+  if (impl == CHB_IMPL_SIMT_DEBUG) {
+    SimtParams sp;
+    memset(&sp, 0, sizeof sp);
+    const chb_conv_desc& d = plan.desc;
+    sp.nseg = d.nseg; sp.B = d.B; sp.H = d.H; sp.W = d.W; sp.N = d.N; sp.BN = d.BN; sp.epi = d.epi;
+    sp.e = plan.kp.e;
+    for (int s = 0; s < d.nseg; ++s) {
+      sp.seg[s].a = reinterpret_cast<const __half*>(d.seg[s].a);
+      sp.seg[s].a_sb = d.seg[s].a_sb; sp.seg[s].a_sy = d.seg[s].a_sy; sp.seg[s].a_sx = d.seg[s].a_sx;
+      sp.seg[s].ch_off = d.seg[s].ch_off; sp.seg[s].C = d.seg[s].C; sp.seg[s].taps = d.seg[s].taps;
+      sp.seg[s].per_image = d.seg[s].per_image;
+      sp.seg[s].w = reinterpret_cast<const __half*>(d.seg[s].w);
+      sp.seg[s].w_sb = d.seg[s].w_sb;
+    }
+    conv_simt_kernel<<<device_sm_count() * 8, 256, 0, stream>>>(sp);
+  } else {
+    int rc = ensure_smem_attr();
+    if (rc != CHB_OK) return rc;
+    if (plan.desc.epi == CHB_EPI_PLAIN) {
+      conv_igemm_kernel<CHB_EPI_PLAIN><<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
+    } else {
+      conv_igemm_kernel<CHB_EPI_MODULATE><<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
+    }
+  }
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error(std::string("conv launch failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+}  // namespace chb
+
+extern "C" {
+
+int chb_version(void) { return 100; }
+const char* chb_last_error(void) { return chb::last_error_cstr(); }
+
+int chb_check_device(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    chb::set_error("no CUDA device");
+    return CHB_ERR_CUDA;
+  }
+  if (major != 10) {
+    chb::set_error("ctrlhair_b200 kernels are built for sm_100a only; current device is not compute capability 10.x");
+    return CHB_ERR_ARCH;
+  }
+  return CHB_OK;
+}
+
+int chb_conv_run(const chb_conv_desc* d, int impl, void* stream) {
+  if (!d) {
+    chb::set_error("chb_conv_run: NULL descriptor");
+    return CHB_ERR_ARG;
+  }
+  int rc = chb_check_device();
+  if (rc != CHB_OK) return rc;
+  chb::ConvPlan plan;
+  rc = chb::build_conv_plan(*d, &plan);
+  if (rc != CHB_OK) return rc;
+  return chb::launch_conv_plan(plan, impl, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

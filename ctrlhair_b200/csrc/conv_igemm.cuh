@@ -1,0 +1,71 @@
+// Internal (C++) interface of the implicit-GEMM convolution operator.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+#include "../../include/ctrlhair_b200.h"
+
+namespace chb {
+
+constexpr int kMaxSeg = 3;
+constexpr int kATileBytes = 16384;  // 128 rows x 128 B
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 200 * 1024;
+constexpr int kConvThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+
+struct SegK {
+  int taps, nchunk, kc, ch_off, per_image, pad;
+};
+
+struct EpiK {
+  int act;
+  const float* bias;
+  int bias_per_image;
+  int nrows;
+  // plain
+  void* out;
+  int out_dtype;
+  long long o_sb, o_sy, o_sx, o_sn;
+  int o_ngroup;
+  long long o_sgroup;
+  const float* res;
+  long long r_sb, r_sy, r_sx;
+  int r_shift;
+  // modulate
+  const float* x;
+  long long x_sb, x_sy, x_sx;
+  int x_shift;
+  const float* noise;
+  const float4* chan;
+};
+
+struct ConvKParams {
+  CUtensorMap tmA[kMaxSeg];
+  CUtensorMap tmW[kMaxSeg];
+  SegK seg[kMaxSeg];
+  int nseg;
+  int B, H, W;
+  int TW, TH, TB, rows;
+  int tiles_x, tiles_y, m_tiles, n_tiles;
+  int BN, N;
+  int nstages, stage_bytes;
+  EpiK e;
+};
+
+struct ConvPlan {
+  ConvKParams kp;
+  chb_conv_desc desc;  // kept for the SIMT checker kernel
+  int grid;
+  int smem_bytes;
+  double flops;  // tensor-core FLOPs issued (padding included)
+};
+
+void set_error(const std::string& msg);
+int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan);
+int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream);
+int device_sm_count();
+int codes_cast_transpose(const float* in, void* out, int B, int NC, int L, cudaStream_t stream);
+
+}  // namespace chb

@@ -1,0 +1,644 @@
+// SEAN/SPADE generator forward as a fixed schedule of conv_igemm launches.
+//
+// Follows sean_codes/models/networks/generator.py:72-109 (SPADEGenerator.forward, 'normal' upsampling),
+// architecture.py:69-96 (SPADEResnetBlock) and normalization.py:108-189 (ACE) in the exactly equivalent
+// region-factored form: the 512-channel piecewise-constant style map is never materialised; instead
+//   mu[b,j]   = relu(fc_mu_j(code[b,j]))                                  (normalization.py:131,148)
+//   Weff[b]   = alpha * conv_{gamma,beta}.weight contracted with mu[b]    -> a per-image 19-channel 3x3 kernel
+//   [g | b]   = conv3x3([one_hot | actv], [Weff[b] | (1-alpha) * mlp_{gamma,beta}.weight]) + folded bias
+// The nearest 2x upsample between blocks (generator.py:85-100) is folded into the readers (y>>1, x>>1).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ctrlhair_b200.h"
+#include "conv_igemm.cuh"
+
+namespace chb {
+
+struct TensorInfo {
+  std::string name;
+  int64_t offset, nbytes;
+  int dtype;
+};
+
+struct AceInfo {
+  int C;          // norm_nc
+  int styled;
+  int actv_off;   // channel offset of this ACE's actv inside the block's actv tensor
+  int style_idx;  // index among styled ACEs (-1 if unstyled)
+  int64_t weff_row0;  // first row of this ACE inside the per-image Weff table
+  int t_gbw, t_gbb, t_chan, t_stylew;  // blob tensor ids
+  int64_t noise_pix0;  // offset (in pixels per image) of this ACE's noise plane
+};
+
+struct BlockInfo {
+  std::string name;
+  int fin, fout, fmid, r, level, in_shift, shortcut, styled;
+  AceInfo ace[3];  // order: s, 0, 1 (s unused when !shortcut)
+  int n_ace;
+  int t_shw, t_shb, t_c0w, t_c0b, t_c1w, t_c1b, t_csw;
+  int64_t ws_xout;  // workspace offset of the block output
+};
+
+struct Step {
+  ConvPlan plan;
+  int noise_ace_block = -1, noise_ace = -1;  // modulate steps: which noise plane
+  bool final_image = false;
+};
+
+}  // namespace chb
+
+using namespace chb;
+
+struct chb_generator {
+  chb_gen_config cfg;
+  int sw;  // latent size = crop / 32
+  std::vector<TensorInfo> tensors;
+  int64_t blob_bytes = 0;
+  std::vector<BlockInfo> blocks;
+  int n_styled = 0;
+  int64_t weff_rows = 0;      // rows per image of the Weff table (each row = 32 fp16)
+  int64_t noise_pix = 0;      // noise floats per image
+  int t_fcw, t_fcb, t_imgw, t_imgb, t_fcmuw, t_fcmub;
+  // workspace layout (byte offsets, sized for max_batch)
+  int64_t ws_bytes = 0;
+  int64_t ws_labels, ws_codes32, ws_out, ws_codes16, ws_noise, ws_mu, ws_weff, ws_x0;
+  int64_t ws_onehot[6];
+  int64_t ws_actv, ws_hs, ws_h0, ws_h1, ws_dx0;
+  const uint8_t* blob = nullptr;
+  uint8_t* ws = nullptr;
+  std::map<int, std::vector<Step>> plans;  // keyed by batch size
+  std::map<std::string, std::pair<int64_t, int>> debug;  // name -> (ws offset, dtype)
+  int step_limit = -1;  // debug: run only the first n conv steps
+};
+
+namespace chb {
+
+static int add_tensor(chb_generator* g, const std::string& name, int64_t nbytes, int dtype) {
+  TensorInfo t;
+  t.name = name;
+  t.offset = g->blob_bytes;
+  t.nbytes = nbytes;
+  t.dtype = dtype;
+  g->tensors.push_back(t);
+  g->blob_bytes += (nbytes + 255) / 256 * 256;
+  return (int)g->tensors.size() - 1;
+}
+
+static int64_t ws_alloc(chb_generator* g, int64_t nbytes) {
+  const int64_t off = g->ws_bytes;
+  g->ws_bytes += (nbytes + 1023) / 1024 * 1024;
+  return off;
+}
+
+static void build_layout(chb_generator* g) {
+  const chb_gen_config& c = g->cfg;
+  const int nf = c.ngf, L = c.style_len, B = c.max_batch;
+  g->sw = c.crop / 32;
+  struct Spec { const char* name; int fin, fout, rmul, styled; };
+  const Spec specs[7] = {{"head_0", 16, 16, 1, 1},     {"G_middle_0", 16, 16, 2, 1}, {"G_middle_1", 16, 16, 2, 1},
+                         {"up_0", 16, 8, 4, 1},        {"up_1", 8, 4, 8, 1},         {"up_2", 4, 2, 16, 1},
+                         {"up_3", 2, 1, 32, 0}};
+  g->t_fcw = add_tensor(g, "fc.w", (int64_t)16 * nf * 9 * 32 * 2, CHB_F16);
+  g->t_fcb = add_tensor(g, "fc.b", (int64_t)16 * nf * 4, CHB_F32);
+  int prev_r = g->sw;
+  int64_t noise_pix = 0;
+  for (int i = 0; i < 7; ++i) {
+    BlockInfo b;
+    b.name = specs[i].name;
+    b.fin = specs[i].fin * nf;
+    b.fout = specs[i].fout * nf;
+    b.fmid = b.fin < b.fout ? b.fin : b.fout;
+    b.r = g->sw * specs[i].rmul;
+    b.level = 0;
+    while ((g->sw << b.level) < b.r) ++b.level;
+    b.in_shift = (b.r == prev_r) ? 0 : 1;
+    prev_r = b.r;
+    b.shortcut = b.fin != b.fout;
+    b.styled = specs[i].styled;
+    b.n_ace = b.shortcut ? 3 : 2;
+    const char* an[3] = {"ace_s", "ace_0", "ace_1"};
+    int actv_off = 0;
+    b.t_shw = add_tensor(g, b.name + ".sh.w", (int64_t)128 * b.n_ace * 9 * 32 * 2, CHB_F16);
+    b.t_shb = add_tensor(g, b.name + ".sh.b", (int64_t)128 * b.n_ace * 4, CHB_F32);
+    for (int a = 0; a < 3; ++a) {
+      AceInfo& A = b.ace[a];
+      memset(&A, 0, sizeof A);
+      A.style_idx = -1;
+      if (a == 0 && !b.shortcut) continue;
+      A.C = (a == 2) ? b.fmid : b.fin;
+      A.styled = b.styled;
+      A.actv_off = actv_off;
+      actv_off += 128;
+      A.noise_pix0 = noise_pix;
+      noise_pix += (int64_t)b.r * b.r;
+      const std::string p = b.name + "." + an[a];
+      A.t_gbw = add_tensor(g, p + ".gb.w", (int64_t)2 * A.C * 9 * 128 * 2, CHB_F16);
+      A.t_gbb = add_tensor(g, p + ".gb.b", (int64_t)2 * A.C * 4, CHB_F32);
+      A.t_chan = add_tensor(g, p + ".chan", (int64_t)A.C * 16, CHB_F32);
+      A.t_stylew = -1;
+      if (A.styled) {
+        A.style_idx = g->n_styled++;
+        A.weff_row0 = g->weff_rows;
+        g->weff_rows += (int64_t)2 * A.C * 9;
+      }
+    }
+    b.t_c0w = add_tensor(g, b.name + ".conv_0.w", (int64_t)b.fmid * 9 * b.fin * 2, CHB_F16);
+    b.t_c0b = add_tensor(g, b.name + ".conv_0.b", (int64_t)b.fmid * 4, CHB_F32);
+    b.t_c1w = add_tensor(g, b.name + ".conv_1.w", (int64_t)b.fout * 9 * b.fmid * 2, CHB_F16);
+    b.t_c1b = add_tensor(g, b.name + ".conv_1.b", (int64_t)b.fout * 4, CHB_F32);
+    b.t_csw = b.shortcut ? add_tensor(g, b.name + ".conv_s.w", (int64_t)b.fout * b.fin * 2, CHB_F16) : -1;
+    g->blocks.push_back(b);
+  }
+  g->noise_pix = noise_pix;
+  // style weights: one tensor per styled ACE, laid out back to back
+  for (auto& b : g->blocks)
+    for (int a = 0; a < 3; ++a) {
+      AceInfo& A = b.ace[a];
+      if (A.C && A.styled) {
+        const char* an[3] = {"ace_s", "ace_0", "ace_1"};
+        A.t_stylew = add_tensor(g, b.name + "." + an[a] + ".style.w", (int64_t)2 * A.C * 9 * L * 2, CHB_F16);
+      }
+    }
+  g->t_fcmuw = add_tensor(g, "fcmu.w", (int64_t)c.label_nc * g->n_styled * L * L * 2, CHB_F16);
+  g->t_fcmub = add_tensor(g, "fcmu.b", (int64_t)c.label_nc * g->n_styled * L * 4, CHB_F32);
+  g->t_imgw = add_tensor(g, "conv_img.w", (int64_t)16 * 9 * nf * 2, CHB_F16);
+  g->t_imgb = add_tensor(g, "conv_img.b", (int64_t)16 * 4, CHB_F32);
+
+  // ---------------- workspace
+  const int64_t S = c.crop;
+  g->ws_labels = ws_alloc(g, (int64_t)B * S * S);
+  g->ws_codes32 = ws_alloc(g, (int64_t)B * c.label_nc * L * 4);
+  g->ws_out = ws_alloc(g, (int64_t)B * 3 * S * S * 4);
+  g->ws_codes16 = ws_alloc(g, (int64_t)B * c.label_nc * L * 2);
+  g->ws_noise = ws_alloc(g, (int64_t)B * g->noise_pix * 4);
+  g->ws_mu = ws_alloc(g, (int64_t)g->n_styled * B * c.label_nc * L * 2);
+  g->ws_weff = ws_alloc(g, (int64_t)B * g->weff_rows * 32 * 2);
+  for (int l = 0; l < 6; ++l) {
+    const int64_t r = (int64_t)g->sw << l;
+    g->ws_onehot[l] = ws_alloc(g, (int64_t)B * r * r * 32 * 2);
+  }
+  g->ws_x0 = ws_alloc(g, (int64_t)B * g->sw * g->sw * 16 * nf * 4);
+  g->debug["x_fc"] = {g->ws_x0, CHB_F32};
+  int64_t m_actv = 0, m_hin = 0, m_h1 = 0, m_dx0 = 0;
+  for (auto& b : g->blocks) {
+    const int64_t px = (int64_t)B * b.r * b.r;
+    m_actv = std::max<int64_t>(m_actv, px * 128 * b.n_ace * 2);
+    m_hin = std::max<int64_t>(m_hin, px * b.fin * 2);
+    m_h1 = std::max<int64_t>(m_h1, px * b.fmid * 2);
+    m_dx0 = std::max<int64_t>(m_dx0, px * b.fmid * 4);
+    const bool last = (&b == &g->blocks.back());
+    b.ws_xout = ws_alloc(g, px * b.fout * (last ? 2 : 4));
+    g->debug["x_" + b.name] = {b.ws_xout, last ? CHB_F16 : CHB_F32};
+  }
+  g->ws_actv = ws_alloc(g, m_actv);
+  g->ws_hs = ws_alloc(g, m_hin);
+  g->ws_h0 = ws_alloc(g, m_hin);
+  g->ws_h1 = ws_alloc(g, m_h1);
+  g->ws_dx0 = ws_alloc(g, m_dx0);
+  g->debug["actv"] = {g->ws_actv, CHB_F16};
+  g->debug["h_s"] = {g->ws_hs, CHB_F16};
+  g->debug["h_0"] = {g->ws_h0, CHB_F16};
+  g->debug["h_1"] = {g->ws_h1, CHB_F16};
+  g->debug["dx0"] = {g->ws_dx0, CHB_F32};
+  g->debug["mu"] = {g->ws_mu, CHB_F16};
+  g->debug["weff"] = {g->ws_weff, CHB_F16};
+  g->debug["noise"] = {g->ws_noise, CHB_F32};
+  g->debug["out"] = {g->ws_out, CHB_F32};
+  for (int l = 0; l < 6; ++l) g->debug["onehot" + std::to_string(l)] = {g->ws_onehot[l], CHB_F16};
+}
+
+static const void* blobp(const chb_generator* g, int t) { return g->blob + g->tensors[t].offset; }
+
+static void tile_for(int r, int* TW, int* TH) {
+  *TW = r < 8 ? r : 8;
+  *TH = r < 16 ? r : 16;
+  if (*TW * *TH > 128) *TH = 128 / *TW;
+}
+
+static chb_conv_seg make_seg(const void* a, int r, int Ca, int ch_off, int C, int taps, const void* w) {
+  chb_conv_seg s;
+  memset(&s, 0, sizeof s);
+  s.a = a;
+  s.a_sx = Ca;
+  s.a_sy = (int64_t)r * Ca;
+  s.a_sb = (int64_t)r * r * Ca;
+  s.Ca = Ca;
+  s.ch_off = ch_off;
+  s.C = C;
+  s.taps = taps;
+  s.w = w;
+  return s;
+}
+
+static chb_conv_desc base_desc(int B, int r) {
+  chb_conv_desc d;
+  memset(&d, 0, sizeof d);
+  d.B = B; d.H = r; d.W = r;
+  tile_for(r, &d.TW, &d.TH);
+  d.TB = 1;
+  return d;
+}
+
+static void nhwc_out(chb_conv_desc* d, void* out, int dtype, int r, int C) {
+  d->out = out; d->out_dtype = dtype;
+  d->o_sn = 1; d->o_sx = C; d->o_sy = (int64_t)r * C; d->o_sb = (int64_t)r * r * C;
+}
+
+static int push_step(std::vector<Step>& steps, const chb_conv_desc& d, int nb = -1, int na = -1, bool fin = false) {
+  Step s;
+  int rc = build_conv_plan(d, &s.plan);
+  if (rc != CHB_OK) return rc;
+  s.noise_ace_block = nb;
+  s.noise_ace = na;
+  s.final_image = fin;
+  steps.push_back(s);
+  return CHB_OK;
+}
+
+static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
+  const chb_gen_config& c = g->cfg;
+  const int nf = c.ngf, L = c.style_len, NC = c.label_nc;
+  uint8_t* ws = g->ws;
+  int rc;
+  // ---- style path 1: mu[a][b][j][:] = relu(fc_mu_j(code[b][j]))  — one grouped launch, image == class j
+  if (g->n_styled > 0) {
+    chb_conv_desc d;
+    memset(&d, 0, sizeof d);
+    d.B = NC; d.H = 1; d.W = B;
+    d.TW = B >= 128 ? 128 : (B + 7) / 8 * 8; d.TH = 1; d.TB = 1;
+    d.nseg = 1;
+    chb_conv_seg& s = d.seg[0];
+    memset(&s, 0, sizeof s);
+    s.a = ws + g->ws_codes16;
+    s.a_sx = L; s.a_sy = (int64_t)B * L; s.a_sb = (int64_t)B * L;  // codes16 is [class][image][L]
+    s.Ca = L; s.ch_off = 0; s.C = L; s.taps = 1;
+    s.w = blobp(g, g->t_fcmuw);
+    s.per_image = 1;
+    d.N = d.Nrows = g->n_styled * L;
+    d.BN = 256;
+    d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_RELU;
+    d.bias = reinterpret_cast<const float*>(blobp(g, g->t_fcmub));
+    d.bias_per_image = 1;
+    d.out = ws + g->ws_mu; d.out_dtype = CHB_F16;
+    d.o_sb = L; d.o_sy = 0; d.o_sx = (int64_t)NC * L; d.o_sn = 1;
+    d.o_ngroup = L; d.o_sgroup = (int64_t)B * NC * L;
+    if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+  }
+  // ---- style path 2: Weff[b][n*9+tap][j] = sum_ci Wstyle[n*9+tap][ci] * mu[b][j][ci]  (per styled ACE)
+  for (auto& b : g->blocks)
+    for (int a = 0; a < 3; ++a) {
+      const AceInfo& A = b.ace[a];
+      if (!A.C || !A.styled) continue;
+      chb_conv_desc d;
+      memset(&d, 0, sizeof d);
+      d.B = B; d.H = 1; d.W = NC;
+      d.TW = 32; d.TH = 1; d.TB = 4;
+      d.nseg = 1;
+      chb_conv_seg& s = d.seg[0];
+      memset(&s, 0, sizeof s);
+      s.a = ws + g->ws_mu + (int64_t)A.style_idx * B * NC * L * 2;
+      s.a_sx = L; s.a_sy = (int64_t)NC * L; s.a_sb = (int64_t)NC * L;
+      s.Ca = L; s.C = L; s.taps = 1;
+      s.w = blobp(g, A.t_stylew);
+      d.N = d.Nrows = 2 * A.C * 9;
+      d.BN = 256;
+      d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
+      d.out = ws + g->ws_weff + A.weff_row0 * 32 * 2; d.out_dtype = CHB_F16;
+      d.o_sb = g->weff_rows * 32; d.o_sy = 0; d.o_sx = 1; d.o_sn = 32;
+      if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+    }
+  // ---- x = fc(one_hot @ sw)   (generator.py:75-76)
+  {
+    chb_conv_desc d = base_desc(B, g->sw);
+    d.nseg = 1;
+    d.seg[0] = make_seg(ws + g->ws_onehot[0], g->sw, 32, 0, 32, 9, blobp(g, g->t_fcw));
+    d.N = d.Nrows = 16 * nf; d.BN = 256;
+    d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
+    d.bias = reinterpret_cast<const float*>(blobp(g, g->t_fcb));
+    nhwc_out(&d, ws + g->ws_x0, CHB_F32, g->sw, 16 * nf);
+    if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+  }
+  const float* xin = reinterpret_cast<const float*>(ws + g->ws_x0);
+  int xin_r = g->sw;
+  for (size_t bi = 0; bi < g->blocks.size(); ++bi) {
+    const BlockInfo& b = g->blocks[bi];
+    const bool last = bi + 1 == g->blocks.size();
+    const int r = b.r, actvC = 128 * b.n_ace;
+    const void* onehot = ws + g->ws_onehot[b.level];
+    // actv = relu(mlp_shared(seg)) for every ACE of the block at once (normalization.py:253)
+    {
+      chb_conv_desc d = base_desc(B, r);
+      d.nseg = 1;
+      d.seg[0] = make_seg(onehot, r, 32, 0, 32, 9, blobp(g, b.t_shw));
+      d.N = d.Nrows = actvC; d.BN = 128;
+      d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_RELU;
+      d.bias = reinterpret_cast<const float*>(blobp(g, b.t_shb));
+      nhwc_out(&d, ws + g->ws_actv, CHB_F16, r, actvC);
+      if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+    }
+    auto modulate = [&](int a, const float* x, int x_r, int x_shift, int xC, void* hout, int act) -> int {
+      const AceInfo& A = b.ace[a];
+      chb_conv_desc d = base_desc(B, r);
+      int ns = 0;
+      if (A.styled) {
+        d.seg[ns] = make_seg(onehot, r, 32, 0, 32, 9, ws + g->ws_weff + A.weff_row0 * 32 * 2);
+        d.seg[ns].per_image = 1;
+        d.seg[ns].w_sb = g->weff_rows * 32;
+        ++ns;
+      }
+      d.seg[ns++] = make_seg(ws + g->ws_actv, r, actvC, A.actv_off, 128, 9, blobp(g, A.t_gbw));
+      d.nseg = ns;
+      d.N = d.Nrows = 2 * A.C;
+      d.BN = d.N < 256 ? d.N : 256;
+      d.epi = CHB_EPI_MODULATE; d.act = act;
+      d.bias = reinterpret_cast<const float*>(blobp(g, A.t_gbb));
+      d.chan = reinterpret_cast<const float*>(blobp(g, A.t_chan));
+      d.x = x; d.x_shift = x_shift;
+      d.x_sx = xC; d.x_sy = (int64_t)x_r * xC; d.x_sb = (int64_t)x_r * x_r * xC;
+      d.noise = reinterpret_cast<const float*>(ws + g->ws_noise) + (int64_t)B * A.noise_pix0;
+      nhwc_out(&d, hout, CHB_F16, r, A.C);
+      return push_step(steps, d, (int)bi, a);
+    };
+    if (b.shortcut) {
+      if ((rc = modulate(0, xin, xin_r, b.in_shift, b.fin, ws + g->ws_hs, CHB_ACT_NONE)) != CHB_OK) return rc;
+    }
+    if ((rc = modulate(1, xin, xin_r, b.in_shift, b.fin, ws + g->ws_h0, CHB_ACT_LRELU)) != CHB_OK) return rc;
+    // dx = conv_0(lrelu(ace_0(x)))   (architecture.py:73-75)
+    {
+      chb_conv_desc d = base_desc(B, r);
+      d.nseg = 1;
+      d.seg[0] = make_seg(ws + g->ws_h0, r, b.fin, 0, b.fin, 9, blobp(g, b.t_c0w));
+      d.N = d.Nrows = b.fmid; d.BN = b.fmid < 256 ? b.fmid : 256;
+      d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
+      d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c0b));
+      nhwc_out(&d, ws + g->ws_dx0, CHB_F32, r, b.fmid);
+      if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+    }
+    if ((rc = modulate(2, reinterpret_cast<const float*>(ws + g->ws_dx0), r, 0, b.fmid, ws + g->ws_h1,
+                       CHB_ACT_LRELU)) != CHB_OK)
+      return rc;
+    // out = x_s + conv_1(lrelu(ace_1(dx)))   (architecture.py:77-84); conv_s rides along as a 1x1 K-segment
+    {
+      chb_conv_desc d = base_desc(B, r);
+      int ns = 0;
+      d.seg[ns++] = make_seg(ws + g->ws_h1, r, b.fmid, 0, b.fmid, 9, blobp(g, b.t_c1w));
+      if (b.shortcut) {
+        d.seg[ns++] = make_seg(ws + g->ws_hs, r, b.fin, 0, b.fin, 1, blobp(g, b.t_csw));
+      } else {
+        d.res = xin; d.r_shift = b.in_shift;
+        d.r_sx = b.fin; d.r_sy = (int64_t)xin_r * b.fin; d.r_sb = (int64_t)xin_r * xin_r * b.fin;
+      }
+      d.nseg = ns;
+      d.N = d.Nrows = b.fout; d.BN = b.fout < 256 ? b.fout : 256;
+      d.epi = CHB_EPI_PLAIN;
+      d.act = last ? CHB_ACT_LRELU : CHB_ACT_NONE;  // generator.py:107 leaky_relu before conv_img
+      d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c1b));
+      nhwc_out(&d, ws + b.ws_xout, last ? CHB_F16 : CHB_F32, r, b.fout);
+      if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+    }
+    xin = reinterpret_cast<const float*>(ws + b.ws_xout);
+    xin_r = r;
+  }
+  // ---- image = tanh(conv_img(lrelu(x)))   (generator.py:107-108), fp32 NCHW
+  {
+    const BlockInfo& b = g->blocks.back();
+    const int r = b.r;
+    chb_conv_desc d = base_desc(B, r);
+    d.nseg = 1;
+    d.seg[0] = make_seg(ws + b.ws_xout, r, b.fout, 0, b.fout, 9, blobp(g, g->t_imgw));
+    d.N = 3; d.Nrows = 16; d.BN = 16;
+    d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_TANH;
+    d.bias = reinterpret_cast<const float*>(blobp(g, g->t_imgb));
+    d.out = ws + g->ws_out; d.out_dtype = CHB_F32;
+    d.o_sn = (int64_t)r * r; d.o_sx = 1; d.o_sy = r; d.o_sb = (int64_t)3 * r * r;
+    if ((rc = push_step(steps, d, -1, -1, true)) != CHB_OK) return rc;
+  }
+  return CHB_OK;
+}
+
+}  // namespace chb
+
+extern "C" {
+
+int chb_generator_create(const chb_gen_config* cfg, chb_generator** out) {
+  if (!cfg || !out) {
+    set_error("chb_generator_create: NULL argument");
+    return CHB_ERR_ARG;
+  }
+  if (cfg->ngf <= 0 || cfg->ngf % 64 != 0 || cfg->label_nc <= 0 || cfg->label_nc > 32 || cfg->crop < 32 ||
+      cfg->crop % 32 != 0 || (cfg->crop & (cfg->crop - 1)) != 0 || cfg->style_len <= 0 || cfg->style_len % 64 != 0 ||
+      cfg->max_batch <= 0) {
+    set_error(
+        "chb_generator_create: need ngf % 64 == 0, label_nc in 1..32, crop a power of two >= 32, style_len % 64 == 0, "
+        "max_batch > 0");
+    return CHB_ERR_ARG;
+  }
+  chb_generator* g = new chb_generator();
+  g->cfg = *cfg;
+  build_layout(g);
+  *out = g;
+  return CHB_OK;
+}
+
+void chb_generator_destroy(chb_generator* g) { delete g; }
+
+int chb_generator_num_tensors(const chb_generator* g) { return g ? (int)g->tensors.size() : 0; }
+
+int chb_generator_tensor_info(const chb_generator* g, int i, char* name, int name_cap, int64_t* offset,
+                              int64_t* nbytes, int* dtype) {
+  if (!g || i < 0 || i >= (int)g->tensors.size()) {
+    set_error("chb_generator_tensor_info: index out of range");
+    return CHB_ERR_ARG;
+  }
+  const TensorInfo& t = g->tensors[i];
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", t.name.c_str());
+  if (offset) *offset = t.offset;
+  if (nbytes) *nbytes = t.nbytes;
+  if (dtype) *dtype = t.dtype;
+  return CHB_OK;
+}
+
+int64_t chb_generator_blob_bytes(const chb_generator* g) { return g ? g->blob_bytes : 0; }
+int64_t chb_generator_workspace_bytes(const chb_generator* g) { return g ? g->ws_bytes : 0; }
+int64_t chb_generator_noise_floats(const chb_generator* g, int B) { return g ? g->noise_pix * B : 0; }
+
+int chb_generator_bind(chb_generator* g, const void* blob, void* workspace) {
+  if (!g || !blob || !workspace) {
+    set_error("chb_generator_bind: NULL argument");
+    return CHB_ERR_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(blob) & 255) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) {
+    set_error("chb_generator_bind: blob must be 256-byte and workspace 1024-byte aligned");
+    return CHB_ERR_ARG;
+  }
+  int rc = chb_check_device();
+  if (rc != CHB_OK) return rc;
+  g->blob = reinterpret_cast<const uint8_t*>(blob);
+  g->ws = reinterpret_cast<uint8_t*>(workspace);
+  g->plans.clear();
+  // Weff columns 19..31 are never written by the style GEMM and must read as zero.
+  cudaError_t err = cudaMemset(g->ws + g->ws_weff, 0, (size_t)g->cfg.max_batch * g->weff_rows * 32 * 2);
+  if (err != cudaSuccess) {
+    set_error(std::string("chb_generator_bind: cudaMemset failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+static int get_steps(chb_generator* g, int B, std::vector<Step>** out) {
+  auto it = g->plans.find(B);
+  if (it == g->plans.end()) {
+    std::vector<Step> steps;
+    int rc = build_steps(g, B, steps);
+    if (rc != CHB_OK) return rc;
+    it = g->plans.emplace(B, std::move(steps)).first;
+  }
+  *out = &it->second;
+  return CHB_OK;
+}
+
+int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
+                          uint64_t seed, float* out, int B, int impl, void* stream_) {
+  if (!g || !labels || !codes || !out) {
+    set_error("chb_generator_forward: NULL argument");
+    return CHB_ERR_ARG;
+  }
+  if (!g->blob || !g->ws) {
+    set_error("chb_generator_forward: generator is not bound to a weight blob / workspace");
+    return CHB_ERR_ARG;
+  }
+  if (B <= 0 || B > g->cfg.max_batch) {
+    set_error("chb_generator_forward: batch exceeds max_batch");
+    return CHB_ERR_ARG;
+  }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  std::vector<Step>* steps = nullptr;
+  int rc = get_steps(g, B, &steps);
+  if (rc != CHB_OK) return rc;
+  const chb_gen_config& c = g->cfg;
+  uint8_t* ws = g->ws;
+  rc = codes_cast_transpose(codes, ws + g->ws_codes16, B, c.label_nc, c.style_len, stream);
+  if (rc != CHB_OK) return rc;
+  int shifts[6];
+  void* outs[6];
+  for (int l = 0; l < 6; ++l) {
+    shifts[l] = 5 - l;
+    outs[l] = ws + g->ws_onehot[l];
+  }
+  rc = chb_onehot_pyramid(labels, B, c.crop, 6, shifts, outs, c.label_nc, stream);
+  if (rc != CHB_OK) return rc;
+  float* nz = reinterpret_cast<float*>(ws + g->ws_noise);
+  if (noise) {
+    if (noise != nz) {
+      cudaError_t err =
+          cudaMemcpyAsync(nz, noise, (size_t)B * g->noise_pix * 4, cudaMemcpyDeviceToDevice, stream);
+      if (err != cudaSuccess) {
+        set_error(std::string("noise copy failed: ") + cudaGetErrorString(err));
+        return CHB_ERR_CUDA;
+      }
+    }
+  } else {
+    rc = chb_noise_fill(nz, (int64_t)B * g->noise_pix, seed, 0, stream);
+    if (rc != CHB_OK) return rc;
+  }
+  int nrun = 0;
+  for (const Step& s : *steps) {
+    if (g->step_limit >= 0 && nrun++ >= g->step_limit) break;
+    if (s.final_image && out != reinterpret_cast<float*>(ws + g->ws_out)) {
+      ConvPlan p = s.plan;
+      p.kp.e.out = out;
+      p.desc.out = out;
+      rc = launch_conv_plan(p, impl, stream);
+    } else {
+      rc = launch_conv_plan(s.plan, impl, stream);
+    }
+    if (rc != CHB_OK) return rc;
+  }
+  return CHB_OK;
+}
+
+int chb_generator_forward_host(chb_generator* g, const uint8_t* labels_host, const float* codes_host,
+                               const float* noise_host, uint64_t seed, float* out_host, int B, int impl,
+                               void* stream_) {
+  if (!g || !labels_host || !codes_host || !out_host || !g->ws) {
+    set_error("chb_generator_forward_host: NULL argument or unbound generator");
+    return CHB_ERR_ARG;
+  }
+  if (B <= 0 || B > g->cfg.max_batch) {
+    set_error("chb_generator_forward_host: batch exceeds max_batch");
+    return CHB_ERR_ARG;
+  }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const chb_gen_config& c = g->cfg;
+  uint8_t* ws = g->ws;
+  const size_t S2 = (size_t)c.crop * c.crop;
+  cudaError_t err = cudaMemcpyAsync(ws + g->ws_labels, labels_host, (size_t)B * S2, cudaMemcpyHostToDevice, stream);
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(ws + g->ws_codes32, codes_host, (size_t)B * c.label_nc * c.style_len * 4,
+                          cudaMemcpyHostToDevice, stream);
+  if (err == cudaSuccess && noise_host)
+    err = cudaMemcpyAsync(ws + g->ws_noise, noise_host, (size_t)B * g->noise_pix * 4, cudaMemcpyHostToDevice, stream);
+  if (err != cudaSuccess) {
+    set_error(std::string("H2D copy failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  float* dev_out = reinterpret_cast<float*>(ws + g->ws_out);
+  int rc = chb_generator_forward(g, ws + g->ws_labels, reinterpret_cast<const float*>(ws + g->ws_codes32),
+                                 noise_host ? reinterpret_cast<const float*>(ws + g->ws_noise) : nullptr, seed,
+                                 dev_out, B, impl, stream_);
+  if (rc != CHB_OK) return rc;
+  err = cudaMemcpyAsync(out_host, dev_out, (size_t)B * 3 * S2 * 4, cudaMemcpyDeviceToHost, stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+  if (err != cudaSuccess) {
+    set_error(std::string("D2H copy / sync failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+int chb_generator_launches(const chb_generator* g) {
+  if (!g) return 0;
+  int n = 3;  // codes cast, one-hot pyramid, noise
+  if (g->n_styled > 0) n += 1 + g->n_styled;
+  n += 1;  // fc
+  for (auto& b : g->blocks) n += 1 + b.n_ace + 2;
+  return n + 1;  // conv_img
+}
+
+double chb_generator_flops(const chb_generator* g_, int B) {
+  chb_generator* g = const_cast<chb_generator*>(g_);
+  if (!g || !g->ws) return 0.0;
+  std::vector<Step>* steps = nullptr;
+  if (get_steps(g, B, &steps) != CHB_OK) return 0.0;
+  double f = 0;
+  for (const Step& s : *steps) f += s.plan.flops;
+  return f;
+}
+
+int chb_generator_set_step_limit(chb_generator* g, int n) {
+  if (!g) return CHB_ERR_ARG;
+  g->step_limit = n;
+  return CHB_OK;
+}
+
+int64_t chb_generator_debug_tensor(const chb_generator* g, const char* name, int B, void** dev_ptr, int* dtype) {
+  if (!g || !name || !g->ws) return -1;
+  auto it = g->debug.find(name);
+  if (it == g->debug.end()) {
+    set_error(std::string("unknown debug tensor ") + name);
+    return -1;
+  }
+  if (dev_ptr) *dev_ptr = g->ws + it->second.first;
+  if (dtype) *dtype = it->second.second;
+  (void)B;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+/*
+ * ctrlhair_b200 — C ABI of the B200 (sm_100a) SEAN/SPADE generator hot path.
+ *
+ * The reference (XuyangGuo/CtrlHair) has no FFI layer: its boundary is the Python call surface
+ *   sean_codes/models/pix2pix_model.py:39-74   Pix2PixModel.forward(data, mode)
+ *   sean_codes/models/networks/generator.py:72-109  SPADEGenerator.forward(input, rgb_img, obj_dic)
+ *   hair_editor.py:159-179                      HairEditor.gen_img(code, parsing)
+ * The entry points below are what a ctypes stub behind those methods binds.
+ * Plain pointers and sizes only; all device pointers are CUDA device memory on the current device,
+ * `stream` is a cudaStream_t passed as void*.  Every function returns 0 on success and a negative
+ * code on failure; chb_last_error() returns a human readable message for the calling thread.
+ * No function allocates device memory: workspaces are sized by the library and owned by the caller.
+ */
+#ifndef CTRLHAIR_B200_H
+#define CTRLHAIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHB_OK 0
+#define CHB_ERR_ARG (-1)
+#define CHB_ERR_CUDA (-2)
+#define CHB_ERR_ARCH (-3)
+
+int chb_version(void);
+const char* chb_last_error(void);
+/* 0 when the current device is compute capability 10.x, CHB_ERR_ARCH otherwise. */
+int chb_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator 1: implicit-GEMM convolution (the tcgen05 kernel every conv of the path runs on).
+ * Replaces nn.Conv2d / F.conv2d call sites of normalization.py:172-173,241-256,
+ * architecture.py:35-45,75,79,90 and generator.py:33,51.
+ *
+ * out[b,y,x,n] = epilogue( sum_seg sum_tap sum_c  A_seg[b, y+dy, x+dx, ch_off+c] * W_seg[(b,) n, tap*C+c] )
+ * A operands are fp16 NHWC, weights fp16 [rows][K] (K-major), accumulation fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a;      /* fp16 activations, logical [B,H,W,Ca] with element strides below        */
+  int64_t a_sb, a_sy, a_sx; /* element strides of image / row / pixel (channel stride is 1)      */
+  int Ca;             /* channels present in the tensor                                          */
+  int ch_off;         /* first channel this segment reads                                        */
+  int C;              /* channels read: 32, or a multiple of 64                                  */
+  int taps;           /* 9 = 3x3 zero-pad 1, 1 = 1x1                                             */
+  const void* w;      /* fp16 weights [(B,) Nrows, taps*C]; k = tap*C + c, tap = ky*3+kx         */
+  int per_image;      /* 1: weights carry a leading image dimension                              */
+  int64_t w_sb;       /* per_image: element stride between images (0 = dense Nrows*taps*C)       */
+} chb_conv_seg;
+
+enum { CHB_EPI_PLAIN = 0, CHB_EPI_MODULATE = 1 };
+enum { CHB_ACT_NONE = 0, CHB_ACT_RELU = 1, CHB_ACT_LRELU = 2, CHB_ACT_TANH = 3 };
+enum { CHB_F16 = 0, CHB_F32 = 1 };
+
+typedef struct {
+  int B, H, W;        /* images, rows, columns of the output (== input) grid                     */
+  int TW, TH, TB;     /* pixel tile: TW*TH*TB <= 128 rows of the MMA                             */
+  int nseg;
+  chb_conv_seg seg[3];
+  int N;              /* valid output columns                                                    */
+  int Nrows;          /* weight rows, multiple of BN                                             */
+  int BN;             /* N tile: 16..256, multiple of 16                                         */
+  int epi, act;
+  const float* bias;  /* [Nrows] (or [B,Nrows] when bias_per_image), may be NULL                 */
+  int bias_per_image;
+  /* PLAIN: out = act(acc + bias (+ res)) */
+  void* out; int out_dtype;
+  int64_t o_sb, o_sy, o_sx, o_sn; /* element strides                                             */
+  int o_ngroup; int64_t o_sgroup; /* n -> (n / ngroup) * sgroup + (n % ngroup) * o_sn             */
+  const float* res; int64_t r_sb, r_sy, r_sx; int r_shift; /* fp32 NHWC residual read at (y>>s,x>>s) */
+  /* MODULATE (ACE, normalization.py:111-112,177-187): tile columns are [gamma | beta] halves;
+     out = act( (x*a + noise*nv + c) * (1+gamma) + beta ), out fp16 */
+  const float* x; int64_t x_sb, x_sy, x_sx; int x_shift;
+  const float* noise; /* [B, W, H] — the reference's randn(B,W,H,1) plane, read transposed; may be NULL */
+  const float* chan;  /* [C] x float4 {a = rstd, c = -mean*rstd, nv = noise_var*rstd, 0}          */
+} chb_conv_desc;
+
+enum { CHB_IMPL_TCGEN05 = 0, CHB_IMPL_SIMT_DEBUG = 1 };
+/* One-shot: encode tensor maps and launch. impl selects the tcgen05 kernel or the slow SIMT checker kernel. */
+int chb_conv_run(const chb_conv_desc* d, int impl, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator 2: label map -> one-hot pyramid (pix2pix_model.py:119-144 scatter_, and the nearest
+ * F.interpolate of normalization.py:115 / generator.py:75).  Integer work, bit exact.
+ * labels u8 [B,S,S]; for each level l: out[l] fp16 [B,r_l,r_l,32] with r_l = S >> shift[l].
+ * ------------------------------------------------------------------------------------------ */
+int chb_onehot_pyramid(const uint8_t* labels, int B, int S, int nlevels, const int* shifts, void* const* outs,
+                       int nclass, void* stream);
+
+/* Standard-normal noise planes (replaces torch.randn of normalization.py:111), Philox4x32-10 + Box-Muller. */
+int chb_noise_fill(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* fp32 -> fp16 conversion of a contiguous buffer (style codes). */
+int chb_f32_to_f16(const float* in, void* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The generator (generator.py:14-109 SPADEGenerator, 'normal' upsampling: 7 SPADE ResBlocks).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int ngf;        /* 64 in the reference (base_options.py:39)                                    */
+  int label_nc;   /* 19                                                                          */
+  int crop;       /* 256 (or 512); multiple of 32                                                */
+  int style_len;  /* 512                                                                         */
+  int max_batch;  /* workspace is sized for this many images per forward                         */
+} chb_gen_config;
+
+typedef struct chb_generator chb_generator;
+
+int chb_generator_create(const chb_gen_config* cfg, chb_generator** out);
+void chb_generator_destroy(chb_generator* g);
+
+/* Packed-weight blob layout: the library owns the layout, the host packer fills it by name. */
+int chb_generator_num_tensors(const chb_generator* g);
+int chb_generator_tensor_info(const chb_generator* g, int i, char* name, int name_cap, int64_t* offset,
+                              int64_t* nbytes, int* dtype /* CHB_F16 / CHB_F32 */);
+int64_t chb_generator_blob_bytes(const chb_generator* g);
+int64_t chb_generator_workspace_bytes(const chb_generator* g);
+/* Both pointers are device memory that must stay alive and unchanged while the generator is used. */
+int chb_generator_bind(chb_generator* g, const void* blob, void* workspace);
+
+/* Device-resident forward.  labels u8 [B,crop,crop] (values < label_nc), codes fp32 [B,label_nc,style_len],
+ * noise fp32: the 18 planes of one forward concatenated in call order (per block ace_s, ace_0, ace_1), each
+ * [B, r, r] in the reference's (w,h) order, or NULL to draw them on the device from `seed`.
+ * out fp32 [B,3,crop,crop] NCHW in [-1,1]. */
+int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
+                          uint64_t seed, float* out, int B, int impl, void* stream);
+/* Same, host buffers in and out (pinned or pageable); copies are issued on `stream` and the call returns
+ * after the output has landed in `out_host`. */
+int chb_generator_forward_host(chb_generator* g, const uint8_t* labels_host, const float* codes_host,
+                               const float* noise_host, uint64_t seed, float* out_host, int B, int impl,
+                               void* stream);
+int64_t chb_generator_noise_floats(const chb_generator* g, int B);
+/* Number of kernel launches one forward issues (for bench accounting). */
+int chb_generator_launches(const chb_generator* g);
+/* FLOPs one forward of B images issues on the tensor cores (2*M*N*K over every tile, padding included). */
+double chb_generator_flops(const chb_generator* g, int B);
+/* Debug: run only the first n conv launches of the schedule (n < 0: all). */
+int chb_generator_set_step_limit(chb_generator* g, int n);
+/* Debug: copy an intermediate tensor by name ("x_head_0", ...) for parity tests; returns element count. */
+int64_t chb_generator_debug_tensor(const chb_generator* g, const char* name, int B, void** dev_ptr, int* dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
