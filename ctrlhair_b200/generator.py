@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference generator call surface on top of the C ABI.
+
+SeanGeneratorB200 stands where `Pix2PixModel.netG` (sean_codes/models/networks/generator.py:14 SPADEGenerator)
+stands in the reference: same `forward(input, rgb_img, obj_dic)` signature and the same state_dict format on
+load, plus batched entry points (`forward_labels`, `forward_host`) the reference lacks.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, packer
+
+
+class SeanGeneratorB200:
+    def __init__(self, ngf=64, label_nc=19, crop=256, style_len=512, max_batch=1, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.ChbError("SeanGeneratorB200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.ngf, self.label_nc, self.crop, self.style_len, self.max_batch = ngf, label_nc, crop, style_len, max_batch
+        cfg = _lib.GenConfig(ngf, label_nc, crop, style_len, max_batch)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_check_device())
+            _lib.check(self.lib.chb_generator_create(C.byref(cfg), C.byref(h)))
+        self.handle = h
+        self.blob = None
+        self.workspace = None
+        self.status = "test"  # the reference flips this attribute on every module (hair_editor.py:34-37)
+        self.impl = _lib.IMPL_TCGEN05
+        self._layout = self._read_layout()
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self.lib.chb_generator_destroy(h)
+            self.handle = None
+
+    # ------------------------------------------------------------------ weights
+    def _read_layout(self):
+        n = self.lib.chb_generator_num_tensors(self.handle)
+        layout = {}
+        name = C.create_string_buffer(128)
+        off, nb, dt = C.c_int64(), C.c_int64(), C.c_int()
+        for i in range(n):
+            _lib.check(self.lib.chb_generator_tensor_info(self.handle, i, name, 128, C.byref(off), C.byref(nb),
+                                                          C.byref(dt)))
+            layout[name.value.decode()] = (off.value, nb.value, dt.value)
+        return layout
+
+    def blob_bytes(self):
+        return self.lib.chb_generator_blob_bytes(self.handle)
+
+    def build_blob(self, state_dict):
+        """Reference-format state_dict (util/util.py:202-208 checkpoint) -> packed CPU uint8 blob."""
+        packed = packer.pack_generator(state_dict, self.ngf, self.label_nc)
+        blob = torch.zeros(self.blob_bytes(), dtype=torch.uint8)
+        missing = set(self._layout) - set(packed)
+        extra = set(packed) - set(self._layout)
+        if missing or extra:
+            raise _lib.ChbError("packer/library layout mismatch: missing %s extra %s" % (sorted(missing), sorted(extra)))
+        for k, (off, nb, dt) in self._layout.items():
+            t = packed[k].contiguous()
+            want = torch.float16 if dt == _lib.F16 else torch.float32
+            if t.dtype != want or t.numel() * t.element_size() != nb:
+                raise _lib.ChbError("packed tensor %s: dtype %s bytes %d, library wants %s bytes %d" %
+                                    (k, t.dtype, t.numel() * t.element_size(), want, nb))
+            blob[off:off + nb] = t.view(torch.uint8).reshape(-1)
+        return blob
+
+    def load_state_dict(self, state_dict, strict=True):
+        self.load_blob(self.build_blob(state_dict))
+        return self
+
+    def load_blob(self, blob):
+        """blob: uint8 tensor (CPU or CUDA) of blob_bytes() — e.g. the buffer a NCCL broadcast delivered."""
+        if blob.numel() != self.blob_bytes():
+            raise _lib.ChbError("blob has %d bytes, expected %d" % (blob.numel(), self.blob_bytes()))
+        self.blob = blob.to(self.device).contiguous()
+        wsb = self.lib.chb_generator_workspace_bytes(self.handle)
+        if self.workspace is None:
+            self.workspace = torch.empty(wsb + 1024, dtype=torch.uint8, device=self.device)
+        ws_ptr = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_generator_bind(self.handle, C.c_void_p(self.blob.data_ptr()), C.c_void_p(ws_ptr)))
+        return self
+
+    # ------------------------------------------------------------------ forward
+    def noise_floats(self, B):
+        return self.lib.chb_generator_noise_floats(self.handle, B)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward_labels(self, labels, codes, noise=None, seed=0, out=None):
+        """labels uint8 [B,S,S] (cuda), codes fp32 [B,19,512] (cuda), noise: flat fp32 of noise_floats(B) or None
+        (drawn on device from `seed`).  Returns fp32 [B,3,S,S] in [-1,1]."""
+        if self.blob is None:
+            raise _lib.ChbError("no weights loaded")
+        if not (labels.is_cuda and codes.is_cuda):
+            raise _lib.ChbError("forward_labels takes CUDA tensors; use forward_host for host buffers")
+        B = labels.shape[0]
+        labels = labels.to(torch.uint8).contiguous()
+        codes = codes.to(torch.float32).contiguous()
+        if labels.shape[1:] != (self.crop, self.crop) or codes.shape != (B, self.label_nc, self.style_len):
+            raise _lib.ChbError("bad input shapes %s %s" % (tuple(labels.shape), tuple(codes.shape)))
+        nptr = None
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
+            if noise.numel() != self.noise_floats(B):
+                raise _lib.ChbError("noise has %d floats, expected %d" % (noise.numel(), self.noise_floats(B)))
+            nptr = C.c_void_p(noise.data_ptr())
+        if out is None:
+            out = torch.empty((B, 3, self.crop, self.crop), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_generator_forward(self.handle, C.c_void_p(labels.data_ptr()),
+                                                      C.c_void_p(codes.data_ptr()), nptr, seed,
+                                                      C.c_void_p(out.data_ptr()), B, self.impl, self._stream()))
+        return out
+
+    def forward_host(self, labels, codes, noise=None, seed=0, out=None):
+        """Host buffers in, host buffer out (numpy or CPU tensors); H2D/D2H copies happen inside the call."""
+        if self.blob is None:
+            raise _lib.ChbError("no weights loaded")
+        labels = torch.as_tensor(labels)
+        codes = torch.as_tensor(codes)
+        B = labels.shape[0]
+        labels = labels.to(torch.uint8).contiguous()
+        codes = codes.to(torch.float32).contiguous()
+        nptr = None
+        if noise is not None:
+            noise = torch.as_tensor(noise).to(torch.float32).contiguous()
+            nptr = C.c_void_p(noise.data_ptr())
+        if out is None:
+            out = torch.empty((B, 3, self.crop, self.crop), dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_generator_forward_host(self.handle, C.c_void_p(labels.data_ptr()),
+                                                           C.c_void_p(codes.data_ptr()), nptr, seed,
+                                                           C.c_void_p(out.data_ptr()), B, self.impl, self._stream()))
+        return out
+
+    def forward(self, input, rgb_img=None, obj_dic=None, noise=None, seed=0):
+        """Reference signature (generator.py:72): input = one-hot seg [B,19,S,S]; styles come from `obj_dic`
+        ({str(j): {'ACE': Tensor[512]}}, the UI path of normalization.py:121-139 — image 0 only, like the
+        reference) or, batched, from a codes tensor passed as `rgb_img` of shape [B,19,512]."""
+        seg = input
+        labels = seg.argmax(1).to(torch.uint8).to(self.device)
+        B = labels.shape[0]
+        if obj_dic is not None:
+            if B != 1:
+                raise _lib.ChbError("UI_mode (obj_dic) styles only image 0 in the reference; pass B == 1")
+            codes = torch.stack([torch.as_tensor(obj_dic[str(j)]["ACE"]).float().reshape(-1)
+                                 for j in range(self.label_nc)])[None].to(self.device)
+        elif rgb_img is not None and rgb_img.dim() == 3:
+            codes = rgb_img.to(self.device)
+        else:
+            raise _lib.ChbError("style encoding from an RGB image (Zencoder) is not part of this build; pass obj_dic "
+                                "or a [B,19,512] codes tensor")
+        return self.forward_labels(labels, codes, noise=noise, seed=seed)
+
+    __call__ = forward
+
+    # ------------------------------------------------------------------ introspection
+    def launches(self):
+        return self.lib.chb_generator_launches(self.handle)
+
+    def flops(self, B):
+        return self.lib.chb_generator_flops(self.handle, B)
+
+    def debug_tensor(self, name, shape, B=1):
+        ptr, dt = C.c_void_p(), C.c_int()
+        rc = self.lib.chb_generator_debug_tensor(self.handle, name.encode(), B, C.byref(ptr), C.byref(dt))
+        if rc < 0:
+            _lib.check(-1)
+        dtype = torch.float16 if dt.value == _lib.F16 else torch.float32
+        n = int(np.prod(shape))
+        ws_ptr = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        off = ptr.value - ws_ptr
+        nbytes = n * (2 if dtype == torch.float16 else 4)
+        return self.workspace[off + (ws_ptr - self.workspace.data_ptr()):][:nbytes].view(dtype).reshape(shape).clone()
+
+    def set_step_limit(self, n):
+        _lib.check(self.lib.chb_generator_set_step_limit(self.handle, n))

@@ -1,0 +1,70 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference (from /root/reference).
+
+Run in the build container only:   python -m oracle.make_golden
+For each case it (1) checks that oracle/synth.py's key set equals SPADEGenerator.state_dict(), (2) runs the
+reference modules on CPU with injected noise planes, (3) runs oracle/sean_oracle.py on the same inputs and prints
+the difference, (4) stores inputs' seeds, the labels and the reference output as a golden fixture.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import ref_harness as rh
+from . import sean_oracle as so
+from . import synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = [
+    # name, crop, B, label kind, mode
+    ("gen_c64_b2_blocky", 64, 2, "blocky", "batched"),
+    ("gen_c64_b2_iid", 64, 2, "iid", "batched"),
+    ("gen_c256_b1_blocky_ui", 256, 1, "blocky", "ui"),
+]
+SD_SEED, LABEL_SEED, CODE_SEED, NOISE_SEED = 1236, 1234, 1235, 1237
+
+
+def main():
+    torch.manual_seed(0)
+    os.makedirs(OUT, exist_ok=True)
+    t0 = time.time()
+    sd = synth.make_state_dict(64, 19, SD_SEED)
+    print("state dict: %d tensors, %.1f M params (%.1fs)" %
+          (len(sd), sum(v.numel() for v in sd.values()) / 1e6, time.time() - t0))
+    for name, crop, B, kind, mode in CASES:
+        net = rh.build_reference_generator(sd, 64, crop)
+        ref_sd = net.state_dict()
+        assert list(ref_sd.keys()) == list(sd.keys()), "synthetic key set differs from the reference's"
+        for k in sd:
+            assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
+        labels = synth.make_labels(B, crop, kind, LABEL_SEED)
+        codes = synth.make_codes(B, CODE_SEED)
+        noise = synth.make_noise(B, crop, NOISE_SEED)
+        onehot = so.one_hot(labels)
+        t0 = time.time()
+        if mode == "ui":
+            ref = rh.run_reference_ui(net, onehot, codes[0], noise)
+        else:
+            ref = rh.run_reference_generator(net, onehot, codes, noise)
+        t_ref = time.time() - t0
+        t0 = time.time()
+        taps = {}
+        mine = so.generator_forward(sd, labels, codes, noise, taps=taps)
+        t_or = time.time() - t0
+        diff = float((mine - ref).abs().max())
+        print("%s: ref %.2fs oracle %.2fs  max|oracle-ref| = %.3e  max|ref| = %.3f  std = %.3f" %
+              (name, t_ref, t_or, diff, float(ref.abs().max()), float(ref.std())))
+        for k, v in taps.items():
+            print("   %-14s absmax %.3f std %.3f" % (k, float(v.abs().max()), float(v.std())))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), labels=labels.numpy(), out=ref.numpy(),
+                            seeds=np.array([SD_SEED, LABEL_SEED, CODE_SEED, NOISE_SEED]), crop=crop,
+                            oracle_diff=diff)
+        del net
+    print("done")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

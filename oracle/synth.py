@@ -1,0 +1,174 @@
+"""TEST INFRASTRUCTURE — synthetic checkpoints and inputs in the reference's formats (no reference code needed).
+
+The reference ships no weights (external_model_params/ is a git-ignored download), so parity and the benchmark
+use a seeded synthetic `latest_net_G.pth`-style state_dict with the exact key set / shapes of
+sean_codes/models/networks/generator.py:24-53 (checked against the real module by oracle/make_golden.py).
+Values are chosen to look like a trained checkpoint rather than a fresh init: converged
+spectral-norm u/v, non-trivial BN running stats, noise_var != 0, blending != 0.5.
+"""
+import math
+
+import torch
+
+BLOCKS = [  # name, fin/nf, fout/nf, styled (generator.py:35-43)
+    ("head_0", 16, 16, True), ("G_middle_0", 16, 16, True), ("G_middle_1", 16, 16, True),
+    ("up_0", 16, 8, True), ("up_1", 8, 4, True), ("up_2", 4, 2, True), ("up_3", 2, 1, False),
+]
+STYLE_LEN = 512
+NHIDDEN = 128
+
+
+def netg_shapes(ngf=64, label_nc=19):
+    """Ordered {key: shape} of SPADEGenerator.state_dict()."""
+    s = {}
+
+    def conv(name, co, ci, k, bias=True):
+        s[name + ".weight"] = (co, ci, k, k)
+        if bias:
+            s[name + ".bias"] = (co,)
+
+    # Zencoder (architecture.py:154-175)
+    conv("Zencoder.model.1", 32, 3, 3)
+    conv("Zencoder.model.4", 64, 32, 3)
+    conv("Zencoder.model.7", 128, 64, 3)
+    s["Zencoder.model.10.weight"] = (128, 256, 3, 3)  # ConvTranspose2d: [in, out, k, k]
+    s["Zencoder.model.10.bias"] = (256,)
+    conv("Zencoder.model.14", STYLE_LEN, 256, 3)
+    conv("fc", 16 * ngf, label_nc, 3)
+    for name, fi, fo, styled in BLOCKS:
+        fin, fout = fi * ngf, fo * ngf
+        fmid = min(fin, fout)
+
+        def sn_conv(n, co, ci, k, bias):
+            if bias:
+                s[n + ".bias"] = (co,)
+            s[n + ".weight_orig"] = (co, ci, k, k)
+            s[n + ".weight_u"] = (co,)
+            s[n + ".weight_v"] = (ci * k * k,)
+
+        sn_conv(name + ".conv_0", fmid, fin, 3, True)
+        sn_conv(name + ".conv_1", fout, fmid, 3, True)
+        if fin != fout:
+            sn_conv(name + ".conv_s", fout, fin, 1, False)
+        aces = [("ace_0", fin), ("ace_1", fmid)] + ([("ace_s", fin)] if fin != fout else [])
+        for an, c in aces:
+            p = "%s.%s" % (name, an)
+            s[p + ".blending_gamma"] = (1,)
+            s[p + ".blending_beta"] = (1,)
+            s[p + ".noise_var"] = (c,)
+            s[p + ".Spade.param_free_norm.running_mean"] = (c,)
+            s[p + ".Spade.param_free_norm.running_var"] = (c,)
+            s[p + ".Spade.param_free_norm.num_batches_tracked"] = ()
+            conv(p + ".Spade.mlp_shared.0", NHIDDEN, label_nc, 3)
+            conv(p + ".Spade.mlp_gamma", c, NHIDDEN, 3)
+            conv(p + ".Spade.mlp_beta", c, NHIDDEN, 3)
+            s[p + ".param_free_norm.running_mean"] = (c,)
+            s[p + ".param_free_norm.running_var"] = (c,)
+            s[p + ".param_free_norm.num_batches_tracked"] = ()
+            if styled:
+                for j in range(label_nc):
+                    s["%s.fc_mu%d.weight" % (p, j)] = (STYLE_LEN, STYLE_LEN)
+                    s["%s.fc_mu%d.bias" % (p, j)] = (STYLE_LEN,)
+                conv(p + ".conv_gamma", c, STYLE_LEN, 3)
+                conv(p + ".conv_beta", c, STYLE_LEN, 3)
+    conv("conv_img", 3, ngf, 3)
+    return s
+
+
+def _power_iteration(w_mat, gen, iters=40):
+    """Converged u, v of torch.nn.utils.spectral_norm (left/right singular vectors of W.flatten(1))."""
+    u = torch.randn(w_mat.shape[0], generator=gen)
+    u = u / u.norm()
+    v = None
+    for _ in range(iters):
+        v = torch.mv(w_mat.t(), u)
+        v = v / (v.norm() + 1e-12)
+        u = torch.mv(w_mat, v)
+        u = u / (u.norm() + 1e-12)
+    return u, v
+
+
+def make_state_dict(ngf=64, label_nc=19, seed=1236):
+    gen = torch.Generator().manual_seed(seed)
+    shapes = netg_shapes(ngf, label_nc)
+    sd = {}
+    for k, shp in shapes.items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.tensor(0, dtype=torch.int64)
+        elif k.endswith("running_mean"):
+            sd[k] = torch.randn(shp, generator=gen) * 0.5
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(shp, generator=gen) * 1.5 + 0.5
+        elif k.endswith("noise_var"):
+            sd[k] = torch.randn(shp, generator=gen) * 0.1
+        elif k.endswith("blending_gamma") or k.endswith("blending_beta"):
+            sd[k] = torch.randn(shp, generator=gen)
+        elif k.endswith("weight_u") or k.endswith("weight_v"):
+            sd[k] = None  # filled below
+        elif k.endswith(".bias"):
+            sd[k] = torch.randn(shp, generator=gen) * 0.1
+        else:  # conv / linear weights
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            if "Zencoder.model.10" in k:
+                fan_in = shp[0] * shp[2] * shp[3]
+            if ".conv_gamma." in k or ".conv_beta." in k:
+                gain = 2.0   # inputs are relu(fc_mu(.)) ~ 0.1-0.3: keep the style term comparable to SPADE's
+            elif ".fc_mu" in k:
+                gain = 1.5
+            elif ".mlp_shared." in k:
+                gain = 1.5   # one-hot input: 9 active taps of 171
+            elif ".mlp_gamma." in k or ".mlp_beta." in k:
+                gain = 0.7
+            elif k.startswith("fc."):
+                gain = 3.0
+            elif k.startswith("conv_img."):
+                gain = 2.0
+            else:
+                gain = 1.0
+            sd[k] = torch.randn(shp, generator=gen) * (gain / math.sqrt(fan_in))
+    for k in shapes:
+        if k.endswith("weight_orig"):
+            base = k[:-len("weight_orig")]
+            u, v = _power_iteration(sd[k].flatten(1), gen)
+            sd[base + "weight_u"] = u
+            sd[base + "weight_v"] = v
+    return sd
+
+
+def make_labels(B, S, kind="blocky", seed=1234):
+    """uint8 [B,S,S] class ids in 0..18: iid-uniform, or an 8x8 grid nearest-upsampled."""
+    gen = torch.Generator().manual_seed(seed)
+    if kind == "iid":
+        return torch.randint(0, 19, (B, S, S), generator=gen, dtype=torch.int64).to(torch.uint8)
+    g = torch.randint(0, 19, (B, 8, 8), generator=gen, dtype=torch.int64)
+    rep = S // 8
+    return g.repeat_interleave(rep, 1).repeat_interleave(rep, 2).to(torch.uint8)
+
+
+def make_codes(B, seed=1235, zero_rows=False):
+    gen = torch.Generator().manual_seed(seed)
+    c = torch.randn((B, 19, STYLE_LEN), generator=gen) * 0.135
+    return c
+
+
+def noise_plane_shapes(B, S, ngf=64):
+    """Shapes of the 18 randn(B, W, H, 1) draws of one forward, in call order (architecture.py:71-78)."""
+    sw = S // 32
+    out = []
+    for (name, fi, fo, styled), mul in zip(BLOCKS, (1, 2, 2, 4, 8, 16, 32)):
+        r = sw * mul
+        n = 3 if fi != fo else 2
+        out += [(B, r, r, 1)] * n
+    return out
+
+
+def make_noise(B, S, seed=1237):
+    gen = torch.Generator().manual_seed(seed)
+    return [torch.randn(shp, generator=gen) for shp in noise_plane_shapes(B, S)]
+
+
+def flatten_noise(planes):
+    """18 planes [B,W,H,1] -> one fp32 vector in the layout chb_generator_forward expects."""
+    return torch.cat([p.reshape(-1) for p in planes])
