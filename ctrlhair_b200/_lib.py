@@ -77,6 +77,10 @@ SYMBOLS = [
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("chb_generator_forward_host", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("chb_generator_forward_timed", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p,
+      C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]),
+    ("chb_generator_step_name", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     ("chb_generator_noise_floats", C.c_int64, [C.c_void_p, C.c_int]),
     ("chb_generator_launches", C.c_int, [C.c_void_p]),
     ("chb_generator_flops", C.c_double, [C.c_void_p, C.c_int]),

@@ -48,6 +48,7 @@ struct BlockInfo {
 
 struct Step {
   ConvPlan plan;
+  std::string name;
   int noise_ace_block = -1, noise_ace = -1;  // modulate steps: which noise plane
   bool final_image = false;
 };
@@ -251,8 +252,10 @@ static void nhwc_out(chb_conv_desc* d, void* out, int dtype, int r, int C) {
   d->o_sn = 1; d->o_sx = C; d->o_sy = (int64_t)r * C; d->o_sb = (int64_t)r * r * C;
 }
 
-static int push_step(std::vector<Step>& steps, const chb_conv_desc& d, int nb = -1, int na = -1, bool fin = false) {
+static int push_step(std::vector<Step>& steps, const chb_conv_desc& d, const std::string& name, int nb = -1,
+                     int na = -1, bool fin = false) {
   Step s;
+  s.name = name;
   int rc = build_conv_plan(d, &s.plan);
   if (rc != CHB_OK) return rc;
   s.noise_ace_block = nb;
@@ -289,7 +292,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     d.out = ws + g->ws_mu; d.out_dtype = CHB_F16;
     d.o_sb = L; d.o_sy = 0; d.o_sx = (int64_t)NC * L; d.o_sn = 1;
     d.o_ngroup = L; d.o_sgroup = (int64_t)B * NC * L;
-    if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+    if ((rc = push_step(steps, d, "fc_mu")) != CHB_OK) return rc;
   }
   // ---- style path 2: Weff[b][n*9+tap][j] = sum_ci Wstyle[n*9+tap][ci] * mu[b][j][ci]  (per styled ACE)
   for (auto& b : g->blocks)
@@ -312,7 +315,8 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
       d.out = ws + g->ws_weff + A.weff_row0 * 32 * 2; d.out_dtype = CHB_F16;
       d.o_sb = g->weff_rows * 32; d.o_sy = 0; d.o_sx = 1; d.o_sn = 32;
-      if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+      const char* an3[3] = {"ace_s", "ace_0", "ace_1"};
+      if ((rc = push_step(steps, d, b.name + "." + an3[a] + ".weff")) != CHB_OK) return rc;
     }
   // ---- x = fc(one_hot @ sw)   (generator.py:75-76)
   {
@@ -323,7 +327,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
     d.bias = reinterpret_cast<const float*>(blobp(g, g->t_fcb));
     nhwc_out(&d, ws + g->ws_x0, CHB_F32, g->sw, 16 * nf);
-    if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+    if ((rc = push_step(steps, d, "fc")) != CHB_OK) return rc;
   }
   const float* xin = reinterpret_cast<const float*>(ws + g->ws_x0);
   int xin_r = g->sw;
@@ -341,7 +345,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_RELU;
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_shb));
       nhwc_out(&d, ws + g->ws_actv, CHB_F16, r, actvC);
-      if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+      if ((rc = push_step(steps, d, b.name + ".mlp_shared")) != CHB_OK) return rc;
     }
     auto modulate = [&](int a, const float* x, int x_r, int x_shift, int xC, void* hout, int act) -> int {
       const AceInfo& A = b.ace[a];
@@ -364,7 +368,8 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.x_sx = xC; d.x_sy = (int64_t)x_r * xC; d.x_sb = (int64_t)x_r * x_r * xC;
       d.noise = reinterpret_cast<const float*>(ws + g->ws_noise) + (int64_t)B * A.noise_pix0;
       nhwc_out(&d, hout, CHB_F16, r, A.C);
-      return push_step(steps, d, (int)bi, a);
+      const char* an3[3] = {"ace_s", "ace_0", "ace_1"};
+      return push_step(steps, d, b.name + "." + an3[a] + ".gamma_beta_mod", (int)bi, a);
     };
     if (b.shortcut) {
       if ((rc = modulate(0, xin, xin_r, b.in_shift, b.fin, ws + g->ws_hs, CHB_ACT_NONE)) != CHB_OK) return rc;
@@ -379,7 +384,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c0b));
       nhwc_out(&d, ws + g->ws_dx0, CHB_F32, r, b.fmid);
-      if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+      if ((rc = push_step(steps, d, b.name + ".conv_0")) != CHB_OK) return rc;
     }
     if ((rc = modulate(2, reinterpret_cast<const float*>(ws + g->ws_dx0), r, 0, b.fmid, ws + g->ws_h1,
                        CHB_ACT_LRELU)) != CHB_OK)
@@ -401,7 +406,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.act = last ? CHB_ACT_LRELU : CHB_ACT_NONE;  // generator.py:107 leaky_relu before conv_img
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c1b));
       nhwc_out(&d, ws + b.ws_xout, last ? CHB_F16 : CHB_F32, r, b.fout);
-      if ((rc = push_step(steps, d)) != CHB_OK) return rc;
+      if ((rc = push_step(steps, d, b.name + (b.shortcut ? ".conv_1+conv_s" : ".conv_1+res"))) != CHB_OK) return rc;
     }
     xin = reinterpret_cast<const float*>(ws + b.ws_xout);
     xin_r = r;
@@ -418,7 +423,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     d.bias = reinterpret_cast<const float*>(blobp(g, g->t_imgb));
     d.out = ws + g->ws_out; d.out_dtype = CHB_F32;
     d.o_sn = (int64_t)r * r; d.o_sx = 1; d.o_sy = r; d.o_sb = (int64_t)3 * r * r;
-    if ((rc = push_step(steps, d, -1, -1, true)) != CHB_OK) return rc;
+    if ((rc = push_step(steps, d, "conv_img", -1, -1, true)) != CHB_OK) return rc;
   }
   return CHB_OK;
 }
@@ -504,8 +509,50 @@ static int get_steps(chb_generator* g, int B, std::vector<Step>** out) {
   return CHB_OK;
 }
 
+static int forward_impl(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
+                        uint64_t seed, float* out, int B, int impl, void* stream_, cudaEvent_t* evs, int nev);
+
 int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
                           uint64_t seed, float* out, int B, int impl, void* stream_) {
+  return forward_impl(g, labels, codes, noise, seed, out, B, impl, stream_, nullptr, 0);
+}
+
+int chb_generator_forward_timed(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
+                                uint64_t seed, float* out, int B, void* stream_, float* ms, double* flops,
+                                int cap) {
+  if (!g || !ms || !flops || !g->ws) {
+    set_error("chb_generator_forward_timed: NULL argument or unbound generator");
+    return CHB_ERR_ARG;
+  }
+  std::vector<Step>* steps = nullptr;
+  int rc = get_steps(g, B, &steps);
+  if (rc != CHB_OK) return rc;
+  const int n = (int)steps->size();
+  if (cap < n) {
+    set_error("chb_generator_forward_timed: output arrays too small");
+    return CHB_ERR_ARG;
+  }
+  std::vector<cudaEvent_t> evs(n + 1);
+  for (auto& e : evs) cudaEventCreate(&e);
+  rc = forward_impl(g, labels, codes, noise, seed, out, B, CHB_IMPL_TCGEN05, stream_, evs.data(), n + 1);
+  if (rc == CHB_OK) {
+    if (cudaEventSynchronize(evs[n]) != cudaSuccess) {
+      set_error(std::string("forward_timed: ") + cudaGetErrorString(cudaGetLastError()));
+      rc = CHB_ERR_CUDA;
+    } else {
+      for (int i = 0; i < n; ++i) {
+        cudaEventElapsedTime(&ms[i], evs[i], evs[i + 1]);
+        flops[i] = (*steps)[i].plan.flops;
+      }
+      rc = n;
+    }
+  }
+  for (auto& e : evs) cudaEventDestroy(e);
+  return rc;
+}
+
+static int forward_impl(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
+                        uint64_t seed, float* out, int B, int impl, void* stream_, cudaEvent_t* evs, int nev) {
   if (!g || !labels || !codes || !out) {
     set_error("chb_generator_forward: NULL argument");
     return CHB_ERR_ARG;
@@ -548,7 +595,8 @@ int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* 
     rc = chb_noise_fill(nz, (int64_t)B * g->noise_pix, seed, 0, stream);
     if (rc != CHB_OK) return rc;
   }
-  int nrun = 0;
+  int nrun = 0, iev = 0;
+  if (evs && iev < nev) cudaEventRecord(evs[iev++], stream);
   for (const Step& s : *steps) {
     if (g->step_limit >= 0 && nrun++ >= g->step_limit) break;
     if (s.final_image && out != reinterpret_cast<float*>(ws + g->ws_out)) {
@@ -560,6 +608,7 @@ int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* 
       rc = launch_conv_plan(s.plan, impl, stream);
     }
     if (rc != CHB_OK) return rc;
+    if (evs && iev < nev) cudaEventRecord(evs[iev++], stream);
   }
   return CHB_OK;
 }
@@ -620,6 +669,16 @@ double chb_generator_flops(const chb_generator* g_, int B) {
   double f = 0;
   for (const Step& s : *steps) f += s.plan.flops;
   return f;
+}
+
+int chb_generator_step_name(chb_generator* g, int B, int i, char* name, int cap) {
+  if (!g || !name || cap <= 0 || !g->ws) return CHB_ERR_ARG;
+  std::vector<Step>* steps = nullptr;
+  int rc = get_steps(g, B, &steps);
+  if (rc != CHB_OK) return rc;
+  if (i < 0 || i >= (int)steps->size()) return CHB_ERR_ARG;
+  snprintf(name, cap, "%s", (*steps)[i].name.c_str());
+  return CHB_OK;
 }
 
 int chb_generator_set_step_limit(chb_generator* g, int n) {

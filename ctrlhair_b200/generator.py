@@ -119,6 +119,31 @@ class SeanGeneratorB200:
                                                       C.c_void_p(out.data_ptr()), B, self.impl, self._stream()))
         return out
 
+    def forward_timed(self, labels, codes, seed=0, out=None):
+        """forward_labels with per-launch CUDA-event timing; returns (out, ms[list], flops[list])."""
+        B = labels.shape[0]
+        labels = labels.to(torch.uint8).contiguous()
+        codes = codes.to(torch.float32).contiguous()
+        if out is None:
+            out = torch.empty((B, 3, self.crop, self.crop), dtype=torch.float32, device=self.device)
+        cap = 128
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        with torch.cuda.device(self.device):
+            n = self.lib.chb_generator_forward_timed(self.handle, C.c_void_p(labels.data_ptr()),
+                                                     C.c_void_p(codes.data_ptr()), None, seed,
+                                                     C.c_void_p(out.data_ptr()), B, self._stream(), ms, fl, cap)
+        if n < 0:
+            _lib.check(n)
+        return out, list(ms[:n]), list(fl[:n])
+
+    def step_names(self, B):
+        names, buf, i = [], C.create_string_buffer(96), 0
+        while self.lib.chb_generator_step_name(self.handle, B, i, buf, 96) == 0:
+            names.append(buf.value.decode())
+            i += 1
+        return names
+
     def forward_host(self, labels, codes, noise=None, seed=0, out=None):
         """Host buffers in, host buffer out (numpy or CPU tensors); H2D/D2H copies happen inside the call."""
         if self.blob is None:

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE — synthetic checkpoints and inputs in the reference's formats (no reference code needed).
+"""Synthetic checkpoints and inputs in the reference's formats (used by bench.py, smoke() and the tests).
 
 The reference ships no weights (external_model_params/ is a git-ignored download), so parity and the benchmark
 use a seeded synthetic `latest_net_G.pth`-style state_dict with the exact key set / shapes of

@@ -132,6 +132,13 @@ int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* 
 int chb_generator_forward_host(chb_generator* g, const uint8_t* labels_host, const float* codes_host,
                                const float* noise_host, uint64_t seed, float* out_host, int B, int impl,
                                void* stream);
+/* Same as chb_generator_forward (tcgen05 path) with a CUDA event recorded on `stream` between consecutive conv
+ * launches: fills ms[i] / flops[i] (tensor-core FLOPs issued) for launch i and returns the number of launches
+ * (or a negative error).  Synchronises on the last event.  Used by bench.py for the live roofline figure. */
+int chb_generator_forward_timed(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
+                                uint64_t seed, float* out, int B, void* stream, float* ms, double* flops, int cap);
+/* Name of conv launch i of the schedule for batch B ("up_3.ace_0.gamma_beta_mod", ...). */
+int chb_generator_step_name(chb_generator* g, int B, int i, char* name, int cap);
 int64_t chb_generator_noise_floats(const chb_generator* g, int B);
 /* Number of kernel launches one forward issues (for bench accounting). */
 int chb_generator_launches(const chb_generator* g);

@@ -14,7 +14,7 @@ import torch
 
 from . import ref_harness as rh
 from . import sean_oracle as so
-from . import synth
+from ctrlhair_b200 import synth
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 

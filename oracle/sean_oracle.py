@@ -22,7 +22,11 @@ file against those vectors.  Functions take the reference-format state_dict (key
 import torch
 import torch.nn.functional as F
 
-from .synth import BLOCKS
+
+BLOCKS = [  # name, fin/ngf, fout/ngf, styled  (generator.py:35-43; up_3 is built with use_rgb=False)
+    ("head_0", 16, 16, True), ("G_middle_0", 16, 16, True), ("G_middle_1", 16, 16, True),
+    ("up_0", 16, 8, True), ("up_1", 8, 4, True), ("up_2", 4, 2, True), ("up_3", 2, 1, False),
+]
 
 BN_EPS = 1e-5  # batchnorm.py:40 default eps
 

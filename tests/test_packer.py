@@ -1,0 +1,69 @@
+"""Host logic: the weight packer's folds/layouts and the region-factored schedule, checked on CPU."""
+import ctypes as C
+
+import pytest
+import torch
+
+import _packed_emulation as pe
+from ctrlhair_b200 import _lib, packer
+from oracle import sean_oracle as so
+from ctrlhair_b200 import synth
+
+
+def test_tile_gamma_beta_roundtrip():
+    g = torch.arange(512.).reshape(512, 1)
+    b = -torch.arange(512.).reshape(512, 1)
+    t = packer.tile_gamma_beta(g, b, 256)
+    assert t.shape == (1024, 1)
+    assert torch.equal(t[:128, 0], g[:128, 0]) and torch.equal(t[128:256, 0], b[:128, 0])
+    assert torch.equal(t[256:384, 0], g[128:256, 0])
+    g2, b2 = pe._untile(t.reshape(1, 1024, 1, 1), 256)
+    assert torch.equal(g2.reshape(-1), g.reshape(-1)) and torch.equal(b2.reshape(-1), b.reshape(-1))
+
+
+@pytest.mark.parametrize("kind", ["blocky", "iid"])
+def test_factored_schedule_is_exact_in_fp32(synthetic_sd, kind):
+    """Packed + factored form == dense reference form, to fp32 round-off."""
+    labels, codes, noise = synth.make_labels(2, 64, kind), synth.make_codes(2), synth.make_noise(2, 64)
+    ref = so.generator_forward(synthetic_sd, labels, codes, noise)
+    packed = packer.pack_generator(synthetic_sd, weight_dtype=torch.float32)
+    out = pe.emulate(packed, labels, codes, noise)
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+def test_fp16_storage_forecast(synthetic_sd):
+    """fp16 weights + fp16 MMA operands, fp32 everywhere else: the error budget the CUDA path is held to."""
+    labels, codes, noise = synth.make_labels(2, 64, "iid"), synth.make_codes(2), synth.make_noise(2, 64)
+    ref = so.generator_forward(synthetic_sd, labels, codes, noise)
+    out = pe.emulate(packer.pack_generator(synthetic_sd), labels, codes, noise, round16=True)
+    assert float((out - ref).norm() / ref.norm()) < 1e-3
+    assert float((out - ref).abs().max() / ref.abs().max()) < 3e-3
+
+
+def test_packer_matches_library_layout(synthetic_sd, lib):
+    """Every tensor the library's blob layout names is produced by the packer with the right dtype and size."""
+    cfg = _lib.GenConfig(64, 19, 256, 512, 4)
+    h = C.c_void_p()
+    assert lib.chb_generator_create(C.byref(cfg), C.byref(h)) == 0
+    try:
+        packed = packer.pack_generator(synthetic_sd)
+        n = lib.chb_generator_num_tensors(h)
+        name = C.create_string_buffer(128)
+        off, nb, dt = C.c_int64(), C.c_int64(), C.c_int()
+        seen, end = set(), 0
+        for i in range(n):
+            assert lib.chb_generator_tensor_info(h, i, name, 128, C.byref(off), C.byref(nb), C.byref(dt)) == 0
+            k = name.value.decode()
+            t = packed[k]
+            assert t.dtype == (torch.float16 if dt.value == _lib.F16 else torch.float32), k
+            assert t.numel() * t.element_size() == nb.value, k
+            assert off.value % 256 == 0 and off.value >= end
+            end = off.value + nb.value
+            seen.add(k)
+        assert seen == set(packed)
+        assert lib.chb_generator_blob_bytes(h) >= end
+        # 267 M reference parameters -> ~534 MB of fp16 (one-hot padding 19->32 adds a little)
+        assert 5.0e8 < lib.chb_generator_blob_bytes(h) < 6.0e8
+        assert lib.chb_generator_launches(h) == 60
+    finally:
+        lib.chb_generator_destroy(h)

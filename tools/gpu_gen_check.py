@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from ctrlhair_b200 import _lib  # noqa: E402
 from ctrlhair_b200.generator import SeanGeneratorB200  # noqa: E402
 from oracle import sean_oracle as so  # noqa: E402
-from oracle import synth  # noqa: E402
+from ctrlhair_b200 import synth  # noqa: E402
 
 
 def main():

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from ctrlhair_b200.generator import SeanGeneratorB200  # noqa: E402
-from oracle import synth  # noqa: E402
+from ctrlhair_b200 import synth  # noqa: E402
 
 
 def main():
