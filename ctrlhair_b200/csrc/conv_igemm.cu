@@ -39,11 +39,19 @@ int device_sm_count() {
 // ------------------------------------------------------------------------------------------------
 // Epilogue math shared by the tcgen05 kernel and the SIMT checker kernel.
 // ------------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == CHB_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == CHB_ACT_LRELU) return fmaxf(v, 0.2f * v);
+  if (ACT == CHB_ACT_TANH) return tanhf(v);
+  return v;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
-    case CHB_ACT_RELU: return fmaxf(v, 0.f);
-    case CHB_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
-    case CHB_ACT_TANH: return tanhf(v);
+    case CHB_ACT_RELU: return act_t<CHB_ACT_RELU>(v);
+    case CHB_ACT_LRELU: return act_t<CHB_ACT_LRELU>(v);
+    case CHB_ACT_TANH: return act_t<CHB_ACT_TANH>(v);
     default: return v;
   }
 }
@@ -58,6 +66,7 @@ __device__ __forceinline__ long long out_offset(const EpiK& e, int b, int y, int
   return off;
 }
 
+template <int ACT>
 __device__ __forceinline__ void plain_store_elem(const EpiK& e, int b, int y, int x, int n, float acc) {
   float v = acc;
   if (e.bias) v += __ldg(e.bias + (e.bias_per_image ? (long long)b * e.nrows : 0) + n);
@@ -65,7 +74,7 @@ __device__ __forceinline__ void plain_store_elem(const EpiK& e, int b, int y, in
     v += __ldg(e.res + (long long)b * e.r_sb + (long long)(y >> e.r_shift) * e.r_sy +
                (long long)(x >> e.r_shift) * e.r_sx + n);
   }
-  v = apply_act(v, e.act);
+  v = act_t<ACT>(v);
   const long long off = out_offset(e, b, y, x, n);
   if (e.out_dtype == CHB_F16) {
     reinterpret_cast<__half*>(e.out)[off] = __float2half_rn(v);
@@ -74,16 +83,80 @@ __device__ __forceinline__ void plain_store_elem(const EpiK& e, int b, int y, in
   }
 }
 
-// xn = (x + noise*noise_var - mean) * rstd  (folded);  out = act(xn * (1 + gamma) + beta)
-__device__ __forceinline__ float modulate_elem(float xv, float nz, float4 ch, float gamma, float beta, int act) {
-  const float xn = fmaf(xv, ch.x, fmaf(nz, ch.z, ch.y));
-  return apply_act(fmaf(xn, 1.f + gamma, beta), act);
+// xn = (x + noise*noise_var - mean) * rstd  (folded: a = rstd, c = -mean*rstd, nv = noise_var*rstd)
+// out = act(xn * (1 + gamma) + beta)
+template <int ACT>
+__device__ __forceinline__ float modulate_elem(float xv, float nz, float a, float c, float nv, float gamma,
+                                               float beta) {
+  const float xn = fmaf(xv, a, fmaf(nz, nv, c));
+  return act_t<ACT>(fmaf(xn, 1.f + gamma, beta));
+}
+
+// One chunk of NC accumulator columns of the PLAIN epilogue: TMEM load and the global loads it needs are all
+// issued before the single wait, so the (few) epilogue warps have the latencies overlapped.
+template <int NC, int ACT>
+__device__ __forceinline__ void plain_chunk(const ConvKParams& p, const EpiK& e, uint32_t taddr, int n, bool valid,
+                                            int b, int y, int x) {
+  float v[NC];
+  tmem_ld<NC>(taddr, v);
+  const bool inb = valid && n < p.N;
+  const bool vec = inb && (n + NC <= p.N) && e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % NC) == 0);
+  float4 bv[NC / 4], rv[NC / 4];
+#pragma unroll
+  for (int i = 0; i < NC / 4; ++i) bv[i] = rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) {
+    if (e.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)b * e.nrows : 0) + n);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) bv[i] = __ldg(bp + i);
+    }
+    if (e.res) {
+      const float4* rp = reinterpret_cast<const float4*>(e.res + (long long)b * e.r_sb +
+                                                         (long long)(y >> e.r_shift) * e.r_sy +
+                                                         (long long)(x >> e.r_shift) * e.r_sx + n);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) rv[i] = __ldg(rp + i);
+    }
+  }
+  tmem_ld_fence(v);
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < NC / 4; ++i) {
+      v[4 * i] = act_t<ACT>(v[4 * i] + bv[i].x + rv[i].x);
+      v[4 * i + 1] = act_t<ACT>(v[4 * i + 1] + bv[i].y + rv[i].y);
+      v[4 * i + 2] = act_t<ACT>(v[4 * i + 2] + bv[i].z + rv[i].z);
+      v[4 * i + 3] = act_t<ACT>(v[4 * i + 3] + bv[i].w + rv[i].w);
+    }
+    const long long off = out_offset(e, b, y, x, n);
+    if (e.out_dtype == CHB_F16) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + off);
+#pragma unroll
+      for (int i = 0; i < NC / 8; ++i) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          __half2 h = __floats2half2_rn(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]);
+          pk[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    } else {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  } else if (inb) {
+#pragma unroll 1
+    for (int i = 0; i < NC; ++i)
+      if (n + i < p.N) plain_store_elem<ACT>(e, b, y, x, n + i, v[i]);
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -111,7 +184,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kEpilogueWarps);
     }
     fence_mbar_init();
   }
@@ -197,8 +270,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+    // ------------------------------------------------------------------ epilogue warps
+    // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int tpix = p.TW * p.TH;
     const int tb = row / tpix;
@@ -222,102 +297,61 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
 
       if (EPI == CHB_EPI_PLAIN) {
+        const int ch = p.BN >> 1;  // columns per warp-half (multiple of 8)
+        int j = chalf * ch;
+        const int jend = j + ch;
         const int n0 = n_tile * p.BN;
-        const bool vec = (e.o_sn == 1);
-        for (int j = 0; j < p.BN; j += 16) {
-          float v[16];
-          tmem_ld16(taddr + (uint32_t)j, v);
-          tmem_ld_wait();
-          const int n = n0 + j;
-          if (!valid || n >= p.N) {
-            // nothing to store for this lane / chunk
-          } else if (vec && n + 16 <= p.N && (e.o_ngroup <= 0 || (e.o_ngroup % 16) == 0)) {
-            if (e.bias) {
-              const float4* bp =
-                  reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)b * e.nrows : 0) + n);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 t = __ldg(bp + i);
-                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-              }
-            }
-            if (e.res) {
-              const float4* rp = reinterpret_cast<const float4*>(
-                  e.res + (long long)b * e.r_sb + (long long)(y >> e.r_shift) * e.r_sy +
-                  (long long)(x >> e.r_shift) * e.r_sx + n);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 t = __ldg(rp + i);
-                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], e.act);
-            const long long off = out_offset(e, b, y, x, n);
-            if (e.out_dtype == CHB_F16) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                pk[i] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + off);
-              op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            } else {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-          } else {
-            for (int i = 0; i < 16; ++i)
-              if (n + i < p.N) plain_store_elem(e, b, y, x, n + i, v[i]);
-          }
-          __syncwarp();
-        }
+        for (; j + 32 <= jend; j += 32) plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+        for (; j + 16 <= jend; j += 16) plain_chunk<16, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+        for (; j + 8 <= jend; j += 8) plain_chunk<8, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
       } else {
         // MODULATE: columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2
         const int half_n = p.BN >> 1;
+        const int cw = half_n >> 1;  // channels per warp-half (multiple of 16)
         const int c0 = n_tile * half_n;
         const int nrow0 = n_tile * p.BN;
         float nz = 0.f;
-        const float* xp = nullptr;
-        __half* hp = nullptr;
+        const float* xp = e.x;
+        __half* hp = reinterpret_cast<__half*>(e.out);
         if (valid) {
           if (e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
-          xp = e.x + (long long)b * e.x_sb + (long long)(y >> e.x_shift) * e.x_sy +
-               (long long)(x >> e.x_shift) * e.x_sx + c0;
-          hp = reinterpret_cast<__half*>(e.out) + (long long)b * e.o_sb + (long long)y * e.o_sy +
-               (long long)x * e.o_sx + c0;
+          xp += (long long)b * e.x_sb + (long long)(y >> e.x_shift) * e.x_sy + (long long)(x >> e.x_shift) * e.x_sx + c0;
+          hp += (long long)b * e.o_sb + (long long)y * e.o_sy + (long long)x * e.o_sx + c0;
         }
-        for (int j = 0; j < half_n; j += 16) {
-          float g[16], bt16[16];
-          tmem_ld16(taddr + (uint32_t)j, g);
-          tmem_ld16(taddr + (uint32_t)(half_n + j), bt16);
-          tmem_ld_wait();
+        const float* ca = reinterpret_cast<const float*>(e.chan) + c0;
+        for (int j = chalf * cw; j < (chalf + 1) * cw; j += 16) {
+          float g[16], be[16];
+          tmem_ld<16>(taddr + (uint32_t)j, g);
+          tmem_ld<16>(taddr + (uint32_t)(half_n + j), be);
+          float4 bg[4], bb[4], xv[4], av[4], cv[4], nv[4];
           if (valid) {
-          const float4* bg = reinterpret_cast<const float4*>(e.bias + nrow0 + j);
-          const float4* bb = reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + j);
-          const float4* xv4 = reinterpret_cast<const float4*>(xp + j);
-          uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 tg = __ldg(bg + i), tb4 = __ldg(bb + i), xv = __ldg(xv4 + i);
-            const float4 ch0 = __ldg(e.chan + c0 + j + 4 * i);
-            const float4 ch1 = __ldg(e.chan + c0 + j + 4 * i + 1);
-            const float4 ch2 = __ldg(e.chan + c0 + j + 4 * i + 2);
-            const float4 ch3 = __ldg(e.chan + c0 + j + 4 * i + 3);
-            const float o0 = modulate_elem(xv.x, nz, ch0, g[4 * i] + tg.x, bt16[4 * i] + tb4.x, e.act);
-            const float o1 = modulate_elem(xv.y, nz, ch1, g[4 * i + 1] + tg.y, bt16[4 * i + 1] + tb4.y, e.act);
-            const float o2 = modulate_elem(xv.z, nz, ch2, g[4 * i + 2] + tg.z, bt16[4 * i + 2] + tb4.z, e.act);
-            const float o3 = modulate_elem(xv.w, nz, ch3, g[4 * i + 3] + tg.w, bt16[4 * i + 3] + tb4.w, e.act);
-            __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
-            pk[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
-            pk[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            for (int i = 0; i < 4; ++i) {
+              bg[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + j) + i);
+              bb[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + j) + i);
+              xv[i] = __ldg(reinterpret_cast<const float4*>(xp + j) + i);
+              av[i] = __ldg(reinterpret_cast<const float4*>(ca + j) + i);
+              cv[i] = __ldg(reinterpret_cast<const float4*>(ca + e.chan_stride + j) + i);
+              nv[i] = __ldg(reinterpret_cast<const float4*>(ca + 2 * e.chan_stride + j) + i);
+            }
           }
-          uint4* op = reinterpret_cast<uint4*>(hp + j);
-          op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          tmem_ld_fence(g);
+          tmem_ld_fence(be);
+          if (valid) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float o0 = modulate_elem<ACT>(xv[i].x, nz, av[i].x, cv[i].x, nv[i].x, g[4 * i] + bg[i].x, be[4 * i] + bb[i].x);
+              const float o1 = modulate_elem<ACT>(xv[i].y, nz, av[i].y, cv[i].y, nv[i].y, g[4 * i + 1] + bg[i].y, be[4 * i + 1] + bb[i].y);
+              const float o2 = modulate_elem<ACT>(xv[i].z, nz, av[i].z, cv[i].z, nv[i].z, g[4 * i + 2] + bg[i].z, be[4 * i + 2] + bb[i].z);
+              const float o3 = modulate_elem<ACT>(xv[i].w, nz, av[i].w, cv[i].w, nv[i].w, g[4 * i + 3] + bg[i].w, be[4 * i + 3] + bb[i].w);
+              __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
+              pk[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
+              pk[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+            uint4* op = reinterpret_cast<uint4*>(hp + j);
+            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
           __syncwarp();
         }
@@ -353,6 +387,15 @@ struct SimtParams {
   EpiK e;
 };
 
+__device__ void plain_store_elem_rt(const EpiK& e, int b, int y, int x, int n, float acc) {
+  switch (e.act) {
+    case CHB_ACT_RELU: plain_store_elem<CHB_ACT_RELU>(e, b, y, x, n, acc); break;
+    case CHB_ACT_LRELU: plain_store_elem<CHB_ACT_LRELU>(e, b, y, x, n, acc); break;
+    case CHB_ACT_TANH: plain_store_elem<CHB_ACT_TANH>(e, b, y, x, n, acc); break;
+    default: plain_store_elem<CHB_ACT_NONE>(e, b, y, x, n, acc); break;
+  }
+}
+
 __device__ float simt_dot(const SimtParams& p, int b, int y, int x, int nrow) {
   float acc = 0.f;
   for (int s = 0; s < p.nseg; ++s) {
@@ -383,7 +426,7 @@ __global__ void conv_simt_kernel(const SimtParams p) {
     const int y = (int)(pix % p.H);
     const int b = (int)(pix / p.H);
     if (p.epi == CHB_EPI_PLAIN) {
-      plain_store_elem(p.e, b, y, x, n, simt_dot(p, b, y, x, n));
+      plain_store_elem_rt(p.e, b, y, x, n, simt_dot(p, b, y, x, n));
     } else {
       const int half_n = p.BN / 2;
       const int t = n / half_n, j = n % half_n;
@@ -393,7 +436,9 @@ __global__ void conv_simt_kernel(const SimtParams p) {
       const float nz = p.e.noise ? __ldg(p.e.noise + ((long long)b * p.W + x) * p.H + y) : 0.f;
       const float xv = __ldg(p.e.x + (long long)b * p.e.x_sb + (long long)(y >> p.e.x_shift) * p.e.x_sy +
                              (long long)(x >> p.e.x_shift) * p.e.x_sx + n);
-      const float o = modulate_elem(xv, nz, __ldg(p.e.chan + n), g, be, p.e.act);
+      const float* cp = reinterpret_cast<const float*>(p.e.chan);
+      const float a = __ldg(cp + n), c = __ldg(cp + p.e.chan_stride + n), nvv = __ldg(cp + 2 * p.e.chan_stride + n);
+      const float o = apply_act(fmaf(fmaf(xv, a, fmaf(nz, nvv, c)), 1.f + g, be), p.e.act);
       reinterpret_cast<__half*>(p.e.out)[(long long)b * p.e.o_sb + (long long)y * p.e.o_sy + (long long)x * p.e.o_sx + n] =
           __float2half_rn(o);
     }
@@ -477,7 +522,8 @@ static int validate_desc(const chb_conv_desc& d) {
   }
   if (d.epi == CHB_EPI_MODULATE) {
     CHB_REQUIRE(d.x && d.chan && d.bias, "modulate epilogue needs x, chan and bias");
-    CHB_REQUIRE(d.BN % 32 == 0 && d.N == d.Nrows, "modulate epilogue needs BN % 32 == 0 and N == Nrows");
+    CHB_REQUIRE(d.BN % 64 == 0 && d.N == d.Nrows, "modulate epilogue needs BN % 64 == 0 and N == Nrows");
+    CHB_REQUIRE(d.act != CHB_ACT_TANH, "modulate epilogue supports none / relu / lrelu");
     CHB_REQUIRE(d.o_sn == 1 || d.o_sn == 0, "modulate output is channels-last");
   }
 #undef CHB_REQUIRE
@@ -540,7 +586,8 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   e.res = d.res; e.r_sb = d.r_sb; e.r_sy = d.r_sy; e.r_sx = d.r_sx; e.r_shift = d.r_shift;
   e.x = d.x; e.x_sb = d.x_sb; e.x_sy = d.x_sy; e.x_sx = d.x_sx; e.x_shift = d.x_shift;
   e.noise = d.noise;
-  e.chan = reinterpret_cast<const float4*>(d.chan);
+  e.chan = d.chan;
+  e.chan_stride = d.N / 2;
   const int total = k.m_tiles * k.n_tiles;
   const int sms = device_sm_count();
   plan->grid = total < sms ? total : sms;
@@ -548,15 +595,32 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   return CHB_OK;
 }
 
+typedef void (*ConvKernelFn)(const ConvKParams);
+
+static ConvKernelFn pick_kernel(int epi, int act) {
+  if (epi == CHB_EPI_PLAIN) {
+    switch (act) {
+      case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_RELU>;
+      case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_LRELU>;
+      case CHB_ACT_TANH: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_TANH>;
+      default: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_NONE>;
+    }
+  }
+  switch (act) {
+    case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_LRELU>;
+    case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_RELU>;
+    default: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_NONE>;
+  }
+}
+
 static int ensure_smem_attr() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(conv_igemm_kernel<CHB_EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               kSmemBudget + 2048);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(conv_igemm_kernel<CHB_EPI_MODULATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kSmemBudget + 2048);
+    for (int epi = 0; epi < 2 && err == cudaSuccess; ++epi)
+      for (int act = 0; act < 4 && err == cudaSuccess; ++act)
+        err = cudaFuncSetAttribute(pick_kernel(epi, act), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kSmemBudget + 2048);
   });
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(err));
@@ -584,11 +648,7 @@ int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
   } else {
     int rc = ensure_smem_attr();
     if (rc != CHB_OK) return rc;
-    if (plan.desc.epi == CHB_EPI_PLAIN) {
-      conv_igemm_kernel<CHB_EPI_PLAIN><<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
-    } else {
-      conv_igemm_kernel<CHB_EPI_MODULATE><<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
-    }
+    pick_kernel(plan.desc.epi, plan.desc.act)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
   }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {

@@ -13,7 +13,8 @@ constexpr int kMaxSeg = 3;
 constexpr int kATileBytes = 16384;  // 128 rows x 128 B
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 200 * 1024;
-constexpr int kConvThreads = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kEpilogueWarps = 8;
+constexpr int kConvThreads = 64 + 32 * kEpilogueWarps;  // warp0 TMA, warp1 MMA, warps 2-9 epilogue
 
 struct SegK {
   int taps, nchunk, kc, ch_off, per_image, pad;
@@ -38,7 +39,8 @@ struct EpiK {
   long long x_sb, x_sy, x_sx;
   int x_shift;
   const float* noise;
-  const float4* chan;
+  const float* chan;   // planar [3][C]: a = rstd | c = -mean*rstd | nv = noise_var*rstd
+  int chan_stride;     // C
 };
 
 struct ConvKParams {

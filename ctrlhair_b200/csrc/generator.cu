@@ -142,7 +142,7 @@ static void build_layout(chb_generator* g) {
       const std::string p = b.name + "." + an[a];
       A.t_gbw = add_tensor(g, p + ".gb.w", (int64_t)2 * A.C * 9 * 128 * 2, CHB_F16);
       A.t_gbb = add_tensor(g, p + ".gb.b", (int64_t)2 * A.C * 4, CHB_F32);
-      A.t_chan = add_tensor(g, p + ".chan", (int64_t)A.C * 16, CHB_F32);
+      A.t_chan = add_tensor(g, p + ".chan", (int64_t)A.C * 12, CHB_F32);
       A.t_stylew = -1;
       if (A.styled) {
         A.style_idx = g->n_styled++;
@@ -179,7 +179,7 @@ static void build_layout(chb_generator* g) {
   g->ws_out = ws_alloc(g, (int64_t)B * 3 * S * S * 4);
   g->ws_codes16 = ws_alloc(g, (int64_t)B * c.label_nc * L * 2);
   g->ws_noise = ws_alloc(g, (int64_t)B * g->noise_pix * 4);
-  g->ws_mu = ws_alloc(g, (int64_t)g->n_styled * B * c.label_nc * L * 2);
+  g->ws_mu = ws_alloc(g, (int64_t)g->n_styled * B * 32 * L * 2);
   g->ws_weff = ws_alloc(g, (int64_t)B * g->weff_rows * 32 * 2);
   for (int l = 0; l < 6; ++l) {
     const int64_t r = (int64_t)g->sw << l;
@@ -290,31 +290,38 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     d.bias = reinterpret_cast<const float*>(blobp(g, g->t_fcmub));
     d.bias_per_image = 1;
     d.out = ws + g->ws_mu; d.out_dtype = CHB_F16;
-    d.o_sb = L; d.o_sy = 0; d.o_sx = (int64_t)NC * L; d.o_sn = 1;
-    d.o_ngroup = L; d.o_sgroup = (int64_t)B * NC * L;
+    // mu is stored [ace][image][32 classes (19 real, rest stay zero)][L]
+    d.o_sb = L; d.o_sy = 0; d.o_sx = (int64_t)32 * L; d.o_sn = 1;
+    d.o_ngroup = L; d.o_sgroup = (int64_t)B * 32 * L;
     if ((rc = push_step(steps, d, "fc_mu")) != CHB_OK) return rc;
   }
-  // ---- style path 2: Weff[b][n*9+tap][j] = sum_ci Wstyle[n*9+tap][ci] * mu[b][j][ci]  (per styled ACE)
+  // ---- style path 2: Weff[b][n*9+tap][j] = sum_ci Wstyle[n*9+tap][ci] * mu[b][j][ci]  (per styled ACE).
+  // GEMM roles are swapped (M = weight rows n*9+tap, N = (image, class)) so that every thread of the epilogue
+  // owns one Weff row and writes its 32 class columns as one contiguous 64-byte run.
+  int gimg = 1;
+  while (gimg < 8 && B % (gimg * 2) == 0) gimg *= 2;
   for (auto& b : g->blocks)
     for (int a = 0; a < 3; ++a) {
       const AceInfo& A = b.ace[a];
       if (!A.C || !A.styled) continue;
+      const int rows = 2 * A.C * 9;
       chb_conv_desc d;
       memset(&d, 0, sizeof d);
-      d.B = B; d.H = 1; d.W = NC;
-      d.TW = 32; d.TH = 1; d.TB = 4;
+      d.B = 1; d.H = 1; d.W = rows;
+      d.TW = 128; d.TH = 1; d.TB = 1;
       d.nseg = 1;
       chb_conv_seg& s = d.seg[0];
       memset(&s, 0, sizeof s);
-      s.a = ws + g->ws_mu + (int64_t)A.style_idx * B * NC * L * 2;
-      s.a_sx = L; s.a_sy = (int64_t)NC * L; s.a_sb = (int64_t)NC * L;
+      s.a = blobp(g, A.t_stylew);
+      s.a_sx = L; s.a_sy = (int64_t)rows * L; s.a_sb = (int64_t)rows * L;
       s.Ca = L; s.C = L; s.taps = 1;
-      s.w = blobp(g, A.t_stylew);
-      d.N = d.Nrows = 2 * A.C * 9;
-      d.BN = 256;
+      s.w = ws + g->ws_mu + (int64_t)A.style_idx * B * 32 * L * 2;
+      d.N = d.Nrows = B * 32;
+      d.BN = 32 * gimg;
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
       d.out = ws + g->ws_weff + A.weff_row0 * 32 * 2; d.out_dtype = CHB_F16;
-      d.o_sb = g->weff_rows * 32; d.o_sy = 0; d.o_sx = 1; d.o_sn = 32;
+      d.o_sb = 0; d.o_sy = 0; d.o_sx = 32; d.o_sn = 1;
+      d.o_ngroup = 32; d.o_sgroup = g->weff_rows * 32;
       const char* an3[3] = {"ace_s", "ace_0", "ace_1"};
       if ((rc = push_step(steps, d, b.name + "." + an3[a] + ".weff")) != CHB_OK) return rc;
     }
@@ -488,8 +495,9 @@ int chb_generator_bind(chb_generator* g, const void* blob, void* workspace) {
   g->blob = reinterpret_cast<const uint8_t*>(blob);
   g->ws = reinterpret_cast<uint8_t*>(workspace);
   g->plans.clear();
-  // Weff columns 19..31 are never written by the style GEMM and must read as zero.
-  cudaError_t err = cudaMemset(g->ws + g->ws_weff, 0, (size_t)g->cfg.max_batch * g->weff_rows * 32 * 2);
+  // mu rows 19..31 (class padding) are never written by the fc_mu GEMM and must read as zero, so that the
+  // Weff columns they produce are exact zeros.
+  cudaError_t err = cudaMemset(g->ws + g->ws_mu, 0, (size_t)g->n_styled * g->cfg.max_batch * 32 * g->cfg.style_len * 2);
   if (err != cudaSuccess) {
     set_error(std::string("chb_generator_bind: cudaMemset failed: ") + cudaGetErrorString(err));
     return CHB_ERR_CUDA;

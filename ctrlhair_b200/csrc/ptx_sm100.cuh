@@ -115,18 +115,53 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i).
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// tcgen05.ld 32x32b: thread i of the warp receives N consecutive fp32 columns of TMEM lane (base_lane + i).
+// The load is asynchronous: values may only be read after tmem_ld_fence(v) (tcgen05.wait::ld).  The fence takes
+// the destination registers as in/out operands so the compiler cannot hoist their uses above the wait.
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
       "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
       : "r"(taddr)
       : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]),
+        "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]),
+        "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_fence(float (&v)[N]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < N; i += 8) {
+    asm volatile(""
+                 : "+f"(v[i]), "+f"(v[i + 1]), "+f"(v[i + 2]), "+f"(v[i + 3]), "+f"(v[i + 4]), "+f"(v[i + 5]),
+                   "+f"(v[i + 6]), "+f"(v[i + 7])
+                 :
+                 : "memory");
+  }
 }
 
 // Shared-memory matrix descriptor, K-major operand, rows of `row_bytes` (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B).

@@ -93,11 +93,8 @@ def pack_generator(sd, ngf=64, label_nc=19, weight_dtype=torch.float16):
             out[p + ".gb.w"] = tile_gamma_beta(wg, wb, bn).to(wd)
             out[p + ".gb.b"] = tile_gamma_beta(bg, bb, bn)
             rstd = torch.rsqrt(sd[p + ".param_free_norm.running_var"].float() + BN_EPS)
-            chan = torch.zeros((C, 4), dtype=torch.float32)
-            chan[:, 0] = rstd
-            chan[:, 1] = -sd[p + ".param_free_norm.running_mean"].float() * rstd
-            chan[:, 2] = sd[p + ".noise_var"].float() * rstd
-            out[p + ".chan"] = chan
+            out[p + ".chan"] = torch.stack([rstd, -sd[p + ".param_free_norm.running_mean"].float() * rstd,
+                                            sd[p + ".noise_var"].float() * rstd])  # planar [3][C]
         out[name + ".conv_0.w"] = _k_major(_sn(sd, name + ".conv_0")).to(wd)
         out[name + ".conv_0.b"] = sd[name + ".conv_0.bias"].float()
         out[name + ".conv_1.w"] = _k_major(_sn(sd, name + ".conv_1")).to(wd)

@@ -75,7 +75,7 @@ typedef struct {
      out = act( (x*a + noise*nv + c) * (1+gamma) + beta ), out fp16 */
   const float* x; int64_t x_sb, x_sy, x_sx; int x_shift;
   const float* noise; /* [B, W, H] — the reference's randn(B,W,H,1) plane, read transposed; may be NULL */
-  const float* chan;  /* [C] x float4 {a = rstd, c = -mean*rstd, nv = noise_var*rstd, 0}          */
+  const float* chan;  /* planar [3][C]: a = rstd | c = -mean*rstd | nv = noise_var*rstd (C = N/2)         */
 } chb_conv_desc;
 
 enum { CHB_IMPL_TCGEN05 = 0, CHB_IMPL_SIMT_DEBUG = 1 };

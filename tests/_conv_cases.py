@@ -68,7 +68,7 @@ def ref_modulate(segs, N, BN, bias, x, x_shift, noise, chan, act):
     xv = x.permute(0, 3, 1, 2)
     if x_shift:
         xv = xv.repeat_interleave(2, 2).repeat_interleave(2, 3)
-    a, c, nv = chan[:, 0], chan[:, 1], chan[:, 2]
+    a, c, nv = chan[0], chan[1], chan[2]
     xn = xv * a[None, :, None, None] + c[None, :, None, None]
     if noise is not None:
         # noise is [B, W, H]; noise[b, c, h, w] = n[b, w, h] * nv[c]  (normalization.py:111)
@@ -127,11 +127,8 @@ def make_cases(device="cuda"):
             xh, xw = H >> x_shift, W >> x_shift
             x = _rand(gen, (B, xh, xw, C), 1.0, torch.float32, device)
             noise = _rand(gen, (B, W, H), 1.0, torch.float32, device) if use_noise else None
-            chan = torch.zeros((C, 4), dtype=torch.float32)
-            chan[:, 0] = torch.rand(C, generator=gen) + 0.5
-            chan[:, 1] = torch.randn(C, generator=gen) * 0.3
-            chan[:, 2] = torch.randn(C, generator=gen) * 0.1
-            chan = chan.to(device)
+            chan = torch.stack([torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen) * 0.3,
+                                torch.randn(C, generator=gen) * 0.1]).to(device)  # planar [3][C]
             got = ops.conv_igemm(segs, N, BN, bias=bias, epi=ops.EPI_MODULATE, act=act, x=x, x_shift=x_shift,
                                  noise=noise, chan=chan, impl=impl)
             got = got.float().permute(0, 3, 1, 2)

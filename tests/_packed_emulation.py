@@ -70,10 +70,10 @@ def emulate(packed, labels, codes, noise_planes, ngf=64, label_nc=19, round16=Fa
                 gb = gb + torch.cat([F.conv2d(oh[b:b + 1, :label_nc], weff[b], padding=1) for b in range(B)])
             g, be = _untile(gb, bn)
             chan = packed[p + ".chan"]
-            xn = xin * chan[:, 0][None, :, None, None] + chan[:, 1][None, :, None, None]
+            xn = xin * chan[0][None, :, None, None] + chan[1][None, :, None, None]
             nz = next(noise)
             if nz is not None:
-                xn = xn + nz[..., 0].transpose(1, 2)[:, None] * chan[:, 2][None, :, None, None]
+                xn = xn + nz[..., 0].transpose(1, 2)[:, None] * chan[2][None, :, None, None]
             h = xn * (1 + g) + be
             if act:
                 h = F.leaky_relu(h, 0.2)

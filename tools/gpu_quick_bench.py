@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--crop", type=int, default=256)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--table", action="store_true")
     a = ap.parse_args()
     sd = synth.make_state_dict()
     gen = SeanGeneratorB200(crop=a.crop, max_batch=a.B)
@@ -45,6 +46,12 @@ def main():
     print("B=%d crop=%d  ms/step: %s" % (a.B, a.crop, ", ".join("%.2f" % m for m in ms)))
     print("best %.2f ms -> %.1f img/s, %.1f TFLOP/s issued (%.2f GFLOP/img), finite=%s" %
           (best, a.B / best * 1e3, fl / best / 1e9, fl / a.B / 1e9, bool(torch.isfinite(out).all())))
+    if a.table:
+        _, ms1, fl1 = gen.forward_timed(labels, codes, seed=3, out=out)
+        names = gen.step_names(a.B)
+        print("per-launch (CUDA events between launches): total %.2f ms" % sum(ms1))
+        for n, m, f in zip(names, ms1, fl1):
+            print("  %-34s %8.3f ms %8.1f TFLOP/s" % (n, m, f / (m * 1e-3) / 1e12 if m > 0 else 0.0))
 
 
 if __name__ == "__main__":
