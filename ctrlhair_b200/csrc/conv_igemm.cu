@@ -4,7 +4,7 @@
 //   A tiles are fetched by TMA straight from the NHWC activation tensor with the tap offset folded into the
 //   box coordinates (out-of-bounds -> zero fill = the conv's zero padding), B tiles by TMA from the K-major
 //   weight matrix (optionally a per-image one: the SEAN region-factored style weights).  One thread issues
-//   tcgen05.mma into a double-buffered fp32 TMEM accumulator, four epilogue warps drain it with tcgen05.ld
+//   tcgen05.mma into a double-buffered fp32 TMEM accumulator, eight epilogue warps drain it with tcgen05.ld
 //   and apply the fused epilogue (bias / residual / activation, or the ACE normalise-modulate of
 //   sean_codes/models/networks/normalization.py:111-112,177-187) while the next tile's main loop runs.
 //
@@ -90,6 +90,148 @@ __device__ __forceinline__ float modulate_elem(float xv, float nz, float a, floa
                                                float beta) {
   const float xn = fmaf(xv, a, fmaf(nz, nv, c));
   return act_t<ACT>(fmaf(xn, 1.f + gamma, beta));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-warp staging block (4 KB of shared memory per epilogue warp): 32 tile rows x (CH16 * 16) bytes.
+// The TMEM accumulator layout gives every lane one tile row (= one pixel), but pixels are C*elem bytes apart in
+// the NHWC tensors, so a row-per-lane global access touches 32 cache lines per instruction.  Going through this
+// block turns the global side into 64/128-byte contiguous runs per row (CH16 lanes per row).  The XOR swizzle
+// makes both access patterns (row per lane / CH16 lanes per row) free of bank conflicts.
+// ------------------------------------------------------------------------------------------------
+template <int CH16>
+__device__ __forceinline__ uint32_t stg_off(int row, int c) {
+  const int swz = CH16 == 8 ? (row & 7) : ((row >> 1) & 3);
+  return (uint32_t)(row * (CH16 * 16) + ((c ^ swz) << 4));
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)
+               : "memory");
+  return v;
+}
+
+// Pixel of tile row m (0..127) for the tile at (b0, y0, x0); returns false when the row is padding / out of range.
+struct TileGeo {
+  int TW, tpix, rows, B, H, W, b0, y0, x0;
+  __device__ __forceinline__ bool pixel(int m, int& b, int& y, int& x) const {
+    const int tb = m / tpix;
+    const int rem = m - tb * tpix;
+    const int ty = rem / TW;
+    b = b0 + tb;
+    y = y0 + ty;
+    x = x0 + rem - ty * TW;
+    return m < rows && b < B && y < H && x < W;
+  }
+};
+
+// global (CH16*16 contiguous bytes per tile row) -> registers, one row per lane.  rowptr(b,y,x) -> const char*.
+template <int CH16, class RowPtr>
+__device__ __forceinline__ void stage_gather(uint32_t stg, int lane, int row_base, const TileGeo& tg, RowPtr rowptr,
+                                             uint4 (&regs)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int cl = lane % CH16, r0 = lane / CH16;
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    const int rl = r0 + RPI * k;
+    int b, y, x;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (tg.pixel(row_base + rl, b, y, x)) v = __ldg(reinterpret_cast<const uint4*>(rowptr(b, y, x) + cl * 16));
+    sts128(stg + stg_off<CH16>(rl, cl), v);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < CH16; ++c) regs[c] = lds128(stg + stg_off<CH16>(lane, c));
+  __syncwarp();
+}
+
+// registers (one row per lane) -> global, CH16*16 contiguous bytes per tile row.  rowptr(b,y,x) -> char*.
+template <int CH16, class RowPtr>
+__device__ __forceinline__ void stage_scatter(uint32_t stg, int lane, int row_base, const TileGeo& tg, RowPtr rowptr,
+                                              const uint4 (&regs)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int cl = lane % CH16, r0 = lane / CH16;
+#pragma unroll
+  for (int c = 0; c < CH16; ++c) sts128(stg + stg_off<CH16>(lane, c), regs[c]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    const int rl = r0 + RPI * k;
+    const uint4 v = lds128(stg + stg_off<CH16>(rl, cl));
+    int b, y, x;
+    if (tg.pixel(row_base + rl, b, y, x)) *reinterpret_cast<uint4*>(rowptr(b, y, x) + cl * 16) = v;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 32 accumulator columns of the PLAIN epilogue through the staging block (channels-last output, full block valid).
+template <int ACT>
+__device__ __forceinline__ void plain_block32(const ConvKParams& p, const EpiK& e, uint32_t taddr, uint32_t stg,
+                                              int lane, int row_base, const TileGeo& tg, int n) {
+  float v[32];
+  tmem_ld<32>(taddr, v);
+  uint4 rr[8];
+  if (e.res) {
+    const float* res = e.res + n;
+    const long long sb = e.r_sb, sy = e.r_sy, sx = e.r_sx;
+    const int sh = e.r_shift;
+    stage_gather<8>(stg, lane, row_base, tg, [=](int b, int y, int x) {
+      return reinterpret_cast<const char*>(res + (long long)b * sb + (long long)(y >> sh) * sy + (long long)(x >> sh) * sx);
+    }, rr);
+  }
+  tmem_ld_fence(v);
+  if (e.bias) {
+    int bi, yi, xi;
+    tg.pixel(row_base + lane, bi, yi, xi);
+    if (bi >= tg.B) bi = tg.B - 1;  // padding rows: any valid image (the value is never stored)
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)bi * e.nrows : 0) + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(bp + i);
+      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  }
+  if (e.res) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[4 * i] += __uint_as_float(rr[i].x); v[4 * i + 1] += __uint_as_float(rr[i].y);
+      v[4 * i + 2] += __uint_as_float(rr[i].z); v[4 * i + 3] += __uint_as_float(rr[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = act_t<ACT>(v[i]);
+  const long long noff = e.o_ngroup > 0 ? (long long)(n / e.o_ngroup) * e.o_sgroup + (long long)(n % e.o_ngroup) : n;
+  const long long sb = e.o_sb, sy = e.o_sy, sx = e.o_sx;
+  if (e.out_dtype == CHB_F16) {
+    uint4 pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                         pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+    __half* out = reinterpret_cast<__half*>(e.out) + noff;
+    stage_scatter<4>(stg, lane, row_base, tg, [=](int b, int y, int x) {
+      return reinterpret_cast<char*>(out + (long long)b * sb + (long long)y * sy + (long long)x * sx);
+    }, pk);
+  } else {
+    uint4 pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                         __float_as_uint(v[4 * i + 3]));
+    float* out = reinterpret_cast<float*>(e.out) + noff;
+    stage_scatter<8>(stg, lane, row_base, tg, [=](int b, int y, int x) {
+      return reinterpret_cast<char*>(out + (long long)b * sb + (long long)y * sy + (long long)x * sx);
+    }, pk);
+  }
 }
 
 // One chunk of NC accumulator columns of the PLAIN epilogue: TMEM load and the global loads it needs are all
@@ -281,6 +423,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int ty = rem / p.TW;
     const int tx = rem - ty * p.TW;
     const EpiK& e = p.e;
+    const uint32_t stg = smem_u32(smem + (size_t)nst * p.stage_bytes + 256 + (size_t)(warp - 2) * 4096);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
@@ -296,64 +439,83 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
 
+      TileGeo tg;
+      tg.TW = p.TW; tg.tpix = tpix; tg.rows = p.rows; tg.B = p.B; tg.H = p.H; tg.W = p.W;
+      tg.b0 = bt * p.TB; tg.y0 = yt * p.TH; tg.x0 = xt * p.TW;
+      const int row_base = q * 32;
+
       if (EPI == CHB_EPI_PLAIN) {
         const int ch = p.BN >> 1;  // columns per warp-half (multiple of 8)
         int j = chalf * ch;
         const int jend = j + ch;
         const int n0 = n_tile * p.BN;
-        for (; j + 32 <= jend; j += 32) plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+        const bool staged = e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % 32) == 0);
+        for (; j + 32 <= jend; j += 32) {
+          if (staged && n0 + j + 32 <= p.N) {
+            plain_block32<ACT>(p, e, taddr + (uint32_t)j, stg, lane, row_base, tg, n0 + j);
+          } else {
+            plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+          }
+        }
         for (; j + 16 <= jend; j += 16) plain_chunk<16, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
         for (; j + 8 <= jend; j += 8) plain_chunk<8, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
       } else {
         // MODULATE: columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2
         const int half_n = p.BN >> 1;
-        const int cw = half_n >> 1;  // channels per warp-half (multiple of 16)
+        const int cw = half_n >> 1;  // channels per warp-half (multiple of 32)
         const int c0 = n_tile * half_n;
         const int nrow0 = n_tile * p.BN;
         float nz = 0.f;
-        const float* xp = e.x;
-        __half* hp = reinterpret_cast<__half*>(e.out);
-        if (valid) {
-          if (e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
-          xp += (long long)b * e.x_sb + (long long)(y >> e.x_shift) * e.x_sy + (long long)(x >> e.x_shift) * e.x_sx + c0;
-          hp += (long long)b * e.o_sb + (long long)y * e.o_sy + (long long)x * e.o_sx + c0;
-        }
-        const float* ca = reinterpret_cast<const float*>(e.chan) + c0;
-        for (int j = chalf * cw; j < (chalf + 1) * cw; j += 16) {
-          float g[16], be[16];
-          tmem_ld<16>(taddr + (uint32_t)j, g);
-          tmem_ld<16>(taddr + (uint32_t)(half_n + j), be);
-          float4 bg[4], bb[4], xv[4], av[4], cv[4], nv[4];
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              bg[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + j) + i);
-              bb[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + j) + i);
-              xv[i] = __ldg(reinterpret_cast<const float4*>(xp + j) + i);
-              av[i] = __ldg(reinterpret_cast<const float4*>(ca + j) + i);
-              cv[i] = __ldg(reinterpret_cast<const float4*>(ca + e.chan_stride + j) + i);
-              nv[i] = __ldg(reinterpret_cast<const float4*>(ca + 2 * e.chan_stride + j) + i);
-            }
+        if (valid && e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
+        const float* ca = e.chan + c0;
+        const int cs = e.chan_stride;
+        for (int j = chalf * cw; j < (chalf + 1) * cw; j += 32) {
+          // x block: 32 rows x 32 fp32 channels, gathered with 128-byte runs per row
+          uint4 xr[8];
+          {
+            const float* xsrc = e.x + c0 + j;
+            const long long sb = e.x_sb, sy = e.x_sy, sx = e.x_sx;
+            const int sh = e.x_shift;
+            stage_gather<8>(stg, lane, row_base, tg, [=](int bb_, int yy, int xx) {
+              return reinterpret_cast<const char*>(xsrc + (long long)bb_ * sb + (long long)(yy >> sh) * sy +
+                                                   (long long)(xx >> sh) * sx);
+            }, xr);
           }
-          tmem_ld_fence(g);
-          tmem_ld_fence(be);
-          if (valid) {
+          uint4 hk[4];
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int jj = j + 16 * sub;
+            float g[16], be[16];
+            tmem_ld<16>(taddr + (uint32_t)jj, g);
+            tmem_ld<16>(taddr + (uint32_t)(half_n + jj), be);
+            tmem_ld_fence(g);
+            tmem_ld_fence(be);
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float o0 = modulate_elem<ACT>(xv[i].x, nz, av[i].x, cv[i].x, nv[i].x, g[4 * i] + bg[i].x, be[4 * i] + bb[i].x);
-              const float o1 = modulate_elem<ACT>(xv[i].y, nz, av[i].y, cv[i].y, nv[i].y, g[4 * i + 1] + bg[i].y, be[4 * i + 1] + bb[i].y);
-              const float o2 = modulate_elem<ACT>(xv[i].z, nz, av[i].z, cv[i].z, nv[i].z, g[4 * i + 2] + bg[i].z, be[4 * i + 2] + bb[i].z);
-              const float o3 = modulate_elem<ACT>(xv[i].w, nz, av[i].w, cv[i].w, nv[i].w, g[4 * i + 3] + bg[i].w, be[4 * i + 3] + bb[i].w);
-              __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
-              pk[2 * i] = *reinterpret_cast<uint32_t*>(&h0);
-              pk[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+              const float4 bg = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + jj) + i);
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + jj) + i);
+              const float4 av = __ldg(reinterpret_cast<const float4*>(ca + jj) + i);
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(ca + cs + jj) + i);
+              const float4 nv = __ldg(reinterpret_cast<const float4*>(ca + 2 * cs + jj) + i);
+              const uint4 xq = xr[4 * sub + i];
+              const float o0 = modulate_elem<ACT>(__uint_as_float(xq.x), nz, av.x, cv.x, nv.x, g[4 * i] + bg.x, be[4 * i] + bb.x);
+              const float o1 = modulate_elem<ACT>(__uint_as_float(xq.y), nz, av.y, cv.y, nv.y, g[4 * i + 1] + bg.y, be[4 * i + 1] + bb.y);
+              const float o2 = modulate_elem<ACT>(__uint_as_float(xq.z), nz, av.z, cv.z, nv.z, g[4 * i + 2] + bg.z, be[4 * i + 2] + bb.z);
+              const float o3 = modulate_elem<ACT>(__uint_as_float(xq.w), nz, av.w, cv.w, nv.w, g[4 * i + 3] + bg.w, be[4 * i + 3] + bb.w);
+              pk[2 * i] = pack_h2(o0, o1);
+              pk[2 * i + 1] = pack_h2(o2, o3);
             }
-            uint4* op = reinterpret_cast<uint4*>(hp + j);
-            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            hk[2 * sub] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            hk[2 * sub + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          __syncwarp();
+          {
+            __half* hdst = reinterpret_cast<__half*>(e.out) + c0 + j;
+            const long long sb = e.o_sb, sy = e.o_sy, sx = e.o_sx;
+            stage_scatter<4>(stg, lane, row_base, tg, [=](int bb_, int yy, int xx) {
+              return reinterpret_cast<char*>(hdst + (long long)bb_ * sb + (long long)yy * sy + (long long)xx * sx);
+            }, hk);
+          }
         }
       }
       tc_fence_before();
@@ -522,7 +684,7 @@ static int validate_desc(const chb_conv_desc& d) {
   }
   if (d.epi == CHB_EPI_MODULATE) {
     CHB_REQUIRE(d.x && d.chan && d.bias, "modulate epilogue needs x, chan and bias");
-    CHB_REQUIRE(d.BN % 64 == 0 && d.N == d.Nrows, "modulate epilogue needs BN % 64 == 0 and N == Nrows");
+    CHB_REQUIRE(d.BN % 128 == 0 && d.N == d.Nrows, "modulate epilogue needs BN % 128 == 0 and N == Nrows");
     CHB_REQUIRE(d.act != CHB_ACT_TANH, "modulate epilogue supports none / relu / lrelu");
     CHB_REQUIRE(d.o_sn == 1 || d.o_sn == 0, "modulate output is channels-last");
   }
@@ -550,7 +712,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   k.stage_bytes = kATileBytes + ((d.BN * 128 + 1023) / 1024) * 1024;
   k.nstages = kSmemBudget / k.stage_bytes;
   if (k.nstages > kMaxStages) k.nstages = kMaxStages;
-  plan->smem_bytes = k.nstages * k.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  plan->smem_bytes = k.nstages * k.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpilogueWarps * 4096;
   long long ktotal = 0;
   for (int s = 0; s < d.nseg; ++s) {
     const chb_conv_seg& g = d.seg[s];
@@ -620,7 +782,7 @@ static int ensure_smem_attr() {
     for (int epi = 0; epi < 2 && err == cudaSuccess; ++epi)
       for (int act = 0; act < 4 && err == cudaSuccess; ++act)
         err = cudaFuncSetAttribute(pick_kernel(epi, act), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kSmemBudget + 2048);
+                                   227 * 1024);
   });
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(err));
