@@ -117,36 +117,67 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 
 // Pixel of tile row m (0..127) for the tile at (b0, y0, x0); returns false when the row is padding / out of range.
 struct TileGeo {
-  int TW, tpix, rows, B, H, W, b0, y0, x0;
+  int TW, TH, TB, tpix, rows, B, H, W, b0, y0, x0;
+  int tw_sh, tpix_sh;  // log2 when TW / TW*TH are powers of two (the generator's tiles), else -1
+  __device__ __forceinline__ void init(const ConvKParams& p) {
+    TW = p.TW; TH = p.TH; TB = p.TB; tpix = p.TW * p.TH; rows = p.rows; B = p.B; H = p.H; W = p.W;
+    tw_sh = (TW & (TW - 1)) == 0 ? 31 - __clz(TW) : -1;
+    tpix_sh = (tpix & (tpix - 1)) == 0 ? 31 - __clz(tpix) : -1;
+    b0 = y0 = x0 = 0;
+  }
+  // positions the geometry on `tile`, returns its n-tile index
+  __device__ __forceinline__ int set_tile(const ConvKParams& p, int tile) {
+    const int n_tile = tile / p.m_tiles;
+    int m = tile - n_tile * p.m_tiles;
+    const int xt = m % p.tiles_x;
+    m /= p.tiles_x;
+    const int yt = m % p.tiles_y;
+    const int bt = m / p.tiles_y;
+    b0 = bt * TB; y0 = yt * TH; x0 = xt * TW;
+    return n_tile;
+  }
   __device__ __forceinline__ bool pixel(int m, int& b, int& y, int& x) const {
-    const int tb = m / tpix;
-    const int rem = m - tb * tpix;
-    const int ty = rem / TW;
+    int tb, rem, ty;
+    if (tpix_sh >= 0) { tb = m >> tpix_sh; rem = m & (tpix - 1); } else { tb = m / tpix; rem = m - tb * tpix; }
+    if (tw_sh >= 0) { ty = rem >> tw_sh; x = x0 + (rem & (TW - 1)); } else { ty = rem / TW; x = x0 + rem - ty * TW; }
     b = b0 + tb;
     y = y0 + ty;
-    x = x0 + rem - ty * TW;
     return m < rows && b < B && y < H && x < W;
   }
 };
 
-// global (CH16*16 contiguous bytes per tile row) -> registers, one row per lane.  rowptr(b,y,x) -> const char*.
+// Issue half of a gather: global (CH16*16 contiguous bytes per tile row, CH16 lanes per row) -> registers, still
+// in the global (coalesced) arrangement.  rowptr(b,y,x) -> const char*.
 template <int CH16, class RowPtr>
-__device__ __forceinline__ void stage_gather(uint32_t stg, int lane, int row_base, const TileGeo& tg, RowPtr rowptr,
-                                             uint4 (&regs)[CH16]) {
+__device__ __forceinline__ void gather_issue(int lane, int row_base, const TileGeo& tg, RowPtr rowptr,
+                                             uint4 (&g)[CH16]) {
   constexpr int RPI = 32 / CH16;
   const int cl = lane % CH16, r0 = lane / CH16;
 #pragma unroll
   for (int k = 0; k < CH16; ++k) {
-    const int rl = r0 + RPI * k;
     int b, y, x;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (tg.pixel(row_base + rl, b, y, x)) v = __ldg(reinterpret_cast<const uint4*>(rowptr(b, y, x) + cl * 16));
-    sts128(stg + stg_off<CH16>(rl, cl), v);
+    g[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (tg.pixel(row_base + r0 + RPI * k, b, y, x)) g[k] = __ldg(reinterpret_cast<const uint4*>(rowptr(b, y, x) + cl * 16));
   }
+}
+// Second half: through the staging block into the one-row-per-lane arrangement.
+template <int CH16>
+__device__ __forceinline__ void gather_commit(uint32_t stg, int lane, const uint4 (&g)[CH16], uint4 (&regs)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int cl = lane % CH16, r0 = lane / CH16;
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) sts128(stg + stg_off<CH16>(r0 + RPI * k, cl), g[k]);
   __syncwarp();
 #pragma unroll
   for (int c = 0; c < CH16; ++c) regs[c] = lds128(stg + stg_off<CH16>(lane, c));
   __syncwarp();
+}
+template <int CH16, class RowPtr>
+__device__ __forceinline__ void stage_gather(uint32_t stg, int lane, int row_base, const TileGeo& tg, RowPtr rowptr,
+                                             uint4 (&regs)[CH16]) {
+  uint4 g[CH16];
+  gather_issue<CH16>(lane, row_base, tg, rowptr, g);
+  gather_commit<CH16>(stg, lane, g, regs);
 }
 
 // registers (one row per lane) -> global, CH16*16 contiguous bytes per tile row.  rowptr(b,y,x) -> char*.
@@ -416,35 +447,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
-    const int tpix = p.TW * p.TH;
-    const int tb = row / tpix;
-    const int rem = row - tb * tpix;
-    const int ty = rem / p.TW;
-    const int tx = rem - ty * p.TW;
+    const int row_base = q * 32;
     const EpiK& e = p.e;
     const uint32_t stg = smem_u32(smem + (size_t)nst * p.stage_bytes + 256 + (size_t)(warp - 2) * 4096);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-      const int n_tile = tile / p.m_tiles;
-      int m = tile - n_tile * p.m_tiles;
-      const int xt = m % p.tiles_x;
-      m /= p.tiles_x;
-      const int yt = m % p.tiles_y;
-      const int bt = m / p.tiles_y;
-      const int x = xt * p.TW + tx, y = yt * p.TH + ty, b = bt * p.TB + tb;
-      const bool valid = (row < p.rows) && (b < p.B) && (y < p.H) && (x < p.W);
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+    TileGeo tg;
+    tg.init(p);
 
-      TileGeo tg;
-      tg.TW = p.TW; tg.tpix = tpix; tg.rows = p.rows; tg.B = p.B; tg.H = p.H; tg.W = p.W;
-      tg.b0 = bt * p.TB; tg.y0 = yt * p.TH; tg.x0 = xt * p.TW;
-      const int row_base = q * 32;
-
-      if (EPI == CHB_EPI_PLAIN) {
+    if (EPI == CHB_EPI_PLAIN) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        const int n_tile = tg.set_tile(p, tile);
+        int b, y, x;
+        const bool valid = tg.pixel(row_base + lane, b, y, x);
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
         const int ch = p.BN >> 1;  // columns per warp-half (multiple of 8)
         int j = chalf * ch;
         const int jend = j + ch;
@@ -459,27 +477,64 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         }
         for (; j + 16 <= jend; j += 16) plain_chunk<16, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
         for (; j + 8 <= jend; j += 8) plain_chunk<8, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
-      } else {
-        // MODULATE: columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2
-        const int half_n = p.BN >> 1;
-        const int cw = half_n >> 1;  // channels per warp-half (multiple of 32)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+    } else {
+      // MODULATE: tile columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2.
+      // Each warp owns 32 rows x cw channels, processed in units of 32 channels.  The x block of the NEXT unit
+      // (possibly of the next tile) is requested from global memory before the current unit is computed, so its
+      // latency overlaps the math instead of stalling the (few) epilogue warps.
+      const int half_n = p.BN >> 1;
+      const int cw = half_n >> 1;  // channels per warp-half (multiple of 32)
+      const int units = cw >> 5;
+      const int cs = e.chan_stride;
+      const long long xsb = e.x_sb, xsy = e.x_sy, xsx = e.x_sx;
+      const int xsh = e.x_shift;
+      uint4 pf[8];
+      if ((int)blockIdx.x < total_tiles) {
+        const int nt0 = tg.set_tile(p, blockIdx.x);
+        const float* xsrc = e.x + nt0 * half_n + chalf * cw;
+        gather_issue<8>(lane, row_base, tg, [=](int bb_, int yy, int xx) {
+          return reinterpret_cast<const char*>(xsrc + (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy +
+                                               (long long)(xx >> xsh) * xsx);
+        }, pf);
+      }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        const int n_tile = tg.set_tile(p, tile);
         const int c0 = n_tile * half_n;
         const int nrow0 = n_tile * p.BN;
+        int b, y, x;
+        const bool valid = tg.pixel(row_base + lane, b, y, x);
         float nz = 0.f;
         if (valid && e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
         const float* ca = e.chan + c0;
-        const int cs = e.chan_stride;
-        for (int j = chalf * cw; j < (chalf + 1) * cw; j += 32) {
-          // x block: 32 rows x 32 fp32 channels, gathered with 128-byte runs per row
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+        for (int u = 0; u < units; ++u) {
+          const int j = chalf * cw + 32 * u;
+          // current x block: registers (global layout) -> staging -> one row per lane
           uint4 xr[8];
-          {
-            const float* xsrc = e.x + c0 + j;
-            const long long sb = e.x_sb, sy = e.x_sy, sx = e.x_sx;
-            const int sh = e.x_shift;
-            stage_gather<8>(stg, lane, row_base, tg, [=](int bb_, int yy, int xx) {
-              return reinterpret_cast<const char*>(xsrc + (long long)bb_ * sb + (long long)(yy >> sh) * sy +
-                                                   (long long)(xx >> sh) * sx);
-            }, xr);
+          gather_commit<8>(stg, lane, pf, xr);
+          // request the next x block
+          if (u + 1 < units) {
+            const float* xsrc = e.x + c0 + j + 32;
+            gather_issue<8>(lane, row_base, tg, [=](int bb_, int yy, int xx) {
+              return reinterpret_cast<const char*>(xsrc + (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy +
+                                                   (long long)(xx >> xsh) * xsx);
+            }, pf);
+          } else if (tile + (int)gridDim.x < total_tiles) {
+            TileGeo tn = tg;
+            const int ntn = tn.set_tile(p, tile + gridDim.x);
+            const float* xsrc = e.x + ntn * half_n + chalf * cw;
+            gather_issue<8>(lane, row_base, tn, [=](int bb_, int yy, int xx) {
+              return reinterpret_cast<const char*>(xsrc + (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy +
+                                                   (long long)(xx >> xsh) * xsx);
+            }, pf);
           }
           uint4 hk[4];
 #pragma unroll
@@ -488,26 +543,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             float g[16], be[16];
             tmem_ld<16>(taddr + (uint32_t)jj, g);
             tmem_ld<16>(taddr + (uint32_t)(half_n + jj), be);
+            float4 bg[4], bb[4], av[4], cv[4], nv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              bg[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + jj) + i);
+              bb[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + jj) + i);
+              av[i] = __ldg(reinterpret_cast<const float4*>(ca + jj) + i);
+              cv[i] = __ldg(reinterpret_cast<const float4*>(ca + cs + jj) + i);
+              nv[i] = __ldg(reinterpret_cast<const float4*>(ca + 2 * cs + jj) + i);
+            }
             tmem_ld_fence(g);
             tmem_ld_fence(be);
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 bg = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + jj) + i);
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + jj) + i);
-              const float4 av = __ldg(reinterpret_cast<const float4*>(ca + jj) + i);
-              const float4 cv = __ldg(reinterpret_cast<const float4*>(ca + cs + jj) + i);
-              const float4 nv = __ldg(reinterpret_cast<const float4*>(ca + 2 * cs + jj) + i);
               const uint4 xq = xr[4 * sub + i];
-              const float o0 = modulate_elem<ACT>(__uint_as_float(xq.x), nz, av.x, cv.x, nv.x, g[4 * i] + bg.x, be[4 * i] + bb.x);
-              const float o1 = modulate_elem<ACT>(__uint_as_float(xq.y), nz, av.y, cv.y, nv.y, g[4 * i + 1] + bg.y, be[4 * i + 1] + bb.y);
-              const float o2 = modulate_elem<ACT>(__uint_as_float(xq.z), nz, av.z, cv.z, nv.z, g[4 * i + 2] + bg.z, be[4 * i + 2] + bb.z);
-              const float o3 = modulate_elem<ACT>(__uint_as_float(xq.w), nz, av.w, cv.w, nv.w, g[4 * i + 3] + bg.w, be[4 * i + 3] + bb.w);
+              const float o0 = modulate_elem<ACT>(__uint_as_float(xq.x), nz, av[i].x, cv[i].x, nv[i].x, g[4 * i] + bg[i].x, be[4 * i] + bb[i].x);
+              const float o1 = modulate_elem<ACT>(__uint_as_float(xq.y), nz, av[i].y, cv[i].y, nv[i].y, g[4 * i + 1] + bg[i].y, be[4 * i + 1] + bb[i].y);
+              const float o2 = modulate_elem<ACT>(__uint_as_float(xq.z), nz, av[i].z, cv[i].z, nv[i].z, g[4 * i + 2] + bg[i].z, be[4 * i + 2] + bb[i].z);
+              const float o3 = modulate_elem<ACT>(__uint_as_float(xq.w), nz, av[i].w, cv[i].w, nv[i].w, g[4 * i + 3] + bg[i].w, be[4 * i + 3] + bb[i].w);
               pk[2 * i] = pack_h2(o0, o1);
               pk[2 * i + 1] = pack_h2(o2, o3);
             }
             hk[2 * sub] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             hk[2 * sub + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (u + 1 == units) {
+            // the accumulator has been fully read: hand the TMEM buffer back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
           }
           {
             __half* hdst = reinterpret_cast<__half*>(e.out) + c0 + j;
@@ -518,9 +583,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
   }
 

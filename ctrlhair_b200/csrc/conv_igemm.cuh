@@ -12,7 +12,7 @@ namespace chb {
 constexpr int kMaxSeg = 3;
 constexpr int kATileBytes = 16384;  // 128 rows x 128 B
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 192 * 1024;  // pipeline stages; + 32 KB epilogue staging + barriers <= 227 KB
 constexpr int kEpilogueWarps = 8;
 constexpr int kConvThreads = 64 + 32 * kEpilogueWarps;  // warp0 TMA, warp1 MMA, warps 2-9 epilogue
 

@@ -348,7 +348,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       chb_conv_desc d = base_desc(B, r);
       d.nseg = 1;
       d.seg[0] = make_seg(onehot, r, 32, 0, 32, 9, blobp(g, b.t_shw));
-      d.N = d.Nrows = actvC; d.BN = 128;
+      d.N = d.Nrows = actvC; d.BN = actvC == 384 ? 192 : 256;  // one-hot A tile is re-read per N tile: keep N tiles few
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_RELU;
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_shb));
       nhwc_out(&d, ws + g->ws_actv, CHB_F16, r, actvC);
