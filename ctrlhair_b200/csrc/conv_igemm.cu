@@ -16,6 +16,7 @@
 
 #include <cuda_fp16.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -340,7 +341,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* hfull = tempty + 2;
+  uint64_t* hempty = hfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty + 2);
+  // [stages][256 B barriers][8 x 4 KB epilogue staging][2 halo buffers (1 KB aligned)]
+  uint8_t* halo_base = smem + (size_t)nst * p.stage_bytes + 1024 + kEpilogueWarps * 4096;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -350,6 +355,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     for (int s = 0; s < p.nseg; ++s) {
       tma_prefetch_desc(&p.tmA[s]);
       tma_prefetch_desc(&p.tmW[s]);
+      if (p.seg[s].halo) tma_prefetch_desc(&p.tmH[s]);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hfull[i], 1);
+      mbar_init(&hempty[i], 1);
     }
     for (int i = 0; i < nst; ++i) {
       mbar_init(&full[i], 1);
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, hs = 0, hphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile / p.m_tiles;
         int m = tile - n_tile * p.m_tiles;
@@ -384,6 +394,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int x0 = xt * p.TW, y0 = yt * p.TH, b0 = bt * p.TB, n0 = n_tile * p.BN;
         for (int s = 0; s < p.nseg; ++s) {
           const SegK sg = p.seg[s];
+          if (sg.halo) {
+            // one halo tile per channel chunk feeds all nine taps; only the weights stream per tap
+            const uint32_t hbytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * (uint32_t)sg.kc * 2u;
+            const uint32_t wbytes = (uint32_t)p.BN * (uint32_t)sg.kc * 2u;
+            for (int c = 0; c < sg.nchunk; ++c) {
+              mbar_wait(&hempty[hs], hphase ^ 1u);
+              mbar_arrive_expect_tx(&hfull[hs], hbytes);
+              tma_load_4d(&p.tmH[s], halo_base + (size_t)hs * kHaloBufBytes, &hfull[hs], sg.ch_off + c * sg.kc, x0 - 1,
+                          y0 - 1, b0);
+              if (++hs == 2u) {
+                hs = 0;
+                hphase ^= 1u;
+              }
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                uint8_t* sb = stage_base + (size_t)stage * p.stage_bytes + kATileBytes;
+                mbar_arrive_expect_tx(&full[stage], wbytes);
+                tma_load_3d(&p.tmW[s], sb, &full[stage], (tap * sg.nchunk + c) * sg.kc, n0, sg.per_image ? b0 : 0);
+                if (++stage == (uint32_t)nst) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+            continue;
+          }
           const uint32_t bytes = (uint32_t)(p.rows + p.BN) * (uint32_t)sg.kc * 2u;
           for (int tap = 0; tap < sg.taps; ++tap) {
             const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
@@ -409,7 +445,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16((uint32_t)p.BN);
-      uint32_t stage = 0, phase = 0, it = 0;
+      uint32_t stage = 0, phase = 0, it = 0, hs = 0, hphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
@@ -418,6 +454,40 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         uint32_t accumulate = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const SegK sg = p.seg[s];
+          if (sg.halo) {
+            const uint32_t hw = (uint32_t)(p.TW + 2);
+            for (int c = 0; c < sg.nchunk; ++c) {
+              mbar_wait(&hfull[hs], hphase);
+              tc_fence_after();
+              const uint32_t hb = smem_u32(halo_base + (size_t)hs * kHaloBufBytes);
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                // tap (ky,kx): tile pixel (y,x) reads halo row (y+ky)*(TW+2) + (x+kx); with TW == 8 every 8-row
+                // core group is one tile row, (TW+2)*128 bytes apart
+                const uint32_t aaddr = hb + ((uint32_t)(tap / 3) * hw + (uint32_t)(tap % 3)) * 128u;
+                const uint32_t bo = p.halo_bo ? ((aaddr >> 7) & 7u) : 0u;
+                const uint64_t adesc = umma_smem_desc_sw128(aaddr, hw * 128u, bo);
+                const uint64_t bdesc =
+                    umma_smem_desc(smem_u32(stage_base + (size_t)stage * p.stage_bytes) + kATileBytes, 128u);
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+                  accumulate = 1;
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == (uint32_t)nst) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+              umma_commit(&hempty[hs]);
+              if (++hs == 2u) {
+                hs = 0;
+                hphase ^= 1u;
+              }
+            }
+            continue;
+          }
           const int chunks = sg.taps * sg.nchunk;
           const uint32_t row_bytes = (uint32_t)sg.kc * 2u;
           const int ksteps = sg.kc / 16;
@@ -449,7 +519,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int chalf = (warp - 2) >> 2;
     const int row_base = q * 32;
     const EpiK& e = p.e;
-    const uint32_t stg = smem_u32(smem + (size_t)nst * p.stage_bytes + 256 + (size_t)(warp - 2) * 4096);
+    const uint32_t stg = smem_u32(smem + (size_t)nst * p.stage_bytes + 1024 + (size_t)(warp - 2) * 4096);
     TileGeo tg;
     tg.init(p);
 
@@ -772,9 +842,22 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   k.BN = d.BN;
   k.N = d.N;
   k.stage_bytes = kATileBytes + ((d.BN * 128 + 1023) / 1024) * 1024;
-  k.nstages = kSmemBudget / k.stage_bytes;
+  // Halo path (CHB_HALO env: 0 = off, 1 = on with base_offset 0, 2 = on with base_offset (addr>>7)&7):
+  // 3x3 segments with 64-channel chunks on 8-wide single-image tiles load a (TH+2)x(TW+2) halo tile once per chunk.
+  int halo_mode = 0;
+  if (const char* hv = getenv("CHB_HALO")) halo_mode = atoi(hv);
+  k.halo_any = 0;
+  k.halo_bo = halo_mode == 2 ? 1 : 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    const chb_conv_seg& g = d.seg[s];
+    k.seg[s].halo = (halo_mode > 0 && g.taps == 9 && g.C % 64 == 0 && d.TW == 8 && d.TB == 1 && d.TH <= 16) ? 1 : 0;
+    k.halo_any |= k.seg[s].halo;
+  }
+  const int budget = kSmemBudget - (k.halo_any ? 2 * kHaloBufBytes : 0);
+  k.nstages = budget / k.stage_bytes;
   if (k.nstages > kMaxStages) k.nstages = kMaxStages;
-  plan->smem_bytes = k.nstages * k.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpilogueWarps * 4096;
+  plan->smem_bytes = k.nstages * k.stage_bytes + 1024 /*align slack*/ + 1024 /*barriers*/ + kEpilogueWarps * 4096 +
+                     (k.halo_any ? 2 * kHaloBufBytes : 0);
   long long ktotal = 0;
   for (int s = 0; s < d.nseg; ++s) {
     const chb_conv_seg& g = d.seg[s];
@@ -791,6 +874,11 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
       cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)d.TW, (cuuint32_t)d.TH, (cuuint32_t)d.TB};
       rc = encode_map(&k.tmA[s], g.a, 4, dims, str, box, kc);
       if (rc != CHB_OK) return rc;
+      if (k.seg[s].halo) {
+        cuuint32_t hbox[4] = {(cuuint32_t)kc, (cuuint32_t)d.TW + 2, (cuuint32_t)d.TH + 2, 1};
+        rc = encode_map(&k.tmH[s], g.a, 4, dims, str, hbox, kc);
+        if (rc != CHB_OK) return rc;
+      }
     }
     {
       const cuuint64_t K = (cuuint64_t)g.taps * g.C;

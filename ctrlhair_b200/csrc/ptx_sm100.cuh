@@ -178,6 +178,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
   return d;
 }
 
+// Same, for a SWIZZLE_128B K-major operand whose 8-row groups are `sbo_bytes` apart and whose start address need
+// not be 1024-byte aligned (a tap view into a halo tile): `base_offset` is the descriptor's 3-bit swizzle phase.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= 1ull << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;
+  d |= static_cast<uint64_t>(base_offset & 7u) << 49;
+  d |= 2ull << 61;
+  return d;
+}
+
 // Instruction descriptor: A,B = fp16 K-major, D = fp32, M = 128, N = n.
 __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
   return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
