@@ -466,8 +466,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 // tap (ky,kx): tile pixel (y,x) reads halo row (y+ky)*(TW+2) + (x+kx); with TW == 8 every 8-row
                 // core group is one tile row, (TW+2)*128 bytes apart
                 const uint32_t aaddr = hb + ((uint32_t)(tap / 3) * hw + (uint32_t)(tap % 3)) * 128u;
-                const uint32_t bo = p.halo_bo ? ((aaddr >> 7) & 7u) : 0u;
-                const uint64_t adesc = umma_smem_desc_sw128(aaddr, hw * 128u, bo);
+                // The 128B swizzle is a function of the absolute shared-memory address bits (measured: the
+                // descriptor's base_offset must stay 0 for views that start off a 1024-byte boundary).
+                const uint64_t adesc = umma_smem_desc_sw128(aaddr, hw * 128u, 0u);
                 const uint64_t bdesc =
                     umma_smem_desc(smem_u32(stage_base + (size_t)stage * p.stage_bytes) + kATileBytes, 128u);
                 for (int k = 0; k < 4; ++k) {
@@ -842,12 +843,12 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   k.BN = d.BN;
   k.N = d.N;
   k.stage_bytes = kATileBytes + ((d.BN * 128 + 1023) / 1024) * 1024;
-  // Halo path (CHB_HALO env: 0 = off, 1 = on with base_offset 0, 2 = on with base_offset (addr>>7)&7):
-  // 3x3 segments with 64-channel chunks on 8-wide single-image tiles load a (TH+2)x(TW+2) halo tile once per chunk.
-  int halo_mode = 0;
+  // Halo path (on by default; CHB_HALO=0 turns it off for A/B comparisons): 3x3 segments with 64-channel chunks on
+  // 8-wide single-image tiles load a (TH+2)x(TW+2) halo tile once per channel chunk and feed all nine taps from it.
+  int halo_mode = 1;
   if (const char* hv = getenv("CHB_HALO")) halo_mode = atoi(hv);
   k.halo_any = 0;
-  k.halo_bo = halo_mode == 2 ? 1 : 0;
+  k.halo_bo = 0;
   for (int s = 0; s < d.nseg; ++s) {
     const chb_conv_seg& g = d.seg[s];
     k.seg[s].halo = (halo_mode > 0 && g.taps == 9 && g.C % 64 == 0 && d.TW == 8 && d.TB == 1 && d.TH <= 16) ? 1 : 0;
