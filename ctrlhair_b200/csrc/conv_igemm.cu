@@ -407,11 +407,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 hs = 0;
                 hphase ^= 1u;
               }
-              for (int tap = 0; tap < 9; ++tap) {
+              // weights: `hg` taps (one kernel row when hg == 3) share a pipeline stage and one barrier round
+              for (int t0 = 0; t0 < 9; t0 += p.hg) {
                 mbar_wait(&empty[stage], phase ^ 1u);
-                uint8_t* sb = stage_base + (size_t)stage * p.stage_bytes + kATileBytes;
-                mbar_arrive_expect_tx(&full[stage], wbytes);
-                tma_load_3d(&p.tmW[s], sb, &full[stage], (tap * sg.nchunk + c) * sg.kc, n0, sg.per_image ? b0 : 0);
+                uint8_t* sb = stage_base + (size_t)stage * p.stage_bytes + p.a_region;
+                mbar_arrive_expect_tx(&full[stage], wbytes * (uint32_t)p.hg);
+                for (int g = 0; g < p.hg; ++g)
+                  tma_load_3d(&p.tmW[s], sb + (size_t)g * wbytes, &full[stage], ((t0 + g) * sg.nchunk + c) * sg.kc, n0,
+                              sg.per_image ? b0 : 0);
                 if (++stage == (uint32_t)nst) {
                   stage = 0;
                   phase ^= 1u;
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             for (int c = 0; c < sg.nchunk; ++c) {
               mbar_wait(&empty[stage], phase ^ 1u);
               uint8_t* sa = stage_base + (size_t)stage * p.stage_bytes;
-              uint8_t* sb = sa + kATileBytes;
+              uint8_t* sb = sa + p.a_region;
               mbar_arrive_expect_tx(&full[stage], bytes);
               tma_load_4d(&p.tmA[s], sa, &full[stage], sg.ch_off + c * sg.kc, x0 + dx, y0 + dy, b0);
               tma_load_3d(&p.tmW[s], sb, &full[stage], (tap * sg.nchunk + c) * sg.kc, n0, sg.per_image ? b0 : 0);
@@ -460,20 +463,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
               mbar_wait(&hfull[hs], hphase);
               tc_fence_after();
               const uint32_t hb = smem_u32(halo_base + (size_t)hs * kHaloBufBytes);
-              for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t wbytes = (uint32_t)p.BN * 128u;
+              for (int t0 = 0; t0 < 9; t0 += p.hg) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                // tap (ky,kx): tile pixel (y,x) reads halo row (y+ky)*(TW+2) + (x+kx); with TW == 8 every 8-row
-                // core group is one tile row, (TW+2)*128 bytes apart
-                const uint32_t aaddr = hb + ((uint32_t)(tap / 3) * hw + (uint32_t)(tap % 3)) * 128u;
-                // The 128B swizzle is a function of the absolute shared-memory address bits (measured: the
-                // descriptor's base_offset must stay 0 for views that start off a 1024-byte boundary).
-                const uint64_t adesc = umma_smem_desc_sw128(aaddr, hw * 128u, 0u);
-                const uint64_t bdesc =
-                    umma_smem_desc(smem_u32(stage_base + (size_t)stage * p.stage_bytes) + kATileBytes, 128u);
-                for (int k = 0; k < 4; ++k) {
-                  umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
-                  accumulate = 1;
+                const uint32_t sb = smem_u32(stage_base + (size_t)stage * p.stage_bytes) + (uint32_t)p.a_region;
+                for (int g = 0; g < p.hg; ++g) {
+                  const int tap = t0 + g;
+                  // tap (ky,kx): tile pixel (y,x) reads halo row (y+ky)*(TW+2) + (x+kx); with TW == 8 every 8-row
+                  // core group is one tile row, (TW+2)*128 bytes apart.  The 128B swizzle is a function of the
+                  // absolute shared-memory address bits (measured: the descriptor's base_offset must stay 0 for
+                  // views that start off a 1024-byte boundary).
+                  const uint32_t aaddr = hb + ((uint32_t)(tap / 3) * hw + (uint32_t)(tap % 3)) * 128u;
+                  const uint64_t adesc = umma_smem_desc_sw128(aaddr, hw * 128u, 0u);
+                  const uint64_t bdesc = umma_smem_desc(sb + (uint32_t)g * wbytes, 128u);
+                  for (int k = 0; k < 4; ++k) {
+                    umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+                    accumulate = 1;
+                  }
                 }
                 umma_commit(&empty[stage]);
                 if (++stage == (uint32_t)nst) {
@@ -497,7 +504,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             tc_fence_after();
             const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.stage_bytes);
             const uint64_t adesc = umma_smem_desc(sa, row_bytes);
-            const uint64_t bdesc = umma_smem_desc(sa + kATileBytes, row_bytes);
+            const uint64_t bdesc = umma_smem_desc(sa + (uint32_t)p.a_region, row_bytes);
             for (int k = 0; k < ksteps; ++k) {
               umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
               accumulate = 1;
@@ -854,6 +861,11 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     k.seg[s].halo = (halo_mode > 0 && g.taps == 9 && g.C % 64 == 0 && d.TW == 8 && d.TB == 1 && d.TH <= 16) ? 1 : 0;
     k.halo_any |= k.seg[s].halo;
   }
+  bool all_halo = true;
+  for (int s = 0; s < d.nseg; ++s) all_halo = all_halo && k.seg[s].halo;
+  k.a_region = all_halo ? 0 : kATileBytes;
+  k.hg = (k.halo_any && d.BN <= 128) ? 3 : 1;
+  k.stage_bytes = k.a_region + ((d.BN * 128 * k.hg + 1023) / 1024) * 1024;
   const int budget = kSmemBudget - (k.halo_any ? 2 * kHaloBufBytes : 0);
   k.nstages = budget / k.stage_bytes;
   if (k.nstages > kMaxStages) k.nstages = kMaxStages;

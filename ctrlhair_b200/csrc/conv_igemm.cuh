@@ -58,6 +58,8 @@ struct ConvKParams {
   int tiles_x, tiles_y, m_tiles, n_tiles;
   int BN, N;
   int nstages, stage_bytes;
+  int a_region;  // bytes of the per-stage A tile (0 when every segment takes its A operand from halo tiles)
+  int hg;        // taps per pipeline stage on the halo path (1 or 3)
   EpiK e;
 };
 
