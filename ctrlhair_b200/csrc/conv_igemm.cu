@@ -200,31 +200,65 @@ __device__ __forceinline__ void stage_scatter(uint32_t stg, int lane, int row_ba
   __syncwarp();
 }
 
+// ---- precomputed row offsets: the pixel decode and 64-bit address math are done once per tile, not per access.
+// o[k] = byte offset / 16 of the k-th row this lane touches in the CH16-lanes-per-row arrangement (~0u: no row).
+template <int CH16, class Fn>
+__device__ __forceinline__ void row_offsets(int lane, int row_base, const TileGeo& tg, int elem_bytes, Fn elem_off,
+                                            uint32_t (&o)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int r0 = lane / CH16;
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    int b, y, x;
+    o[k] = tg.pixel(row_base + r0 + RPI * k, b, y, x) ? (uint32_t)((elem_off(b, y, x) * elem_bytes) >> 4) : 0xFFFFFFFFu;
+  }
+}
+template <int CH16>
+__device__ __forceinline__ void gather_issue_o(const char* base, const uint32_t (&o)[CH16], uint4 (&g)[CH16]) {
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    g[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (o[k] != 0xFFFFFFFFu) g[k] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)o[k] << 4)));
+  }
+}
+template <int CH16>
+__device__ __forceinline__ void scatter_o(uint32_t stg, int lane, char* base, const uint32_t (&o)[CH16],
+                                          const uint4 (&regs)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int cl = lane % CH16, r0 = lane / CH16;
+#pragma unroll
+  for (int c = 0; c < CH16; ++c) sts128(stg + stg_off<CH16>(lane, c), regs[c]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    const uint4 v = lds128(stg + stg_off<CH16>(r0 + RPI * k, cl));
+    if (o[k] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(base + ((size_t)o[k] << 4)) = v;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // 32 accumulator columns of the PLAIN epilogue through the staging block (channels-last output, full block valid).
+// ro / oo4 / oo8: per-tile row offsets (16-byte units) of the residual and of the output in the 8- and 4-lanes-per-row
+// arrangements; bi = image of this lane's own row (for per-image bias).
 template <int ACT>
-__device__ __forceinline__ void plain_block32(const ConvKParams& p, const EpiK& e, uint32_t taddr, uint32_t stg,
-                                              int lane, int row_base, const TileGeo& tg, int n) {
+__device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uint32_t stg, int lane, int n, int bi,
+                                              const uint32_t (&ro)[8], const uint32_t (&oo4)[4],
+                                              const uint32_t (&oo8)[8]) {
   float v[32];
   tmem_ld<32>(taddr, v);
   uint4 rr[8];
   if (e.res) {
-    const float* res = e.res + n;
-    const long long sb = e.r_sb, sy = e.r_sy, sx = e.r_sx;
-    const int sh = e.r_shift;
-    stage_gather<8>(stg, lane, row_base, tg, [=](int b, int y, int x) {
-      return reinterpret_cast<const char*>(res + (long long)b * sb + (long long)(y >> sh) * sy + (long long)(x >> sh) * sx);
-    }, rr);
+    uint4 g[8];
+    gather_issue_o<8>(reinterpret_cast<const char*>(e.res + n) + (lane & 7) * 16, ro, g);
+    gather_commit<8>(stg, lane, g, rr);
   }
   tmem_ld_fence(v);
   if (e.bias) {
-    int bi, yi, xi;
-    tg.pixel(row_base + lane, bi, yi, xi);
-    if (bi >= tg.B) bi = tg.B - 1;  // padding rows: any valid image (the value is never stored)
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)bi * e.nrows : 0) + n);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -242,27 +276,20 @@ __device__ __forceinline__ void plain_block32(const ConvKParams& p, const EpiK& 
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = act_t<ACT>(v[i]);
   const long long noff = e.o_ngroup > 0 ? (long long)(n / e.o_ngroup) * e.o_sgroup + (long long)(n % e.o_ngroup) : n;
-  const long long sb = e.o_sb, sy = e.o_sy, sx = e.o_sx;
   if (e.out_dtype == CHB_F16) {
     uint4 pk[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
                          pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
-    __half* out = reinterpret_cast<__half*>(e.out) + noff;
-    stage_scatter<4>(stg, lane, row_base, tg, [=](int b, int y, int x) {
-      return reinterpret_cast<char*>(out + (long long)b * sb + (long long)y * sy + (long long)x * sx);
-    }, pk);
+    scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, oo4, pk);
   } else {
     uint4 pk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
                          __float_as_uint(v[4 * i + 3]));
-    float* out = reinterpret_cast<float*>(e.out) + noff;
-    stage_scatter<8>(stg, lane, row_base, tg, [=](int b, int y, int x) {
-      return reinterpret_cast<char*>(out + (long long)b * sb + (long long)y * sy + (long long)x * sx);
-    }, pk);
+    scatter_o<8>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<float*>(e.out) + noff) + (lane & 7) * 16, oo8, pk);
   }
 }
 
@@ -546,9 +573,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int jend = j + ch;
         const int n0 = n_tile * p.BN;
         const bool staged = e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % 32) == 0);
+        uint32_t ro[8], oo4[4], oo8[8];
+        if (staged) {
+          const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
+          auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
+          if (e.out_dtype == CHB_F16) row_offsets<4>(lane, row_base, tg, 2, o_elem, oo4);
+          else row_offsets<8>(lane, row_base, tg, 4, o_elem, oo8);
+          if (e.res) {
+            const long long rsb = e.r_sb, rsy = e.r_sy, rsx = e.r_sx;
+            const int rsh = e.r_shift;
+            row_offsets<8>(lane, row_base, tg, 4, [=](int bb_, int yy, int xx) {
+              return (long long)bb_ * rsb + (long long)(yy >> rsh) * rsy + (long long)(xx >> rsh) * rsx;
+            }, ro);
+          }
+        }
+        const int bi = b < p.B ? b : p.B - 1;
         for (; j + 32 <= jend; j += 32) {
           if (staged && n0 + j + 32 <= p.N) {
-            plain_block32<ACT>(p, e, taddr + (uint32_t)j, stg, lane, row_base, tg, n0 + j);
+            plain_block32<ACT>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
           } else {
             plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
           }
@@ -570,14 +612,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       const int cs = e.chan_stride;
       const long long xsb = e.x_sb, xsy = e.x_sy, xsx = e.x_sx;
       const int xsh = e.x_shift;
+      const int cl8 = lane & 7, cl4 = lane & 3;
+      auto x_elem = [=](int bb_, int yy, int xx) {
+        return (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy + (long long)(xx >> xsh) * xsx;
+      };
+      const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
+      auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
       uint4 pf[8];
+      uint32_t xo[8], xon[8];
       if ((int)blockIdx.x < total_tiles) {
         const int nt0 = tg.set_tile(p, blockIdx.x);
-        const float* xsrc = e.x + nt0 * half_n + chalf * cw;
-        gather_issue<8>(lane, row_base, tg, [=](int bb_, int yy, int xx) {
-          return reinterpret_cast<const char*>(xsrc + (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy +
-                                               (long long)(xx >> xsh) * xsx);
-        }, pf);
+        row_offsets<8>(lane, row_base, tg, 4, x_elem, xon);
+        gather_issue_o<8>(reinterpret_cast<const char*>(e.x + nt0 * half_n + chalf * cw) + cl8 * 16, xon, pf);
       }
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -590,6 +636,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         float nz = 0.f;
         if (valid && e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
         const float* ca = e.chan + c0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xo[k] = xon[k];
+        uint32_t oo[4];
+        row_offsets<4>(lane, row_base, tg, 2, o_elem, oo);
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
@@ -600,19 +650,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           gather_commit<8>(stg, lane, pf, xr);
           // request the next x block
           if (u + 1 < units) {
-            const float* xsrc = e.x + c0 + j + 32;
-            gather_issue<8>(lane, row_base, tg, [=](int bb_, int yy, int xx) {
-              return reinterpret_cast<const char*>(xsrc + (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy +
-                                                   (long long)(xx >> xsh) * xsx);
-            }, pf);
+            gather_issue_o<8>(reinterpret_cast<const char*>(e.x + c0 + j + 32) + cl8 * 16, xo, pf);
           } else if (tile + (int)gridDim.x < total_tiles) {
             TileGeo tn = tg;
             const int ntn = tn.set_tile(p, tile + gridDim.x);
-            const float* xsrc = e.x + ntn * half_n + chalf * cw;
-            gather_issue<8>(lane, row_base, tn, [=](int bb_, int yy, int xx) {
-              return reinterpret_cast<const char*>(xsrc + (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy +
-                                                   (long long)(xx >> xsh) * xsx);
-            }, pf);
+            row_offsets<8>(lane, row_base, tn, 4, x_elem, xon);
+            gather_issue_o<8>(reinterpret_cast<const char*>(e.x + ntn * half_n + chalf * cw) + cl8 * 16, xon, pf);
           }
           uint4 hk[4];
 #pragma unroll
@@ -652,13 +695,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          {
-            __half* hdst = reinterpret_cast<__half*>(e.out) + c0 + j;
-            const long long sb = e.o_sb, sy = e.o_sy, sx = e.o_sx;
-            stage_scatter<4>(stg, lane, row_base, tg, [=](int bb_, int yy, int xx) {
-              return reinterpret_cast<char*>(hdst + (long long)bb_ * sb + (long long)yy * sy + (long long)xx * sx);
-            }, hk);
-          }
+          scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + c0 + j) + cl4 * 16, oo, hk);
         }
       }
     }
