@@ -1,0 +1,512 @@
+// Epilogue of the implicit-GEMM conv kernel: helpers shared with the SIMT checker kernel, the per-warp staging
+// block, and the epilogue warp role (TMEM -> registers -> fused math -> global).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "conv_igemm.cuh"
+#include "ptx_sm100.cuh"
+
+namespace chb {
+
+// Shared-memory carve-up of one CTA (see conv_igemm.cu for the layout) and the persistent tile schedule.
+struct Smem {
+  uint8_t* stage_base;   // pipeline stages (A tile | weight chunks)
+  uint64_t *full, *empty, *tfull, *tempty, *hfull, *hempty, *wbar;
+  uint32_t* tmem_slot;
+  uint8_t* stg_base;     // 8 x 4 KB epilogue staging blocks
+  uint8_t* halo_base;    // halo tiles (ring of p.nhalo buffers)
+  uint8_t* wstat_base;   // resident weights (weight-stationary mode)
+};
+
+// t-th tile of this CTA, or -1.  Normal mode: round robin over all (n_tile, m_tile).  Weight-stationary mode: the
+// CTA keeps one n_tile for its whole life (its weights stay in shared memory) and strides over the m tiles.
+__device__ __forceinline__ int sched_tile(const ConvKParams& p, uint32_t t) {
+  if (p.wstat) {
+    const int n_tile = (int)blockIdx.x % p.n_tiles;
+    const long long m = (long long)((int)blockIdx.x / p.n_tiles) + (long long)t * ((int)gridDim.x / p.n_tiles);
+    return m < p.m_tiles ? n_tile * p.m_tiles + (int)m : -1;
+  }
+  const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+  return tile < (long long)p.m_tiles * p.n_tiles ? (int)tile : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue math shared by the tcgen05 kernel and the SIMT checker kernel.
+// ------------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == CHB_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == CHB_ACT_LRELU) return fmaxf(v, 0.2f * v);
+  if (ACT == CHB_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case CHB_ACT_RELU: return act_t<CHB_ACT_RELU>(v);
+    case CHB_ACT_LRELU: return act_t<CHB_ACT_LRELU>(v);
+    case CHB_ACT_TANH: return act_t<CHB_ACT_TANH>(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ long long out_offset(const EpiK& e, int b, int y, int x, int n) {
+  long long off = (long long)b * e.o_sb + (long long)y * e.o_sy + (long long)x * e.o_sx;
+  if (e.o_ngroup > 0) {
+    off += (long long)(n / e.o_ngroup) * e.o_sgroup + (long long)(n % e.o_ngroup) * e.o_sn;
+  } else {
+    off += (long long)n * e.o_sn;
+  }
+  return off;
+}
+
+template <int ACT>
+__device__ __forceinline__ void plain_store_elem(const EpiK& e, int b, int y, int x, int n, float acc) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + (e.bias_per_image ? (long long)b * e.nrows : 0) + n);
+  if (e.res) {
+    v += __ldg(e.res + (long long)b * e.r_sb + (long long)(y >> e.r_shift) * e.r_sy +
+               (long long)(x >> e.r_shift) * e.r_sx + n);
+  }
+  v = act_t<ACT>(v);
+  const long long off = out_offset(e, b, y, x, n);
+  if (e.out_dtype == CHB_F16) {
+    reinterpret_cast<__half*>(e.out)[off] = __float2half_rn(v);
+  } else {
+    reinterpret_cast<float*>(e.out)[off] = v;
+  }
+}
+
+// xn = (x + noise*noise_var - mean) * rstd  (folded: a = rstd, c = -mean*rstd, nv = noise_var*rstd)
+// out = act(xn * (1 + gamma) + beta)
+template <int ACT>
+__device__ __forceinline__ float modulate_elem(float xv, float nz, float a, float c, float nv, float gamma,
+                                               float beta) {
+  const float xn = fmaf(xv, a, fmaf(nz, nv, c));
+  return act_t<ACT>(fmaf(xn, 1.f + gamma, beta));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-warp staging block (4 KB of shared memory per epilogue warp): 32 tile rows x (CH16 * 16) bytes.
+// The TMEM accumulator layout gives every lane one tile row (= one pixel), but pixels are C*elem bytes apart in
+// the NHWC tensors, so a row-per-lane global access touches 32 cache lines per instruction.  Going through this
+// block turns the global side into 64/128-byte contiguous runs per row (CH16 lanes per row).  The XOR swizzle
+// makes both access patterns (row per lane / CH16 lanes per row) free of bank conflicts.
+// ------------------------------------------------------------------------------------------------
+template <int CH16>
+__device__ __forceinline__ uint32_t stg_off(int row, int c) {
+  const int swz = CH16 == 8 ? (row & 7) : ((row >> 1) & 3);
+  return (uint32_t)(row * (CH16 * 16) + ((c ^ swz) << 4));
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)
+               : "memory");
+  return v;
+}
+
+// Pixel of tile row m (0..127) for the tile at (b0, y0, x0); returns false when the row is padding / out of range.
+struct TileGeo {
+  int TW, TH, TB, tpix, rows, B, H, W, b0, y0, x0;
+  int tw_sh, tpix_sh;  // log2 when TW / TW*TH are powers of two (the generator's tiles), else -1
+  __device__ __forceinline__ void init(const ConvKParams& p) {
+    TW = p.TW; TH = p.TH; TB = p.TB; tpix = p.TW * p.TH; rows = p.rows; B = p.B; H = p.H; W = p.W;
+    tw_sh = (TW & (TW - 1)) == 0 ? 31 - __clz(TW) : -1;
+    tpix_sh = (tpix & (tpix - 1)) == 0 ? 31 - __clz(tpix) : -1;
+    b0 = y0 = x0 = 0;
+  }
+  // positions the geometry on `tile`, returns its n-tile index
+  __device__ __forceinline__ int set_tile(const ConvKParams& p, int tile) {
+    const int n_tile = tile / p.m_tiles;
+    int m = tile - n_tile * p.m_tiles;
+    const int xt = m % p.tiles_x;
+    m /= p.tiles_x;
+    const int yt = m % p.tiles_y;
+    const int bt = m / p.tiles_y;
+    b0 = bt * TB; y0 = yt * TH; x0 = xt * TW;
+    return n_tile;
+  }
+  __device__ __forceinline__ bool pixel(int m, int& b, int& y, int& x) const {
+    int tb, rem, ty;
+    if (tpix_sh >= 0) { tb = m >> tpix_sh; rem = m & (tpix - 1); } else { tb = m / tpix; rem = m - tb * tpix; }
+    if (tw_sh >= 0) { ty = rem >> tw_sh; x = x0 + (rem & (TW - 1)); } else { ty = rem / TW; x = x0 + rem - ty * TW; }
+    b = b0 + tb;
+    y = y0 + ty;
+    return m < rows && b < B && y < H && x < W;
+  }
+};
+
+// Issue half of a gather: global (CH16*16 contiguous bytes per tile row, CH16 lanes per row) -> registers, still
+// in the global (coalesced) arrangement.  rowptr(b,y,x) -> const char*.
+template <int CH16, class RowPtr>
+__device__ __forceinline__ void gather_issue(int lane, int row_base, const TileGeo& tg, RowPtr rowptr,
+                                             uint4 (&g)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int cl = lane % CH16, r0 = lane / CH16;
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    int b, y, x;
+    g[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (tg.pixel(row_base + r0 + RPI * k, b, y, x)) g[k] = __ldg(reinterpret_cast<const uint4*>(rowptr(b, y, x) + cl * 16));
+  }
+}
+// Second half: through the staging block into the one-row-per-lane arrangement.
+template <int CH16>
+__device__ __forceinline__ void gather_commit(uint32_t stg, int lane, const uint4 (&g)[CH16], uint4 (&regs)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int cl = lane % CH16, r0 = lane / CH16;
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) sts128(stg + stg_off<CH16>(r0 + RPI * k, cl), g[k]);
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < CH16; ++c) regs[c] = lds128(stg + stg_off<CH16>(lane, c));
+  __syncwarp();
+}
+template <int CH16, class RowPtr>
+__device__ __forceinline__ void stage_gather(uint32_t stg, int lane, int row_base, const TileGeo& tg, RowPtr rowptr,
+                                             uint4 (&regs)[CH16]) {
+  uint4 g[CH16];
+  gather_issue<CH16>(lane, row_base, tg, rowptr, g);
+  gather_commit<CH16>(stg, lane, g, regs);
+}
+
+// registers (one row per lane) -> global, CH16*16 contiguous bytes per tile row.  rowptr(b,y,x) -> char*.
+template <int CH16, class RowPtr>
+__device__ __forceinline__ void stage_scatter(uint32_t stg, int lane, int row_base, const TileGeo& tg, RowPtr rowptr,
+                                              const uint4 (&regs)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int cl = lane % CH16, r0 = lane / CH16;
+#pragma unroll
+  for (int c = 0; c < CH16; ++c) sts128(stg + stg_off<CH16>(lane, c), regs[c]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    const int rl = r0 + RPI * k;
+    const uint4 v = lds128(stg + stg_off<CH16>(rl, cl));
+    int b, y, x;
+    if (tg.pixel(row_base + rl, b, y, x)) *reinterpret_cast<uint4*>(rowptr(b, y, x) + cl * 16) = v;
+  }
+  __syncwarp();
+}
+
+// ---- precomputed row offsets: the pixel decode and 64-bit address math are done once per tile, not per access.
+// o[k] = byte offset / 16 of the k-th row this lane touches in the CH16-lanes-per-row arrangement (~0u: no row).
+template <int CH16, class Fn>
+__device__ __forceinline__ void row_offsets(int lane, int row_base, const TileGeo& tg, int elem_bytes, Fn elem_off,
+                                            uint32_t (&o)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int r0 = lane / CH16;
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    int b, y, x;
+    o[k] = tg.pixel(row_base + r0 + RPI * k, b, y, x) ? (uint32_t)((elem_off(b, y, x) * elem_bytes) >> 4) : 0xFFFFFFFFu;
+  }
+}
+template <int CH16>
+__device__ __forceinline__ void gather_issue_o(const char* base, const uint32_t (&o)[CH16], uint4 (&g)[CH16]) {
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    g[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (o[k] != 0xFFFFFFFFu) g[k] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)o[k] << 4)));
+  }
+}
+template <int CH16>
+__device__ __forceinline__ void scatter_o(uint32_t stg, int lane, char* base, const uint32_t (&o)[CH16],
+                                          const uint4 (&regs)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int cl = lane % CH16, r0 = lane / CH16;
+#pragma unroll
+  for (int c = 0; c < CH16; ++c) sts128(stg + stg_off<CH16>(lane, c), regs[c]);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    const uint4 v = lds128(stg + stg_off<CH16>(r0 + RPI * k, cl));
+    if (o[k] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(base + ((size_t)o[k] << 4)) = v;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 32 accumulator columns of the PLAIN epilogue through the staging block (channels-last output, full block valid).
+// ro / oo4 / oo8: per-tile row offsets (16-byte units) of the residual and of the output in the 8- and 4-lanes-per-row
+// arrangements; bi = image of this lane's own row (for per-image bias).
+template <int ACT>
+__device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uint32_t stg, int lane, int n, int bi,
+                                              const uint32_t (&ro)[8], const uint32_t (&oo4)[4],
+                                              const uint32_t (&oo8)[8]) {
+  float v[32];
+  tmem_ld<32>(taddr, v);
+  uint4 rr[8];
+  if (e.res) {
+    uint4 g[8];
+    gather_issue_o<8>(reinterpret_cast<const char*>(e.res + n) + (lane & 7) * 16, ro, g);
+    gather_commit<8>(stg, lane, g, rr);
+  }
+  tmem_ld_fence(v);
+  if (e.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)bi * e.nrows : 0) + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(bp + i);
+      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  }
+  if (e.res) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[4 * i] += __uint_as_float(rr[i].x); v[4 * i + 1] += __uint_as_float(rr[i].y);
+      v[4 * i + 2] += __uint_as_float(rr[i].z); v[4 * i + 3] += __uint_as_float(rr[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = act_t<ACT>(v[i]);
+  const long long noff = e.o_ngroup > 0 ? (long long)(n / e.o_ngroup) * e.o_sgroup + (long long)(n % e.o_ngroup) : n;
+  if (e.out_dtype == CHB_F16) {
+    uint4 pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                         pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+    scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, oo4, pk);
+  } else {
+    uint4 pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                         __float_as_uint(v[4 * i + 3]));
+    scatter_o<8>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<float*>(e.out) + noff) + (lane & 7) * 16, oo8, pk);
+  }
+}
+
+// One chunk of NC accumulator columns of the PLAIN epilogue: TMEM load and the global loads it needs are all
+// issued before the single wait, so the (few) epilogue warps have the latencies overlapped.
+template <int NC, int ACT>
+__device__ __forceinline__ void plain_chunk(const ConvKParams& p, const EpiK& e, uint32_t taddr, int n, bool valid,
+                                            int b, int y, int x) {
+  float v[NC];
+  tmem_ld<NC>(taddr, v);
+  const bool inb = valid && n < p.N;
+  const bool vec = inb && (n + NC <= p.N) && e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % NC) == 0);
+  float4 bv[NC / 4], rv[NC / 4];
+#pragma unroll
+  for (int i = 0; i < NC / 4; ++i) bv[i] = rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) {
+    if (e.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)b * e.nrows : 0) + n);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) bv[i] = __ldg(bp + i);
+    }
+    if (e.res) {
+      const float4* rp = reinterpret_cast<const float4*>(e.res + (long long)b * e.r_sb +
+                                                         (long long)(y >> e.r_shift) * e.r_sy +
+                                                         (long long)(x >> e.r_shift) * e.r_sx + n);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) rv[i] = __ldg(rp + i);
+    }
+  }
+  tmem_ld_fence(v);
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < NC / 4; ++i) {
+      v[4 * i] = act_t<ACT>(v[4 * i] + bv[i].x + rv[i].x);
+      v[4 * i + 1] = act_t<ACT>(v[4 * i + 1] + bv[i].y + rv[i].y);
+      v[4 * i + 2] = act_t<ACT>(v[4 * i + 2] + bv[i].z + rv[i].z);
+      v[4 * i + 3] = act_t<ACT>(v[4 * i + 3] + bv[i].w + rv[i].w);
+    }
+    const long long off = out_offset(e, b, y, x, n);
+    if (e.out_dtype == CHB_F16) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + off);
+#pragma unroll
+      for (int i = 0; i < NC / 8; ++i) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          __half2 h = __floats2half2_rn(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]);
+          pk[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    } else {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  } else if (inb) {
+#pragma unroll 1
+    for (int i = 0; i < NC; ++i)
+      if (n + i < p.N) plain_store_elem<ACT>(e, b, y, x, n + i, v[i]);
+  }
+  __syncwarp();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue warp role
+// ------------------------------------------------------------------------------------------------
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base, int warp,
+                                              int lane) {
+    // ------------------------------------------------------------------ epilogue warps
+    // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int row_base = q * 32;
+    const EpiK& e = p.e;
+    const uint32_t stg = smem_u32(sm.stg_base + (size_t)(warp - 2) * 4096);
+    uint64_t* tfull = sm.tfull;
+    uint64_t* tempty = sm.tempty;
+    TileGeo tg;
+    tg.init(p);
+
+    if (EPI == CHB_EPI_PLAIN) {
+      uint32_t it = 0;
+      for (int tile = sched_tile(p, it); tile >= 0; tile = sched_tile(p, ++it)) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        const int n_tile = tg.set_tile(p, tile);
+        int b, y, x;
+        const bool valid = tg.pixel(row_base + lane, b, y, x);
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+        const int ch = p.BN >> 1;  // columns per warp-half (multiple of 8)
+        int j = chalf * ch;
+        const int jend = j + ch;
+        const int n0 = n_tile * p.BN;
+        const bool staged = e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % 32) == 0);
+        uint32_t ro[8], oo4[4], oo8[8];
+        if (staged) {
+          const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
+          auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
+          if (e.out_dtype == CHB_F16) row_offsets<4>(lane, row_base, tg, 2, o_elem, oo4);
+          else row_offsets<8>(lane, row_base, tg, 4, o_elem, oo8);
+          if (e.res) {
+            const long long rsb = e.r_sb, rsy = e.r_sy, rsx = e.r_sx;
+            const int rsh = e.r_shift;
+            row_offsets<8>(lane, row_base, tg, 4, [=](int bb_, int yy, int xx) {
+              return (long long)bb_ * rsb + (long long)(yy >> rsh) * rsy + (long long)(xx >> rsh) * rsx;
+            }, ro);
+          }
+        }
+        const int bi = b < p.B ? b : p.B - 1;
+        for (; j + 32 <= jend; j += 32) {
+          if (staged && n0 + j + 32 <= p.N) {
+            plain_block32<ACT>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
+          } else {
+            plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+          }
+        }
+        for (; j + 16 <= jend; j += 16) plain_chunk<16, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+        for (; j + 8 <= jend; j += 8) plain_chunk<8, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+    } else {
+      // MODULATE: tile columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2.
+      // Each warp owns 32 rows x cw channels, processed in units of 32 channels.  The x block of the NEXT unit
+      // (possibly of the next tile) is requested from global memory before the current unit is computed, so its
+      // latency overlaps the math instead of stalling the (few) epilogue warps.
+      const int half_n = p.BN >> 1;
+      const int cw = half_n >> 1;  // channels per warp-half (multiple of 32)
+      const int units = cw >> 5;
+      const int cs = e.chan_stride;
+      const long long xsb = e.x_sb, xsy = e.x_sy, xsx = e.x_sx;
+      const int xsh = e.x_shift;
+      const int cl8 = lane & 7, cl4 = lane & 3;
+      auto x_elem = [=](int bb_, int yy, int xx) {
+        return (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy + (long long)(xx >> xsh) * xsx;
+      };
+      const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
+      auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
+      uint4 pf[8];
+      uint32_t xo[8], xon[8];
+      if (sched_tile(p, 0) >= 0) {
+        const int nt0 = tg.set_tile(p, sched_tile(p, 0));
+        row_offsets<8>(lane, row_base, tg, 4, x_elem, xon);
+        gather_issue_o<8>(reinterpret_cast<const char*>(e.x + nt0 * half_n + chalf * cw) + cl8 * 16, xon, pf);
+      }
+      uint32_t it = 0;
+      for (int tile = sched_tile(p, it); tile >= 0; tile = sched_tile(p, ++it)) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        const int n_tile = tg.set_tile(p, tile);
+        const int c0 = n_tile * half_n;
+        const int nrow0 = n_tile * p.BN;
+        int b, y, x;
+        const bool valid = tg.pixel(row_base + lane, b, y, x);
+        float nz = 0.f;
+        if (valid && e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
+        const float* ca = e.chan + c0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xo[k] = xon[k];
+        uint32_t oo[4];
+        row_offsets<4>(lane, row_base, tg, 2, o_elem, oo);
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+        for (int u = 0; u < units; ++u) {
+          const int j = chalf * cw + 32 * u;
+          // current x block: registers (global layout) -> staging -> one row per lane
+          uint4 xr[8];
+          gather_commit<8>(stg, lane, pf, xr);
+          // request the next x block
+          if (u + 1 < units) {
+            gather_issue_o<8>(reinterpret_cast<const char*>(e.x + c0 + j + 32) + cl8 * 16, xo, pf);
+          } else if (sched_tile(p, it + 1) >= 0) {
+            TileGeo tn = tg;
+            const int ntn = tn.set_tile(p, sched_tile(p, it + 1));
+            row_offsets<8>(lane, row_base, tn, 4, x_elem, xon);
+            gather_issue_o<8>(reinterpret_cast<const char*>(e.x + ntn * half_n + chalf * cw) + cl8 * 16, xon, pf);
+          }
+          uint4 hk[4];
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int jj = j + 16 * sub;
+            float g[16], be[16];
+            tmem_ld<16>(taddr + (uint32_t)jj, g);
+            tmem_ld<16>(taddr + (uint32_t)(half_n + jj), be);
+            float4 bg[4], bb[4], av[4], cv[4], nv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              bg[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + jj) + i);
+              bb[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + jj) + i);
+              av[i] = __ldg(reinterpret_cast<const float4*>(ca + jj) + i);
+              cv[i] = __ldg(reinterpret_cast<const float4*>(ca + cs + jj) + i);
+              nv[i] = __ldg(reinterpret_cast<const float4*>(ca + 2 * cs + jj) + i);
+            }
+            tmem_ld_fence(g);
+            tmem_ld_fence(be);
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 xq = xr[4 * sub + i];
+              const float o0 = modulate_elem<ACT>(__uint_as_float(xq.x), nz, av[i].x, cv[i].x, nv[i].x, g[4 * i] + bg[i].x, be[4 * i] + bb[i].x);
+              const float o1 = modulate_elem<ACT>(__uint_as_float(xq.y), nz, av[i].y, cv[i].y, nv[i].y, g[4 * i + 1] + bg[i].y, be[4 * i + 1] + bb[i].y);
+              const float o2 = modulate_elem<ACT>(__uint_as_float(xq.z), nz, av[i].z, cv[i].z, nv[i].z, g[4 * i + 2] + bg[i].z, be[4 * i + 2] + bb[i].z);
+              const float o3 = modulate_elem<ACT>(__uint_as_float(xq.w), nz, av[i].w, cv[i].w, nv[i].w, g[4 * i + 3] + bg[i].w, be[4 * i + 3] + bb[i].w);
+              pk[2 * i] = pack_h2(o0, o1);
+              pk[2 * i + 1] = pack_h2(o2, o3);
+            }
+            hk[2 * sub] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            hk[2 * sub + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (u + 1 == units) {
+            // the accumulator has been fully read: hand the TMEM buffer back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + c0 + j) + cl4 * 16, oo, hk);
+        }
+      }
+    }
+}
+
+}  // namespace chb

@@ -12,6 +12,7 @@ namespace chb {
 constexpr int kMaxSeg = 3;
 constexpr int kATileBytes = 16384;  // 128 rows x 128 B
 constexpr int kMaxStages = 8;
+constexpr int kMaxHalo = 6;
 constexpr int kHaloBufBytes = 24576;  // (16+2) x (8+2) rows x 128 B, rounded up to 1 KB
 constexpr int kSmemBudget = 192 * 1024;  // pipeline stages; + 32 KB epilogue staging + barriers <= 227 KB
 constexpr int kEpilogueWarps = 8;
@@ -19,6 +20,7 @@ constexpr int kConvThreads = 64 + 32 * kEpilogueWarps;  // warp0 TMA, warp1 MMA,
 
 struct SegK {
   int taps, nchunk, kc, ch_off, per_image;
+  int wofs;  // weight-stationary mode: byte offset of this segment inside the resident weight slab
   int halo;  // 1: the A operand of this 3x3 segment is loaded once per channel chunk as a (TH+2)x(TW+2) halo tile
 };
 
@@ -50,6 +52,10 @@ struct ConvKParams {
   CUtensorMap tmW[kMaxSeg];
   CUtensorMap tmH[kMaxSeg];  // halo boxes (segments with halo = 1)
   SegK seg[kMaxSeg];
+  int wstat;          // weight-stationary mode
+  int wstat_bytes;    // resident weight slab size
+  int nhalo;          // halo buffers in the ring
+  int halo_buf_bytes;
   int halo_any;   // some segment uses the halo path: two halo buffers follow the pipeline stages
   int halo_bo;    // descriptor base-offset mode for non-1024B-aligned tap views (0: none, 1: (addr >> 7) & 7)
   int nseg;

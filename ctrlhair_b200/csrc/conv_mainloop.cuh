@@ -1,0 +1,191 @@
+// Main loop of the implicit-GEMM conv kernel: the TMA producer role and the tcgen05 MMA issuer role.
+//
+// Three ways an A operand (activations) reaches the tensor core:
+//   * per-tap tiles   — one 128-row TMA box per (tap, 64/32-channel chunk), tap offset folded into the coordinates
+//   * halo tiles      — one (TH+2)x(TW+2) box per channel chunk; the taps are shifted UMMA views of it
+// and two ways for the B operand (weights):
+//   * streamed        — 64-K chunks through the mbarrier stage ring (1 or 3 taps per stage)
+//   * weight-stationary (p.wstat) — the whole [BN x K] weight slab of this CTA's n_tile is loaded once and stays
+//     in shared memory; only halo tiles stream.  Used by the layers whose weights are small (mlp_shared, conv_img,
+//     the 64-channel convs of up_3): those are bound by per-chunk barrier/TMA overhead, not by math.
+#pragma once
+#include "conv_epilogue.cuh"
+
+namespace chb {
+
+struct TileOrigin {
+  int x0, y0, b0, n0;
+};
+__device__ __forceinline__ TileOrigin tile_origin(const ConvKParams& p, int tile) {
+  const int n_tile = tile / p.m_tiles;
+  int m = tile - n_tile * p.m_tiles;
+  const int xt = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int yt = m % p.tiles_y;
+  const int bt = m / p.tiles_y;
+  TileOrigin o;
+  o.x0 = xt * p.TW; o.y0 = yt * p.TH; o.b0 = bt * p.TB; o.n0 = n_tile * p.BN;
+  return o;
+}
+
+__device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& sm) {
+  const uint32_t nst = (uint32_t)p.nstages, nh = (uint32_t)p.nhalo;
+  uint32_t stage = 0, phase = 0, hs = 0, hphase = 0;
+  if (p.wstat) {
+    const int n0 = ((int)blockIdx.x % p.n_tiles) * p.BN;
+    mbar_arrive_expect_tx(sm.wbar, (uint32_t)p.wstat_bytes);
+    for (int s = 0; s < p.nseg; ++s) {
+      const SegK sg = p.seg[s];
+      const uint32_t wbytes = (uint32_t)p.BN * (uint32_t)sg.kc * 2u;
+      for (int i = 0; i < sg.taps * sg.nchunk; ++i)
+        tma_load_3d(&p.tmW[s], sm.wstat_base + sg.wofs + (size_t)i * wbytes, sm.wbar, i * sg.kc, n0, 0);
+    }
+  }
+  for (uint32_t t = 0;; ++t) {
+    const int tile = sched_tile(p, t);
+    if (tile < 0) break;
+    const TileOrigin o = tile_origin(p, tile);
+    for (int s = 0; s < p.nseg; ++s) {
+      const SegK sg = p.seg[s];
+      const uint32_t wbytes = (uint32_t)p.BN * (uint32_t)sg.kc * 2u;
+      if (sg.halo) {
+        const uint32_t hbytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * (uint32_t)sg.kc * 2u;
+        const int tg = sg.taps == 9 ? p.hg : 1;  // taps per weight stage
+        for (int c = 0; c < sg.nchunk; ++c) {
+          mbar_wait(&sm.hempty[hs], hphase ^ 1u);
+          mbar_arrive_expect_tx(&sm.hfull[hs], hbytes);
+          tma_load_4d(&p.tmH[s], sm.halo_base + (size_t)hs * p.halo_buf_bytes, &sm.hfull[hs], sg.ch_off + c * sg.kc,
+                      o.x0 - 1, o.y0 - 1, o.b0);
+          if (++hs == nh) {
+            hs = 0;
+            hphase ^= 1u;
+          }
+          if (p.wstat) continue;
+          for (int t0 = 0; t0 < sg.taps; t0 += tg) {
+            mbar_wait(&sm.empty[stage], phase ^ 1u);
+            uint8_t* sb = sm.stage_base + (size_t)stage * p.stage_bytes + p.a_region;
+            mbar_arrive_expect_tx(&sm.full[stage], wbytes * (uint32_t)tg);
+            for (int g = 0; g < tg; ++g)
+              tma_load_3d(&p.tmW[s], sb + (size_t)g * wbytes, &sm.full[stage], ((t0 + g) * sg.nchunk + c) * sg.kc, o.n0,
+                          sg.per_image ? o.b0 : 0);
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      } else {
+        const uint32_t bytes = (uint32_t)p.rows * (uint32_t)sg.kc * 2u + wbytes;
+        for (int tap = 0; tap < sg.taps; ++tap) {
+          const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
+          const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;
+          for (int c = 0; c < sg.nchunk; ++c) {
+            mbar_wait(&sm.empty[stage], phase ^ 1u);
+            uint8_t* sa = sm.stage_base + (size_t)stage * p.stage_bytes;
+            mbar_arrive_expect_tx(&sm.full[stage], bytes);
+            tma_load_4d(&p.tmA[s], sa, &sm.full[stage], sg.ch_off + c * sg.kc, o.x0 + dx, o.y0 + dy, o.b0);
+            tma_load_3d(&p.tmW[s], sa + p.a_region, &sm.full[stage], (tap * sg.nchunk + c) * sg.kc, o.n0,
+                        sg.per_image ? o.b0 : 0);
+            if (++stage == nst) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base) {
+  const uint32_t nst = (uint32_t)p.nstages, nh = (uint32_t)p.nhalo;
+  const uint32_t idesc = umma_idesc_f16((uint32_t)p.BN);
+  const uint32_t hw = (uint32_t)(p.TW + 2);
+  uint32_t stage = 0, phase = 0, hs = 0, hphase = 0;
+  if (p.wstat) {
+    mbar_wait(sm.wbar, 0u);
+    tc_fence_after();
+  }
+  for (uint32_t t = 0;; ++t) {
+    const int tile = sched_tile(p, t);
+    if (tile < 0) break;
+    const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
+    mbar_wait(&sm.tempty[acc], acc_phase ^ 1u);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * 256u;
+    uint32_t accumulate = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      const SegK sg = p.seg[s];
+      const uint32_t row_bytes = (uint32_t)sg.kc * 2u;
+      const uint32_t wbytes = (uint32_t)p.BN * row_bytes;
+      const int ksteps = sg.kc / 16;
+      if (sg.halo) {
+        // tap (ky,kx): tile pixel (y,x) reads halo row (y+ky)*(TW+2) + (x+kx).  With TW == 8 every 8-row core group
+        // of the UMMA operand is one tile row, (TW+2)*row_bytes apart.  The swizzle is a function of the absolute
+        // shared-memory address bits (verified on B200: base_offset must stay 0 for views that start off the
+        // swizzle-atom boundary), so a shifted start address is all a tap needs.
+        const int tg = sg.taps == 9 ? p.hg : 1;
+        for (int c = 0; c < sg.nchunk; ++c) {
+          mbar_wait(&sm.hfull[hs], hphase);
+          tc_fence_after();
+          const uint32_t hb = smem_u32(sm.halo_base + (size_t)hs * p.halo_buf_bytes);
+          for (int t0 = 0; t0 < sg.taps; t0 += tg) {
+            uint32_t sb;
+            if (p.wstat) {
+              sb = smem_u32(sm.wstat_base + sg.wofs) + (uint32_t)(t0 * sg.nchunk + c) * wbytes;
+            } else {
+              mbar_wait(&sm.full[stage], phase);
+              tc_fence_after();
+              sb = smem_u32(sm.stage_base + (size_t)stage * p.stage_bytes) + (uint32_t)p.a_region;
+            }
+            for (int g = 0; g < tg; ++g) {
+              const int tap = t0 + g;
+              const uint32_t ky = sg.taps == 9 ? (uint32_t)(tap / 3) : 1u, kx = sg.taps == 9 ? (uint32_t)(tap % 3) : 1u;
+              const uint64_t adesc = umma_smem_desc_k(hb + (ky * hw + kx) * row_bytes, row_bytes, hw * row_bytes);
+              // weight-stationary: taps are nchunk slabs apart; streamed: consecutive slabs of this stage
+              const uint32_t boff = p.wstat ? (uint32_t)(g * sg.nchunk) * wbytes : (uint32_t)g * wbytes;
+              const uint64_t bdesc = umma_smem_desc_k(sb + boff, row_bytes, row_bytes * 8u);
+              for (int k = 0; k < ksteps; ++k) {
+                umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            if (!p.wstat) {
+              umma_commit(&sm.empty[stage]);
+              if (++stage == nst) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+          umma_commit(&sm.hempty[hs]);
+          if (++hs == nh) {
+            hs = 0;
+            hphase ^= 1u;
+          }
+        }
+      } else {
+        const int chunks = sg.taps * sg.nchunk;
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait(&sm.full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sm.stage_base + (size_t)stage * p.stage_bytes);
+          const uint64_t adesc = umma_smem_desc_k(sa, row_bytes, row_bytes * 8u);
+          const uint64_t bdesc = umma_smem_desc_k(sa + (uint32_t)p.a_region, row_bytes, row_bytes * 8u);
+          for (int k = 0; k < ksteps; ++k) {
+            umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(&sm.empty[stage]);
+          if (++stage == nst) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    umma_commit(&sm.tfull[acc]);
+  }
+}
+
+}  // namespace chb

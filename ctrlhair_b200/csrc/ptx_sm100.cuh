@@ -178,6 +178,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
   return d;
 }
 
+// General K-major operand: rows of `row_bytes` (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row groups `sbo_bytes`
+// apart, any 16-byte aligned start address (the hardware swizzles on absolute address bits; base_offset = 0).
+__device__ __forceinline__ uint64_t umma_smem_desc_k(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= 1ull << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;
+  d |= (row_bytes == 128 ? 2ull : 4ull) << 61;
+  return d;
+}
+
 // Same, for a SWIZZLE_128B K-major operand whose 8-row groups are `sbo_bytes` apart and whose start address need
 // not be 1024-byte aligned (a tap view into a halo tile): `base_offset` is the descriptor's 3-bit swizzle phase.
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
