@@ -95,7 +95,7 @@ def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.lib_path()
+    path = os.environ.get("CHB_LIB_PATH") or _build.lib_path()  # override: A/B runs of two builds on one box
     if not os.path.exists(path):
         if not build_if_missing:
             raise ChbError("ctrlhair_b200: %s is missing (run __graft_entry__.build())" % path)

@@ -98,9 +98,15 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
 }
 
 __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base) {
+  // This single thread feeds the tensor core: every instruction between two tcgen05.mma counts.  Descriptor high
+  // words are hoisted per segment, the K steps of a chunk go out in one asm block, tap offsets are tabulated.
   const uint32_t nst = (uint32_t)p.nstages, nh = (uint32_t)p.nhalo;
   const uint32_t idesc = umma_idesc_f16((uint32_t)p.BN);
   const uint32_t hw = (uint32_t)(p.TW + 2);
+  const uint32_t stage_base = smem_u32(sm.stage_base), stage_bytes = (uint32_t)p.stage_bytes;
+  const uint32_t halo_base = smem_u32(sm.halo_base), halo_bytes = (uint32_t)p.halo_buf_bytes;
+  const uint32_t wstat_base = smem_u32(sm.wstat_base);
+  const uint32_t a_region = (uint32_t)p.a_region;
   uint32_t stage = 0, phase = 0, hs = 0, hphase = 0;
   if (p.wstat) {
     mbar_wait(sm.wbar, 0u);
@@ -118,36 +124,46 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
       const SegK sg = p.seg[s];
       const uint32_t row_bytes = (uint32_t)sg.kc * 2u;
       const uint32_t wbytes = (uint32_t)p.BN * row_bytes;
-      const int ksteps = sg.kc / 16;
+      const uint32_t hiB = umma_desc_hi(row_bytes, row_bytes * 8u);
+      const bool k64 = sg.kc == 64;
       if (sg.halo) {
         // tap (ky,kx): tile pixel (y,x) reads halo row (y+ky)*(TW+2) + (x+kx).  With TW == 8 every 8-row core group
         // of the UMMA operand is one tile row, (TW+2)*row_bytes apart.  The swizzle is a function of the absolute
         // shared-memory address bits (verified on B200: base_offset must stay 0 for views that start off the
         // swizzle-atom boundary), so a shifted start address is all a tap needs.
-        const int tg = sg.taps == 9 ? p.hg : 1;
+        const uint32_t hiA = umma_desc_hi(row_bytes, hw * row_bytes);
+        const int ntaps = sg.taps;
+        const int tg = ntaps == 9 ? p.hg : 1;
+        const uint32_t bstep = p.wstat ? (uint32_t)sg.nchunk * wbytes : wbytes;  // weight slab of the next tap
+        const uint32_t row_step = hw * row_bytes;
         for (int c = 0; c < sg.nchunk; ++c) {
           mbar_wait(&sm.hfull[hs], hphase);
           tc_fence_after();
-          const uint32_t hb = smem_u32(sm.halo_base + (size_t)hs * p.halo_buf_bytes);
-          for (int t0 = 0; t0 < sg.taps; t0 += tg) {
+          const uint32_t hb = halo_base + hs * halo_bytes;
+          uint32_t voff = ntaps == 9 ? 0u : row_step + row_bytes;  // view offset of the current tap
+          uint32_t kx = 0;
+          for (int t0 = 0; t0 < ntaps; t0 += tg) {
             uint32_t sb;
             if (p.wstat) {
-              sb = smem_u32(sm.wstat_base + sg.wofs) + (uint32_t)(t0 * sg.nchunk + c) * wbytes;
+              sb = wstat_base + (uint32_t)sg.wofs + (uint32_t)(t0 * sg.nchunk + c) * wbytes;
             } else {
               mbar_wait(&sm.full[stage], phase);
               tc_fence_after();
-              sb = smem_u32(sm.stage_base + (size_t)stage * p.stage_bytes) + (uint32_t)p.a_region;
+              sb = stage_base + stage * stage_bytes + a_region;
             }
             for (int g = 0; g < tg; ++g) {
-              const int tap = t0 + g;
-              const uint32_t ky = sg.taps == 9 ? (uint32_t)(tap / 3) : 1u, kx = sg.taps == 9 ? (uint32_t)(tap % 3) : 1u;
-              const uint64_t adesc = umma_smem_desc_k(hb + (ky * hw + kx) * row_bytes, row_bytes, hw * row_bytes);
-              // weight-stationary: taps are nchunk slabs apart; streamed: consecutive slabs of this stage
-              const uint32_t boff = p.wstat ? (uint32_t)(g * sg.nchunk) * wbytes : (uint32_t)g * wbytes;
-              const uint64_t bdesc = umma_smem_desc_k(sb + boff, row_bytes, row_bytes * 8u);
-              for (int k = 0; k < ksteps; ++k) {
-                umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
-                accumulate = 1;
+              const uint64_t adesc = umma_desc_make(hiA, hb + voff);
+              const uint64_t bdesc = umma_desc_make(hiB, sb);
+              if (k64) umma_f16_ss_k<4>(d_tmem, adesc, bdesc, idesc, accumulate);
+              else umma_f16_ss_k<2>(d_tmem, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+              sb += bstep;
+              // next tap: one pixel right, or to the start of the next halo row
+              if (++kx == 3u) {
+                kx = 0;
+                voff += row_step - 2u * row_bytes;
+              } else {
+                voff += row_bytes;
               }
             }
             if (!p.wstat) {
@@ -169,13 +185,12 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
         for (int c = 0; c < chunks; ++c) {
           mbar_wait(&sm.full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(sm.stage_base + (size_t)stage * p.stage_bytes);
-          const uint64_t adesc = umma_smem_desc_k(sa, row_bytes, row_bytes * 8u);
-          const uint64_t bdesc = umma_smem_desc_k(sa + (uint32_t)p.a_region, row_bytes, row_bytes * 8u);
-          for (int k = 0; k < ksteps; ++k) {
-            umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accumulate);
-            accumulate = 1;
-          }
+          const uint32_t sa = stage_base + stage * stage_bytes;
+          const uint64_t adesc = umma_desc_make(hiB, sa);
+          const uint64_t bdesc = umma_desc_make(hiB, sa + a_region);
+          if (k64) umma_f16_ss_k<4>(d_tmem, adesc, bdesc, idesc, accumulate);
+          else umma_f16_ss_k<2>(d_tmem, adesc, bdesc, idesc, accumulate);
+          accumulate = 1;
           umma_commit(&sm.empty[stage]);
           if (++stage == nst) {
             stage = 0;

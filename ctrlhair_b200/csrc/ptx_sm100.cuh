@@ -108,6 +108,61 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// KS (2 or 4) MMAs over consecutive 16-element K steps of one smem chunk, issued from a single asm block so that
+// the issuing thread spends as few instructions per MMA as possible (it is the only thread feeding the tensor
+// core).  Descriptor low words advance by 2 (= 32 bytes >> 4) per K step; `accumulate` only gates the first MMA.
+template <int KS>
+__device__ __forceinline__ void umma_f16_ss_k(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate);
+template <>
+__device__ __forceinline__ void umma_f16_ss_k<4>(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 pt, %4, %4;\n\t"
+      "add.u64 a1, %1, 2;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "add.u64 a2, %1, 4;\n\t"
+      "add.u64 b2, %2, 4;\n\t"
+      "add.u64 a3, %1, 6;\n\t"
+      "add.u64 b3, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void umma_f16_ss_k<2>(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b64 a1, b1;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 pt, %4, %4;\n\t"
+      "add.u64 a1, %1, 2;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Descriptor from a precomputed high word (stride / version / layout) and a shared-memory address.
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t row_bytes, uint32_t sbo_bytes) {
+  return (sbo_bytes >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc_make(uint32_t hi, uint32_t saddr) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
