@@ -20,8 +20,9 @@ struct Smem {
 
 // t-th tile of this CTA, or -1.  Normal mode: round robin over all (n_tile, m_tile).  Weight-stationary mode: the
 // CTA keeps one n_tile for its whole life (its weights stay in shared memory) and strides over the m tiles.
+template <bool WSTAT>
 __device__ __forceinline__ int sched_tile(const ConvKParams& p, uint32_t t) {
-  if (p.wstat) {
+  if (WSTAT) {
     const int n_tile = (int)blockIdx.x % p.n_tiles;
     const long long m = (long long)((int)blockIdx.x / p.n_tiles) + (long long)t * ((int)gridDim.x / p.n_tiles);
     return m < p.m_tiles ? n_tile * p.m_tiles + (int)m : -1;
@@ -351,7 +352,7 @@ __device__ __forceinline__ void plain_chunk(const ConvKParams& p, const EpiK& e,
 // ------------------------------------------------------------------------------------------------
 // Epilogue warp role
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int ACT>
+template <int EPI, int ACT, bool WSTAT>
 __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base, int warp,
                                               int lane) {
     // ------------------------------------------------------------------ epilogue warps
@@ -368,7 +369,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
 
     if (EPI == CHB_EPI_PLAIN) {
       uint32_t it = 0;
-      for (int tile = sched_tile(p, it); tile >= 0; tile = sched_tile(p, ++it)) {
+      for (int tile = sched_tile<WSTAT>(p, it); tile >= 0; tile = sched_tile<WSTAT>(p, ++it)) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
         const int n_tile = tg.set_tile(p, tile);
         int b, y, x;
@@ -428,13 +429,13 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
       auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
       uint4 pf[8];
       uint32_t xo[8], xon[8];
-      if (sched_tile(p, 0) >= 0) {
-        const int nt0 = tg.set_tile(p, sched_tile(p, 0));
+      if (sched_tile<WSTAT>(p, 0) >= 0) {
+        const int nt0 = tg.set_tile(p, sched_tile<WSTAT>(p, 0));
         row_offsets<8>(lane, row_base, tg, 4, x_elem, xon);
         gather_issue_o<8>(reinterpret_cast<const char*>(e.x + nt0 * half_n + chalf * cw) + cl8 * 16, xon, pf);
       }
       uint32_t it = 0;
-      for (int tile = sched_tile(p, it); tile >= 0; tile = sched_tile(p, ++it)) {
+      for (int tile = sched_tile<WSTAT>(p, it); tile >= 0; tile = sched_tile<WSTAT>(p, ++it)) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
         const int n_tile = tg.set_tile(p, tile);
         const int c0 = n_tile * half_n;
@@ -459,9 +460,9 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
           // request the next x block
           if (u + 1 < units) {
             gather_issue_o<8>(reinterpret_cast<const char*>(e.x + c0 + j + 32) + cl8 * 16, xo, pf);
-          } else if (sched_tile(p, it + 1) >= 0) {
+          } else if (sched_tile<WSTAT>(p, it + 1) >= 0) {
             TileGeo tn = tg;
-            const int ntn = tn.set_tile(p, sched_tile(p, it + 1));
+            const int ntn = tn.set_tile(p, sched_tile<WSTAT>(p, it + 1));
             row_offsets<8>(lane, row_base, tn, 4, x_elem, xon);
             gather_issue_o<8>(reinterpret_cast<const char*>(e.x + ntn * half_n + chalf * cw) + cl8 * 16, xon, pf);
           }

@@ -43,7 +43,7 @@ int device_sm_count() {
 //   [nstages x stage_bytes pipeline][1 KB mbarriers + TMEM slot][8 x 4 KB epilogue staging]
 //   [nhalo x halo_buf_bytes halo tiles][wstat_bytes resident weights]
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int ACT>
+template <int EPI, int ACT, bool WSTAT>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,13 +96,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const uint32_t tmem_base = *sm.tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) producer_role(p, sm);
+    if (lane == 0) producer_role<WSTAT>(p, sm);
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) mma_role(p, sm, tmem_base);
+    if (lane == 0) mma_role<WSTAT>(p, sm, tmem_base);
     __syncwarp();
   } else {
-    epilogue_role<EPI, ACT>(p, sm, tmem_base, warp, lane);
+    epilogue_role<EPI, ACT, WSTAT>(p, sm, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -397,20 +397,24 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
 
 typedef void (*ConvKernelFn)(const ConvKParams);
 
-static ConvKernelFn pick_kernel(int epi, int act) {
+template <bool WSTAT>
+static ConvKernelFn pick_kernel_w(int epi, int act) {
   if (epi == CHB_EPI_PLAIN) {
     switch (act) {
-      case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_RELU>;
-      case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_LRELU>;
-      case CHB_ACT_TANH: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_TANH>;
-      default: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_NONE>;
+      case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_RELU, WSTAT>;
+      case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_LRELU, WSTAT>;
+      case CHB_ACT_TANH: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_TANH, WSTAT>;
+      default: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_NONE, WSTAT>;
     }
   }
   switch (act) {
-    case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_LRELU>;
-    case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_RELU>;
-    default: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_NONE>;
+    case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_LRELU, WSTAT>;
+    case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_RELU, WSTAT>;
+    default: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_NONE, WSTAT>;
   }
+}
+static ConvKernelFn pick_kernel(int epi, int act, int wstat) {
+  return wstat ? pick_kernel_w<true>(epi, act) : pick_kernel_w<false>(epi, act);
 }
 
 static int ensure_smem_attr() {
@@ -419,8 +423,8 @@ static int ensure_smem_attr() {
   std::call_once(once, [] {
     for (int epi = 0; epi < 2 && err == cudaSuccess; ++epi)
       for (int act = 0; act < 4 && err == cudaSuccess; ++act)
-        err = cudaFuncSetAttribute(pick_kernel(epi, act), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024);
+        for (int w = 0; w < 2 && err == cudaSuccess; ++w)
+          err = cudaFuncSetAttribute(pick_kernel(epi, act, w), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(err));
@@ -448,7 +452,7 @@ int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
   } else {
     int rc = ensure_smem_attr();
     if (rc != CHB_OK) return rc;
-    pick_kernel(plan.desc.epi, plan.desc.act)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
+    pick_kernel(plan.desc.epi, plan.desc.act, plan.kp.wstat)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
   }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {

@@ -28,10 +28,11 @@ __device__ __forceinline__ TileOrigin tile_origin(const ConvKParams& p, int tile
   return o;
 }
 
+template <bool WSTAT>
 __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& sm) {
   const uint32_t nst = (uint32_t)p.nstages, nh = (uint32_t)p.nhalo;
   uint32_t stage = 0, phase = 0, hs = 0, hphase = 0;
-  if (p.wstat) {
+  if (WSTAT) {
     const int n0 = ((int)blockIdx.x % p.n_tiles) * p.BN;
     mbar_arrive_expect_tx(sm.wbar, (uint32_t)p.wstat_bytes);
     for (int s = 0; s < p.nseg; ++s) {
@@ -42,13 +43,13 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
     }
   }
   for (uint32_t t = 0;; ++t) {
-    const int tile = sched_tile(p, t);
+    const int tile = sched_tile<WSTAT>(p, t);
     if (tile < 0) break;
     const TileOrigin o = tile_origin(p, tile);
     for (int s = 0; s < p.nseg; ++s) {
       const SegK sg = p.seg[s];
       const uint32_t wbytes = (uint32_t)p.BN * (uint32_t)sg.kc * 2u;
-      if (sg.halo) {
+      if (WSTAT || sg.halo) {
         const uint32_t hbytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * (uint32_t)sg.kc * 2u;
         const int tg = sg.taps == 9 ? p.hg : 1;  // taps per weight stage
         for (int c = 0; c < sg.nchunk; ++c) {
@@ -60,7 +61,7 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
             hs = 0;
             hphase ^= 1u;
           }
-          if (p.wstat) continue;
+          if (WSTAT) continue;
           for (int t0 = 0; t0 < sg.taps; t0 += tg) {
             mbar_wait(&sm.empty[stage], phase ^ 1u);
             uint8_t* sb = sm.stage_base + (size_t)stage * p.stage_bytes + p.a_region;
@@ -97,6 +98,7 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
   }
 }
 
+template <bool WSTAT>
 __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base) {
   // This single thread feeds the tensor core: every instruction between two tcgen05.mma counts.  Descriptor high
   // words are hoisted per segment, the K steps of a chunk go out in one asm block, tap offsets are tabulated.
@@ -108,12 +110,12 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
   const uint32_t wstat_base = smem_u32(sm.wstat_base);
   const uint32_t a_region = (uint32_t)p.a_region;
   uint32_t stage = 0, phase = 0, hs = 0, hphase = 0;
-  if (p.wstat) {
+  if (WSTAT) {
     mbar_wait(sm.wbar, 0u);
     tc_fence_after();
   }
   for (uint32_t t = 0;; ++t) {
-    const int tile = sched_tile(p, t);
+    const int tile = sched_tile<WSTAT>(p, t);
     if (tile < 0) break;
     const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
     mbar_wait(&sm.tempty[acc], acc_phase ^ 1u);
@@ -126,7 +128,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
       const uint32_t wbytes = (uint32_t)p.BN * row_bytes;
       const uint32_t hiB = umma_desc_hi(row_bytes, row_bytes * 8u);
       const bool k64 = sg.kc == 64;
-      if (sg.halo) {
+      if (WSTAT || sg.halo) {
         // tap (ky,kx): tile pixel (y,x) reads halo row (y+ky)*(TW+2) + (x+kx).  With TW == 8 every 8-row core group
         // of the UMMA operand is one tile row, (TW+2)*row_bytes apart.  The swizzle is a function of the absolute
         // shared-memory address bits (verified on B200: base_offset must stay 0 for views that start off the
@@ -134,7 +136,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
         const uint32_t hiA = umma_desc_hi(row_bytes, hw * row_bytes);
         const int ntaps = sg.taps;
         const int tg = ntaps == 9 ? p.hg : 1;
-        const uint32_t bstep = p.wstat ? (uint32_t)sg.nchunk * wbytes : wbytes;  // weight slab of the next tap
+        const uint32_t bstep = WSTAT ? (uint32_t)sg.nchunk * wbytes : wbytes;  // weight slab of the next tap
         const uint32_t row_step = hw * row_bytes;
         for (int c = 0; c < sg.nchunk; ++c) {
           mbar_wait(&sm.hfull[hs], hphase);
@@ -144,7 +146,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
           uint32_t kx = 0;
           for (int t0 = 0; t0 < ntaps; t0 += tg) {
             uint32_t sb;
-            if (p.wstat) {
+            if (WSTAT) {
               sb = wstat_base + (uint32_t)sg.wofs + (uint32_t)(t0 * sg.nchunk + c) * wbytes;
             } else {
               mbar_wait(&sm.full[stage], phase);
@@ -166,7 +168,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
                 voff += row_bytes;
               }
             }
-            if (!p.wstat) {
+            if (!WSTAT) {
               umma_commit(&sm.empty[stage]);
               if (++stage == nst) {
                 stage = 0;
