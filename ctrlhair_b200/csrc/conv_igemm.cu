@@ -306,6 +306,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     const int kc = g.C == 32 ? 32 : 64;
     if (kc > kc_max) kc_max = kc;
     if (g.per_image) wstat_ok = false;
+    if (kc == 32 && wstat_mode < 2) wstat_ok = false;  // measured on B200: one-hot (64-byte row) layers run faster streamed
     wbytes_total += (long long)g.taps * g.C * d.BN * 2;
   }
   const int halo_buf = kc_max == 64 ? kHaloBufBytes : kHaloBufBytes / 2;
