@@ -37,38 +37,45 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons through NVML (every ~5 ms) while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
         self.stop_flag = False
+        self.err = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((mhz, reasons, watts))
+                time.sleep(0.005)
+        except Exception as e:  # NVML missing: report it, do not fail the run
+            self.err = repr(e)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        mhz = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled: %s" % self.err]}
+        mhz = sorted(s[0] for s in self.samples)
+        bits = 0
+        for s in self.samples:
+            bits |= s[1]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        reasons = [n for b, n in names.items() if bits & b]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.max_mhz), "reasons": reasons,
+                "power_w_max": max(s[2] for s in self.samples), "samples": len(self.samples)}
 
 
 def cpu_oracle_throughput(n_images, crop, warm=0):
@@ -205,9 +212,17 @@ def run_ours(args):
     peaks = load_peaks()
     achieved = algo_flops / (conv_ms * 1e-3) / 1e12
     top = sorted(zip(ms, names, fl), reverse=True)[:5]
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if B == 64 and crop == 256:
+            traffic = tj["dram_bytes_per_launch_avg"]
+    except Exception:
+        pass
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+        "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
+        "traffic_note": "DRAM bytes per conv launch, averaged over the 57 launches of one step (ncu, profiles/)",
         "kernel": "chb::conv_igemm_kernel (all %d conv launches of one step, CUDA events between launches)" % len(ms),
         "algorithmic_gflop_per_image": 2.0 * fact_macs / 1e9, "issued_gflop_per_image": sum(fl) / B / 1e9,
         "reference_dense_gflop_per_image": 2.0 * dense_macs / 1e9, "kernel_ms_per_step": conv_ms,
