@@ -45,6 +45,12 @@ class ConvDesc(C.Structure):
     ]
 
 
+class MlpLayer(C.Structure):
+    _fields_ = [("in_dim", C.c_int), ("out_dim", C.c_int), ("wt", C.c_void_p), ("bias", C.c_void_p),
+                ("pre_act", C.c_int), ("post_act", C.c_int), ("inj_u", C.c_void_p), ("inj_l", C.c_void_p),
+                ("inj_mu", C.c_void_p), ("inj_nb", C.c_int), ("inj_zoff", C.c_int)]
+
+
 class GenConfig(C.Structure):
     _fields_ = [("ngf", C.c_int), ("label_nc", C.c_int), ("crop", C.c_int), ("style_len", C.c_int),
                 ("max_batch", C.c_int)]
@@ -65,6 +71,8 @@ SYMBOLS = [
      [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     ("chb_noise_fill", C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
     ("chb_f32_to_f16", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("chb_mlp_forward", C.c_int,
+     [C.POINTER(MlpLayer), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_generator_create", C.c_int, [C.POINTER(GenConfig), C.POINTER(C.c_void_p)]),
     ("chb_generator_destroy", None, [C.c_void_p]),
     ("chb_generator_num_tensors", C.c_int, [C.c_void_p]),

@@ -172,3 +172,50 @@ def make_noise(B, S, seed=1237):
 def flatten_noise(planes):
     """18 planes [B,W,H,1] -> one fp32 vector in the layout chb_generator_forward expects."""
     return torch.cat([p.reshape(-1) for p in planes])
+
+
+def make_ct_state_dicts(seed=1240, code_dim=512, hidden=256, g_layers=4, d_layers=4, p_layers=3, noise_dim=8,
+                        curliness_dim=1):
+    """Seeded state_dicts of the colour/texture nets in the reference's key format (config 045 / predictor p004):
+    (Model_G EigenGenerator, Model_D Discriminator, Predictor)."""
+    gen = torch.Generator().manual_seed(seed)
+
+    def lin(out_d, in_d, gain=1.0):
+        return torch.randn((out_d, in_d), generator=gen) * (gain / math.sqrt(in_d)), torch.randn(out_d, generator=gen) * 0.1
+
+    g = {}
+    g["main_layer_in.weight"], g["main_layer_in.bias"] = lin(hidden, 3 + 1 + curliness_dim, 1.5)
+    for i in range(g_layers):
+        od = hidden if i < g_layers - 1 else code_dim
+        g["main_layer_mid.%d.1.weight" % i], g["main_layer_mid.%d.1.bias" % i] = lin(od, hidden, 1.4)
+    sub = noise_dim // g_layers
+    for i in range(g_layers):
+        q, _ = torch.linalg.qr(torch.randn((hidden, sub), generator=gen))
+        g["subspaces.%d.U" % i] = q.t().contiguous()
+        g["subspaces.%d.L" % i] = torch.tensor([3.0 * k for k in range(sub, 0, -1)]) * (1 + 0.1 * torch.randn(sub, generator=gen))
+        g["subspaces.%d.mu" % i] = torch.randn(hidden, generator=gen) * 0.1
+    d = {}
+    out_dim = 1 + noise_dim + 1 + curliness_dim  # model.py:95-104 for config 045
+    for i in range(d_layers + 1):
+        in_d = code_dim if i == 0 else hidden
+        od = hidden if i < d_layers else out_dim
+        d["net.%d.fc.weight" % i], d["net.%d.fc.bias" % i] = lin(od, in_d, 1.4)
+    pr = {}
+    for i in range(p_layers + 1):
+        in_d = code_dim if i == 0 else hidden
+        od = hidden if i < p_layers else 4
+        pr["net.%d.fc.weight" % i], pr["net.%d.fc.bias" % i] = lin(od, in_d, 1.4)
+        if i < p_layers:
+            pr["net.%d.norm.weight" % i] = 1 + 0.2 * torch.randn(od, generator=gen)
+            pr["net.%d.norm.bias" % i] = 0.1 * torch.randn(od, generator=gen)
+            pr["net.%d.norm.running_mean" % i] = 0.3 * torch.randn(od, generator=gen)
+            pr["net.%d.norm.running_var" % i] = torch.rand(od, generator=gen) + 0.5
+            pr["net.%d.norm.num_batches_tracked" % i] = torch.tensor(100, dtype=torch.int64)
+    return g, d, pr
+
+
+def make_ct_inputs(B, seed=1241):
+    gen = torch.Generator().manual_seed(seed)
+    return {"code": torch.randn((B, 512), generator=gen) * 0.135,
+            "noise": torch.randn((B, 8), generator=gen), "noise_curliness": torch.randn((B, 1), generator=gen),
+            "rgb_mean": torch.rand((B, 3), generator=gen), "pca_std": torch.rand((B, 1), generator=gen)}

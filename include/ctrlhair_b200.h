@@ -97,6 +97,26 @@ int chb_noise_fill(float* out, int64_t n, uint64_t seed, uint64_t offset, void* 
 int chb_f32_to_f16(const float* in, void* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Operator 3: fused dense chain for the colour/texture MLPs (color_texture_branch/model_eigengan.py:62-83,
+ * model.py:108-127, predictor/predictor_model.py:32-41 with my_torchlib/module.py:56-64 LinearBlock).
+ * Per layer:  x <- act_pre(x + [(inj_l * z[zoff:zoff+nb]) @ inj_u + inj_mu]);  y = act_post(wt^T x + bias).
+ * wt is stored transposed [in_dim][out_dim]; eval-mode BatchNorm1d is folded into wt/bias by the host packer.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int in_dim, out_dim;
+  const float* wt;      /* [in_dim][out_dim] */
+  const float* bias;    /* [out_dim] or NULL */
+  int pre_act, post_act;/* CHB_ACT_* */
+  const float* inj_u;   /* [inj_nb][in_dim] or NULL  (SubspaceLayer.U,  model_eigengan.py:17) */
+  const float* inj_l;   /* [inj_nb]                  (SubspaceLayer.L)  */
+  const float* inj_mu;  /* [in_dim]                  (SubspaceLayer.mu) */
+  int inj_nb, inj_zoff; /* number of basis vectors, offset into the per-sample z vector */
+} chb_mlp_layer;
+/* x fp32 [B, layers[0].in_dim], z fp32 [B, zdim] (or NULL), out fp32 [B, layers[n-1].out_dim]; device pointers. */
+int chb_mlp_forward(const chb_mlp_layer* layers, int nlayers, const float* x, const float* z, int zdim, float* out,
+                    int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The generator (generator.py:14-109 SPADEGenerator, 'normal' upsampling: 7 SPADE ResBlocks).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {

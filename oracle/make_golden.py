@@ -66,5 +66,49 @@ def main():
     print("done")
 
 
+class _ADict(dict):
+    """Minimal stand-in for addict.Dict (absent from the image): missing keys read as an empty, falsy dict."""
+
+    def __getattr__(self, k):
+        return self[k] if k in self else _ADict()
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def main_ct():
+    """Golden vectors of the colour/texture MLPs from the unmodified reference modules (config 045 / p004)."""
+    from . import ct_oracle as co
+    g, d, pr = synth.make_ct_state_dicts()
+    cfg = _ADict(lambda_rgb=0.01, lambda_pca_std=0.01, lambda_cls_curliness={0: 0.1}, curliness_dim=1,
+                 g_hidden_dim=256, g_hidden_layer_num=4, SEAN_code=512, subspace_dim=2, noise_dim=8,
+                 d_hidden_dim=256, d_hidden_layer_num=4, d_norm="none", d_activ="lrelu",
+                 predictor=_ADict(curliness=1, rgb=1))
+    pcfg = _ADict(SEAN_code=512, hidden_dim=256, hidden_layer_num=3, norm="bn", activ="lrelu", dropout=0.2,
+                  predict_dict={"rgb_mean": 3, "pca_std": 1})
+    with rh.reference_on_path():
+        from color_texture_branch.model import Discriminator
+        from color_texture_branch.model_eigengan import EigenGenerator
+        from color_texture_branch.predictor.predictor_model import Predictor
+        G, D, P = EigenGenerator(cfg), Discriminator(cfg), Predictor(pcfg)
+    G.load_state_dict(g, strict=True)
+    D.load_state_dict(d, strict=True)
+    P.load_state_dict(pr, strict=True)
+    G.eval(), D.eval(), P.eval()
+    inp = synth.make_ct_inputs(7)
+    with torch.no_grad():
+        rg, rd, rp = G(inp)["code"], D({"code": inp["code"]}), P({"code": inp["code"]})
+    og, od, op = co.eigen_generator(g, inp)["code"], co.discriminator(d, inp), co.predictor(pr, inp)
+    print("ct: max|oracle-ref| G %.2e D %.2e P %.2e" % (
+        float((rg - og).abs().max()), max(float((rd[k] - od[k]).abs().max()) for k in od),
+        max(float((rp[k] - op[k]).abs().max()) for k in op)))
+    np.savez_compressed(os.path.join(OUT, "ct_mlps.npz"), gen_code=rg.numpy(), dis_adv=rd["adv"].numpy(),
+                        dis_noise=rd["noise"].numpy(), dis_curl=rd["noise_curliness"].numpy(),
+                        pred_rgb=rp["rgb_mean"].numpy(), pred_std=rp["pca_std"].numpy(),
+                        seeds=np.array([1240, 1241]), B=7)
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    if "--ct-only" not in sys.argv:
+        main()
+    main_ct()
