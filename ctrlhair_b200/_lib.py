@@ -23,6 +23,7 @@ class ConvSeg(C.Structure):
         ("w", C.c_void_p),
         ("per_image", C.c_int),
         ("w_sb", C.c_int64),
+        ("a_pad", C.c_int),
     ]
 
 
@@ -54,6 +55,10 @@ class MlpLayer(C.Structure):
 class GenConfig(C.Structure):
     _fields_ = [("ngf", C.c_int), ("label_nc", C.c_int), ("crop", C.c_int), ("style_len", C.c_int),
                 ("max_batch", C.c_int)]
+
+
+class ZencConfig(C.Structure):
+    _fields_ = [("crop", C.c_int), ("label_nc", C.c_int), ("max_batch", C.c_int)]
 
 
 EPI_PLAIN, EPI_MODULATE = 0, 1
@@ -95,6 +100,16 @@ SYMBOLS = [
     ("chb_generator_set_step_limit", C.c_int, [C.c_void_p, C.c_int]),
     ("chb_generator_debug_tensor", C.c_int64,
      [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    ("chb_zencoder_create", C.c_int, [C.POINTER(ZencConfig), C.POINTER(C.c_void_p)]),
+    ("chb_zencoder_destroy", None, [C.c_void_p]),
+    ("chb_zencoder_num_tensors", C.c_int, [C.c_void_p]),
+    ("chb_zencoder_tensor_info", C.c_int,
+     [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    ("chb_zencoder_blob_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_zencoder_workspace_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_zencoder_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("chb_zencoder_forward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_zencoder_forward_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 ]
 
 

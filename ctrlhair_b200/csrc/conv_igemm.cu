@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 struct SimtSeg {
   const __half* a;
   long long a_sb, a_sy, a_sx;
-  int ch_off, C, taps, per_image;
+  int ch_off, C, taps, per_image, a_pad;
   const __half* w;
   long long w_sb;
 };
@@ -146,9 +146,9 @@ __device__ float simt_dot(const SimtParams& p, int b, int y, int x, int nrow) {
     const int K = sg.taps * sg.C;
     const __half* wrow = sg.w + (sg.per_image ? (long long)b * (sg.w_sb > 0 ? sg.w_sb : (long long)p.e.nrows * K) : 0) + (long long)nrow * K;
     for (int tap = 0; tap < sg.taps; ++tap) {
-      const int yy = y + (sg.taps == 9 ? tap / 3 - 1 : 0);
-      const int xx = x + (sg.taps == 9 ? tap % 3 - 1 : 0);
-      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+      const int yy = y + sg.a_pad + (sg.taps == 9 ? tap / 3 - 1 : 0);
+      const int xx = x + sg.a_pad + (sg.taps == 9 ? tap % 3 - 1 : 0);
+      if (yy < 0 || yy >= p.H + 2 * sg.a_pad || xx < 0 || xx >= p.W + 2 * sg.a_pad) continue;
       const __half* ap = sg.a + (long long)b * sg.a_sb + (long long)yy * sg.a_sy + (long long)xx * sg.a_sx + sg.ch_off;
       const __half* wp = wrow + tap * sg.C;
       for (int c = 0; c < sg.C; ++c) acc = fmaf(__half2float(ap[c]), __half2float(wp[c]), acc);
@@ -260,6 +260,7 @@ static int validate_desc(const chb_conv_desc& d) {
     CHB_REQUIRE((g.a_sx % 8) == 0 && (g.a_sy % 8) == 0 && (g.a_sb % 8) == 0 && (g.ch_off % 8) == 0,
                 "activation strides must be multiples of 8 elements (16 B)");
     CHB_REQUIRE(!g.per_image || d.TB == 1, "per-image weights need TB == 1");
+    CHB_REQUIRE(g.a_pad >= 0 && g.a_pad <= 8, "a_pad in 0..8");
     CHB_REQUIRE((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0,
                 "operands must be 16-byte aligned");
   }
@@ -350,10 +351,12 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     k.seg[s].nchunk = g.C / kc;
     k.seg[s].ch_off = g.ch_off;
     k.seg[s].per_image = g.per_image;
+    k.seg[s].xy_off = g.a_pad;
     k.seg[s].wofs = (int)(ktotal * d.BN * 2);  // offset of this segment inside the resident weight slab
     ktotal += (long long)g.taps * g.C;
     {
-      cuuint64_t dims[4] = {(cuuint64_t)g.Ca, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+      cuuint64_t dims[4] = {(cuuint64_t)g.Ca, (cuuint64_t)(d.W + 2 * g.a_pad), (cuuint64_t)(d.H + 2 * g.a_pad),
+                            (cuuint64_t)d.B};
       cuuint64_t str[3] = {(cuuint64_t)g.a_sx * 2, (cuuint64_t)g.a_sy * 2, (cuuint64_t)g.a_sb * 2};
       cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)d.TW, (cuuint32_t)d.TH, (cuuint32_t)d.TB};
       rc = encode_map(&k.tmA[s], g.a, 4, dims, str, box, kc);
@@ -446,6 +449,7 @@ int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
       sp.seg[s].a_sb = d.seg[s].a_sb; sp.seg[s].a_sy = d.seg[s].a_sy; sp.seg[s].a_sx = d.seg[s].a_sx;
       sp.seg[s].ch_off = d.seg[s].ch_off; sp.seg[s].C = d.seg[s].C; sp.seg[s].taps = d.seg[s].taps;
       sp.seg[s].per_image = d.seg[s].per_image;
+      sp.seg[s].a_pad = d.seg[s].a_pad;
       sp.seg[s].w = reinterpret_cast<const __half*>(d.seg[s].w);
       sp.seg[s].w_sb = d.seg[s].w_sb;
     }

@@ -20,6 +20,7 @@ constexpr int kConvThreads = 64 + 32 * kEpilogueWarps;  // warp0 TMA, warp1 MMA,
 
 struct SegK {
   int taps, nchunk, kc, ch_off, per_image;
+  int xy_off;  // explicit input border (chb_conv_seg.a_pad): added to the TMA x / y coordinates
   int wofs;  // weight-stationary mode: byte offset of this segment inside the resident weight slab
   int halo;  // 1: the A operand of this 3x3 segment is loaded once per channel chunk as a (TH+2)x(TW+2) halo tile
 };

@@ -56,7 +56,7 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
           mbar_wait(&sm.hempty[hs], hphase ^ 1u);
           mbar_arrive_expect_tx(&sm.hfull[hs], hbytes);
           tma_load_4d(&p.tmH[s], sm.halo_base + (size_t)hs * p.halo_buf_bytes, &sm.hfull[hs], sg.ch_off + c * sg.kc,
-                      o.x0 - 1, o.y0 - 1, o.b0);
+                      o.x0 - 1 + sg.xy_off, o.y0 - 1 + sg.xy_off, o.b0);
           if (++hs == nh) {
             hs = 0;
             hphase ^= 1u;
@@ -84,7 +84,8 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
             mbar_wait(&sm.empty[stage], phase ^ 1u);
             uint8_t* sa = sm.stage_base + (size_t)stage * p.stage_bytes;
             mbar_arrive_expect_tx(&sm.full[stage], bytes);
-            tma_load_4d(&p.tmA[s], sa, &sm.full[stage], sg.ch_off + c * sg.kc, o.x0 + dx, o.y0 + dy, o.b0);
+            tma_load_4d(&p.tmA[s], sa, &sm.full[stage], sg.ch_off + c * sg.kc, o.x0 + dx + sg.xy_off,
+                        o.y0 + dy + sg.xy_off, o.b0);
             tma_load_3d(&p.tmW[s], sa + p.a_region, &sm.full[stage], (tap * sg.nchunk + c) * sg.kc, o.n0,
                         sg.per_image ? o.b0 : 0);
             if (++stage == nst) {

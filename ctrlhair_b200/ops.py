@@ -38,7 +38,8 @@ def conv_igemm(segs, N, BN, *, bias=None, bias_per_image=False, epi=EPI_PLAIN, a
     """
     lib = _lib.load()
     a0 = _require_cuda(segs[0]["a"], "segs[0].a", torch.float16)
-    B, H, W = a0.shape[0], a0.shape[1], a0.shape[2]
+    pad0 = segs[0].get("a_pad", 0)
+    B, H, W = a0.shape[0], a0.shape[1] - 2 * pad0, a0.shape[2] - 2 * pad0
     d = ConvDesc()
     d.B, d.H, d.W = B, H, W
     d.TW, d.TH, d.TB = tile if tile is not None else default_tile(H, W)
@@ -66,6 +67,7 @@ def conv_igemm(segs, N, BN, *, bias=None, bias_per_image=False, epi=EPI_PLAIN, a
         g.w = w.data_ptr()
         g.per_image = 1 if per_image else 0
         g.w_sb = 0
+        g.a_pad = s.get("a_pad", 0)
     d.N, d.Nrows, d.BN = N, nrows, BN
     d.epi, d.act = epi, act
     if bias is not None:

@@ -219,3 +219,11 @@ def make_ct_inputs(B, seed=1241):
     return {"code": torch.randn((B, 512), generator=gen) * 0.135,
             "noise": torch.randn((B, 8), generator=gen), "noise_curliness": torch.randn((B, 1), generator=gen),
             "rgb_mean": torch.rand((B, 3), generator=gen), "pca_std": torch.rand((B, 1), generator=gen)}
+
+
+def make_image(B, S, seed=1250):
+    """fp32 [B,3,S,S] in [-1,1]: smooth low-frequency content plus noise (stands in for imgs/*.png)."""
+    gen = torch.Generator().manual_seed(seed)
+    low = torch.rand((B, 3, 8, 8), generator=gen) * 2 - 1
+    img = torch.nn.functional.interpolate(low, size=(S, S), mode="bilinear", align_corners=False)
+    return (img + 0.2 * torch.randn((B, 3, S, S), generator=gen)).clamp(-1, 1)

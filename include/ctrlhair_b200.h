@@ -49,6 +49,8 @@ typedef struct {
   const void* w;      /* fp16 weights [(B,) Nrows, taps*C]; k = tap*C + c, tap = ky*3+kx         */
   int per_image;      /* 1: weights carry a leading image dimension                              */
   int64_t w_sb;       /* per_image: element stride between images (0 = dense Nrows*taps*C)       */
+  int a_pad;          /* the A tensor carries an explicit border of a_pad pixels per side (e.g. a reflection
+                         pad): its extent is (H+2*a_pad) x (W+2*a_pad); output (y,x) reads (y+a_pad+dy, x+a_pad+dx) */
 } chb_conv_seg;
 
 enum { CHB_EPI_PLAIN = 0, CHB_EPI_MODULATE = 1 };
@@ -168,6 +170,30 @@ double chb_generator_flops(const chb_generator* g, int B);
 int chb_generator_set_step_limit(chb_generator* g, int n);
 /* Debug: copy an intermediate tensor by name ("x_head_0", ...) for parity tests; returns element count. */
 int64_t chb_generator_debug_tensor(const chb_generator* g, const char* name, int B, void** dev_ptr, int* dtype);
+
+/* ------------------------------------------------------------------------------------------
+ * The style encoder (architecture.py:154-207 Zencoder; called through Pix2PixModel.forward(data, 'style_code'),
+ * pix2pix_model.py:69-72, from HairEditor.get_code, hair_editor.py:149-157).
+ * img fp32 [B,3,crop,crop] in [-1,1] (NCHW, the reference layout), labels u8 [B,crop,crop]
+ * -> style codes fp32 [B,label_nc,512]; rows of absent classes are zero.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int crop;       /* 256 */
+  int label_nc;   /* 19 */
+  int max_batch;
+} chb_zenc_config;
+typedef struct chb_zencoder chb_zencoder;
+int chb_zencoder_create(const chb_zenc_config* cfg, chb_zencoder** out);
+void chb_zencoder_destroy(chb_zencoder* z);
+int chb_zencoder_num_tensors(const chb_zencoder* z);
+int chb_zencoder_tensor_info(const chb_zencoder* z, int i, char* name, int name_cap, int64_t* offset, int64_t* nbytes,
+                             int* dtype);
+int64_t chb_zencoder_blob_bytes(const chb_zencoder* z);
+int64_t chb_zencoder_workspace_bytes(const chb_zencoder* z);
+int chb_zencoder_bind(chb_zencoder* z, const void* blob, void* workspace);
+int chb_zencoder_forward(chb_zencoder* z, const float* img, const uint8_t* labels, float* out, int B, void* stream);
+int chb_zencoder_forward_host(chb_zencoder* z, const float* img_host, const uint8_t* labels_host, float* out_host,
+                              int B, void* stream);
 
 #ifdef __cplusplus
 }

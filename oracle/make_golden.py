@@ -108,7 +108,33 @@ def main_ct():
                         seeds=np.array([1240, 1241]), B=7)
 
 
+def main_zencoder():
+    """Golden style codes from the unmodified reference Zencoder (architecture.py:154-207)."""
+    import warnings
+    from . import zencoder_oracle as zo
+    sd = synth.make_state_dict(64, 19, SD_SEED)
+    net = rh.build_reference_generator(sd, 64, 256)
+    for name, S, B, kind in (("zencoder_c64_b2", 64, 2, "blocky"), ("zencoder_c256_b1", 256, 1, "blocky")):
+        img = synth.make_image(B, S)
+        labels = synth.make_labels(B, S, kind, LABEL_SEED)
+        if S == 64:
+            labels[1, :, :] = 3          # image 1: two classes only -> 17 absent rows
+            labels[1, :20, :] = 11
+        with warnings.catch_warnings(), torch.no_grad():
+            warnings.simplefilter("ignore")
+            ref = net.Zencoder(input=img, segmap=so.one_hot(labels))
+        mine = zo.zencoder_forward(sd, img, labels)
+        print("%s: max|oracle-ref| = %.3e  max|ref| = %.3f  zero rows %d" %
+              (name, float((mine - ref).abs().max()), float(ref.abs().max()), int((ref.abs().sum(2) == 0).sum())))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), labels=labels.numpy(), out=ref.numpy(), crop=S)
+
+
 if __name__ == "__main__":
-    if "--ct-only" not in sys.argv:
+    if "--ct-only" in sys.argv:
+        main_ct()
+    elif "--zencoder-only" in sys.argv:
+        main_zencoder()
+    else:
         main()
-    main_ct()
+        main_ct()
+        main_zencoder()

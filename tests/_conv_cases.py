@@ -25,7 +25,10 @@ def ref_accumulate(segs):
         taps = s.get("taps", 9)
         x = a[..., off:off + C].float().permute(0, 3, 1, 2)
         w = s["w"]
-        pad = 1 if taps == 9 else 0
+        pad = (1 if taps == 9 else 0) - s.get("a_pad", 0)  # an explicit border replaces the implicit zero pad
+        if pad < 0:
+            x = x[:, :, -pad:pad, -pad:pad]
+            pad = 0
         if w.dim() == 3:
             y = torch.cat([F.conv2d(x[b:b + 1], _w_to_conv(w[b], taps, C), padding=pad) for b in range(x.shape[0])])
         else:
@@ -151,6 +154,19 @@ def make_cases(device="cuda"):
     plain_case("plain_deep_k_c1024", 1, 16, 16, [(1024, 0, 1024, 9, False)], 256, 256, out_dtype=torch.float32, seed=8)
     plain_case("plain_chan_window", 2, 16, 16, [(384, 128, 128, 9, False)], 128, 128, seed=9)
     plain_case("plain_ragged_24x20", 2, 24, 20, [(64, 0, 64, 9, False)], 64, 64, seed=10)
+    def padded_case(name, B, H, W, C, N, BN, seed):
+        def run(impl):
+            gen = torch.Generator().manual_seed(3000 + seed)
+            a = _rand(gen, (B, H + 2, W + 2, C), 1.0, device=device)  # e.g. a reflection-padded map
+            w = _rand(gen, (N, 9 * C), (1.0 / (9 * C)) ** 0.5, device=device)
+            bias = _rand(gen, (N,), 0.5, torch.float32, device)
+            segs = [dict(a=a, w=w, C=C, taps=9, a_pad=1)]
+            got = ops.conv_igemm(segs, N, BN, bias=bias, act=ops.ACT_TANH, out_dtype=torch.float32, impl=impl)
+            return got.float().permute(0, 3, 1, 2), ref_plain(segs, N, bias, False, ops.ACT_TANH)
+        cases.append((name, run))
+
+    padded_case("plain_explicit_border_c128_n256", 2, 32, 32, 128, 256, 256, 1)
+    padded_case("plain_explicit_border_c64_n64_wstat", 2, 16, 24, 64, 64, 64, 2)
     plain_case("plain_per_image_w_1x1", 5, 1, 24, [(512, 0, 512, 1, True)], 512, 256, tile=(24, 1, 1),
                act=ops.ACT_RELU, seed=11)
     plain_case("plain_tb4_rows", 6, 1, 19, [(512, 0, 512, 1, False)], 256, 256, tile=(32, 1, 4), use_bias=False,

@@ -27,7 +27,7 @@ def test_header_symbols_exported(lib):
 
 def test_struct_sizes_match_header(lib):
     # chb_conv_seg: 2 pointers, 4 int64, 5 ints (+pad); guards against silent ABI drift of the ctypes mirror
-    assert C.sizeof(_lib.ConvSeg) == 72
+    assert C.sizeof(_lib.ConvSeg) == 80
     assert C.sizeof(_lib.GenConfig) == 20
 
 

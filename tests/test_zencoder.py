@@ -1,0 +1,48 @@
+"""Style encoder (Zencoder): oracle vs the reference's golden vectors (CPU), CUDA vs oracle/golden (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ctrlhair_b200 import synth
+from oracle import zencoder_oracle as zo
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _case(name, S, B):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    return synth.make_image(B, S), torch.from_numpy(g["labels"]), torch.from_numpy(g["out"])
+
+
+@pytest.mark.parametrize("name,S,B", [("zencoder_c64_b2", 64, 2), ("zencoder_c256_b1", 256, 1)])
+def test_zencoder_oracle_matches_reference_golden(synthetic_sd, name, S, B):
+    img, labels, gold = _case(name, S, B)
+    out = zo.zencoder_forward(synthetic_sd, img, labels)
+    assert float((out - gold).abs().max()) < 2e-5
+    if S == 64:  # image 1 has two classes: the other 17 rows are exactly zero (architecture.py:197-204)
+        assert int((gold[1].abs().sum(1) == 0).sum()) == 17
+        assert int((out[1].abs().sum(1) == 0).sum()) == 17
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,S,B", [("zencoder_c64_b2", 64, 2), ("zencoder_c256_b1", 256, 1)])
+def test_zencoder_cuda_matches_oracle_and_golden(synthetic_sd, name, S, B):
+    from ctrlhair_b200.zencoder import ZencoderB200
+    img, labels, gold = _case(name, S, B)
+    enc = ZencoderB200(crop=S, max_batch=B).load_state_dict(synthetic_sd)
+    out = enc(img.cuda(), labels.cuda()).cpu()
+    ref = zo.zencoder_forward(synthetic_sd, img, labels)
+    for want in (ref, gold):
+        d = out - want
+        # fp16 tensor-core operands after four InstanceNorms: same budget as the generator
+        assert float(d.norm() / want.norm()) < 2e-3, float(d.norm() / want.norm())
+        assert float(d.abs().max() / want.abs().max()) < 5e-3, float(d.abs().max() / want.abs().max())
+    assert torch.equal(out.abs().sum(2) == 0, gold.abs().sum(2) == 0)  # absent classes: exactly zero rows
+    # reference signature with a one-hot segmap, and the host-buffer entry point
+    from oracle import sean_oracle as so
+    out2 = enc(img.cuda(), so.one_hot(labels).cuda()).cpu()
+    assert torch.equal(out, out2)
+    out3 = enc.forward_host(img.numpy(), labels.numpy())
+    assert torch.equal(out, out3)

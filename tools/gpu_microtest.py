@@ -36,7 +36,7 @@ def child(start):
 def master():
     start = 0
     import _conv_cases  # noqa: F401  (import check only; needs torch)
-    n = 15
+    n = len(_conv_cases.make_cases(device="cpu"))
     while start < n:
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "--from", str(start)], capture_output=True,
                            text=True, timeout=900)
