@@ -42,7 +42,9 @@ def test_zencoder_cuda_matches_oracle_and_golden(synthetic_sd, name, S, B):
     assert torch.equal(out.abs().sum(2) == 0, gold.abs().sum(2) == 0)  # absent classes: exactly zero rows
     # reference signature with a one-hot segmap, and the host-buffer entry point
     from oracle import sean_oracle as so
+    # (InstanceNorm statistics and the region sums are accumulated with atomics: run-to-run differences are at
+    # fp32 round-off, not bitwise zero)
     out2 = enc(img.cuda(), so.one_hot(labels).cuda()).cpu()
-    assert torch.equal(out, out2)
+    assert float((out - out2).abs().max()) < 1e-4
     out3 = enc.forward_host(img.numpy(), labels.numpy())
-    assert torch.equal(out, out3)
+    assert float((out - out3).abs().max()) < 1e-4
