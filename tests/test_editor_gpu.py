@@ -1,0 +1,44 @@
+"""The reference-facing facade (Pix2PixModel.forward modes, HairEditor.gen_img / get_code) on the GPU path."""
+import pytest
+import torch
+
+from ctrlhair_b200 import synth
+from oracle import sean_oracle as so
+from oracle import zencoder_oracle as zo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def editor(synthetic_sd):
+    from ctrlhair_b200.editor import HairEditorB200
+    gen = torch.Generator().manual_seed(77)
+    median = torch.randn((19, 512), generator=gen) * 0.135
+    return HairEditorB200(synthetic_sd, median_codes=median, img_size=64), median
+
+
+def test_gen_img_uses_median_for_zero_rows(synthetic_sd, editor):
+    ed, median = editor
+    labels = synth.make_labels(1, 64, "blocky")
+    code = synth.make_codes(1)
+    code[0, 4] = 0  # an all-zero row means "use the median default" (hair_editor.py:165-168)
+    code[0, 13] = 0
+    noise = synth.make_noise(1, 64)
+    img = ed.gen_img(code, labels[:, None].numpy(), noise=synth.flatten_noise(noise)).cpu()
+    eff = code.clone()
+    eff[0, 4], eff[0, 13] = median[4], median[13]
+    ref = so.generator_forward(synthetic_sd, labels, eff, noise)[0]
+    assert img.shape == (3, 64, 64)
+    assert float((img - ref).norm() / ref.norm()) < 1e-3
+
+
+def test_style_code_mode_and_invalid_mode(synthetic_sd, editor):
+    ed, _ = editor
+    img = synth.make_image(1, 64)
+    labels = synth.make_labels(1, 64, "blocky")
+    codes = ed.get_code(img.numpy(), labels[:, None].numpy()).cpu()
+    ref = zo.zencoder_forward(synthetic_sd, img, labels)
+    assert codes.shape == (1, 19, 512)
+    assert float((codes - ref).norm() / ref.norm()) < 2e-3
+    with pytest.raises(ValueError):
+        ed.sean_model({"label": labels[:, None].float(), "image": img}, mode="generator")
