@@ -61,6 +61,10 @@ class ZencConfig(C.Structure):
     _fields_ = [("crop", C.c_int), ("label_nc", C.c_int), ("max_batch", C.c_int)]
 
 
+class ShapeConfig(C.Structure):
+    _fields_ = [("crop", C.c_int), ("max_batch", C.c_int)]
+
+
 EPI_PLAIN, EPI_MODULATE = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 F16, F32 = 0, 1
@@ -110,6 +114,16 @@ SYMBOLS = [
     ("chb_zencoder_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("chb_zencoder_forward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_zencoder_forward_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_shape_create", C.c_int, [C.POINTER(ShapeConfig), C.POINTER(C.c_void_p)]),
+    ("chb_shape_destroy", None, [C.c_void_p]),
+    ("chb_shape_num_tensors", C.c_int, [C.c_void_p]),
+    ("chb_shape_tensor_info", C.c_int,
+     [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    ("chb_shape_blob_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_shape_workspace_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_shape_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("chb_shape_encode", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_shape_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 ]
 
 

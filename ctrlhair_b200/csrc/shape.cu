@@ -1,0 +1,502 @@
+// Shape branch generator (mask encoders / decoders): shape_branch/model.py:69-199, layers from
+// my_torchlib/module.py (Conv2dBlock :67-137, custom LayerNorm :177-205, LinearBlock :16-64).
+//
+// Every convolution and both fully-connected layers run on the tcgen05 implicit-GEMM kernel:
+//   * encoder conv4x4 stride 2 pad 1  ==  conv3x3 stride 1 pad 1 over the space-to-depth map [H/2, W/2, 4C]
+//     (input row 2y-1+ky lives in block row y-1 / y / y / y+1 with parity 1 / 0 / 1 / 0); the packer scatters the 16
+//     taps into the 9 x 4 (tap, parity) slots and leaves the impossible combinations zero
+//   * decoder [nearest up2, conv3x3]: the LayerNorm-apply kernel writes the upsampled fp16 map the conv reads
+//   * fc layers are 1x1 "convs" over a [1, B] image; the packer permutes their rows/columns between the reference's
+//     NCHW flatten order and the NHWC order used here
+// LayerNorm (per-sample mean / UNBIASED std over C*H*W, (x-mean)/(std+eps)*gamma_c+beta_c) + LeakyReLU(0.2) is a
+// statistics kernel (double accumulation) plus an apply kernel that also produces the next conv's layout.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ctrlhair_b200.h"
+#include "conv_igemm.cuh"
+
+namespace chb {
+
+constexpr int kPosCh = 40;  // 4 * pos_encoding_order (shape_branch/config.py:20, model.py:18-30)
+
+// positional embedding table fp16 [S][S][40]: channel k < 20: sin(2^(k/2) pi c), else cos; even k -> x, odd k -> y
+// (np.meshgrid(c, c) stacks [x-grid, y-grid]; gamma1 = sin(nums * bi) reshaped to [-1, S, S] -> channel = 2*o + axis)
+__global__ void shape_pos_kernel(__half* pos, int S) {
+  const long long total = (long long)S * S * kPosCh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kPosCh);
+    const int x = (int)((i / kPosCh) % S);
+    const int y = (int)(i / ((long long)kPosCh * S));
+    const int kk = k % 20;
+    const int order = kk / 2, axis = kk % 2;
+    const double c = (double)(axis == 0 ? x : y) / (double)S;
+    const double arg = ldexp(3.14159265358979323846, order) * c;
+    const float v = (float)(k < 20 ? sin(arg) : cos(arg));
+    pos[i] = __float2half_rn(v);
+  }
+}
+
+// layer-0 encoder input: mask fp32 NCHW [B,Cm,S,S] ++ pos -> space-to-depth fp16 [B, S/2, S/2, Cpad],
+// channel = (py*2+px) * (Cm+40) + c; channels >= 4*(Cm+40) are zero padding.
+__global__ void shape_prep_kernel(const float* __restrict__ mask, const __half* __restrict__ pos, __half* __restrict__ out,
+                                  int B, int Cm, int S, int Cpad) {
+  const int Cin = Cm + kPosCh, Hh = S / 2;
+  const long long total = (long long)B * Hh * Hh * Cpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % Cpad);
+    long long p = i / Cpad;
+    const int bx = (int)(p % Hh);
+    p /= Hh;
+    const int by = (int)(p % Hh);
+    const int b = (int)(p / Hh);
+    __half v = __float2half_rn(0.f);
+    if (ch < 4 * Cin) {
+      const int par = ch / Cin, c = ch % Cin;
+      const int y = 2 * by + (par >> 1), x = 2 * bx + (par & 1);
+      v = c < Cm ? __float2half_rn(mask[(((long long)b * Cm + c) * S + y) * S + x])
+                 : pos[((long long)y * S + x) * kPosCh + (c - Cm)];
+    }
+    out[i] = v;
+  }
+}
+
+// per-sample sum / sum of squares over all n elements (double)
+__global__ void ln_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, long long n) {
+  const int b = blockIdx.y;
+  const float* xb = x + (long long)b * n;
+  double d1 = 0.0, d2 = 0.0;
+  float s1 = 0.f, s2 = 0.f;
+  int cnt = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = xb[i];
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+    if (++cnt == 32) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+  }
+  d1 += s1; d2 += s2;
+  for (int o = 16; o > 0; o >>= 1) {
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[b * 2], d1);
+    atomicAdd(&sums[b * 2 + 1], d2);
+  }
+}
+
+// y = lrelu(((x - mean) / (std + eps)) * gamma_c + beta_c)   (norm = 1)   or   y = x  (norm = 0, the decoder fc output)
+// x fp32 NHWC [B,H,W,C] -> fp16:  mode 0 plain [B,H,W,C];  mode 1 space-to-depth [B,H/2,W/2,4C];
+//                                 mode 2 nearest upsample x2 [B,2H,2W,C]
+__global__ void ln_apply_kernel(const float* __restrict__ x, const double* __restrict__ sums,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out,
+                                int B, int H, int W, int C, int mode, int norm) {
+  const long long n = (long long)H * W * C;
+  const long long total = (long long)B * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int xx = (int)(p % W);
+    p /= W;
+    const int yy = (int)(p % H);
+    const int b = (int)(p / H);
+    float v = x[i];
+    if (norm) {
+      const double mean = sums[b * 2] / (double)n;
+      const double var = (sums[b * 2 + 1] - (double)n * mean * mean) / (double)(n - 1);  // unbiased (torch.std)
+      const float inv = (float)(1.0 / (sqrt(var > 0.0 ? var : 0.0) + 1e-5));
+      v = (v - (float)mean) * inv * gamma[c] + beta[c];
+      v = v > 0.f ? v : 0.2f * v;
+    }
+    const __half h = __float2half_rn(v);
+    if (mode == 0) {
+      out[i] = h;
+    } else if (mode == 1) {
+      const int par = (yy & 1) * 2 + (xx & 1);
+      out[(((long long)b * (H / 2) + (yy >> 1)) * (W / 2) + (xx >> 1)) * (4LL * C) + (long long)par * C + c] = h;
+    } else {
+      const long long o = (((long long)b * 2 * H + 2 * yy) * 2 * W + 2 * xx) * C + c;
+      out[o] = h;
+      out[o + C] = h;
+      out[o + 2LL * W * C] = h;
+      out[o + 2LL * W * C + C] = h;
+    }
+  }
+}
+
+// code fp32 [B, K] -> fp16 [B, Kpad] (zero padded): decoder fc input
+__global__ void code_pad_kernel(const float* __restrict__ a, int Ka, const float* __restrict__ b2, int Kb,
+                                __half* __restrict__ out, int B, int Kpad) {
+  const long long total = (long long)B * Kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    const int b = (int)(i / Kpad);
+    float v = 0.f;
+    if (k < Ka) v = a[(long long)b * Ka + k];
+    else if (k < Ka + Kb) v = b2[(long long)b * Kb + (k - Ka)];
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// mask = softmax([face[:13], hair, face[13:]])  (model.py:184-187) -> fp32 NCHW [B,19,S,S]
+__global__ void shape_softmax_kernel(const float* __restrict__ hair /*[B,S,S,16]*/, const float* __restrict__ face
+                                     /*[B,S,S,32]*/, float* __restrict__ out, int B, int S) {
+  const long long total = (long long)B * S * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float l[19];
+    const float* f = face + i * 32;
+#pragma unroll
+    for (int k = 0; k < 13; ++k) l[k] = f[k];
+    l[13] = hair[i * 16];
+#pragma unroll
+    for (int k = 13; k < 18; ++k) l[k + 1] = f[k];
+    float m = l[0];
+#pragma unroll
+    for (int k = 1; k < 19; ++k) m = fmaxf(m, l[k]);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+      l[k] = expf(l[k] - m);
+      s += l[k];
+    }
+    const float inv = 1.f / s;
+    const long long b = i / ((long long)S * S), pix = i % ((long long)S * S);
+#pragma unroll
+    for (int k = 0; k < 19; ++k) out[(b * 19 + k) * (long long)S * S + pix] = l[k] * inv;
+  }
+}
+
+static int sgrid(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 16;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+struct STensor {
+  std::string name;
+  int64_t offset, nbytes;
+  int dtype;
+};
+
+struct NetLayout {
+  int w[8], b[8], g[8], be[8];  // conv weights / bias / LN gamma / beta per layer (enc: 0..6; dec: 0..6 + out conv at 7)
+  int fcw, fcb;
+};
+
+}  // namespace chb
+
+using namespace chb;
+
+struct chb_shape {
+  chb_shape_config cfg;
+  std::vector<STensor> tensors;
+  int64_t blob_bytes = 0, ws_bytes = 0;
+  NetLayout enc[2], dec[2];  // 0 = hair, 1 = face
+  int64_t ws_pos, ws_in, ws_conv, ws_act, ws_feat, ws_fcout, ws_code16, ws_logit[2], ws_sums, ws_io;
+  const uint8_t* blob = nullptr;
+  uint8_t* ws = nullptr;
+  bool pos_ready = false;
+  std::map<int, std::vector<ConvPlan>> enc_plans[2], dec_plans[2];
+};
+
+namespace chb {
+static const int kEncCm[2] = {1, 18};
+static const int kEncPad0[2] = {192, 256};   // 4*(Cm+40) rounded up to a multiple of 64
+static const int kEncOut[2] = {32, 1024};    // hair: mean(16) ++ std(16); face: 1024
+static const int kDecIn[2] = {1088, 1024};   // hair decoder input 1024+16 padded to a multiple of 64
+static const int kDecOutRows[2] = {16, 32};  // out conv rows (1 / 18 valid)
+
+static int sadd(chb_shape* z, const std::string& name, int64_t nbytes, int dtype) {
+  STensor t{name, z->blob_bytes, nbytes, dtype};
+  z->tensors.push_back(t);
+  z->blob_bytes += (nbytes + 255) / 256 * 256;
+  return (int)z->tensors.size() - 1;
+}
+static int64_t sws(chb_shape* z, int64_t n) {
+  const int64_t o = z->ws_bytes;
+  z->ws_bytes += (n + 1023) / 1024 * 1024;
+  return o;
+}
+static int enc_cout(int i) { return 32 << i > 2048 ? 2048 : 32 << i; }
+static int dec_cout(int i) { return 32 << (6 - i) > 2048 ? 2048 : 32 << (6 - i); }
+
+static chb_conv_desc conv_desc(int B, int H, int W, const void* a, int C, const void* w, const float* bias, int N, int BN,
+                               void* out) {
+  chb_conv_desc d;
+  memset(&d, 0, sizeof d);
+  d.B = B; d.H = H; d.W = W;
+  d.TW = W < 8 ? W : 8;
+  d.TH = H < 16 ? H : 16;
+  d.TB = 1;
+  d.nseg = 1;
+  chb_conv_seg& s = d.seg[0];
+  s.a = a; s.Ca = C; s.C = C; s.taps = 9; s.w = w;
+  s.a_sx = C; s.a_sy = (int64_t)W * C; s.a_sb = (int64_t)H * W * C;
+  d.N = d.Nrows = N; d.BN = BN;
+  d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE; d.bias = bias;
+  d.out = out; d.out_dtype = CHB_F32;
+  d.o_sn = 1; d.o_sx = N; d.o_sy = (int64_t)W * N; d.o_sb = (int64_t)H * W * N;
+  return d;
+}
+static chb_conv_desc fc_desc(int B, const void* a, int K, const void* w, const float* bias, int N, int BN, void* out) {
+  chb_conv_desc d;
+  memset(&d, 0, sizeof d);
+  d.B = 1; d.H = 1; d.W = B;
+  d.TW = B >= 128 ? 128 : (B + 7) / 8 * 8; d.TH = 1; d.TB = 1;
+  d.nseg = 1;
+  chb_conv_seg& s = d.seg[0];
+  s.a = a; s.Ca = K; s.C = K; s.taps = 1; s.w = w;
+  s.a_sx = K; s.a_sy = (int64_t)B * K; s.a_sb = (int64_t)B * K;
+  d.N = d.Nrows = N; d.BN = BN;
+  d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE; d.bias = bias;
+  d.out = out; d.out_dtype = CHB_F32;
+  d.o_sn = 1; d.o_sx = N; d.o_sy = 0; d.o_sb = 0;
+  return d;
+}
+static const void* bp(const chb_shape* z, int t) { return z->blob + z->tensors[t].offset; }
+static const float* bpf(const chb_shape* z, int t) { return reinterpret_cast<const float*>(z->blob + z->tensors[t].offset); }
+
+static int build_enc_plans(chb_shape* z, int net, int B, std::vector<ConvPlan>& plans) {
+  const int S = z->cfg.crop;
+  plans.resize(8);
+  int cin = kEncPad0[net];
+  for (int i = 0; i < 7; ++i) {
+    const int Hh = (S / 2) >> i, co = enc_cout(i);
+    // layer i reads the space-to-depth map [B,Hh,Hh,cin] and writes fp32 [B,Hh,Hh,co]
+    chb_conv_desc d = conv_desc(B, Hh, Hh, z->ws + (i == 0 ? z->ws_in : z->ws_act), cin, bp(z, z->enc[net].w[i]),
+                                bpf(z, z->enc[net].b[i]), co, co < 256 ? co : 256, z->ws + z->ws_conv);
+    int rc = build_conv_plan(d, &plans[i]);
+    if (rc != CHB_OK) return rc;
+    cin = 4 * co;
+  }
+  chb_conv_desc f = fc_desc(B, z->ws + z->ws_feat, 8192, bp(z, z->enc[net].fcw), bpf(z, z->enc[net].fcb), kEncOut[net],
+                            kEncOut[net] < 256 ? kEncOut[net] : 256, z->ws + z->ws_fcout);
+  return build_conv_plan(f, &plans[7]);
+}
+
+static int build_dec_plans(chb_shape* z, int net, int B, std::vector<ConvPlan>& plans) {
+  const int S = z->cfg.crop;
+  plans.resize(9);
+  chb_conv_desc f = fc_desc(B, z->ws + z->ws_code16, kDecIn[net], bp(z, z->dec[net].fcw), bpf(z, z->dec[net].fcb), 8192,
+                            256, z->ws + z->ws_fcout);
+  int rc = build_conv_plan(f, &plans[0]);
+  if (rc != CHB_OK) return rc;
+  int cin = 2048;
+  for (int i = 0; i < 7; ++i) {
+    const int r = 4 << i, co = dec_cout(i);
+    chb_conv_desc d = conv_desc(B, r, r, z->ws + z->ws_act, cin, bp(z, z->dec[net].w[i]), bpf(z, z->dec[net].b[i]), co,
+                                co < 256 ? co : 256, z->ws + z->ws_conv);
+    if ((rc = build_conv_plan(d, &plans[1 + i])) != CHB_OK) return rc;
+    cin = co;
+  }
+  chb_conv_desc o = conv_desc(B, S, S, z->ws + z->ws_act, 32, bp(z, z->dec[net].w[7]), bpf(z, z->dec[net].b[7]),
+                              kDecOutRows[net], kDecOutRows[net], z->ws + z->ws_logit[net]);
+  return build_conv_plan(o, &plans[8]);
+}
+
+static void ln(chb_shape* z, cudaStream_t st, int B, int H, int W, int C, const float* gamma, const float* beta,
+               __half* out, int mode, int norm) {
+  const float* x = reinterpret_cast<const float*>(z->ws + (norm == 2 ? z->ws_fcout : z->ws_conv));
+  double* sums = reinterpret_cast<double*>(z->ws + z->ws_sums);
+  const long long n = (long long)H * W * C;
+  if (norm == 1) {
+    cudaMemsetAsync(sums, 0, (size_t)B * 2 * sizeof(double), st);
+    long long blocks = (n + 256 * 64 - 1) / (256 * 64);
+    if (blocks > 256) blocks = 256;
+    ln_stats_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, st>>>(x, sums, n);
+  }
+  ln_apply_kernel<<<sgrid((long long)B * n, 256), 256, 0, st>>>(x, sums, gamma, beta, out, B, H, W, C, mode,
+                                                                norm == 1 ? 1 : 0);
+}
+}  // namespace chb
+
+extern "C" {
+
+int chb_shape_create(const chb_shape_config* cfg, chb_shape** out) {
+  if (!cfg || !out || cfg->crop != 256 || cfg->max_batch <= 0) {
+    set_error("chb_shape_create: need crop == 256 (the reference's fixed mask size) and max_batch > 0");
+    return CHB_ERR_ARG;
+  }
+  chb_shape* z = new chb_shape();
+  z->cfg = *cfg;
+  const char* nm[2] = {"hair", "face"};
+  for (int net = 0; net < 2; ++net) {
+    int cin = kEncPad0[net];
+    const std::string p = std::string(nm[net]) + "_encoder.";
+    for (int i = 0; i < 7; ++i) {
+      const int co = enc_cout(i);
+      z->enc[net].w[i] = sadd(z, p + std::to_string(i) + ".w", (int64_t)co * 9 * cin * 2, CHB_F16);
+      z->enc[net].b[i] = sadd(z, p + std::to_string(i) + ".b", (int64_t)co * 4, CHB_F32);
+      z->enc[net].g[i] = sadd(z, p + std::to_string(i) + ".gamma", (int64_t)co * 4, CHB_F32);
+      z->enc[net].be[i] = sadd(z, p + std::to_string(i) + ".beta", (int64_t)co * 4, CHB_F32);
+      cin = 4 * co;
+    }
+    z->enc[net].fcw = sadd(z, p + "fc.w", (int64_t)kEncOut[net] * 8192 * 2, CHB_F16);
+    z->enc[net].fcb = sadd(z, p + "fc.b", (int64_t)kEncOut[net] * 4, CHB_F32);
+  }
+  for (int net = 0; net < 2; ++net) {
+    const std::string p = std::string(nm[net]) + "_decoder.";
+    z->dec[net].fcw = sadd(z, p + "fc.w", (int64_t)8192 * kDecIn[net] * 2, CHB_F16);
+    z->dec[net].fcb = sadd(z, p + "fc.b", (int64_t)8192 * 4, CHB_F32);
+    int cin = 2048;
+    for (int i = 0; i < 7; ++i) {
+      const int co = dec_cout(i);
+      z->dec[net].w[i] = sadd(z, p + std::to_string(i) + ".w", (int64_t)co * 9 * cin * 2, CHB_F16);
+      z->dec[net].b[i] = sadd(z, p + std::to_string(i) + ".b", (int64_t)co * 4, CHB_F32);
+      z->dec[net].g[i] = sadd(z, p + std::to_string(i) + ".gamma", (int64_t)co * 4, CHB_F32);
+      z->dec[net].be[i] = sadd(z, p + std::to_string(i) + ".beta", (int64_t)co * 4, CHB_F32);
+      cin = co;
+    }
+    z->dec[net].w[7] = sadd(z, p + "out.w", (int64_t)kDecOutRows[net] * 9 * 32 * 2, CHB_F16);
+    z->dec[net].b[7] = sadd(z, p + "out.b", (int64_t)kDecOutRows[net] * 4, CHB_F32);
+  }
+  const int64_t B = cfg->max_batch, S = cfg->crop;
+  z->ws_pos = sws(z, S * S * kPosCh * 2);
+  z->ws_in = sws(z, B * (S / 2) * (S / 2) * 256 * 2);
+  z->ws_conv = sws(z, B * S * S * 32 * 4);          // largest fp32 conv output: 256x256x32 (== 128x128x32x... all smaller)
+  z->ws_act = sws(z, B * S * S * 32 * 2 * 2);       // largest fp16 activation: 256x256x32 plain / 128x128x64 upsampled
+  z->ws_feat = sws(z, B * 8192 * 2);
+  z->ws_fcout = sws(z, B * 8192 * 4);
+  z->ws_code16 = sws(z, B * 1088 * 2);
+  z->ws_logit[0] = sws(z, B * S * S * 16 * 4);
+  z->ws_logit[1] = sws(z, B * S * S * 32 * 4);
+  z->ws_sums = sws(z, B * 2 * 8);
+  z->ws_io = sws(z, B * 19 * S * S * 4);
+  *out = z;
+  return CHB_OK;
+}
+
+void chb_shape_destroy(chb_shape* z) { delete z; }
+int chb_shape_num_tensors(const chb_shape* z) { return z ? (int)z->tensors.size() : 0; }
+int chb_shape_tensor_info(const chb_shape* z, int i, char* name, int cap, int64_t* offset, int64_t* nbytes, int* dtype) {
+  if (!z || i < 0 || i >= (int)z->tensors.size()) {
+    set_error("chb_shape_tensor_info: index out of range");
+    return CHB_ERR_ARG;
+  }
+  const STensor& t = z->tensors[i];
+  if (name && cap > 0) snprintf(name, cap, "%s", t.name.c_str());
+  if (offset) *offset = t.offset;
+  if (nbytes) *nbytes = t.nbytes;
+  if (dtype) *dtype = t.dtype;
+  return CHB_OK;
+}
+int64_t chb_shape_blob_bytes(const chb_shape* z) { return z ? z->blob_bytes : 0; }
+int64_t chb_shape_workspace_bytes(const chb_shape* z) { return z ? z->ws_bytes : 0; }
+
+int chb_shape_bind(chb_shape* z, const void* blob, void* workspace) {
+  if (!z || !blob || !workspace || (reinterpret_cast<uintptr_t>(blob) & 255) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 1023)) {
+    set_error("chb_shape_bind: NULL or misaligned pointers (blob 256 B, workspace 1024 B)");
+    return CHB_ERR_ARG;
+  }
+  int rc = chb_check_device();
+  if (rc != CHB_OK) return rc;
+  z->blob = reinterpret_cast<const uint8_t*>(blob);
+  z->ws = reinterpret_cast<uint8_t*>(workspace);
+  for (int n = 0; n < 2; ++n) {
+    z->enc_plans[n].clear();
+    z->dec_plans[n].clear();
+  }
+  shape_pos_kernel<<<sgrid((long long)z->cfg.crop * z->cfg.crop * kPosCh, 256), 256>>>(
+      reinterpret_cast<__half*>(z->ws + z->ws_pos), z->cfg.crop);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    set_error(std::string("chb_shape_bind: positional table kernel failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+// net: 0 = hair encoder (mask [B,1,S,S] -> out [B,32] = mean(16) ++ |std|(16)), 1 = face encoder ([B,18,S,S] -> [B,1024])
+int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B, void* stream_) {
+  if (!z || !mask || !out || !z->ws || net < 0 || net > 1 || B <= 0 || B > z->cfg.max_batch) {
+    set_error("chb_shape_encode: bad arguments or unbound object");
+    return CHB_ERR_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  auto it = z->enc_plans[net].find(B);
+  if (it == z->enc_plans[net].end()) {
+    std::vector<ConvPlan> pl;
+    int rc = build_enc_plans(z, net, B, pl);
+    if (rc != CHB_OK) return rc;
+    it = z->enc_plans[net].emplace(B, std::move(pl)).first;
+  }
+  const std::vector<ConvPlan>& pl = it->second;
+  const int S = z->cfg.crop;
+  shape_prep_kernel<<<sgrid((long long)B * (S / 2) * (S / 2) * kEncPad0[net], 256), 256, 0, st>>>(
+      mask, reinterpret_cast<const __half*>(z->ws + z->ws_pos), reinterpret_cast<__half*>(z->ws + z->ws_in), B,
+      kEncCm[net], S, kEncPad0[net]);
+  for (int i = 0; i < 7; ++i) {
+    int rc = launch_conv_plan(pl[i], CHB_IMPL_TCGEN05, st);
+    if (rc != CHB_OK) return rc;
+    const int Hh = (S / 2) >> i, co = enc_cout(i);
+    // layers 0..5 feed another 4x4/s2 conv (space-to-depth); layer 6 feeds the fc (plain NHWC flatten)
+    ln(z, st, B, Hh, Hh, co, bpf(z, z->enc[net].g[i]), bpf(z, z->enc[net].be[i]),
+       reinterpret_cast<__half*>(z->ws + (i < 6 ? z->ws_act : z->ws_feat)), i < 6 ? 1 : 0, 1);
+  }
+  int rc = launch_conv_plan(pl[7], CHB_IMPL_TCGEN05, st);
+  if (rc != CHB_OK) return rc;
+  cudaError_t err = cudaMemcpyAsync(out, z->ws + z->ws_fcout, (size_t)B * kEncOut[net] * 4, cudaMemcpyDeviceToDevice, st);
+  if (err != cudaSuccess) {
+    set_error(std::string("chb_shape_encode: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+// hair_code fp32 [B,16], face_code fp32 [B,1024] -> mask probabilities fp32 [B,19,S,S]  (model.py:195-199)
+int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_code, float* mask_out, int B,
+                     void* stream_) {
+  if (!z || !hair_code || !face_code || !mask_out || !z->ws || B <= 0 || B > z->cfg.max_batch) {
+    set_error("chb_shape_decode: bad arguments or unbound object");
+    return CHB_ERR_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  const int S = z->cfg.crop;
+  for (int net = 0; net < 2; ++net) {
+    auto it = z->dec_plans[net].find(B);
+    if (it == z->dec_plans[net].end()) {
+      std::vector<ConvPlan> pl;
+      int rc = build_dec_plans(z, net, B, pl);
+      if (rc != CHB_OK) return rc;
+      it = z->dec_plans[net].emplace(B, std::move(pl)).first;
+    }
+    const std::vector<ConvPlan>& pl = it->second;
+    // hair decoder input = cat([face_code, hair_code]) (model.py:175-178), face decoder input = face_code
+    code_pad_kernel<<<sgrid((long long)B * kDecIn[net], 256), 256, 0, st>>>(
+        face_code, 1024, hair_code, net == 0 ? 16 : 0, reinterpret_cast<__half*>(z->ws + z->ws_code16), B, kDecIn[net]);
+    int rc = launch_conv_plan(pl[0], CHB_IMPL_TCGEN05, st);
+    if (rc != CHB_OK) return rc;
+    // fc output [B,8192] is already NHWC [B,2,2,2048] (rows permuted by the packer): cast + upsample to 4x4
+    ln(z, st, B, 2, 2, 2048, nullptr, nullptr, reinterpret_cast<__half*>(z->ws + z->ws_act), 2, 2);
+    for (int i = 0; i < 7; ++i) {
+      if ((rc = launch_conv_plan(pl[1 + i], CHB_IMPL_TCGEN05, st)) != CHB_OK) return rc;
+      const int r = 4 << i, co = dec_cout(i);
+      ln(z, st, B, r, r, co, bpf(z, z->dec[net].g[i]), bpf(z, z->dec[net].be[i]),
+         reinterpret_cast<__half*>(z->ws + z->ws_act), i < 6 ? 2 : 0, 1);
+    }
+    if ((rc = launch_conv_plan(pl[8], CHB_IMPL_TCGEN05, st)) != CHB_OK) return rc;
+  }
+  shape_softmax_kernel<<<sgrid((long long)B * S * S, 256), 256, 0, st>>>(
+      reinterpret_cast<const float*>(z->ws + z->ws_logit[0]), reinterpret_cast<const float*>(z->ws + z->ws_logit[1]),
+      mask_out, B, S);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error(std::string("chb_shape_decode: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+}  // extern "C"

@@ -227,3 +227,62 @@ def make_image(B, S, seed=1250):
     low = torch.rand((B, 3, 8, 8), generator=gen) * 2 - 1
     img = torch.nn.functional.interpolate(low, size=(S, S), mode="bilinear", align_corners=False)
     return (img + 0.2 * torch.randn((B, 3, S, S), generator=gen)).clamp(-1, 1)
+
+
+def shape_shapes(hair_dim=16, order=10):
+    """Ordered {key: shape} of shape_branch.model.Generator.state_dict() (config 054: g_norm 'ln', VAE hair encoder)."""
+    s = {}
+    for name, cin, out_dim, vae in (("hair_encoder", 1, hair_dim, True), ("face_encoder", 18, 1024, False)):
+        c = cin + 4 * order
+        for i in range(7):
+            co = min(2048, 32 * 2 ** i)
+            s["%s.layers.%d.conv.weight" % (name, i)] = (co, c, 4, 4)
+            s["%s.layers.%d.conv.bias" % (name, i)] = (co,)
+            s["%s.layers.%d.norm.gamma" % (name, i)] = (co,)
+            s["%s.layers.%d.norm.beta" % (name, i)] = (co,)
+            c = co
+        s[name + ".out_layer.fc.weight"] = (out_dim, 8192)
+        s[name + ".out_layer.fc.bias"] = (out_dim,)
+        if vae:
+            s[name + ".std_out_layer.fc.weight"] = (out_dim, 8192)
+            s[name + ".std_out_layer.fc.bias"] = (out_dim,)
+    for name, in_dim, cout in (("hair_decoder", 1024 + hair_dim, 1), ("face_decoder", 1024, 18)):
+        s[name + ".in_layer.fc.weight"] = (8192, in_dim)
+        s[name + ".in_layer.fc.bias"] = (8192,)
+        c = 2048
+        for i in range(7):
+            co = min(32 * 2 ** (6 - i), 2048)
+            q = "%s.layers.%d." % (name, 2 * i + 1)
+            s[q + "conv.weight"] = (co, c, 3, 3)
+            s[q + "conv.bias"] = (co,)
+            s[q + "norm.gamma"] = (co,)
+            s[q + "norm.beta"] = (co,)
+            c = co
+        s[name + ".out_layer.conv.weight"] = (cout, c, 3, 3)
+        s[name + ".out_layer.conv.bias"] = (cout,)
+    return s
+
+
+def make_shape_state_dict(seed=1260):
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in shape_shapes().items():
+        if k.endswith("norm.gamma"):
+            sd[k] = torch.rand(shp, generator=gen) * 0.8 + 0.4
+        elif k.endswith("norm.beta"):
+            sd[k] = torch.randn(shp, generator=gen) * 0.1
+        elif k.endswith(".bias"):
+            sd[k] = torch.randn(shp, generator=gen) * 0.1
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            sd[k] = torch.randn(shp, generator=gen) * (1.4 / math.sqrt(fan_in))
+    return sd
+
+
+def make_shape_inputs(B, S=256, seed=1261):
+    """(hair one-hot [B,1,S,S], face one-hot [B,18,S,S]) from blocky labels, as shape_util.split_hair_face gives."""
+    labels = make_labels(B, S, "blocky", seed).long()
+    oh = torch.zeros((B, 19, S, S)).scatter_(1, labels[:, None], 1.0)
+    return oh[:, [13]], torch.cat([oh[:, :13], oh[:, 14:]], 1)

@@ -195,6 +195,31 @@ int chb_zencoder_forward(chb_zencoder* z, const float* img, const uint8_t* label
 int chb_zencoder_forward_host(chb_zencoder* z, const float* img_host, const uint8_t* labels_host, float* out_host,
                               int B, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The shape branch generator (shape_branch/model.py:146-199; HairEditor.mask_generator, hair_editor.py:96;
+ * call sites ui/backend.py:85-89,282-283,312,416-419).  Masks are fp32 NCHW one-hot planes as
+ * shape_util.split_hair_face (shape_util.py:23-26) produces them; crop is fixed at 256 like the reference.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int crop;       /* 256 */
+  int max_batch;
+} chb_shape_config;
+typedef struct chb_shape chb_shape;
+int chb_shape_create(const chb_shape_config* cfg, chb_shape** out);
+void chb_shape_destroy(chb_shape* z);
+int chb_shape_num_tensors(const chb_shape* z);
+int chb_shape_tensor_info(const chb_shape* z, int i, char* name, int name_cap, int64_t* offset, int64_t* nbytes,
+                          int* dtype);
+int64_t chb_shape_blob_bytes(const chb_shape* z);
+int64_t chb_shape_workspace_bytes(const chb_shape* z);
+int chb_shape_bind(chb_shape* z, const void* blob, void* workspace);
+/* net 0: hair encoder, mask [B,1,256,256] -> out [B,32] = mean(16) ++ raw std head(16) (model.py:102-107; the caller
+ * takes |.| of the second half); net 1: face encoder, mask [B,18,256,256] -> out [B,1024]. */
+int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B, void* stream);
+/* forward_decode_by_code (model.py:195-199): -> softmax mask fp32 [B,19,256,256]. */
+int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_code, float* mask_out, int B,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,8 +129,34 @@ def main_zencoder():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), labels=labels.numpy(), out=ref.numpy(), crop=S)
 
 
+def main_shape():
+    """Golden codes / masks from the unmodified reference shape Generator (shape_branch/model.py:146-199)."""
+    from . import shape_oracle as sho
+    sd = synth.make_shape_state_dict()
+    cfg = _ADict(hair_dim=16, g_norm="ln", vae_hair_mode=True, pos_encoding_order=10, total_batch_size=4,
+                 sample_batch_size=16)
+    with rh.reference_on_path():
+        from shape_branch.model import Generator
+        G = Generator(cfg)
+    G.load_state_dict(sd, strict=True)
+    G.eval()
+    hair, face = synth.make_shape_inputs(2)
+    with torch.no_grad():
+        hc = G.forward_hair_encoder(hair, testing=True)
+        fc = G.forward_face_encoder(face)
+        m = G.forward_decode_by_code(hc, fc)
+    ohc, ofc = sho.forward_hair_encoder(sd, hair), sho.forward_face_encoder(sd, face)
+    om = sho.forward_decode_by_code(sd, ohc, ofc)
+    print("shape: max|oracle-ref| hair %.2e face %.2e mask %.2e" %
+          (float((hc - ohc).abs().max()), float((fc - ofc).abs().max()), float((m - om).abs().max())))
+    np.savez_compressed(os.path.join(OUT, "shape_b2.npz"), hair_code=hc.numpy(), face_code=fc.numpy(),
+                        mask_argmax=m.argmax(1).to(torch.uint8).numpy(), mask_sub=m[:, :, ::8, ::8].numpy(), B=2)
+
+
 if __name__ == "__main__":
-    if "--ct-only" in sys.argv:
+    if "--shape-only" in sys.argv:
+        main_shape()
+    elif "--ct-only" in sys.argv:
         main_ct()
     elif "--zencoder-only" in sys.argv:
         main_zencoder()
@@ -138,3 +164,4 @@ if __name__ == "__main__":
         main()
         main_ct()
         main_zencoder()
+        main_shape()

@@ -1,0 +1,69 @@
+"""Shape branch nets: oracle vs the reference's golden vectors (CPU), CUDA vs oracle/golden (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ctrlhair_b200 import synth
+from oracle import shape_oracle as sho
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shape_b2.npz")
+
+
+@pytest.fixture(scope="module")
+def shape_sd():
+    return synth.make_shape_state_dict()
+
+
+def test_shape_oracle_matches_reference_golden(shape_sd):
+    g = np.load(GOLD)
+    hair, face = synth.make_shape_inputs(2)
+    hc, fc = sho.forward_hair_encoder(shape_sd, hair), sho.forward_face_encoder(shape_sd, face)
+    m = sho.forward_decode_by_code(shape_sd, hc, fc)
+    assert float((hc - torch.from_numpy(g["hair_code"])).abs().max()) < 2e-5
+    assert float((fc - torch.from_numpy(g["face_code"])).abs().max()) < 2e-5
+    assert float((m[:, :, ::8, ::8] - torch.from_numpy(g["mask_sub"])).abs().max()) < 2e-5
+    assert float((m.sum(1) - 1).abs().max()) < 1e-5
+    assert np.array_equal(m.argmax(1).to(torch.uint8).numpy(), g["mask_argmax"])
+
+
+def test_positional_embedding_matches_numpy_formula():
+    """shape_branch/model.py:18-30 restated; checked against the same numpy expression."""
+    n, order = 16, 3
+    c = np.linspace(0, 1, n, endpoint=False)
+    bi = np.stack(np.meshgrid(c, c), 0)[None]
+    nums = (2 ** np.arange(order) * np.pi)[:, None, None, None]
+    ref = np.concatenate([np.sin(nums * bi), np.cos(nums * bi)], 0).reshape(-1, n, n).astype(np.float32)
+    assert np.allclose(sho.pos_embedding(n, order).numpy(), ref, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_shape_cuda_matches_oracle_and_golden(shape_sd):
+    from ctrlhair_b200 import _lib
+    from ctrlhair_b200.shape import ShapeGeneratorB200
+    g = np.load(GOLD)
+    net = ShapeGeneratorB200(max_batch=2).load_state_dict(shape_sd)
+    hair, face = synth.make_shape_inputs(2)
+    hc = net.forward_hair_encoder(hair.cuda(), testing=True).cpu()
+    fc = net.forward_face_encoder(face.cuda()).cpu()
+    rh, rf = torch.from_numpy(g["hair_code"]), torch.from_numpy(g["face_code"])
+    # fp16 tensor-core operands through 7 LayerNorm'd conv layers
+    assert float((hc - rh).norm() / rh.norm()) < 3e-3, float((hc - rh).norm() / rh.norm())
+    assert float((fc - rf).norm() / rf.norm()) < 3e-3, float((fc - rf).norm() / rf.norm())
+    # decode from the *reference* codes so that encoder error does not leak into the decoder check
+    m = net.forward_decode_by_code(rh.cuda(), rf.cuda()).cpu()
+    ref = sho.forward_decode_by_code(shape_sd, rh, rf)
+    assert float((m.sum(1) - 1).abs().max()) < 1e-5
+    assert float((m - ref).abs().max()) < 5e-3, float((m - ref).abs().max())
+    agree = float((m.argmax(1) == ref.argmax(1)).float().mean())
+    assert agree > 0.995, agree
+    # VAE path returns (code, mean, std) like the reference (model.py:164-169)
+    code, mean, std = net.forward_hair_encoder(hair.cuda())
+    assert code.shape == (2, 16) and torch.equal(mean.cpu(), hc) and bool((std >= 0).all())
+    with pytest.raises(_lib.ChbError):
+        net.forward_face_encoder(face)  # host tensor
+    bad = dict(shape_sd)
+    bad.pop("face_decoder.out_layer.conv.bias")
+    with pytest.raises(RuntimeError):
+        ShapeGeneratorB200(max_batch=1).load_state_dict(bad)
