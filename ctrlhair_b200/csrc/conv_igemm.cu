@@ -96,11 +96,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const uint32_t tmem_base = *sm.tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) producer_role<WSTAT>(p, sm);
-    __syncwarp();
+    producer_role<WSTAT>(p, sm);
   } else if (warp == 1) {
-    if (lane == 0) mma_role<WSTAT>(p, sm, tmem_base);
-    __syncwarp();
+    mma_role<WSTAT>(p, sm, tmem_base);
   } else {
     epilogue_role<EPI, ACT, WSTAT>(p, sm, tmem_base, warp, lane);
   }

@@ -32,14 +32,20 @@ template <bool WSTAT>
 __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& sm) {
   const uint32_t nst = (uint32_t)p.nstages, nh = (uint32_t)p.nhalo;
   uint32_t stage = 0, phase = 0, hs = 0, hphase = 0;
+  // The whole warp executes these loops in lock step and one elected lane issues: loop state stays in uniform
+  // registers, which keeps the compiler from wrapping every TMA / mbarrier instruction in a per-thread loop.
   if (WSTAT) {
     const int n0 = ((int)blockIdx.x % p.n_tiles) * p.BN;
-    mbar_arrive_expect_tx(sm.wbar, (uint32_t)p.wstat_bytes);
+    if (elect_one()) mbar_arrive_expect_tx(sm.wbar, (uint32_t)p.wstat_bytes);
+    __syncwarp();
     for (int s = 0; s < p.nseg; ++s) {
       const SegK sg = p.seg[s];
       const uint32_t wbytes = (uint32_t)p.BN * (uint32_t)sg.kc * 2u;
-      for (int i = 0; i < sg.taps * sg.nchunk; ++i)
-        tma_load_3d(&p.tmW[s], sm.wstat_base + sg.wofs + (size_t)i * wbytes, sm.wbar, i * sg.kc, n0, 0);
+      for (int i = 0; i < sg.taps * sg.nchunk; ++i) {
+        if (elect_one())
+          tma_load_3d(&p.tmW[s], sm.wstat_base + sg.wofs + (size_t)i * wbytes, sm.wbar, i * sg.kc, n0, 0);
+        __syncwarp();
+      }
     }
   }
   for (uint32_t t = 0;; ++t) {
@@ -54,9 +60,12 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
         const int tg = sg.taps == 9 ? p.hg : 1;  // taps per weight stage
         for (int c = 0; c < sg.nchunk; ++c) {
           mbar_wait(&sm.hempty[hs], hphase ^ 1u);
-          mbar_arrive_expect_tx(&sm.hfull[hs], hbytes);
-          tma_load_4d(&p.tmH[s], sm.halo_base + (size_t)hs * p.halo_buf_bytes, &sm.hfull[hs], sg.ch_off + c * sg.kc,
-                      o.x0 - 1 + sg.xy_off, o.y0 - 1 + sg.xy_off, o.b0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&sm.hfull[hs], hbytes);
+            tma_load_4d(&p.tmH[s], sm.halo_base + (size_t)hs * p.halo_buf_bytes, &sm.hfull[hs], sg.ch_off + c * sg.kc,
+                        o.x0 - 1 + sg.xy_off, o.y0 - 1 + sg.xy_off, o.b0);
+          }
+          __syncwarp();
           if (++hs == nh) {
             hs = 0;
             hphase ^= 1u;
@@ -65,10 +74,13 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
           for (int t0 = 0; t0 < sg.taps; t0 += tg) {
             mbar_wait(&sm.empty[stage], phase ^ 1u);
             uint8_t* sb = sm.stage_base + (size_t)stage * p.stage_bytes + p.a_region;
-            mbar_arrive_expect_tx(&sm.full[stage], wbytes * (uint32_t)tg);
-            for (int g = 0; g < tg; ++g)
-              tma_load_3d(&p.tmW[s], sb + (size_t)g * wbytes, &sm.full[stage], ((t0 + g) * sg.nchunk + c) * sg.kc, o.n0,
-                          sg.per_image ? o.b0 : 0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&sm.full[stage], wbytes * (uint32_t)tg);
+              for (int g = 0; g < tg; ++g)
+                tma_load_3d(&p.tmW[s], sb + (size_t)g * wbytes, &sm.full[stage], ((t0 + g) * sg.nchunk + c) * sg.kc,
+                            o.n0, sg.per_image ? o.b0 : 0);
+            }
+            __syncwarp();
             if (++stage == nst) {
               stage = 0;
               phase ^= 1u;
@@ -83,11 +95,14 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
           for (int c = 0; c < sg.nchunk; ++c) {
             mbar_wait(&sm.empty[stage], phase ^ 1u);
             uint8_t* sa = sm.stage_base + (size_t)stage * p.stage_bytes;
-            mbar_arrive_expect_tx(&sm.full[stage], bytes);
-            tma_load_4d(&p.tmA[s], sa, &sm.full[stage], sg.ch_off + c * sg.kc, o.x0 + dx + sg.xy_off,
-                        o.y0 + dy + sg.xy_off, o.b0);
-            tma_load_3d(&p.tmW[s], sa + p.a_region, &sm.full[stage], (tap * sg.nchunk + c) * sg.kc, o.n0,
-                        sg.per_image ? o.b0 : 0);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&sm.full[stage], bytes);
+              tma_load_4d(&p.tmA[s], sa, &sm.full[stage], sg.ch_off + c * sg.kc, o.x0 + dx + sg.xy_off,
+                          o.y0 + dy + sg.xy_off, o.b0);
+              tma_load_3d(&p.tmW[s], sa + p.a_region, &sm.full[stage], (tap * sg.nchunk + c) * sg.kc, o.n0,
+                          sg.per_image ? o.b0 : 0);
+            }
+            __syncwarp();
             if (++stage == nst) {
               stage = 0;
               phase ^= 1u;
@@ -101,8 +116,10 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
 
 template <bool WSTAT>
 __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base) {
-  // This single thread feeds the tensor core: every instruction between two tcgen05.mma counts.  Descriptor high
-  // words are hoisted per segment, the K steps of a chunk go out in one asm block, tap offsets are tabulated.
+  // One elected lane feeds the tensor core, but the whole warp walks the loops in lock step so that descriptors and
+  // loop state live in uniform registers (code issued from a divergent `if (lane == 0)` region gets every tcgen05
+  // instruction wrapped in a per-thread "waterfall" loop, ~100 cycles per MMA).  Descriptor high words are hoisted
+  // per segment, the K steps of a chunk go out in one asm block, tap offsets advance incrementally.
   const uint32_t nst = (uint32_t)p.nstages, nh = (uint32_t)p.nhalo;
   const uint32_t idesc = umma_idesc_f16((uint32_t)p.BN);
   const uint32_t hw = (uint32_t)(p.TW + 2);
@@ -157,8 +174,11 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
             for (int g = 0; g < tg; ++g) {
               const uint64_t adesc = umma_desc_make(hiA, hb + voff);
               const uint64_t bdesc = umma_desc_make(hiB, sb);
-              if (k64) umma_f16_ss_k<4>(d_tmem, adesc, bdesc, idesc, accumulate);
-              else umma_f16_ss_k<2>(d_tmem, adesc, bdesc, idesc, accumulate);
+              if (elect_one()) {
+                if (k64) umma_f16_ss_k<4>(d_tmem, adesc, bdesc, idesc, accumulate);
+                else umma_f16_ss_k<2>(d_tmem, adesc, bdesc, idesc, accumulate);
+              }
+              __syncwarp();
               accumulate = 1;
               sb += bstep;
               // next tap: one pixel right, or to the start of the next halo row
@@ -170,14 +190,16 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
               }
             }
             if (!WSTAT) {
-              umma_commit(&sm.empty[stage]);
+              if (elect_one()) umma_commit(&sm.empty[stage]);
+              __syncwarp();
               if (++stage == nst) {
                 stage = 0;
                 phase ^= 1u;
               }
             }
           }
-          umma_commit(&sm.hempty[hs]);
+          if (elect_one()) umma_commit(&sm.hempty[hs]);
+          __syncwarp();
           if (++hs == nh) {
             hs = 0;
             hphase ^= 1u;
@@ -191,10 +213,13 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
           const uint32_t sa = stage_base + stage * stage_bytes;
           const uint64_t adesc = umma_desc_make(hiB, sa);
           const uint64_t bdesc = umma_desc_make(hiB, sa + a_region);
-          if (k64) umma_f16_ss_k<4>(d_tmem, adesc, bdesc, idesc, accumulate);
-          else umma_f16_ss_k<2>(d_tmem, adesc, bdesc, idesc, accumulate);
+          if (elect_one()) {
+            if (k64) umma_f16_ss_k<4>(d_tmem, adesc, bdesc, idesc, accumulate);
+            else umma_f16_ss_k<2>(d_tmem, adesc, bdesc, idesc, accumulate);
+            umma_commit(&sm.empty[stage]);
+          }
+          __syncwarp();
           accumulate = 1;
-          umma_commit(&sm.empty[stage]);
           if (++stage == nst) {
             stage = 0;
             phase ^= 1u;
@@ -202,7 +227,8 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
         }
       }
     }
-    umma_commit(&sm.tfull[acc]);
+    if (elect_one()) umma_commit(&sm.tfull[acc]);
+    __syncwarp();
   }
 }
 
