@@ -412,23 +412,28 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
       }
     } else {
       // MODULATE: tile columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2.
-      // Each warp owns 32 rows x cw channels, processed in units of 32 channels.  The math runs in the COALESCED
-      // arrangement (lane = (row r0 + 4k, 4 channels cl*4..cl*4+3), k = 0..7): x is read and h written straight
-      // from/to global memory in 128/64-byte runs per row, the per-channel constants are 5 registers-resident
-      // float4 per unit instead of 40 loads, and only gamma / beta (which TMEM hands out one row per lane) go
-      // through the swizzled staging block.
+      // Each warp owns 32 rows x cw channels, processed in units of 32 channels.  The x block of the NEXT unit
+      // (possibly of the next tile) is requested from global memory before the current unit is computed, so its
+      // latency overlaps the math instead of stalling the (few) epilogue warps.
       const int half_n = p.BN >> 1;
       const int cw = half_n >> 1;  // channels per warp-half (multiple of 32)
       const int units = cw >> 5;
       const int cs = e.chan_stride;
       const long long xsb = e.x_sb, xsy = e.x_sy, xsx = e.x_sx;
       const int xsh = e.x_shift;
-      const int cl8 = lane & 7, r0 = lane >> 3;
+      const int cl8 = lane & 7, cl4 = lane & 3;
       auto x_elem = [=](int bb_, int yy, int xx) {
         return (long long)bb_ * xsb + (long long)(yy >> xsh) * xsy + (long long)(xx >> xsh) * xsx;
       };
       const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
       auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
+      uint4 pf[8];
+      uint32_t xo[8], xon[8];
+      if (sched_tile<WSTAT>(p, 0) >= 0) {
+        const int nt0 = tg.set_tile(p, sched_tile<WSTAT>(p, 0));
+        row_offsets<8>(lane, row_base, tg, 4, x_elem, xon);
+        gather_issue_o<8>(reinterpret_cast<const char*>(e.x + nt0 * half_n + chalf * cw) + cl8 * 16, xon, pf);
+      }
       uint32_t it = 0;
       for (int tile = sched_tile<WSTAT>(p, it); tile >= 0; tile = sched_tile<WSTAT>(p, ++it)) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
@@ -437,75 +442,69 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         const int nrow0 = n_tile * p.BN;
         int b, y, x;
         const bool valid = tg.pixel(row_base + lane, b, y, x);
-        float nz_own = 0.f;
-        if (valid && e.noise) nz_own = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
-        float nzk[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) nzk[k] = __shfl_sync(0xffffffffu, nz_own, r0 + 4 * k);
-        uint32_t xo[8], oo[8];
-        row_offsets<8>(lane, row_base, tg, 4, x_elem, xo);
-        row_offsets<8>(lane, row_base, tg, 2, o_elem, oo);
+        float nz = 0.f;
+        if (valid && e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
         const float* ca = e.chan + c0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xo[k] = xon[k];
+        uint32_t oo[4];
+        row_offsets<4>(lane, row_base, tg, 2, o_elem, oo);
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
         for (int u = 0; u < units; ++u) {
           const int j = chalf * cw + 32 * u;
-          const int jc = j + cl8 * 4;  // this lane's 4 channels inside the n-tile
-          // x rows (128-byte runs) and this lane's per-channel constants: all requested before the TMEM traffic
-          uint4 xq[8];
-          gather_issue_o<8>(reinterpret_cast<const char*>(e.x + c0 + j) + cl8 * 16, xo, xq);
-          const float4 bg = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + jc));
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + jc));
-          const float4 av = __ldg(reinterpret_cast<const float4*>(ca + jc));
-          const float4 cv = __ldg(reinterpret_cast<const float4*>(ca + cs + jc));
-          const float4 nv = __ldg(reinterpret_cast<const float4*>(ca + 2 * cs + jc));
-          // gamma, beta: TMEM (row per lane) -> staging -> coalesced arrangement
-          uint4 gq[8], bq[8];
-          {
-            float t[32];
-            tmem_ld<32>(taddr + (uint32_t)j, t);
-            tmem_ld_fence(t);
+          // current x block: registers (global layout) -> staging -> one row per lane
+          uint4 xr[8];
+          gather_commit<8>(stg, lane, pf, xr);
+          // request the next x block
+          if (u + 1 < units) {
+            gather_issue_o<8>(reinterpret_cast<const char*>(e.x + c0 + j + 32) + cl8 * 16, xo, pf);
+          } else if (sched_tile<WSTAT>(p, it + 1) >= 0) {
+            TileGeo tn = tg;
+            const int ntn = tn.set_tile(p, sched_tile<WSTAT>(p, it + 1));
+            row_offsets<8>(lane, row_base, tn, 4, x_elem, xon);
+            gather_issue_o<8>(reinterpret_cast<const char*>(e.x + ntn * half_n + chalf * cw) + cl8 * 16, xon, pf);
+          }
+          uint4 hk[4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              sts128(stg + stg_off<8>(lane, c), make_uint4(__float_as_uint(t[4 * c]), __float_as_uint(t[4 * c + 1]),
-                                                           __float_as_uint(t[4 * c + 2]), __float_as_uint(t[4 * c + 3])));
-            __syncwarp();
+          for (int sub = 0; sub < 2; ++sub) {
+            const int jj = j + 16 * sub;
+            float g[16], be[16];
+            tmem_ld<16>(taddr + (uint32_t)jj, g);
+            tmem_ld<16>(taddr + (uint32_t)(half_n + jj), be);
+            float4 bg[4], bb[4], av[4], cv[4], nv[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) gq[k] = lds128(stg + stg_off<8>(r0 + 4 * k, cl8));
-            __syncwarp();
-            tmem_ld<32>(taddr + (uint32_t)(half_n + j), t);
-            tmem_ld_fence(t);
-            if (u + 1 == units) {
-              // the accumulator has been fully read: hand the TMEM buffer back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty[acc]);
+            for (int i = 0; i < 4; ++i) {
+              bg[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + jj) + i);
+              bb[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + jj) + i);
+              av[i] = __ldg(reinterpret_cast<const float4*>(ca + jj) + i);
+              cv[i] = __ldg(reinterpret_cast<const float4*>(ca + cs + jj) + i);
+              nv[i] = __ldg(reinterpret_cast<const float4*>(ca + 2 * cs + jj) + i);
             }
+            tmem_ld_fence(g);
+            tmem_ld_fence(be);
+            uint32_t pk[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              sts128(stg + stg_off<8>(lane, c), make_uint4(__float_as_uint(t[4 * c]), __float_as_uint(t[4 * c + 1]),
-                                                           __float_as_uint(t[4 * c + 2]), __float_as_uint(t[4 * c + 3])));
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) bq[k] = lds128(stg + stg_off<8>(r0 + 4 * k, cl8));
-            __syncwarp();
+            for (int i = 0; i < 4; ++i) {
+              const uint4 xq = xr[4 * sub + i];
+              const float o0 = modulate_elem<ACT>(__uint_as_float(xq.x), nz, av[i].x, cv[i].x, nv[i].x, g[4 * i] + bg[i].x, be[4 * i] + bb[i].x);
+              const float o1 = modulate_elem<ACT>(__uint_as_float(xq.y), nz, av[i].y, cv[i].y, nv[i].y, g[4 * i + 1] + bg[i].y, be[4 * i + 1] + bb[i].y);
+              const float o2 = modulate_elem<ACT>(__uint_as_float(xq.z), nz, av[i].z, cv[i].z, nv[i].z, g[4 * i + 2] + bg[i].z, be[4 * i + 2] + bb[i].z);
+              const float o3 = modulate_elem<ACT>(__uint_as_float(xq.w), nz, av[i].w, cv[i].w, nv[i].w, g[4 * i + 3] + bg[i].w, be[4 * i + 3] + bb[i].w);
+              pk[2 * i] = pack_h2(o0, o1);
+              pk[2 * i + 1] = pack_h2(o2, o3);
+            }
+            hk[2 * sub] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            hk[2 * sub + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          char* obase = reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + c0 + jc);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float nz = nzk[k];
-            const float o0 = modulate_elem<ACT>(__uint_as_float(xq[k].x), nz, av.x, cv.x, nv.x,
-                                                __uint_as_float(gq[k].x) + bg.x, __uint_as_float(bq[k].x) + bb.x);
-            const float o1 = modulate_elem<ACT>(__uint_as_float(xq[k].y), nz, av.y, cv.y, nv.y,
-                                                __uint_as_float(gq[k].y) + bg.y, __uint_as_float(bq[k].y) + bb.y);
-            const float o2 = modulate_elem<ACT>(__uint_as_float(xq[k].z), nz, av.z, cv.z, nv.z,
-                                                __uint_as_float(gq[k].z) + bg.z, __uint_as_float(bq[k].z) + bb.z);
-            const float o3 = modulate_elem<ACT>(__uint_as_float(xq[k].w), nz, av.w, cv.w, nv.w,
-                                                __uint_as_float(gq[k].w) + bg.w, __uint_as_float(bq[k].w) + bb.w);
-            if (oo[k] != 0xFFFFFFFFu)
-              *reinterpret_cast<uint2*>(obase + ((size_t)oo[k] << 4)) = make_uint2(pack_h2(o0, o1), pack_h2(o2, o3));
+          if (u + 1 == units) {
+            // the accumulator has been fully read: hand the TMEM buffer back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
           }
+          scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + c0 + j) + cl4 * 16, oo, hk);
         }
       }
     }
