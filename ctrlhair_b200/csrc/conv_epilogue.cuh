@@ -355,12 +355,12 @@ template <int EPI, int ACT, bool WSTAT>
 __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base, int warp,
                                               int lane) {
     // ------------------------------------------------------------------ epilogue warps
-    // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
+    // 8 warps (4..11): TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 4) / 4.
     const int q = warp & 3;
-    const int chalf = (warp - 2) >> 2;
+    const int chalf = (warp - kFirstEpilogueWarp) >> 2;
     const int row_base = q * 32;
     const EpiK& e = p.e;
-    const uint32_t stg = smem_u32(sm.stg_base + (size_t)(warp - 2) * 4096);
+    const uint32_t stg = smem_u32(sm.stg_base + (size_t)(warp - kFirstEpilogueWarp) * 4096);
     uint64_t* tfull = sm.tfull;
     uint64_t* tempty = sm.tempty;
     TileGeo tg;
