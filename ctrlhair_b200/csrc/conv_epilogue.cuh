@@ -239,17 +239,19 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // 32 accumulator columns of the PLAIN epilogue through the staging block (channels-last output, full block valid).
 // ro / oo4 / oo8: per-tile row offsets (16-byte units) of the residual and of the output in the 8- and 4-lanes-per-row
 // arrangements; bi = image of this lane's own row (for per-image bias).
-// The accumulator values v[] have already been loaded from TMEM and fenced by the caller (which keeps the next
-// block's tcgen05.ld in flight while this one is processed).
 template <int ACT>
-__device__ __forceinline__ void plain_block32(const EpiK& e, float (&v)[32], uint32_t stg, int lane, int n, int bi,
-                                              const uint32_t (&ro)[8], const uint32_t (&oo)[8]) {
+__device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uint32_t stg, int lane, int n, int bi,
+                                              const uint32_t (&ro)[8], const uint32_t (&oo4)[4],
+                                              const uint32_t (&oo8)[8]) {
+  float v[32];
+  tmem_ld<32>(taddr, v);
   uint4 rr[8];
   if (e.res) {
     uint4 g[8];
     gather_issue_o<8>(reinterpret_cast<const char*>(e.res + n) + (lane & 7) * 16, ro, g);
     gather_commit<8>(stg, lane, g, rr);
   }
+  tmem_ld_fence(v);
   if (e.bias) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)bi * e.nrows : 0) + n);
 #pragma unroll
@@ -274,15 +276,14 @@ __device__ __forceinline__ void plain_block32(const EpiK& e, float (&v)[32], uin
     for (int i = 0; i < 4; ++i)
       pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
                          pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
-    const uint32_t o4[4] = {oo[0], oo[1], oo[2], oo[3]};
-    scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, o4, pk);
+    scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, oo4, pk);
   } else {
     uint4 pk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
                          __float_as_uint(v[4 * i + 3]));
-    scatter_o<8>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<float*>(e.out) + noff) + (lane & 7) * 16, oo, pk);
+    scatter_o<8>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<float*>(e.out) + noff) + (lane & 7) * 16, oo8, pk);
   }
 }
 
@@ -355,12 +356,12 @@ template <int EPI, int ACT, bool WSTAT>
 __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base, int warp,
                                               int lane) {
     // ------------------------------------------------------------------ epilogue warps
-    // 8 warps (4..11): TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 4) / 4.
+    // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
     const int q = warp & 3;
-    const int chalf = (warp - kFirstEpilogueWarp) >> 2;
+    const int chalf = (warp - 2) >> 2;
     const int row_base = q * 32;
     const EpiK& e = p.e;
-    const uint32_t stg = smem_u32(sm.stg_base + (size_t)(warp - kFirstEpilogueWarp) * 4096);
+    const uint32_t stg = smem_u32(sm.stg_base + (size_t)(warp - 2) * 4096);
     uint64_t* tfull = sm.tfull;
     uint64_t* tempty = sm.tempty;
     TileGeo tg;
@@ -381,20 +382,12 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         const int jend = j + ch;
         const int n0 = n_tile * p.BN;
         const bool staged = e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % 32) == 0);
-        uint32_t ro[8], oo[8];  // oo: 4 entries (fp16 rows, 4 lanes per row) or 8 (fp32 rows, 8 lanes per row)
+        uint32_t ro[8], oo4[4], oo8[8];
         if (staged) {
           const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
           auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
-          if (e.out_dtype == CHB_F16) {
-            uint32_t o4[4];
-            row_offsets<4>(lane, row_base, tg, 2, o_elem, o4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) oo[k] = o4[k];
-#pragma unroll
-            for (int k = 4; k < 8; ++k) oo[k] = 0xFFFFFFFFu;
-          } else {
-            row_offsets<8>(lane, row_base, tg, 4, o_elem, oo);
-          }
+          if (e.out_dtype == CHB_F16) row_offsets<4>(lane, row_base, tg, 2, o_elem, oo4);
+          else row_offsets<8>(lane, row_base, tg, 4, o_elem, oo8);
           if (e.res) {
             const long long rsb = e.r_sb, rsy = e.r_sy, rsx = e.r_sx;
             const int rsh = e.r_shift;
@@ -404,42 +397,18 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
           }
         }
         const int bi = b < p.B ? b : p.B - 1;
-        if (staged && (ch & 31) == 0 && n0 + jend <= p.N) {
-          // fast path: whole 32-column blocks; ping-pong two register arrays so that the tcgen05.ld of block i+1
-          // overlaps the processing of block i, and hand the TMEM buffer back as soon as the last load has landed
-          const int nb = ch >> 5;
-          float va[32], vb[32];
-          tmem_ld<32>(taddr + (uint32_t)j, va);
-          for (int i = 0; i < nb; i += 2) {
-            tmem_ld_fence(va);
-            if (i + 1 < nb) {
-              tmem_ld<32>(taddr + (uint32_t)(j + 32 * (i + 1)), vb);
-            } else {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty[acc]);
-            }
-            plain_block32<ACT>(e, va, stg, lane, n0 + j + 32 * i, bi, ro, oo);
-            if (i + 1 < nb) {
-              tmem_ld_fence(vb);
-              if (i + 2 < nb) {
-                tmem_ld<32>(taddr + (uint32_t)(j + 32 * (i + 2)), va);
-              } else {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
-              }
-              plain_block32<ACT>(e, vb, stg, lane, n0 + j + 32 * (i + 1), bi, ro, oo);
-            }
+        for (; j + 32 <= jend; j += 32) {
+          if (staged && n0 + j + 32 <= p.N) {
+            plain_block32<ACT>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
+          } else {
+            plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
           }
-        } else {
-          for (; j + 32 <= jend; j += 32) plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
-          for (; j + 16 <= jend; j += 16) plain_chunk<16, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
-          for (; j + 8 <= jend; j += 8) plain_chunk<8, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
         }
+        for (; j + 16 <= jend; j += 16) plain_chunk<16, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+        for (; j + 8 <= jend; j += 8) plain_chunk<8, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
     } else {
       // MODULATE: tile columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2.

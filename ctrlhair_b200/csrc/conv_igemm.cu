@@ -95,17 +95,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
 
-  // Register re-allocation between warpgroups (setmaxnreg): the producer / MMA warpgroup needs almost no registers,
-  // the epilogue warpgroups want room to keep TMEM loads, global loads and staging traffic in flight.
-  if (warp < kFirstEpilogueWarp) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
-    if (warp == 0) {
-      producer_role<WSTAT>(p, sm);
-    } else if (warp == 1) {
-      mma_role<WSTAT>(p, sm, tmem_base);
-    }
+  if (warp == 0) {
+    producer_role<WSTAT>(p, sm);
+  } else if (warp == 1) {
+    mma_role<WSTAT>(p, sm, tmem_base);
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
     epilogue_role<EPI, ACT, WSTAT>(p, sm, tmem_base, warp, lane);
   }
 

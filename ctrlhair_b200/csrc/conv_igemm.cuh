@@ -16,8 +16,7 @@ constexpr int kMaxHalo = 6;
 constexpr int kHaloBufBytes = 24576;  // (16+2) x (8+2) rows x 128 B, rounded up to 1 KB
 constexpr int kSmemBudget = 192 * 1024;  // pipeline stages; + 32 KB epilogue staging + barriers <= 227 KB
 constexpr int kEpilogueWarps = 8;
-constexpr int kFirstEpilogueWarp = 4;  // warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}
-constexpr int kConvThreads = 32 * (kFirstEpilogueWarp + kEpilogueWarps);  // 384: warps 4-11 are the epilogue
+constexpr int kConvThreads = 64 + 32 * kEpilogueWarps;  // warp0 TMA, warp1 MMA, warps 2-9 epilogue
 
 struct SegK {
   int taps, nchunk, kc, ch_off, per_image;
