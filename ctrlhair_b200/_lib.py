@@ -65,6 +65,23 @@ class ShapeConfig(C.Structure):
     _fields_ = [("crop", C.c_int), ("max_batch", C.c_int)]
 
 
+class CtTrainConfig(C.Structure):
+    _fields_ = [("batch", C.c_int)] + [(k, C.c_float) for k in (
+        "lambda_adv", "lambda_gp", "lambda_info", "lambda_info_curliness", "lambda_rec", "lambda_rgb", "lambda_pca_std",
+        "lambda_moment_1", "lambda_moment_2", "lambda_cls_curliness", "lambda_orthogonal", "lr", "beta1", "beta2",
+        "eps")] + [("use_graph", C.c_int)]
+
+
+class CtTrainBatch(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "code", "rgb_mean", "pca_std", "noise", "noise_curliness", "curliness_label", "perm_rgb", "perm_curliness",
+        "perm_noise", "alpha_gp")] + [("noise_from_encoder", C.c_int)]
+
+
+CTT_D, CTT_G, CTT_FROZEN = 0, 1, 2
+CTT_LOSS_NAMES = ("lambda_adv", "lambda_gp", "lambda_info", "lambda_rec", "lambda_moment_1", "lambda_moment_2",
+                  "lambda_info_curliness", "lambda_rgb", "lambda_pca_std", "lambda_cls_curliness", "lambda_orthogonal",
+                  "total")
 EPI_PLAIN, EPI_MODULATE = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 F16, F32 = 0, 1
@@ -124,6 +141,18 @@ SYMBOLS = [
     ("chb_shape_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("chb_shape_encode", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_shape_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_cttrain_create", C.c_int, [C.POINTER(CtTrainConfig), C.POINTER(C.c_void_p)]),
+    ("chb_cttrain_destroy", None, [C.c_void_p]),
+    ("chb_cttrain_num_tensors", C.c_int, [C.c_void_p]),
+    ("chb_cttrain_tensor_info", C.c_int,
+     [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    ("chb_cttrain_state_floats", C.c_int64, [C.c_void_p]),
+    ("chb_cttrain_region", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("chb_cttrain_workspace_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_cttrain_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("chb_cttrain_step", C.c_int, [C.c_void_p, C.c_int, C.POINTER(CtTrainBatch), C.c_void_p, C.c_void_p]),
+    ("chb_cttrain_adam", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_cttrain_launches", C.c_int, [C.c_void_p, C.c_int]),
 ]
 
 

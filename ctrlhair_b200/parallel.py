@@ -59,3 +59,13 @@ def gather_shards(local, n_total, dst=0):
     if rank != dst:
         return None
     return torch.cat([o[:e - s] for o, (s, e) in zip(outs, sizes)])
+
+
+def allreduce_mean_(flat):
+    """In-place mean of one flat gradient buffer over all ranks (what DDP does per bucket, solver.py:68-74): one
+    collective per optimizer step, NCCL over NVLink on GPUs, gloo in the CPU tests.  No-op for a single process."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(dist.get_world_size())
+    return flat

@@ -221,6 +221,46 @@ def make_ct_inputs(B, seed=1241):
             "rgb_mean": torch.rand((B, 3), generator=gen), "pca_std": torch.rand((B, 1), generator=gen)}
 
 
+def make_curliness_predictor_state_dict(seed=1242, code_dim=512, hidden=32, p_layers=3):
+    """Seeded state_dict of the frozen curliness classifier (predictor config p002: hidden 32, BatchNorm1d, 1 logit)."""
+    gen = torch.Generator().manual_seed(seed)
+    pr = {}
+    for i in range(p_layers + 1):
+        in_d = code_dim if i == 0 else hidden
+        od = hidden if i < p_layers else 1
+        pr["net.%d.fc.weight" % i] = torch.randn((od, in_d), generator=gen) * (1.4 / math.sqrt(in_d))
+        pr["net.%d.fc.bias" % i] = torch.randn(od, generator=gen) * 0.1
+        if i < p_layers:
+            pr["net.%d.norm.weight" % i] = 1 + 0.2 * torch.randn(od, generator=gen)
+            pr["net.%d.norm.bias" % i] = 0.1 * torch.randn(od, generator=gen)
+            pr["net.%d.norm.running_mean" % i] = 0.3 * torch.randn(od, generator=gen)
+            pr["net.%d.norm.running_var" % i] = torch.rand(od, generator=gen) + 0.5
+            pr["net.%d.norm.num_batches_tracked" % i] = torch.tensor(100, dtype=torch.int64)
+    return pr
+
+
+def make_ct_train_state_dicts():
+    """(G, D, P_rgb, P_curliness) for the training-step tests: make_ct_state_dicts() with the subspace bases pushed
+    off orthonormality, so the orthogonal regulariser (model_eigengan.py:27-31) has a non-zero gradient."""
+    g, d, pr = make_ct_state_dicts()
+    for k in g:
+        if k.endswith(".U"):
+            n = g[k].numel()
+            g[k] = g[k] + 0.05 * torch.sin(torch.arange(n, dtype=torch.float32) * 0.37).reshape(g[k].shape)
+    return g, d, pr, make_curliness_predictor_state_dict()
+
+
+def make_ct_train_batch(B, seed=1243):
+    """One training batch in the shape train.py:118-126 builds it: dataset fields (code, rgb_mean, pca_std) plus the
+    per-step draws (noise, curliness_label in {-1, 1}, noise_curliness = |N(0,1)| * label)."""
+    gen = torch.Generator().manual_seed(seed)
+    label = (torch.randint(0, 2, (B, 1), generator=gen) * 2 - 1)
+    return {"code": torch.randn((B, 512), generator=gen) * 0.135,
+            "rgb_mean": torch.rand((B, 3), generator=gen), "pca_std": torch.rand((B, 1), generator=gen),
+            "noise": torch.randn((B, 8), generator=gen), "curliness_label": label,
+            "noise_curliness": (torch.randn((B, 1), generator=gen).abs() * label).float()}
+
+
 def make_image(B, S, seed=1250):
     """fp32 [B,3,S,S] in [-1,1]: smooth low-frequency content plus noise (stands in for imgs/*.png)."""
     gen = torch.Generator().manual_seed(seed)

@@ -220,6 +220,65 @@ int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B
 int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_code, float* mask_out, int B,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Colour/texture training step, config 045 (color_texture_branch/train.py:115-148 loop body;
+ * solver.py:85-117 forward, :218-245 forward_d incl. the WGAN-GP double backward :204-216, :119-166 forward_g;
+ * my_torchlib/train_utils.py:54-89 train(); Adam solver.py:52-55).  fp32 throughout.
+ *
+ * One call = forward + losses + backward of ONE sub-step (which = 0: discriminator update, 1: generator update)
+ * on this rank's batch; gradients land in the `grads` region of the state buffer so that the host can all-reduce
+ * them (DDP, solver.py:68-74) before chb_cttrain_adam applies the update.  Every random draw of the reference
+ * (three shuffles + encoder-noise coin of solver.py:98-111, alpha_gp of :199) is an explicit input.
+ * The whole sub-step is captured once into a CUDA graph and replayed.
+ * ------------------------------------------------------------------------------------------ */
+enum { CHB_CTT_D = 0, CHB_CTT_G = 1, CHB_CTT_FROZEN = 2 };
+enum {  /* slots of the losses[] output (unweighted values, the reference's loss_dict keys) */
+  CHB_CTT_L_ADV = 0, CHB_CTT_L_GP, CHB_CTT_L_INFO, CHB_CTT_L_REC, CHB_CTT_L_MOMENT_1, CHB_CTT_L_MOMENT_2,
+  CHB_CTT_L_INFO_CURLINESS, CHB_CTT_L_RGB, CHB_CTT_L_PCA_STD, CHB_CTT_L_CLS_CURLINESS, CHB_CTT_L_ORTHOGONAL,
+  CHB_CTT_L_TOTAL, CHB_CTT_NUM_LOSSES
+};
+typedef struct {
+  int batch;            /* samples per call on this rank (cfg.batch_size = total_batch_size / gpu_num)        */
+  float lambda_adv, lambda_gp, lambda_info, lambda_info_curliness, lambda_rec, lambda_rgb, lambda_pca_std,
+      lambda_moment_1, lambda_moment_2, lambda_cls_curliness, lambda_orthogonal; /* config.py:16-39,52-96   */
+  float lr, beta1, beta2, eps;                                                      /* 2e-4, .5, .999, 1e-8    */
+  int use_graph;        /* 1: capture each sub-step into a CUDA graph on first use (0: plain launches)         */
+} chb_cttrain_config;
+typedef struct {  /* device pointers, fp32 unless noted; rows = batch */
+  const float* code;             /* [B,512]  data['code']                                   */
+  const float* rgb_mean;         /* [B,3]                                                   */
+  const float* pca_std;          /* [B,1]                                                   */
+  const float* noise;            /* [B,8]    generate_noise (train_utils.py:44-51)          */
+  const float* noise_curliness;  /* [B,1]    |N(0,1)| * label                               */
+  const float* curliness_label;  /* [B,1]    -1 / +1 as float                               */
+  const int* perm_rgb;           /* [B] int32: first shuffle  (rgb_mean, pca_std)           */
+  const int* perm_curliness;     /* [B] second shuffle (noise_curliness, curliness_label)   */
+  const int* perm_noise;         /* [B] third shuffle  (noise)                              */
+  const float* alpha_gp;         /* [B,1] U(0,1); D sub-step only (may be NULL for G)       */
+  int noise_from_encoder;        /* the gan_input_from_encoder_prob coin (solver.py:107-111) */
+} chb_cttrain_batch;
+typedef struct chb_cttrain chb_cttrain;
+int chb_cttrain_create(const chb_cttrain_config* cfg, chb_cttrain** out);
+void chb_cttrain_destroy(chb_cttrain* t);
+/* Parameter table: names are "D." / "G." + the reference state_dict key (trainable), "P." / "C." + key for the frozen
+ * rgb / curliness predictors (fc weights with the eval BatchNorm1d folded in by the host packer).  `offset` and
+ * `numel` are in floats inside the region of `group` (CHB_CTT_D / _G / _FROZEN). */
+int chb_cttrain_num_tensors(const chb_cttrain* t);
+int chb_cttrain_tensor_info(const chb_cttrain* t, int i, char* name, int name_cap, int64_t* offset, int64_t* numel,
+                            int* group);
+/* State buffer (fp32, caller-owned device memory): [params D | params G | grads D | grads G | adam m | adam v |
+ * frozen].  region: 0 params, 1 grads, 2 adam m, 3 adam v (group D or G), or group FROZEN (region ignored). */
+int64_t chb_cttrain_state_floats(const chb_cttrain* t);
+int chb_cttrain_region(const chb_cttrain* t, int region, int group, int64_t* offset, int64_t* numel);
+int64_t chb_cttrain_workspace_bytes(const chb_cttrain* t);
+int chb_cttrain_bind(chb_cttrain* t, float* state, void* workspace);
+/* forward + losses + backward of one sub-step; losses_out: device float[CHB_CTT_NUM_LOSSES] (slots a sub-step does
+ * not compute are written as 0).  Gradients of the stepped net replace the previous content of its grads region. */
+int chb_cttrain_step(chb_cttrain* t, int which, const chb_cttrain_batch* batch, float* losses_out, void* stream);
+/* Adam update of one net from its grads region (after the optional all-reduce); advances that net's step count. */
+int chb_cttrain_adam(chb_cttrain* t, int which, void* stream);
+int chb_cttrain_launches(const chb_cttrain* t, int which);
+
 #ifdef __cplusplus
 }
 #endif

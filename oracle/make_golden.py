@@ -153,11 +153,103 @@ def main_shape():
                         mask_argmax=m.argmax(1).to(torch.uint8).numpy(), mask_sub=m[:, :, ::8, ::8].numpy(), B=2)
 
 
+def _param_sample(sd, stride=8):
+    """Every `stride`-th element of every tensor, concatenated in key order (keeps the fixture small; Adam is
+    elementwise, so each sampled element checks the gradient at that element independently)."""
+    return np.concatenate([v.detach().reshape(-1)[::stride].numpy() for k, v in sd.items()])
+
+
+def main_ct_train(B=32, n_steps=2):
+    """Golden losses / updated parameters of the unmodified reference Solver + train() (config 045) over n_steps
+    iterations of the loop body of color_texture_branch/train.py:115-148, from fixed seeds."""
+    import random
+    import types
+    import warnings
+    from . import ct_train_oracle as to
+    addict = types.ModuleType("addict")
+    addict.Dict = _ADict
+    sys.modules["addict"] = addict
+    g, d, pr, cu = synth.make_ct_train_state_dicts()
+    argv, sys.argv = sys.argv, ["make_golden"]
+    with rh.reference_on_path(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from color_texture_branch.config import cfg
+        from color_texture_branch.solver import Solver
+        from my_torchlib.train_utils import LossUpdater, train
+        solver = Solver(cfg, torch.device("cpu"), local_rank=-1, training=True)
+    sys.argv = argv
+    solver.gen.load_state_dict(g, strict=True)
+    solver.dis.load_state_dict(d, strict=True)
+    solver.rgb_model.load_state_dict(pr, strict=True)
+    solver.curliness_model.load_state_dict(cu, strict=True)
+    LossUpdater(cfg).update(0)
+    lam = {k: float(cfg[k]) for k in to.LAMBDAS}
+    assert lam == to.LAMBDAS, lam
+    assert cfg.gan_input_from_encoder_prob == to.ENC_PROB and cfg.lr_d == to.LR and cfg.beta1 == to.BETA1
+    oracle = to.TrainOracle(g, d, pr, cu)
+    random.seed(77)
+    torch.manual_seed(78)
+    st_py, st_t = random.getstate(), torch.get_rng_state()
+    ref_losses, out = [], {}
+    for step in range(n_steps):
+        for i in range(2):
+            data = synth.make_ct_train_batch(B, 1243 + 2 * step + i)
+            loss_dict = {}
+            solver.forward(data)
+            if i == 0:
+                solver.forward_d(loss_dict)
+                train(cfg, loss_dict, optimizers=[solver.D_optimizer], step=step, writer=None, flag="D")
+            else:
+                solver.forward_g(loss_dict)
+                train(cfg, loss_dict, optimizers=[solver.G_optimizer], step=step, writer=None, flag="G")
+            ref_losses.append({k: float(v.detach()) for k, v in loss_dict.items()})
+    # the oracle, replaying the same random streams
+    random.setstate(st_py)
+    torch.set_rng_state(st_t)
+    worst = 0.0
+    for step in range(n_steps):
+        for i in range(2):
+            data = synth.make_ct_train_batch(B, 1243 + 2 * step + i)
+            rnd = to.draw_randomness(B)
+            tag = "s%d_%s" % (step, "dg"[i])
+            if i == 0:
+                alpha = torch.rand(B, 1)
+                L = oracle.step_d(data, rnd, alpha)
+                out[tag + "_alpha"] = alpha.numpy()
+            else:
+                L = oracle.step_g(data, rnd)
+            for k in ("p1", "p2", "p3"):
+                out[tag + "_" + k] = np.array(rnd[k], dtype=np.int32)
+            out[tag + "_use_enc"] = np.array(int(rnd["use_enc"]))
+            rl = ref_losses[2 * step + i]
+            assert set(rl) == set(L), (set(rl), set(L))
+            for k in rl:
+                worst = max(worst, abs(rl[k] - float(L[k])) / max(1e-6, abs(rl[k])))
+            out[tag + "_loss_names"] = np.array(sorted(rl))
+            out[tag + "_losses"] = np.array([rl[k] for k in sorted(rl)], dtype=np.float64)
+    rg = {k: v.detach() for k, v in solver.gen.state_dict().items()}
+    rd = {k: v.detach() for k, v in solver.dis.state_dict().items()}
+    dg = max(float((rg[k] - oracle.G[k]).abs().max()) for k in rg)
+    dd = max(float((rd[k] - oracle.D[k]).abs().max()) for k in rd)
+    mv = max(float((rg[k] - g[k]).abs().max()) for k in rg), max(float((rd[k] - d[k]).abs().max()) for k in rd)
+    print("ct_train: worst rel loss diff oracle-ref %.2e; max|param diff| G %.2e D %.2e (params moved by G %.2e D %.2e)"
+          % (worst, dg, dd, mv[0], mv[1]))
+    for s in range(2 * n_steps):
+        print("   ", ref_losses[s])
+    out["gen_keys"] = np.array(list(rg))
+    out["dis_keys"] = np.array(list(rd))
+    out["gen_sample"] = _param_sample(rg)
+    out["dis_sample"] = _param_sample(rd)
+    np.savez_compressed(os.path.join(OUT, "ct_train_step.npz"), B=B, n_steps=n_steps, seeds=np.array([77, 78, 1243]), **out)
+
+
 if __name__ == "__main__":
     if "--shape-only" in sys.argv:
         main_shape()
     elif "--ct-only" in sys.argv:
         main_ct()
+    elif "--ct-train-only" in sys.argv:
+        main_ct_train()
     elif "--zencoder-only" in sys.argv:
         main_zencoder()
     else:
@@ -165,3 +257,4 @@ if __name__ == "__main__":
         main_ct()
         main_zencoder()
         main_shape()
+        main_ct_train()

@@ -48,6 +48,10 @@ def _worker(rank, world, port, ret):
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = ok and float(t) == float(world)
+    # gradient all-reduce of the colour/texture training step (mean over ranks, as DDP: solver.py:68-74)
+    grads = torch.arange(6, dtype=torch.float32) * (rank + 1)
+    parallel.allreduce_mean_(grads)
+    ok = ok and bool(torch.allclose(grads, torch.arange(6, dtype=torch.float32) * 1.5))
     ret[rank] = ok
     dist.destroy_process_group()
 
