@@ -90,18 +90,47 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+def _kink_margin(fn):
+    """Smallest |pre-activation| any leaky-ReLU sees while fn() runs.  The losses (the gradient penalty above all) and
+    the gradients are discontinuous where a pre-activation crosses zero, so two correct fp32 implementations can
+    legitimately land on different sides when one sits within rounding distance of it."""
+    import torch.nn.functional as F
+    orig, seen = F.leaky_relu, []
+
+    def spy(x, *a, **k):
+        seen.append(float(x.detach().abs().min()))
+        return orig(x, *a, **k)
+    F.leaky_relu = spy
+    try:
+        out = fn()
+    finally:
+        F.leaky_relu = orig
+    return min(seen), out
+
+
+def _well_conditioned_batch(orc, B, use_enc, alpha, first_seed=4321, margin=4e-6):
+    """First seeded batch whose leaky-ReLU pre-activations all stay `margin` away from zero in the oracle (fp32 rounding
+    of these pre-activations is ~3e-7), so that the comparison below tests arithmetic and not which side of a kink a rounding error fell."""
+    for seed in range(first_seed, first_seed + 64):
+        data = synth.make_ct_train_batch(B, seed)
+        random.seed(5)
+        rnd = to.draw_randomness(B)
+        rnd["use_enc"] = use_enc
+        m_d, d_res = _kink_margin(lambda: orc.grads_d(data, rnd, alpha))
+        m_g, g_res = _kink_margin(lambda: orc.grads_g(data, rnd))
+        if min(m_d, m_g) > margin:
+            return data, rnd, d_res, g_res
+    raise AssertionError("no well-conditioned batch found")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,use_enc", [(32, False), (32, True), (50, False)])
 def test_cuda_gradients_match_oracle_autograd(B, use_enc):
     s, (G, D, P, Cp) = _make_solver(B)
     orc = to.TrainOracle(G, D, P, Cp)
-    data = synth.make_ct_train_batch(B, 4321)
-    random.seed(5)
-    rnd = to.draw_randomness(B)
-    rnd["use_enc"] = use_enc
     alpha = torch.rand(B, 1, generator=torch.Generator().manual_seed(9))
+    data, rnd, (Ld, gd), (Lg, gg) = _well_conditioned_batch(orc, B, use_enc, alpha)
     # discriminator sub-step
-    Ld, gd = orc.grads_d(data, rnd, alpha)
     s.forward(data, rnd)
     ld = {}
     s.forward_d(ld, alpha)
@@ -112,7 +141,6 @@ def test_cuda_gradients_match_oracle_autograd(B, use_enc):
     for k in gd:
         assert _rel(mine[k].cpu(), gd[k]) < GRAD_RTOL or float(gd[k].abs().max()) == 0.0, ("D", k, _rel(mine[k].cpu(), gd[k]))
     # generator sub-step (same parameters: no optimizer step was taken)
-    Lg, gg = orc.grads_g(data, rnd)
     lg = {}
     s.forward_g(lg)
     s.synchronize()
