@@ -120,6 +120,18 @@ struct TileGeo {
     tpix_sh = (tpix & (tpix - 1)) == 0 ? 31 - __clz(tpix) : -1;
     b0 = y0 = x0 = 0;
   }
+  // fast geometry (p.fast): 16 x 8 tiles, power-of-two tile grid -> shifts only
+  __device__ __forceinline__ int set_tile_fast(const ConvKParams& p, int tile) {
+    const int n_tile = p.n_tiles == 1 ? 0 : tile / p.m_tiles;
+    const int m = tile - n_tile * p.m_tiles;
+    x0 = (m & (p.tiles_x - 1)) << 3;
+    y0 = ((m >> p.tx_sh) & (p.tiles_y - 1)) << 4;
+    b0 = m >> (p.tx_sh + p.ty_sh);
+    return n_tile;
+  }
+  __device__ __forceinline__ void pixel_fast(int m, int& b, int& y, int& x) const {
+    b = b0; y = y0 + (m >> 3); x = x0 + (m & 7);
+  }
   // positions the geometry on `tile`, returns its n-tile index
   __device__ __forceinline__ int set_tile(const ConvKParams& p, int tile) {
     const int n_tile = tile / p.m_tiles;
@@ -194,6 +206,67 @@ __device__ __forceinline__ void stage_scatter(uint32_t stg, int lane, int row_ba
   __syncwarp();
 }
 
+// Streaming 16-byte load that does not allocate in L1: the x / residual streams are read once, keeping them out of
+// L1 leaves the per-channel constants (bias, BN fold, noise scale) resident there.
+__device__ __forceinline__ uint4 ldg_stream(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_keep(const float4* ptr) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  return v;
+}
+
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100): two lanes of fp32 math per issue slot.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// Fast geometry: offsets (16-byte units) of the rows this lane touches in the CH16-lanes-per-row arrangement of the
+// warp's 32 tile rows (tile row m = q*32 + r -> ty = m >> 3, tx = m & 7), for a tensor read at (y >> sh, x >> sh).
+// base16 = offset of the tile origin, sy16 / sx16 = row / pixel strides, all in 16-byte units.
+template <int CH16>
+__device__ __forceinline__ void row_offsets_fast(int lane, int q, int sh, uint32_t base16, uint32_t sy16, uint32_t sx16,
+                                                 uint32_t (&o)[CH16]) {
+  constexpr int RPI = 32 / CH16;
+  const int r0 = lane / CH16;
+#pragma unroll
+  for (int k = 0; k < CH16; ++k) {
+    const int r = r0 + RPI * k;
+    const int ty = q * 4 + (r >> 3), tx = r & 7;
+    o[k] = base16 + (uint32_t)(ty >> sh) * sy16 + (uint32_t)(tx >> sh) * sx16;
+  }
+}
+__device__ __forceinline__ uint32_t tile_base16(const TileGeo& tg, long long sb, long long sy, long long sx, int sh,
+                                                int elem_bytes) {
+  return (uint32_t)((((long long)tg.b0 * sb + (long long)(tg.y0 >> sh) * sy + (long long)(tg.x0 >> sh) * sx) *
+                     elem_bytes) >> 4);
+}
+
 // ---- precomputed row offsets: the pixel decode and 64-bit address math are done once per tile, not per access.
 // o[k] = byte offset / 16 of the k-th row this lane touches in the CH16-lanes-per-row arrangement (~0u: no row).
 template <int CH16, class Fn>
@@ -207,15 +280,19 @@ __device__ __forceinline__ void row_offsets(int lane, int row_base, const TileGe
     o[k] = tg.pixel(row_base + r0 + RPI * k, b, y, x) ? (uint32_t)((elem_off(b, y, x) * elem_bytes) >> 4) : 0xFFFFFFFFu;
   }
 }
-template <int CH16>
+template <int CH16, bool ALLV = false>
 __device__ __forceinline__ void gather_issue_o(const char* base, const uint32_t (&o)[CH16], uint4 (&g)[CH16]) {
 #pragma unroll
   for (int k = 0; k < CH16; ++k) {
-    g[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (o[k] != 0xFFFFFFFFu) g[k] = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)o[k] << 4)));
+    if (ALLV) {
+      g[k] = ldg_stream(base + ((size_t)o[k] << 4));
+    } else {
+      g[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (o[k] != 0xFFFFFFFFu) g[k] = ldg_stream(base + ((size_t)o[k] << 4));
+    }
   }
 }
-template <int CH16>
+template <int CH16, bool ALLV = false>
 __device__ __forceinline__ void scatter_o(uint32_t stg, int lane, char* base, const uint32_t (&o)[CH16],
                                           const uint4 (&regs)[CH16]) {
   constexpr int RPI = 32 / CH16;
@@ -226,7 +303,7 @@ __device__ __forceinline__ void scatter_o(uint32_t stg, int lane, char* base, co
 #pragma unroll
   for (int k = 0; k < CH16; ++k) {
     const uint4 v = lds128(stg + stg_off<CH16>(r0 + RPI * k, cl));
-    if (o[k] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(base + ((size_t)o[k] << 4)) = v;
+    if (ALLV || o[k] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(base + ((size_t)o[k] << 4)) = v;
   }
   __syncwarp();
 }
@@ -239,7 +316,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // 32 accumulator columns of the PLAIN epilogue through the staging block (channels-last output, full block valid).
 // ro / oo4 / oo8: per-tile row offsets (16-byte units) of the residual and of the output in the 8- and 4-lanes-per-row
 // arrangements; bi = image of this lane's own row (for per-image bias).
-template <int ACT>
+template <int ACT, bool ALLV = false>
 __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uint32_t stg, int lane, int n, int bi,
                                               const uint32_t (&ro)[8], const uint32_t (&oo4)[4],
                                               const uint32_t (&oo8)[8]) {
@@ -248,7 +325,7 @@ __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uin
   uint4 rr[8];
   if (e.res) {
     uint4 g[8];
-    gather_issue_o<8>(reinterpret_cast<const char*>(e.res + n) + (lane & 7) * 16, ro, g);
+    gather_issue_o<8, ALLV>(reinterpret_cast<const char*>(e.res + n) + (lane & 7) * 16, ro, g);
     gather_commit<8>(stg, lane, g, rr);
   }
   tmem_ld_fence(v);
@@ -256,7 +333,7 @@ __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uin
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)bi * e.nrows : 0) + n);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 t = __ldg(bp + i);
+      const float4 t = ldg_keep(bp + i);
       v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
     }
   }
@@ -276,14 +353,14 @@ __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uin
     for (int i = 0; i < 4; ++i)
       pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
                          pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
-    scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, oo4, pk);
+    scatter_o<4, ALLV>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, oo4, pk);
   } else {
     uint4 pk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
                          __float_as_uint(v[4 * i + 3]));
-    scatter_o<8>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<float*>(e.out) + noff) + (lane & 7) * 16, oo8, pk);
+    scatter_o<8, ALLV>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<float*>(e.out) + noff) + (lane & 7) * 16, oo8, pk);
   }
 }
 
@@ -350,12 +427,59 @@ __device__ __forceinline__ void plain_chunk(const ConvKParams& p, const EpiK& e,
 
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue warp role
+// MODULATE math on 16 channels: out = act((x*a + (nz*nv + c)) * (1 + gamma + bias_g) + (beta + bias_b)), packed fp32
+// pairs (FFMA2/FADD2/FMUL2), fp16 output.  g / be: accumulator columns, xr: 4 x uint4 of fp32 x values, cst: the
+// five per-channel constant vectors of these 16 channels.
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int ACT, bool WSTAT>
+template <int ACT>
+__device__ __forceinline__ void modulate16(const float (&g)[16], const float (&be)[16], const uint4* xr, float nz,
+                                           const float4 (&bg)[4], const float4 (&bb)[4], const float4 (&av)[4],
+                                           const float4 (&cv)[4], const float4 (&nv)[4], uint4& h0, uint4& h1) {
+  const uint64_t nz2 = pk2(nz, nz);
+  const uint64_t slope2 = pk2(0.2f, 0.2f);
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 xq = xr[i];
+    const uint64_t x01 = pk2(__uint_as_float(xq.x), __uint_as_float(xq.y));
+    const uint64_t x23 = pk2(__uint_as_float(xq.z), __uint_as_float(xq.w));
+    // xn = x*a + (nz*nv + c)
+    const uint64_t xn01 = fma2(x01, pk2(av[i].x, av[i].y), fma2(nz2, pk2(nv[i].x, nv[i].y), pk2(cv[i].x, cv[i].y)));
+    const uint64_t xn23 = fma2(x23, pk2(av[i].z, av[i].w), fma2(nz2, pk2(nv[i].z, nv[i].w), pk2(cv[i].z, cv[i].w)));
+    // gamma + bias_g, beta + bias_b
+    const uint64_t g01 = add2(pk2(g[4 * i], g[4 * i + 1]), pk2(bg[i].x, bg[i].y));
+    const uint64_t g23 = add2(pk2(g[4 * i + 2], g[4 * i + 3]), pk2(bg[i].z, bg[i].w));
+    const uint64_t b01 = add2(pk2(be[4 * i], be[4 * i + 1]), pk2(bb[i].x, bb[i].y));
+    const uint64_t b23 = add2(pk2(be[4 * i + 2], be[4 * i + 3]), pk2(bb[i].z, bb[i].w));
+    // xn * (1 + gamma) + beta = xn*gamma + (xn + beta)
+    uint64_t o01 = fma2(xn01, g01, add2(xn01, b01));
+    uint64_t o23 = fma2(xn23, g23, add2(xn23, b23));
+    float o0, o1, o2, o3;
+    if (ACT == CHB_ACT_LRELU) {
+      float s0, s1, s2, s3;
+      upk2(mul2(o01, slope2), s0, s1);
+      upk2(mul2(o23, slope2), s2, s3);
+      upk2(o01, o0, o1);
+      upk2(o23, o2, o3);
+      o0 = fmaxf(o0, s0); o1 = fmaxf(o1, s1); o2 = fmaxf(o2, s2); o3 = fmaxf(o3, s3);
+    } else {
+      upk2(o01, o0, o1);
+      upk2(o23, o2, o3);
+      o0 = act_t<ACT>(o0); o1 = act_t<ACT>(o1); o2 = act_t<ACT>(o2); o3 = act_t<ACT>(o3);
+    }
+    pk[2 * i] = pack_h2(o0, o1);
+    pk[2 * i + 1] = pack_h2(o2, o3);
+  }
+  h0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  h1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue warp role.  FAST: p.fast geometry (full 16 x 8 tiles, affine addresses, no bounds predicates).
+// ------------------------------------------------------------------------------------------------
+template <int EPI, int ACT, bool WSTAT, bool FAST>
 __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base, int warp,
                                               int lane) {
-    // ------------------------------------------------------------------ epilogue warps
     // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;
@@ -368,44 +492,58 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
     tg.init(p);
 
     if (EPI == CHB_EPI_PLAIN) {
+      const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
+      const long long rsb = e.r_sb, rsy = e.r_sy, rsx = e.r_sx;
+      const int rsh = e.r_shift;
+      const int obytes = e.out_dtype == CHB_F16 ? 2 : 4;
       uint32_t it = 0;
       for (int tile = sched_tile<WSTAT>(p, it); tile >= 0; tile = sched_tile<WSTAT>(p, ++it)) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-        const int n_tile = tg.set_tile(p, tile);
+        const int n_tile = FAST ? tg.set_tile_fast(p, tile) : tg.set_tile(p, tile);
         int b, y, x;
-        const bool valid = tg.pixel(row_base + lane, b, y, x);
-        mbar_wait(&tfull[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+        bool valid = true;
+        if (FAST) tg.pixel_fast(row_base + lane, b, y, x);
+        else valid = tg.pixel(row_base + lane, b, y, x);
         const int ch = p.BN >> 1;  // columns per warp-half (multiple of 8)
         int j = chalf * ch;
         const int jend = j + ch;
         const int n0 = n_tile * p.BN;
-        const bool staged = e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % 32) == 0);
+        const bool staged = FAST || (e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % 32) == 0));
         uint32_t ro[8], oo4[4], oo8[8];
-        if (staged) {
-          const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
+        if (FAST) {
+          const uint32_t ob = tile_base16(tg, osb, osy, osx, 0, obytes);
+          if (e.out_dtype == CHB_F16) row_offsets_fast<4>(lane, q, 0, ob, (uint32_t)(osy >> 3), (uint32_t)(osx >> 3), oo4);
+          else row_offsets_fast<8>(lane, q, 0, ob, (uint32_t)(osy >> 2), (uint32_t)(osx >> 2), oo8);
+          if (e.res)
+            row_offsets_fast<8>(lane, q, rsh, tile_base16(tg, rsb, rsy, rsx, rsh, 4), (uint32_t)(rsy >> 2),
+                                (uint32_t)(rsx >> 2), ro);
+        } else if (staged) {
           auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
           if (e.out_dtype == CHB_F16) row_offsets<4>(lane, row_base, tg, 2, o_elem, oo4);
           else row_offsets<8>(lane, row_base, tg, 4, o_elem, oo8);
           if (e.res) {
-            const long long rsb = e.r_sb, rsy = e.r_sy, rsx = e.r_sx;
-            const int rsh = e.r_shift;
             row_offsets<8>(lane, row_base, tg, 4, [=](int bb_, int yy, int xx) {
               return (long long)bb_ * rsb + (long long)(yy >> rsh) * rsy + (long long)(xx >> rsh) * rsx;
             }, ro);
           }
         }
         const int bi = b < p.B ? b : p.B - 1;
-        for (; j + 32 <= jend; j += 32) {
-          if (staged && n0 + j + 32 <= p.N) {
-            plain_block32<ACT>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
-          } else {
-            plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+        if (FAST) {
+          for (; j < jend; j += 32) plain_block32<ACT, true>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
+        } else {
+          for (; j + 32 <= jend; j += 32) {
+            if (staged && n0 + j + 32 <= p.N) {
+              plain_block32<ACT>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
+            } else {
+              plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+            }
           }
+          for (; j + 16 <= jend; j += 16) plain_chunk<16, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
+          for (; j + 8 <= jend; j += 8) plain_chunk<8, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
         }
-        for (; j + 16 <= jend; j += 16) plain_chunk<16, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
-        for (; j + 8 <= jend; j += 8) plain_chunk<8, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -427,28 +565,37 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
       };
       const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
       auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
+      auto x_offsets = [&](const TileGeo& t, uint32_t (&o)[8]) {
+        if (FAST) row_offsets_fast<8>(lane, q, xsh, tile_base16(t, xsb, xsy, xsx, xsh, 4), (uint32_t)(xsy >> 2),
+                                      (uint32_t)(xsx >> 2), o);
+        else row_offsets<8>(lane, row_base, t, 4, x_elem, o);
+      };
       uint4 pf[8];
       uint32_t xo[8], xon[8];
       if (sched_tile<WSTAT>(p, 0) >= 0) {
-        const int nt0 = tg.set_tile(p, sched_tile<WSTAT>(p, 0));
-        row_offsets<8>(lane, row_base, tg, 4, x_elem, xon);
-        gather_issue_o<8>(reinterpret_cast<const char*>(e.x + nt0 * half_n + chalf * cw) + cl8 * 16, xon, pf);
+        const int nt0 = FAST ? tg.set_tile_fast(p, sched_tile<WSTAT>(p, 0)) : tg.set_tile(p, sched_tile<WSTAT>(p, 0));
+        x_offsets(tg, xon);
+        gather_issue_o<8, FAST>(reinterpret_cast<const char*>(e.x + nt0 * half_n + chalf * cw) + cl8 * 16, xon, pf);
       }
       uint32_t it = 0;
       for (int tile = sched_tile<WSTAT>(p, it); tile >= 0; tile = sched_tile<WSTAT>(p, ++it)) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
-        const int n_tile = tg.set_tile(p, tile);
+        const int n_tile = FAST ? tg.set_tile_fast(p, tile) : tg.set_tile(p, tile);
         const int c0 = n_tile * half_n;
         const int nrow0 = n_tile * p.BN;
         int b, y, x;
-        const bool valid = tg.pixel(row_base + lane, b, y, x);
+        bool valid = true;
+        if (FAST) tg.pixel_fast(row_base + lane, b, y, x);
+        else valid = tg.pixel(row_base + lane, b, y, x);
         float nz = 0.f;
         if (valid && e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
         const float* ca = e.chan + c0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) xo[k] = xon[k];
         uint32_t oo[4];
-        row_offsets<4>(lane, row_base, tg, 2, o_elem, oo);
+        if (FAST) row_offsets_fast<4>(lane, q, 0, tile_base16(tg, osb, osy, osx, 0, 2), (uint32_t)(osy >> 3),
+                                      (uint32_t)(osx >> 3), oo);
+        else row_offsets<4>(lane, row_base, tg, 2, o_elem, oo);
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
@@ -459,12 +606,13 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
           gather_commit<8>(stg, lane, pf, xr);
           // request the next x block
           if (u + 1 < units) {
-            gather_issue_o<8>(reinterpret_cast<const char*>(e.x + c0 + j + 32) + cl8 * 16, xo, pf);
+            gather_issue_o<8, FAST>(reinterpret_cast<const char*>(e.x + c0 + j + 32) + cl8 * 16, xo, pf);
           } else if (sched_tile<WSTAT>(p, it + 1) >= 0) {
             TileGeo tn = tg;
-            const int ntn = tn.set_tile(p, sched_tile<WSTAT>(p, it + 1));
-            row_offsets<8>(lane, row_base, tn, 4, x_elem, xon);
-            gather_issue_o<8>(reinterpret_cast<const char*>(e.x + ntn * half_n + chalf * cw) + cl8 * 16, xon, pf);
+            const int ntn = FAST ? tn.set_tile_fast(p, sched_tile<WSTAT>(p, it + 1))
+                                 : tn.set_tile(p, sched_tile<WSTAT>(p, it + 1));
+            x_offsets(tn, xon);
+            gather_issue_o<8, FAST>(reinterpret_cast<const char*>(e.x + ntn * half_n + chalf * cw) + cl8 * 16, xon, pf);
           }
           uint4 hk[4];
 #pragma unroll
@@ -476,27 +624,15 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
             float4 bg[4], bb[4], av[4], cv[4], nv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              bg[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + jj) + i);
-              bb[i] = __ldg(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + jj) + i);
-              av[i] = __ldg(reinterpret_cast<const float4*>(ca + jj) + i);
-              cv[i] = __ldg(reinterpret_cast<const float4*>(ca + cs + jj) + i);
-              nv[i] = __ldg(reinterpret_cast<const float4*>(ca + 2 * cs + jj) + i);
+              bg[i] = ldg_keep(reinterpret_cast<const float4*>(e.bias + nrow0 + jj) + i);
+              bb[i] = ldg_keep(reinterpret_cast<const float4*>(e.bias + nrow0 + half_n + jj) + i);
+              av[i] = ldg_keep(reinterpret_cast<const float4*>(ca + jj) + i);
+              cv[i] = ldg_keep(reinterpret_cast<const float4*>(ca + cs + jj) + i);
+              nv[i] = ldg_keep(reinterpret_cast<const float4*>(ca + 2 * cs + jj) + i);
             }
             tmem_ld_fence(g);
             tmem_ld_fence(be);
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 xq = xr[4 * sub + i];
-              const float o0 = modulate_elem<ACT>(__uint_as_float(xq.x), nz, av[i].x, cv[i].x, nv[i].x, g[4 * i] + bg[i].x, be[4 * i] + bb[i].x);
-              const float o1 = modulate_elem<ACT>(__uint_as_float(xq.y), nz, av[i].y, cv[i].y, nv[i].y, g[4 * i + 1] + bg[i].y, be[4 * i + 1] + bb[i].y);
-              const float o2 = modulate_elem<ACT>(__uint_as_float(xq.z), nz, av[i].z, cv[i].z, nv[i].z, g[4 * i + 2] + bg[i].z, be[4 * i + 2] + bb[i].z);
-              const float o3 = modulate_elem<ACT>(__uint_as_float(xq.w), nz, av[i].w, cv[i].w, nv[i].w, g[4 * i + 3] + bg[i].w, be[4 * i + 3] + bb[i].w);
-              pk[2 * i] = pack_h2(o0, o1);
-              pk[2 * i + 1] = pack_h2(o2, o3);
-            }
-            hk[2 * sub] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            hk[2 * sub + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            modulate16<ACT>(g, be, &xr[4 * sub], nz, bg, bb, av, cv, nv, hk[2 * sub], hk[2 * sub + 1]);
           }
           if (u + 1 == units) {
             // the accumulator has been fully read: hand the TMEM buffer back before the stores
@@ -504,7 +640,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          scatter_o<4>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + c0 + j) + cl4 * 16, oo, hk);
+          scatter_o<4, FAST>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + c0 + j) + cl4 * 16, oo, hk);
         }
       }
     }

@@ -43,7 +43,7 @@ int device_sm_count() {
 //   [nstages x stage_bytes pipeline][1 KB mbarriers + TMEM slot][8 x 4 KB epilogue staging]
 //   [nhalo x halo_buf_bytes halo tiles][wstat_bytes resident weights]
 // ------------------------------------------------------------------------------------------------
-template <int EPI, int ACT, bool WSTAT>
+template <int EPI, int ACT, bool WSTAT, bool FAST>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   } else if (warp == 1) {
     mma_role<WSTAT>(p, sm, tmem_base);
   } else {
-    epilogue_role<EPI, ACT, WSTAT>(p, sm, tmem_base, warp, lane);
+    epilogue_role<EPI, ACT, WSTAT, FAST>(p, sm, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -385,6 +385,26 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   e.noise = d.noise;
   e.chan = d.chan;
   e.chan_stride = d.N / 2;
+  // Fast tile geometry (see ConvKParams::fast).  CHB_FAST=0 turns it off for A/B comparisons.
+  {
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
+    const long long ob = d.out_dtype == CHB_F16 ? 2 : 4;
+    bool fast = d.TB == 1 && d.TW == 8 && d.TH == 16 && d.H % 16 == 0 && d.W % 8 == 0 && pow2(k.tiles_x) &&
+                pow2(k.tiles_y) && d.N == d.Nrows && d.BN % 64 == 0 && (d.o_sn == 1 || d.epi == CHB_EPI_MODULATE) &&
+                (d.o_ngroup <= 0 || d.o_ngroup % 32 == 0) && (d.o_sb * ob) % 16 == 0 && (d.o_sy * ob) % 16 == 0 &&
+                (d.o_sx * ob) % 16 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0;
+    if (d.epi == CHB_EPI_PLAIN && d.res)
+      fast = fast && d.r_sb % 4 == 0 && d.r_sy % 4 == 0 && d.r_sx % 4 == 0 && (d.r_shift == 0 || d.r_shift == 1) &&
+             (reinterpret_cast<uintptr_t>(d.res) & 15) == 0;
+    if (d.epi == CHB_EPI_MODULATE)
+      fast = fast && d.out_dtype == CHB_F16 && d.x_sb % 4 == 0 && d.x_sy % 4 == 0 && d.x_sx % 4 == 0 &&
+             (d.x_shift == 0 || d.x_shift == 1) && (reinterpret_cast<uintptr_t>(d.x) & 15) == 0;
+    if (const char* fv = getenv("CHB_FAST")) fast = fast && atoi(fv) != 0;
+    k.fast = fast ? 1 : 0;
+    k.tx_sh = ilog2(k.tiles_x);
+    k.ty_sh = ilog2(k.tiles_y);
+  }
   const int total = k.m_tiles * k.n_tiles;
   const int sms = device_sm_count();
   plan->grid = total < sms ? total : sms;
@@ -399,24 +419,25 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
 
 typedef void (*ConvKernelFn)(const ConvKParams);
 
-template <bool WSTAT>
-static ConvKernelFn pick_kernel_w(int epi, int act) {
+template <bool WSTAT, bool FAST>
+static ConvKernelFn pick_kernel_wf(int epi, int act) {
   if (epi == CHB_EPI_PLAIN) {
     switch (act) {
-      case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_RELU, WSTAT>;
-      case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_LRELU, WSTAT>;
-      case CHB_ACT_TANH: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_TANH, WSTAT>;
-      default: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_NONE, WSTAT>;
+      case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_RELU, WSTAT, FAST>;
+      case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_LRELU, WSTAT, FAST>;
+      case CHB_ACT_TANH: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_TANH, WSTAT, FAST>;
+      default: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_NONE, WSTAT, FAST>;
     }
   }
   switch (act) {
-    case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_LRELU, WSTAT>;
-    case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_RELU, WSTAT>;
-    default: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_NONE, WSTAT>;
+    case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_LRELU, WSTAT, FAST>;
+    case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_RELU, WSTAT, FAST>;
+    default: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_NONE, WSTAT, FAST>;
   }
 }
-static ConvKernelFn pick_kernel(int epi, int act, int wstat) {
-  return wstat ? pick_kernel_w<true>(epi, act) : pick_kernel_w<false>(epi, act);
+static ConvKernelFn pick_kernel(int epi, int act, int wstat, int fast) {
+  if (fast) return wstat ? pick_kernel_wf<true, true>(epi, act) : pick_kernel_wf<false, true>(epi, act);
+  return wstat ? pick_kernel_wf<true, false>(epi, act) : pick_kernel_wf<false, false>(epi, act);
 }
 
 static int ensure_smem_attr() {
@@ -425,8 +446,9 @@ static int ensure_smem_attr() {
   std::call_once(once, [] {
     for (int epi = 0; epi < 2 && err == cudaSuccess; ++epi)
       for (int act = 0; act < 4 && err == cudaSuccess; ++act)
-        for (int w = 0; w < 2 && err == cudaSuccess; ++w)
-          err = cudaFuncSetAttribute(pick_kernel(epi, act, w), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        for (int w = 0; w < 4 && err == cudaSuccess; ++w)
+          err = cudaFuncSetAttribute(pick_kernel(epi, act, w & 1, w >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024);
   });
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(err));
@@ -455,7 +477,7 @@ int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
   } else {
     int rc = ensure_smem_attr();
     if (rc != CHB_OK) return rc;
-    pick_kernel(plan.desc.epi, plan.desc.act, plan.kp.wstat)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
+    pick_kernel(plan.desc.epi, plan.desc.act, plan.kp.wstat, plan.kp.fast)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
   }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {

@@ -67,6 +67,10 @@ struct ConvKParams {
   int nstages, stage_bytes;
   int a_region;  // bytes of the per-stage A tile (0 when every segment takes its A operand from halo tiles)
   int hg;        // taps per pipeline stage on the halo path (1 or 3)
+  // Fast tile geometry: every tile is a full 16 x 8 pixel block of one image, the tile grid is a power of two in x
+  // and y and all epilogue tensors have 16-byte aligned rows, so per-tile addresses are an affine function of the
+  // tile coordinates (no per-row pixel decode, no bounds predicates).
+  int fast, tx_sh, ty_sh;
   EpiK e;
 };
 

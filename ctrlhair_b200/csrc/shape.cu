@@ -177,6 +177,44 @@ __global__ void shape_softmax_kernel(const float* __restrict__ hair /*[B,S,S,16]
   }
 }
 
+// decoder logits fp32 NHWC [B,S,S,ld] (first C channels valid) -> fp32 NCHW [B,C,S,S]  (what MaskDecoder returns)
+__global__ void logits_nchw_kernel(const float* __restrict__ in, int ld, int C, float* __restrict__ out, int B, int S) {
+  const long long total = (long long)B * S * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / ((long long)S * S), pix = i % ((long long)S * S);
+    for (int k = 0; k < C; ++k) out[(b * C + k) * (long long)S * S + pix] = in[i * ld + k];
+  }
+}
+
+// forward_decoder on caller-provided logits (model.py:184-187): hair fp32 [B,1,S,S], face fp32 [B,18,S,S] (NCHW)
+__global__ void softmax_nchw_kernel(const float* __restrict__ hair, const float* __restrict__ face,
+                                    float* __restrict__ out, int B, int S) {
+  const long long plane = (long long)S * S, total = (long long)B * plane;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / plane, pix = i % plane;
+    float l[19];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) l[k] = face[(b * 18 + k) * plane + pix];
+    l[13] = hair[b * plane + pix];
+#pragma unroll
+    for (int k = 13; k < 18; ++k) l[k + 1] = face[(b * 18 + k) * plane + pix];
+    float m = l[0];
+#pragma unroll
+    for (int k = 1; k < 19; ++k) m = fmaxf(m, l[k]);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+      l[k] = expf(l[k] - m);
+      s += l[k];
+    }
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int k = 0; k < 19; ++k) out[(b * 19 + k) * plane + pix] = l[k] * inv;
+  }
+}
+
 static int sgrid(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   const long long cap = (long long)device_sm_count() * 16;
@@ -455,6 +493,41 @@ int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B
   return CHB_OK;
 }
 
+// One MaskDecoder (model.py:116-143): net 0 = hair decoder on cat([face_code, hair_code]) (model.py:175-178),
+// net 1 = face decoder on face_code (:180-182).  Leaves the logits fp32 NHWC in ws_logit[net].
+static int run_decoder(chb_shape* z, int net, const float* hair_code, const float* face_code, int B, cudaStream_t st) {
+  auto it = z->dec_plans[net].find(B);
+  if (it == z->dec_plans[net].end()) {
+    std::vector<ConvPlan> pl;
+    int rc = build_dec_plans(z, net, B, pl);
+    if (rc != CHB_OK) return rc;
+    it = z->dec_plans[net].emplace(B, std::move(pl)).first;
+  }
+  const std::vector<ConvPlan>& pl = it->second;
+  code_pad_kernel<<<sgrid((long long)B * kDecIn[net], 256), 256, 0, st>>>(
+      face_code, 1024, hair_code, net == 0 ? 16 : 0, reinterpret_cast<__half*>(z->ws + z->ws_code16), B, kDecIn[net]);
+  int rc = launch_conv_plan(pl[0], CHB_IMPL_TCGEN05, st);
+  if (rc != CHB_OK) return rc;
+  // fc output [B,8192] is already NHWC [B,2,2,2048] (rows permuted by the packer): cast + upsample to 4x4
+  ln(z, st, B, 2, 2, 2048, nullptr, nullptr, reinterpret_cast<__half*>(z->ws + z->ws_act), 2, 2);
+  for (int i = 0; i < 7; ++i) {
+    if ((rc = launch_conv_plan(pl[1 + i], CHB_IMPL_TCGEN05, st)) != CHB_OK) return rc;
+    const int r = 4 << i, co = dec_cout(i);
+    ln(z, st, B, r, r, co, bpf(z, z->dec[net].g[i]), bpf(z, z->dec[net].be[i]),
+       reinterpret_cast<__half*>(z->ws + z->ws_act), i < 6 ? 2 : 0, 1);
+  }
+  return launch_conv_plan(pl[8], CHB_IMPL_TCGEN05, st);
+}
+
+static int last_launch(const char* who) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error(std::string(who) + ": " + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
 // hair_code fp32 [B,16], face_code fp32 [B,1024] -> mask probabilities fp32 [B,19,S,S]  (model.py:195-199)
 int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_code, float* mask_out, int B,
                      void* stream_) {
@@ -465,38 +538,46 @@ int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_cod
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const int S = z->cfg.crop;
   for (int net = 0; net < 2; ++net) {
-    auto it = z->dec_plans[net].find(B);
-    if (it == z->dec_plans[net].end()) {
-      std::vector<ConvPlan> pl;
-      int rc = build_dec_plans(z, net, B, pl);
-      if (rc != CHB_OK) return rc;
-      it = z->dec_plans[net].emplace(B, std::move(pl)).first;
-    }
-    const std::vector<ConvPlan>& pl = it->second;
-    // hair decoder input = cat([face_code, hair_code]) (model.py:175-178), face decoder input = face_code
-    code_pad_kernel<<<sgrid((long long)B * kDecIn[net], 256), 256, 0, st>>>(
-        face_code, 1024, hair_code, net == 0 ? 16 : 0, reinterpret_cast<__half*>(z->ws + z->ws_code16), B, kDecIn[net]);
-    int rc = launch_conv_plan(pl[0], CHB_IMPL_TCGEN05, st);
+    int rc = run_decoder(z, net, hair_code, face_code, B, st);
     if (rc != CHB_OK) return rc;
-    // fc output [B,8192] is already NHWC [B,2,2,2048] (rows permuted by the packer): cast + upsample to 4x4
-    ln(z, st, B, 2, 2, 2048, nullptr, nullptr, reinterpret_cast<__half*>(z->ws + z->ws_act), 2, 2);
-    for (int i = 0; i < 7; ++i) {
-      if ((rc = launch_conv_plan(pl[1 + i], CHB_IMPL_TCGEN05, st)) != CHB_OK) return rc;
-      const int r = 4 << i, co = dec_cout(i);
-      ln(z, st, B, r, r, co, bpf(z, z->dec[net].g[i]), bpf(z, z->dec[net].be[i]),
-         reinterpret_cast<__half*>(z->ws + z->ws_act), i < 6 ? 2 : 0, 1);
-    }
-    if ((rc = launch_conv_plan(pl[8], CHB_IMPL_TCGEN05, st)) != CHB_OK) return rc;
   }
   shape_softmax_kernel<<<sgrid((long long)B * S * S, 256), 256, 0, st>>>(
       reinterpret_cast<const float*>(z->ws + z->ws_logit[0]), reinterpret_cast<const float*>(z->ws + z->ws_logit[1]),
       mask_out, B, S);
-  cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) {
-    set_error(std::string("chb_shape_decode: ") + cudaGetErrorString(err));
-    return CHB_ERR_CUDA;
+  return last_launch("chb_shape_decode");
+}
+
+// forward_hair_decoder (net 0, model.py:175-178) / forward_face_decoder (net 1, :180-182): logits fp32 NCHW,
+// [B,1,S,S] for the hair decoder, [B,18,S,S] for the face decoder.  hair_code is ignored for net 1 (may be NULL).
+int chb_shape_decode_logits(chb_shape* z, int net, const float* hair_code, const float* face_code, float* logits_out,
+                            int B, void* stream_) {
+  if (!z || (net != 0 && net != 1) || (net == 0 && !hair_code) || !face_code || !logits_out || !z->ws || B <= 0 ||
+      B > z->cfg.max_batch) {
+    set_error("chb_shape_decode_logits: bad arguments or unbound object");
+    return CHB_ERR_ARG;
   }
-  return CHB_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  const int S = z->cfg.crop;
+  int rc = run_decoder(z, net, hair_code, face_code, B, st);
+  if (rc != CHB_OK) return rc;
+  logits_nchw_kernel<<<sgrid((long long)B * S * S, 256), 256, 0, st>>>(
+      reinterpret_cast<const float*>(z->ws + z->ws_logit[net]), net == 0 ? 16 : 32, net == 0 ? 1 : 18, logits_out, B, S);
+  return last_launch("chb_shape_decode_logits");
+}
+
+// forward_decoder (model.py:184-187): softmax over [face[:13], hair, face[13:]]; inputs and output fp32 NCHW.
+int chb_shape_softmax(chb_shape* z, const float* hair_logit, const float* face_logit, float* mask_out, int B,
+                      void* stream_) {
+  if (!z || !hair_logit || !face_logit || !mask_out || B <= 0) {
+    set_error("chb_shape_softmax: bad arguments");
+    return CHB_ERR_ARG;
+  }
+  int rc = chb_check_device();
+  if (rc != CHB_OK) return rc;
+  const int S = z->cfg.crop;
+  softmax_nchw_kernel<<<sgrid((long long)B * S * S, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      hair_logit, face_logit, mask_out, B, S);
+  return last_launch("chb_shape_softmax");
 }
 
 }  // extern "C"

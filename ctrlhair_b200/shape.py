@@ -169,5 +169,42 @@ class ShapeGeneratorB200:
                                                  self._stream()))
         return out
 
+    def _decode_logits(self, net, hair_code, face_code, channels):
+        B = face_code.shape[0]
+        face_code = face_code.to(device=self.device, dtype=torch.float32).contiguous()
+        hp = None
+        if hair_code is not None:
+            hair_code = hair_code.to(device=self.device, dtype=torch.float32).contiguous()
+            hp = C.c_void_p(hair_code.data_ptr())
+        out = torch.empty((B, channels, 256, 256), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_shape_decode_logits(self.handle, net, hp, C.c_void_p(face_code.data_ptr()),
+                                                        C.c_void_p(out.data_ptr()), B, self._stream()))
+        return out
+
+    def forward_hair_decoder(self, hair_code, face_code):
+        """shape_branch/model.py:175-178: hair logit [B,1,256,256] from cat([face_code, hair_code])."""
+        return self._decode_logits(0, hair_code, face_code, 1)
+
+    def forward_face_decoder(self, face_code):
+        """shape_branch/model.py:180-182: face logits [B,18,256,256] (ui/backend.py:416)."""
+        return self._decode_logits(1, None, face_code, 18)
+
+    def forward_decoder(self, hair_logit, face_logit):
+        """shape_branch/model.py:184-187: softmax over [face[:13], hair, face[13:]] (ui/backend.py:419)."""
+        B = face_logit.shape[0]
+        if not (hair_logit.is_cuda and face_logit.is_cuda):
+            raise _lib.ChbError("shape nets take CUDA tensors (there is no CPU path)")
+        if tuple(hair_logit.shape) != (B, 1, 256, 256) or tuple(face_logit.shape) != (B, 18, 256, 256):
+            raise ValueError("forward_decoder wants hair [B,1,256,256] and face [B,18,256,256] logits")
+        hair_logit = hair_logit.to(torch.float32).contiguous()
+        face_logit = face_logit.to(torch.float32).contiguous()
+        out = torch.empty((B, 19, 256, 256), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_shape_softmax(self.handle, C.c_void_p(hair_logit.data_ptr()),
+                                                  C.c_void_p(face_logit.data_ptr()), C.c_void_p(out.data_ptr()), B,
+                                                  self._stream()))
+        return out
+
     def forward_edit_directly_in_test(self, hair, face):
         return self.forward_decode_by_code(self.forward_hair_encoder(hair, testing=True), self.forward_face_encoder(face))

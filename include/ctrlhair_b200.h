@@ -219,6 +219,15 @@ int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B
 /* forward_decode_by_code (model.py:195-199): -> softmax mask fp32 [B,19,256,256]. */
 int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_code, float* mask_out, int B,
                      void* stream);
+/* forward_hair_decoder (net 0, model.py:175-178; input cat([face_code, hair_code])) and forward_face_decoder (net 1,
+ * model.py:180-182; hair_code ignored, may be NULL): logits fp32 NCHW, [B,1,256,256] / [B,18,256,256]
+ * (ui/backend.py:416 directly_change_hair_mask reads the face logits). */
+int chb_shape_decode_logits(chb_shape* z, int net, const float* hair_code, const float* face_code, float* logits_out,
+                            int B, void* stream);
+/* forward_decoder (model.py:184-187; ui/backend.py:419): softmax over [face[:13], hair, face[13:]] of caller-provided
+ * logits (fp32 NCHW) -> mask fp32 [B,19,256,256]. */
+int chb_shape_softmax(chb_shape* z, const float* hair_logit, const float* face_logit, float* mask_out, int B,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Colour/texture training step, config 045 (color_texture_branch/train.py:115-148 loop body;

@@ -67,3 +67,33 @@ def test_shape_cuda_matches_oracle_and_golden(shape_sd):
     bad.pop("face_decoder.out_layer.conv.bias")
     with pytest.raises(RuntimeError):
         ShapeGeneratorB200(max_batch=1).load_state_dict(bad)
+
+
+@pytest.mark.gpu
+def test_shape_split_decoders_and_directly_change_hair_mask(shape_sd):
+    """forward_hair_decoder / forward_face_decoder / forward_decoder (model.py:175-187) and the way
+    Backend.directly_change_hair_mask composes them (ui/backend.py:409-420)."""
+    from ctrlhair_b200.shape import ShapeGeneratorB200
+    g = np.load(GOLD)
+    net = ShapeGeneratorB200(max_batch=2).load_state_dict(shape_sd)
+    rh, rf = torch.from_numpy(g["hair_code"]), torch.from_numpy(g["face_code"])
+    hl = net.forward_hair_decoder(rh.cuda(), rf.cuda())
+    fl = net.forward_face_decoder(rf.cuda())
+    assert hl.shape == (2, 1, 256, 256) and fl.shape == (2, 18, 256, 256)
+    ref_h = sho.mask_decoder(shape_sd, "hair_decoder", torch.cat([rf, rh], 1))
+    ref_f = sho.mask_decoder(shape_sd, "face_decoder", rf)
+    assert float((hl.cpu() - ref_h).norm() / ref_h.norm()) < 3e-3
+    assert float((fl.cpu() - ref_f).norm() / ref_f.norm()) < 3e-3
+    # the pieces compose to forward_decode_by_code bit for bit (same kernels, same logits)
+    m = net.forward_decoder(hl, fl)
+    assert torch.equal(m, net.forward_decode_by_code(rh.cuda(), rf.cuda()))
+    # softmax on caller-made logits: exact same arithmetic as the oracle up to expf rounding
+    hair_mask = (torch.rand((2, 1, 256, 256), generator=torch.Generator().manual_seed(3)) > 0.7).float()
+    fl_c = fl.cpu()
+    hair_logit = hair_mask * (fl_c.max() - fl_c.min() + 2) + fl_c.min() - 1          # ui/backend.py:417-418
+    m2 = net.forward_decoder(hair_logit.cuda(), fl).cpu()
+    ref2 = sho.forward_decoder(hair_logit, fl_c)
+    assert float((m2 - ref2).abs().max()) < 1e-6
+    assert torch.equal(m2.argmax(1), ref2.argmax(1))
+    with pytest.raises(ValueError):
+        net.forward_decoder(hl[:, :, :128], fl)
