@@ -1,0 +1,220 @@
+"""Secondary paths of SURVEY §8 on the GPU, one JSON line each (development / profiles aid; bench.py is the contract).
+
+  python tools/bench_paths.py --what zencoder,shape,ct,pipeline,train,gen512 [--B 32] [--steps 10] [--warmup 3]
+  train under torchrun:  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_paths.py --what train
+
+zencoder  a8   style encode, images/s                        (config 3 encode half)
+shape     a10  hair+face encode and decode-by-code, images/s
+ct        a11  encoder -> generator -> predictor MLP chain, codes/s
+pipeline       config 3: encode -> edit -> decode chain with every network call on the B200 path, images/s
+train     a12  config 5: one train.py loop iteration (D sub-step + G sub-step + both Adam updates), steps/s;
+               world size > 1 adds the flat gradient all-reduce (NCCL)
+gen512         config 4 per-GPU share: generator forward at 512x512, images/s
+All timings: CUDA events on the launching stream, W warm-up + K timed iterations, inputs resident on the device.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ctrlhair_b200 import parallel, synth  # noqa: E402
+
+HAIR = 13
+ZENC_GFLOP, SHAPE_GFLOP = 42.4, 37.1   # SURVEY §8d per image
+PEAK_TF = 1363.8
+
+
+def timed(fn, steps, warmup, stream=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if stream is None:
+        e0.record()
+    else:
+        e0.record(stream)
+    for _ in range(steps):
+        fn()
+    if stream is None:
+        e1.record()
+    else:
+        e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def emit(d):
+    print(json.dumps(d), flush=True)
+
+
+def bench_zencoder(a, sd):
+    from ctrlhair_b200.zencoder import ZencoderB200
+    z = ZencoderB200(max_batch=a.B).load_state_dict(sd)
+    img, lab = synth.make_image(a.B, 256).cuda(), synth.make_labels(a.B, 256, "blocky").cuda()
+    ms = timed(lambda: z(img, lab), a.steps, a.warmup)
+    emit({"path": "zencoder (a8)", "B": a.B, "ms": ms, "images_per_s": a.B / ms * 1e3,
+          "tflops_algorithmic": ZENC_GFLOP * a.B / ms, "frac_of_sustained_peak": ZENC_GFLOP * a.B / ms / PEAK_TF})
+
+
+def bench_shape(a):
+    from ctrlhair_b200.shape import ShapeGeneratorB200
+    s = ShapeGeneratorB200(max_batch=a.B).load_state_dict(synth.make_shape_state_dict())
+    hair, face = synth.make_shape_inputs(a.B)
+    hair, face = hair.cuda(), face.cuda()
+    hc, fc = s.forward_hair_encoder(hair, testing=True), s.forward_face_encoder(face)
+    ms_e = timed(lambda: (s.forward_hair_encoder(hair, testing=True), s.forward_face_encoder(face)), a.steps, a.warmup)
+    ms_d = timed(lambda: s.forward_decode_by_code(hc, fc), a.steps, a.warmup)
+    emit({"path": "shape nets (a10)", "B": a.B, "encode_ms": ms_e, "decode_ms": ms_d,
+          "images_per_s": a.B / (ms_e + ms_d) * 1e3, "tflops_algorithmic": SHAPE_GFLOP * a.B / (ms_e + ms_d),
+          "weights_mb_fp16": 482, "note": "241 M parameters: weight-bandwidth-bound at small B"})
+
+
+def bench_ct(a):
+    from ctrlhair_b200 import color_texture as ct
+    g_sd, d_sd, p_sd = synth.make_ct_state_dicts()
+    G, D, P = (ct.EigenGeneratorB200().load_state_dict(g_sd), ct.CodeEncoderB200().load_state_dict(d_sd),
+               ct.PredictorB200().load_state_dict(p_sd))
+    code = synth.make_ct_inputs(a.B)["code"].cuda()
+
+    def chain():
+        pred = P({"code": code})
+        return ct.edit_infer(D, G, code, {"rgb_mean": pred["rgb_mean"], "pca_std": pred["pca_std"]})
+    ms = timed(chain, a.steps * 5, a.warmup)
+    emit({"path": "colour/texture MLPs (a11): predictor + encoder + generator", "B": a.B, "ms": ms,
+          "codes_per_s": a.B / ms * 1e3, "launches": 3, "bound": "launch latency (0.93 M parameters)"})
+
+
+def bench_pipeline(a, sd):
+    """Config 3: Backend.parse_img + Backend.output network calls (ui/backend.py:67-106,147-175), batch B."""
+    from ctrlhair_b200 import color_texture as ct
+    from ctrlhair_b200.generator import SeanGeneratorB200
+    from ctrlhair_b200.shape import ShapeGeneratorB200
+    from ctrlhair_b200.zencoder import ZencoderB200
+    B = a.B
+    shp = ShapeGeneratorB200(max_batch=B).load_state_dict(synth.make_shape_state_dict())
+    zen = ZencoderB200(max_batch=B).load_state_dict(sd)
+    gen = SeanGeneratorB200(max_batch=B).load_state_dict(sd)
+    g_sd, d_sd, p_sd = synth.make_ct_state_dicts()
+    G, D, P = (ct.EigenGeneratorB200().load_state_dict(g_sd), ct.CodeEncoderB200().load_state_dict(d_sd),
+               ct.PredictorB200().load_state_dict(p_sd))
+    labels_h = synth.make_labels(B, 256, "blocky", seed=99).pin_memory()
+    img_h = synth.make_image(B, 256).pin_memory()
+    out_h = torch.empty((B, 3, 256, 256)).pin_memory()
+
+    def chain():
+        labels = labels_h.cuda(non_blocking=True)
+        img = img_h.cuda(non_blocking=True)
+        oh = torch.zeros((B, 19, 256, 256), device="cuda").scatter_(1, labels[:, None].long(), 1.0)
+        hair, face = oh[:, [HAIR]], torch.cat([oh[:, :HAIR], oh[:, HAIR + 1:]], 1)
+        hc, fc = shp.forward_hair_encoder(hair, testing=True), shp.forward_face_encoder(face)
+        lab = shp.forward_decode_by_code(hc, fc).argmax(1).to(torch.uint8)
+        codes = zen(img, labels)
+        hair_code = codes[:, HAIR].contiguous()
+        pred = P({"code": hair_code})
+        feat = ct.edit_infer(D, G, hair_code, {"rgb_mean": pred["rgb_mean"] * 0.5 + 0.2, "pca_std": pred["pca_std"]})
+        codes[:, HAIR] = feat
+        out = gen.forward_labels(lab, codes, seed=1)
+        out_h.copy_(out, non_blocking=True)
+    ms = timed(chain, a.steps, a.warmup)
+    emit({"path": "config 3: Backend encode -> edit -> decode (network calls only; parsing/blending out of scope)",
+          "B": B, "ms": ms, "images_per_s": B / ms * 1e3, "h2d_bytes": int(labels_h.numel() + img_h.numel() * 4),
+          "d2h_bytes": int(out_h.numel() * 4)})
+
+
+def bench_train(a):
+    from ctrlhair_b200 import ct_train
+    rank, local_rank, world = parallel.init_process_group()
+    torch.cuda.set_device(local_rank)
+    B = a.train_batch
+    s = ct_train.SolverB200(None, "cuda:%d" % local_rank, batch_size=B)
+    s.load_state_dicts(*synth.make_ct_train_state_dicts())
+    batches = [synth.make_ct_train_batch(B, 5000 + 100 * rank + i) for i in range(4)]   # rank-distinct data
+    batches = [{k: v.cuda() for k, v in b.items()} for b in batches]
+    it = [0]
+
+    def step():
+        for i in range(2):
+            ld = {}
+            s.forward(batches[(it[0] * 2 + i) % 4])
+            if i == 0:
+                s.forward_d(ld)
+                ct_train.train(s.cfg, ld, optimizers=[s.D_optimizer])
+            else:
+                s.forward_g(ld)
+                ct_train.train(s.cfg, ld, optimizers=[s.G_optimizer])
+        it[0] += 1
+    for _ in range(a.warmup):
+        step()
+    s.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s.stream)
+    n = a.steps * 5
+    for _ in range(n):
+        step()
+    e1.record(s.stream)
+    s.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    finite = bool(torch.isfinite(s.losses).all())
+    if rank == 0:
+        emit({"path": "config 5: colour/texture train.py iteration (D + G sub-steps, 2 Adam updates)", "n_gpus": world,
+              "batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms, "steps_per_s": 1e3 / ms,
+              "samples_per_s": B * world / ms * 1e3, "launches_per_step": s.launches(0) + s.launches(1) + 2,
+              "graph_launches_per_step": 2, "allreduce_per_step": 2 if world > 1 else 0, "dtype": "f32",
+              "losses_finite": finite})
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def bench_gen512(a, sd):
+    from ctrlhair_b200 import flops as flopmodel
+    from ctrlhair_b200.generator import SeanGeneratorB200
+    B = a.B512
+    gen = SeanGeneratorB200(crop=512, max_batch=B).load_state_dict(sd)
+    labels, codes = synth.make_labels(B, 512, "blocky").cuda(), synth.make_codes(B).cuda()
+    out = torch.empty((B, 3, 512, 512), device="cuda")
+    ms = timed(lambda: gen.forward_labels(labels, codes, seed=1, out=out), max(2, a.steps // 2), a.warmup)
+    _, fact = flopmodel.generator_macs(512)
+    emit({"path": "config 4 per-GPU share: generator forward 512x512", "B": B, "ms": ms, "images_per_s": B / ms * 1e3,
+          "tflops_algorithmic": 2 * fact * B / ms / 1e9, "frac_of_sustained_peak": 2 * fact * B / ms / 1e9 / PEAK_TF,
+          "finite": bool(torch.isfinite(out).all())})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="zencoder,shape,ct,pipeline,train")
+    ap.add_argument("--B", type=int, default=32)
+    ap.add_argument("--B512", type=int, default=16)
+    ap.add_argument("--train-batch", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    a = ap.parse_args()
+    what = a.what.split(",")
+    sd = synth.make_state_dict() if any(w in what for w in ("zencoder", "pipeline", "gen512")) else None
+    if "zencoder" in what:
+        bench_zencoder(a, sd)
+    if "shape" in what:
+        bench_shape(a)
+    if "ct" in what:
+        bench_ct(a)
+    if "pipeline" in what:
+        bench_pipeline(a, sd)
+    if "gen512" in what:
+        bench_gen512(a, sd)
+    if "train" in what:
+        bench_train(a)
+
+
+if __name__ == "__main__":
+    main()
