@@ -191,17 +191,28 @@ def run_ours(args):
     finite = bool(torch.isfinite(out_d).all())
     value = world * B * args.steps / (ms_total * 1e-3)
 
-    # ---------------- end to end through the host-buffer entry point (`e2e`)
+    # ---------------- end to end through the host-buffer entry point (`e2e`): every step copies its labels + codes
+    # from pinned host memory and its image back to pinned host memory; the streamed entry point double-buffers them
+    # so batch n's copies overlap batch n-1 / n+1's kernels.  The clock stops when the last image is on the host.
     for i in range(2):
-        gen.forward_host(labels_h, codes_h, seed=i, out=out_h)
+        gen.forward_host_async(labels_h, codes_h, out_h, seed=i)
+    gen.host_sync()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        gen.forward_host(labels_h, codes_h, seed=200 + i, out=out_h)
+        gen.forward_host_async(labels_h, codes_h, out_h, seed=200 + i)
+    gen.host_sync()
     torch.cuda.synchronize(dev)
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * B * args.steps / t_e2e
+    # the same through the blocking per-call entry point (copies serialised with the kernels), for reference
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        gen.forward_host(labels_h, codes_h, seed=300 + i, out=out_h)
+    torch.cuda.synchronize(dev)
+    t_e2e_blocking = max_over_ranks(time.perf_counter() - t0)
+    barrier()
 
     # ---------------- live roofline of the dominant kernel (conv_igemm: every conv launch of the step)
     _, ms, fl = gen.forward_timed(labels_d, codes_d, seed=7, out=out_d)
@@ -248,7 +259,9 @@ def run_ours(args):
                              "no explicit flush", "outputs_finite": finite},
             "clocks": sampler.summary() if sampler else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(labels_h.numel() + codes_h.numel() * 4),
-                    "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": t_e2e / args.steps * 1e3},
+                    "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": t_e2e / args.steps * 1e3,
+                    "api": "SeanGeneratorB200.forward_host_async + host_sync (chb_generator_forward_host_async)",
+                    "blocking_api_value": world * B * args.steps / t_e2e_blocking},
             "gpu_launches": gen.launches() * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,

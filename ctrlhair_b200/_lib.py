@@ -111,6 +111,9 @@ SYMBOLS = [
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("chb_generator_forward_host", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("chb_generator_forward_host_async", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_generator_host_sync", C.c_int, [C.c_void_p]),
     ("chb_generator_forward_timed", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p,
       C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]),

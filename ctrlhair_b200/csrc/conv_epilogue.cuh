@@ -246,21 +246,47 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   return r;
 }
 
-// Fast geometry: offsets (16-byte units) of the rows this lane touches in the CH16-lanes-per-row arrangement of the
-// warp's 32 tile rows (tile row m = q*32 + r -> ty = m >> 3, tx = m & 7), for a tensor read at (y >> sh, x >> sh).
-// base16 = offset of the tile origin, sy16 / sx16 = row / pixel strides, all in 16-byte units.
-template <int CH16>
-__device__ __forceinline__ void row_offsets_fast(int lane, int q, int sh, uint32_t base16, uint32_t sy16, uint32_t sx16,
-                                                 uint32_t (&o)[CH16]) {
-  constexpr int RPI = 32 / CH16;
-  const int r0 = lane / CH16;
-#pragma unroll
-  for (int k = 0; k < CH16; ++k) {
-    const int r = r0 + RPI * k;
-    const int ty = q * 4 + (r >> 3), tx = r & 7;
-    o[k] = base16 + (uint32_t)(ty >> sh) * sy16 + (uint32_t)(tx >> sh) * sx16;
+// Row offsets (16-byte units) of the rows a lane touches in the CH16-lanes-per-row arrangement of its warp's 32 tile
+// rows: k-th access -> tile row m = q*32 + lane/CH16 + (32/CH16)*k (ty = m >> 3, tx = m & 7), tensor read at
+// (y >> sh, x >> sh).  Generic geometry keeps one precomputed offset per access (~0u = row outside the image); fast
+// geometry is affine in k, so it keeps a per-tile base and three strides instead of 4-8 live registers per tensor:
+//   CH16 = 8: ty = q*4 + (k >> 1), tx = lane/8 + 4*(k & 1)   ->  base + (k>>2)*syB + ((k>>1)&1)*syA + (k&1)*sxs
+//             with (syA, syB) = (sy, 2 sy) for sh = 0 and (0, sy) for sh = 1, sxs = (4 >> sh) * sx
+//   CH16 = 4: ty = q*4 + k,        tx = lane/4               ->  base + k*sy            (sh = 0 only: outputs)
+template <int CH16, bool FAST>
+struct RowOff {
+  uint32_t o[CH16];
+  __device__ __forceinline__ uint32_t get(int k) const { return o[k]; }
+  __device__ __forceinline__ bool valid(int k) const { return o[k] != 0xFFFFFFFFu; }
+};
+template <>
+struct RowOff<8, true> {
+  uint32_t lane_part, syA, syB, sxs, base;
+  __device__ __forceinline__ void setup(int lane, int q, int sh, uint32_t sy16, uint32_t sx16) {
+    lane_part = (uint32_t)((q * 4) >> sh) * sy16 + (uint32_t)((lane >> 3) >> sh) * sx16;
+    syA = sh ? 0u : sy16;
+    syB = sh ? sy16 : 2u * sy16;
+    sxs = (uint32_t)(4 >> sh) * sx16;
+    base = lane_part;
   }
-}
+  __device__ __forceinline__ void retile(uint32_t tile16) { base = tile16 + lane_part; }
+  __device__ __forceinline__ uint32_t get(int k) const {
+    return base + (uint32_t)(k >> 2) * syB + (uint32_t)((k >> 1) & 1) * syA + (uint32_t)(k & 1) * sxs;
+  }
+  __device__ __forceinline__ bool valid(int) const { return true; }
+};
+template <>
+struct RowOff<4, true> {
+  uint32_t lane_part, sy, base;
+  __device__ __forceinline__ void setup(int lane, int q, int /*sh*/, uint32_t sy16, uint32_t sx16) {
+    lane_part = (uint32_t)(q * 4) * sy16 + (uint32_t)(lane >> 2) * sx16;
+    sy = sy16;
+    base = lane_part;
+  }
+  __device__ __forceinline__ void retile(uint32_t tile16) { base = tile16 + lane_part; }
+  __device__ __forceinline__ uint32_t get(int k) const { return base + (uint32_t)k * sy; }
+  __device__ __forceinline__ bool valid(int) const { return true; }
+};
 __device__ __forceinline__ uint32_t tile_base16(const TileGeo& tg, long long sb, long long sy, long long sx, int sh,
                                                 int elem_bytes) {
   return (uint32_t)((((long long)tg.b0 * sb + (long long)(tg.y0 >> sh) * sy + (long long)(tg.x0 >> sh) * sx) *
@@ -280,20 +306,20 @@ __device__ __forceinline__ void row_offsets(int lane, int row_base, const TileGe
     o[k] = tg.pixel(row_base + r0 + RPI * k, b, y, x) ? (uint32_t)((elem_off(b, y, x) * elem_bytes) >> 4) : 0xFFFFFFFFu;
   }
 }
-template <int CH16, bool ALLV = false>
-__device__ __forceinline__ void gather_issue_o(const char* base, const uint32_t (&o)[CH16], uint4 (&g)[CH16]) {
+template <int CH16, bool FAST>
+__device__ __forceinline__ void gather_issue_o(const char* base, const RowOff<CH16, FAST>& ro, uint4 (&g)[CH16]) {
 #pragma unroll
   for (int k = 0; k < CH16; ++k) {
-    if (ALLV) {
-      g[k] = ldg_stream(base + ((size_t)o[k] << 4));
+    if (FAST) {
+      g[k] = ldg_stream(base + ((size_t)ro.get(k) << 4));
     } else {
       g[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (o[k] != 0xFFFFFFFFu) g[k] = ldg_stream(base + ((size_t)o[k] << 4));
+      if (ro.valid(k)) g[k] = ldg_stream(base + ((size_t)ro.get(k) << 4));
     }
   }
 }
-template <int CH16, bool ALLV = false>
-__device__ __forceinline__ void scatter_o(uint32_t stg, int lane, char* base, const uint32_t (&o)[CH16],
+template <int CH16, bool FAST>
+__device__ __forceinline__ void scatter_o(uint32_t stg, int lane, char* base, const RowOff<CH16, FAST>& ro,
                                           const uint4 (&regs)[CH16]) {
   constexpr int RPI = 32 / CH16;
   const int cl = lane % CH16, r0 = lane / CH16;
@@ -303,7 +329,7 @@ __device__ __forceinline__ void scatter_o(uint32_t stg, int lane, char* base, co
 #pragma unroll
   for (int k = 0; k < CH16; ++k) {
     const uint4 v = lds128(stg + stg_off<CH16>(r0 + RPI * k, cl));
-    if (ALLV || o[k] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(base + ((size_t)o[k] << 4)) = v;
+    if (FAST || ro.valid(k)) *reinterpret_cast<uint4*>(base + ((size_t)ro.get(k) << 4)) = v;
   }
   __syncwarp();
 }
@@ -316,16 +342,16 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // 32 accumulator columns of the PLAIN epilogue through the staging block (channels-last output, full block valid).
 // ro / oo4 / oo8: per-tile row offsets (16-byte units) of the residual and of the output in the 8- and 4-lanes-per-row
 // arrangements; bi = image of this lane's own row (for per-image bias).
-template <int ACT, bool ALLV = false>
+template <int ACT, bool FAST>
 __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uint32_t stg, int lane, int n, int bi,
-                                              const uint32_t (&ro)[8], const uint32_t (&oo4)[4],
-                                              const uint32_t (&oo8)[8]) {
+                                              const RowOff<8, FAST>& ro, const RowOff<4, FAST>& oo4,
+                                              const RowOff<8, FAST>& oo8) {
   float v[32];
   tmem_ld<32>(taddr, v);
   uint4 rr[8];
   if (e.res) {
     uint4 g[8];
-    gather_issue_o<8, ALLV>(reinterpret_cast<const char*>(e.res + n) + (lane & 7) * 16, ro, g);
+    gather_issue_o<8, FAST>(reinterpret_cast<const char*>(e.res + n) + (lane & 7) * 16, ro, g);
     gather_commit<8>(stg, lane, g, rr);
   }
   tmem_ld_fence(v);
@@ -353,14 +379,14 @@ __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uin
     for (int i = 0; i < 4; ++i)
       pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
                          pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
-    scatter_o<4, ALLV>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, oo4, pk);
+    scatter_o<4, FAST>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, oo4, pk);
   } else {
     uint4 pk[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
                          __float_as_uint(v[4 * i + 3]));
-    scatter_o<8, ALLV>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<float*>(e.out) + noff) + (lane & 7) * 16, oo8, pk);
+    scatter_o<8, FAST>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<float*>(e.out) + noff) + (lane & 7) * 16, oo8, pk);
   }
 }
 
@@ -496,6 +522,13 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
       const long long rsb = e.r_sb, rsy = e.r_sy, rsx = e.r_sx;
       const int rsh = e.r_shift;
       const int obytes = e.out_dtype == CHB_F16 ? 2 : 4;
+      RowOff<8, FAST> ro, oo8;
+      RowOff<4, FAST> oo4;
+      if constexpr (FAST) {
+        oo4.setup(lane, q, 0, (uint32_t)(osy >> 3), (uint32_t)(osx >> 3));
+        oo8.setup(lane, q, 0, (uint32_t)(osy >> 2), (uint32_t)(osx >> 2));
+        ro.setup(lane, q, rsh, (uint32_t)(rsy >> 2), (uint32_t)(rsx >> 2));
+      }
       uint32_t it = 0;
       for (int tile = sched_tile<WSTAT>(p, it); tile >= 0; tile = sched_tile<WSTAT>(p, ++it)) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
@@ -509,22 +542,19 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         const int jend = j + ch;
         const int n0 = n_tile * p.BN;
         const bool staged = FAST || (e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % 32) == 0));
-        uint32_t ro[8], oo4[4], oo8[8];
-        if (FAST) {
+        if constexpr (FAST) {
           const uint32_t ob = tile_base16(tg, osb, osy, osx, 0, obytes);
-          if (e.out_dtype == CHB_F16) row_offsets_fast<4>(lane, q, 0, ob, (uint32_t)(osy >> 3), (uint32_t)(osx >> 3), oo4);
-          else row_offsets_fast<8>(lane, q, 0, ob, (uint32_t)(osy >> 2), (uint32_t)(osx >> 2), oo8);
-          if (e.res)
-            row_offsets_fast<8>(lane, q, rsh, tile_base16(tg, rsb, rsy, rsx, rsh, 4), (uint32_t)(rsy >> 2),
-                                (uint32_t)(rsx >> 2), ro);
+          oo4.retile(ob);
+          oo8.retile(ob);
+          if (e.res) ro.retile(tile_base16(tg, rsb, rsy, rsx, rsh, 4));
         } else if (staged) {
           auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
-          if (e.out_dtype == CHB_F16) row_offsets<4>(lane, row_base, tg, 2, o_elem, oo4);
-          else row_offsets<8>(lane, row_base, tg, 4, o_elem, oo8);
+          if (e.out_dtype == CHB_F16) row_offsets<4>(lane, row_base, tg, 2, o_elem, oo4.o);
+          else row_offsets<8>(lane, row_base, tg, 4, o_elem, oo8.o);
           if (e.res) {
             row_offsets<8>(lane, row_base, tg, 4, [=](int bb_, int yy, int xx) {
               return (long long)bb_ * rsb + (long long)(yy >> rsh) * rsy + (long long)(xx >> rsh) * rsx;
-            }, ro);
+            }, ro.o);
           }
         }
         const int bi = b < p.B ? b : p.B - 1;
@@ -532,11 +562,11 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
         if (FAST) {
-          for (; j < jend; j += 32) plain_block32<ACT, true>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
+          for (; j < jend; j += 32) plain_block32<ACT, FAST>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
         } else {
           for (; j + 32 <= jend; j += 32) {
             if (staged && n0 + j + 32 <= p.N) {
-              plain_block32<ACT>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
+              plain_block32<ACT, FAST>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
             } else {
               plain_chunk<32, ACT>(p, e, taddr + (uint32_t)j, n0 + j, valid, b, y, x);
             }
@@ -565,13 +595,17 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
       };
       const long long osb = e.o_sb, osy = e.o_sy, osx = e.o_sx;
       auto o_elem = [=](int bb_, int yy, int xx) { return (long long)bb_ * osb + (long long)yy * osy + (long long)xx * osx; };
-      auto x_offsets = [&](const TileGeo& t, uint32_t (&o)[8]) {
-        if (FAST) row_offsets_fast<8>(lane, q, xsh, tile_base16(t, xsb, xsy, xsx, xsh, 4), (uint32_t)(xsy >> 2),
-                                      (uint32_t)(xsx >> 2), o);
-        else row_offsets<8>(lane, row_base, t, 4, x_elem, o);
+      RowOff<8, FAST> xo, xon;
+      RowOff<4, FAST> oo;
+      if constexpr (FAST) {
+        xon.setup(lane, q, xsh, (uint32_t)(xsy >> 2), (uint32_t)(xsx >> 2));
+        oo.setup(lane, q, 0, (uint32_t)(osy >> 3), (uint32_t)(osx >> 3));
+      }
+      auto x_offsets = [&](const TileGeo& t, RowOff<8, FAST>& o) {
+        if constexpr (FAST) o.retile(tile_base16(t, xsb, xsy, xsx, xsh, 4));
+        else row_offsets<8>(lane, row_base, t, 4, x_elem, o.o);
       };
       uint4 pf[8];
-      uint32_t xo[8], xon[8];
       if (sched_tile<WSTAT>(p, 0) >= 0) {
         const int nt0 = FAST ? tg.set_tile_fast(p, sched_tile<WSTAT>(p, 0)) : tg.set_tile(p, sched_tile<WSTAT>(p, 0));
         x_offsets(tg, xon);
@@ -590,12 +624,9 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         float nz = 0.f;
         if (valid && e.noise) nz = __ldg(e.noise + ((long long)b * p.W + x) * p.H + y);
         const float* ca = e.chan + c0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) xo[k] = xon[k];
-        uint32_t oo[4];
-        if (FAST) row_offsets_fast<4>(lane, q, 0, tile_base16(tg, osb, osy, osx, 0, 2), (uint32_t)(osy >> 3),
-                                      (uint32_t)(osx >> 3), oo);
-        else row_offsets<4>(lane, row_base, tg, 2, o_elem, oo);
+        xo = xon;
+        if constexpr (FAST) oo.retile(tile_base16(tg, osb, osy, osx, 0, 2));
+        else row_offsets<4>(lane, row_base, tg, 2, o_elem, oo.o);
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;

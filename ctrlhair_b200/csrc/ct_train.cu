@@ -41,38 +41,54 @@ struct Gemm {
   int a_act, b_act, accumulate;
 };
 
+// 32 x 32 output tile per CTA, K consumed in chunks of 128 so that every thread has 32 independent global loads in
+// flight per chunk: these GEMMs are a few MFLOP each and their duration is the dependent-load latency chain, not math.
+constexpr int kGemmKC = 128;
 __global__ void __launch_bounds__(256) gemm_kernel(const Gemm g) {
-  __shared__ float As[32][33];
-  __shared__ float Bs[32][33];
+  __shared__ float As[kGemmKC][33];
+  __shared__ float Bs[kGemmKC][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < g.K; k0 += 32) {
+  for (int k0 = 0; k0 < g.K; k0 += kGemmKC) {
+    float av[16], bv[16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int j = 0; j < 16; ++j) {
       int m, k;
-      if (g.a_sk == 1) { m = ty + 8 * r; k = tx; } else { m = tx; k = ty + 8 * r; }
+      if (g.a_sk == 1) { m = ty + 8 * (j >> 2); k = tx + 32 * (j & 3); } else { m = tx; k = ty + 8 * j; }
       float v = 0.f;
-      if (m0 + m < g.M && k0 + k < g.K) {
-        v = g.A[(long)(m0 + m) * g.a_sm + (long)(k0 + k) * g.a_sk];
-        if (g.a_act) v = lrelu(v);
-      }
-      As[k][m] = v;
+      if (m0 + m < g.M && k0 + k < g.K) v = g.A[(long)(m0 + m) * g.a_sm + (long)(k0 + k) * g.a_sk];
+      av[j] = v;
       int n, kb;
-      if (g.b_sn == 1) { kb = ty + 8 * r; n = tx; } else { n = ty + 8 * r; kb = tx; }
+      if (g.b_sn == 1) { kb = ty + 8 * j; n = tx; } else { n = ty + 8 * (j >> 2); kb = tx + 32 * (j & 3); }
       float w = 0.f;
-      if (n0 + n < g.N && k0 + kb < g.K) {
-        w = g.B ? g.B[(long)(k0 + kb) * g.b_sk + (long)(n0 + n) * g.b_sn] : 1.f;
-        if (g.b_act) w = lrelu(w);
-      }
-      Bs[kb][n] = w;
+      if (n0 + n < g.N && k0 + kb < g.K) w = g.B ? g.B[(long)(k0 + kb) * g.b_sk + (long)(n0 + n) * g.b_sn] : 1.f;
+      bv[j] = w;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int m, k;
+      if (g.a_sk == 1) { m = ty + 8 * (j >> 2); k = tx + 32 * (j & 3); } else { m = tx; k = ty + 8 * j; }
+      As[k][m] = g.a_act ? lrelu(av[j]) : av[j];
+      int n, kb;
+      if (g.b_sn == 1) { kb = ty + 8 * j; n = tx; } else { n = ty + 8 * (j >> 2); kb = tx + 32 * (j & 3); }
+      Bs[kb][n] = g.b_act ? lrelu(bv[j]) : bv[j];
     }
     __syncthreads();
+    const int kend = g.K - k0 < kGemmKC ? g.K - k0 : kGemmKC;
+    if (kend == kGemmKC) {
+#pragma unroll 16
+      for (int kk = 0; kk < kGemmKC; ++kk) {
+        const float b = Bs[kk][tx];
 #pragma unroll
-    for (int kk = 0; kk < 32; ++kk) {
-      const float b = Bs[kk][tx];
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[kk][ty + 8 * r], b, acc[r]);
+      }
+    } else {
+      for (int kk = 0; kk < kend; ++kk) {
+        const float b = Bs[kk][tx];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[kk][ty + 8 * r], b, acc[r]);
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[kk][ty + 8 * r], b, acc[r]);
+      }
     }
     __syncthreads();
   }

@@ -70,6 +70,11 @@ struct chb_generator {
   // workspace layout (byte offsets, sized for max_batch)
   int64_t ws_bytes = 0;
   int64_t ws_labels, ws_codes32, ws_out, ws_codes16, ws_noise, ws_mu, ws_weff, ws_x0;
+  int64_t ws_labels_b, ws_codes32_b, ws_out_b;  // second set of host-I/O buffers (forward_host_async double buffering)
+  // forward_host_async state: H2D and D2H run on their own streams so they overlap the neighbouring batches' compute
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  uint64_t async_calls = 0;
   int64_t ws_onehot[6];
   int64_t ws_actv, ws_hs, ws_h0, ws_h1, ws_dx0;
   const uint8_t* blob = nullptr;
@@ -177,6 +182,9 @@ static void build_layout(chb_generator* g) {
   g->ws_labels = ws_alloc(g, (int64_t)B * S * S);
   g->ws_codes32 = ws_alloc(g, (int64_t)B * c.label_nc * L * 4);
   g->ws_out = ws_alloc(g, (int64_t)B * 3 * S * S * 4);
+  g->ws_labels_b = ws_alloc(g, (int64_t)B * S * S);
+  g->ws_codes32_b = ws_alloc(g, (int64_t)B * c.label_nc * L * 4);
+  g->ws_out_b = ws_alloc(g, (int64_t)B * 3 * S * S * 4);
   g->ws_codes16 = ws_alloc(g, (int64_t)B * c.label_nc * L * 2);
   g->ws_noise = ws_alloc(g, (int64_t)B * g->noise_pix * 4);
   g->ws_mu = ws_alloc(g, (int64_t)g->n_styled * B * 32 * L * 2);
@@ -459,7 +467,17 @@ int chb_generator_create(const chb_gen_config* cfg, chb_generator** out) {
   return CHB_OK;
 }
 
-void chb_generator_destroy(chb_generator* g) { delete g; }
+void chb_generator_destroy(chb_generator* g) {
+  if (!g) return;
+  for (int i = 0; i < 2; ++i) {
+    if (g->ev_in[i]) cudaEventDestroy(g->ev_in[i]);
+    if (g->ev_done[i]) cudaEventDestroy(g->ev_done[i]);
+    if (g->ev_copied[i]) cudaEventDestroy(g->ev_copied[i]);
+  }
+  if (g->h2d_stream) cudaStreamDestroy(g->h2d_stream);
+  if (g->d2h_stream) cudaStreamDestroy(g->d2h_stream);
+  delete g;
+}
 
 int chb_generator_num_tensors(const chb_generator* g) { return g ? (int)g->tensors.size() : 0; }
 
@@ -655,6 +673,85 @@ int chb_generator_forward_host(chb_generator* g, const uint8_t* labels_host, con
   if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
   if (err != cudaSuccess) {
     set_error(std::string("D2H copy / sync failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+// Streamed form of forward_host: batch n's H2D (own stream) overlaps batch n-1's compute, its D2H (own stream) overlaps
+// batch n+1's compute; inputs and the output image are double buffered in the workspace.
+int chb_generator_forward_host_async(chb_generator* g, const uint8_t* labels_host, const float* codes_host,
+                                     uint64_t seed, float* out_host, int B, void* stream_) {
+  if (!g || !labels_host || !codes_host || !out_host || !g->ws) {
+    set_error("chb_generator_forward_host_async: NULL argument or unbound generator");
+    return CHB_ERR_ARG;
+  }
+  if (B <= 0 || B > g->cfg.max_batch) {
+    set_error("chb_generator_forward_host_async: batch exceeds max_batch");
+    return CHB_ERR_ARG;
+  }
+  cudaError_t err = cudaSuccess;
+  if (!g->h2d_stream) {
+    err = cudaStreamCreateWithFlags(&g->h2d_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&g->d2h_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && err == cudaSuccess; ++i) {
+      err = cudaEventCreateWithFlags(&g->ev_in[i], cudaEventDisableTiming);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&g->ev_done[i], cudaEventDisableTiming);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&g->ev_copied[i], cudaEventDisableTiming);
+    }
+    if (err != cudaSuccess) {
+      set_error(std::string("forward_host_async: stream/event creation failed: ") + cudaGetErrorString(err));
+      return CHB_ERR_CUDA;
+    }
+  }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const chb_gen_config& c = g->cfg;
+  uint8_t* ws = g->ws;
+  const size_t S2 = (size_t)c.crop * c.crop;
+  const int p = (int)(g->async_calls & 1);
+  const bool reuse = g->async_calls >= 2;  // buffer set p was last used by call n-2
+  uint8_t* d_labels = ws + (p ? g->ws_labels_b : g->ws_labels);
+  float* d_codes = reinterpret_cast<float*>(ws + (p ? g->ws_codes32_b : g->ws_codes32));
+  float* d_out = reinterpret_cast<float*>(ws + (p ? g->ws_out_b : g->ws_out));
+  // H2D of this batch: may start as soon as call n-2 (same buffers) has finished computing
+  if (reuse) err = cudaStreamWaitEvent(g->h2d_stream, g->ev_done[p], 0);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(d_labels, labels_host, (size_t)B * S2, cudaMemcpyHostToDevice, g->h2d_stream);
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(d_codes, codes_host, (size_t)B * c.label_nc * c.style_len * 4, cudaMemcpyHostToDevice,
+                          g->h2d_stream);
+  if (err == cudaSuccess) err = cudaEventRecord(g->ev_in[p], g->h2d_stream);
+  // compute: needs the inputs, and the D2H of call n-2 must have drained the output buffer
+  if (err == cudaSuccess) err = cudaStreamWaitEvent(stream, g->ev_in[p], 0);
+  if (err == cudaSuccess && reuse) err = cudaStreamWaitEvent(stream, g->ev_copied[p], 0);
+  if (err != cudaSuccess) {
+    set_error(std::string("forward_host_async: H2D stage failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  int rc = chb_generator_forward(g, d_labels, d_codes, nullptr, seed, d_out, B, CHB_IMPL_TCGEN05, stream_);
+  if (rc != CHB_OK) return rc;
+  err = cudaEventRecord(g->ev_done[p], stream);
+  if (err == cudaSuccess) err = cudaStreamWaitEvent(g->d2h_stream, g->ev_done[p], 0);
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(out_host, d_out, (size_t)B * 3 * S2 * 4, cudaMemcpyDeviceToHost, g->d2h_stream);
+  if (err == cudaSuccess) err = cudaEventRecord(g->ev_copied[p], g->d2h_stream);
+  if (err != cudaSuccess) {
+    set_error(std::string("forward_host_async: D2H stage failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  g->async_calls++;
+  return CHB_OK;
+}
+
+// Waits until every image enqueued by chb_generator_forward_host_async has landed in its host buffer.
+int chb_generator_host_sync(chb_generator* g) {
+  if (!g) {
+    set_error("chb_generator_host_sync: NULL generator");
+    return CHB_ERR_ARG;
+  }
+  if (!g->d2h_stream) return CHB_OK;
+  cudaError_t err = cudaStreamSynchronize(g->d2h_stream);
+  if (err != cudaSuccess) {
+    set_error(std::string("chb_generator_host_sync: ") + cudaGetErrorString(err));
     return CHB_ERR_CUDA;
   }
   return CHB_OK;

@@ -165,6 +165,28 @@ class SeanGeneratorB200:
                                                            C.c_void_p(out.data_ptr()), B, self.impl, self._stream()))
         return out
 
+    def forward_host_async(self, labels, codes, out, seed=0):
+        """Streamed form of forward_host for loops over many batches: enqueues H2D -> forward -> D2H and returns.
+        `labels` (uint8 [B,S,S]), `codes` (float32 [B,19,512]) and `out` (float32 [B,3,S,S]) are host tensors, pinned
+        for real overlap, and must stay untouched until host_sync()."""
+        if self.blob is None:
+            raise _lib.ChbError("no weights loaded")
+        for t, dt in ((labels, torch.uint8), (codes, torch.float32), (out, torch.float32)):
+            if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != dt or not t.is_contiguous():
+                raise _lib.ChbError("forward_host_async takes contiguous host tensors (uint8 labels, float32 codes/out)")
+        B = labels.shape[0]
+        if tuple(out.shape) != (B, 3, self.crop, self.crop) or tuple(codes.shape) != (B, self.label_nc, 512):
+            raise _lib.ChbError("forward_host_async: bad shapes")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_generator_forward_host_async(self.handle, C.c_void_p(labels.data_ptr()),
+                                                                 C.c_void_p(codes.data_ptr()), seed,
+                                                                 C.c_void_p(out.data_ptr()), B, self._stream()))
+        return out
+
+    def host_sync(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_generator_host_sync(self.handle))
+
     def forward(self, input, rgb_img=None, obj_dic=None, noise=None, seed=0):
         """Reference signature (generator.py:72): input = one-hot seg [B,19,S,S]; styles come from `obj_dic`
         ({str(j): {'ACE': Tensor[512]}}, the UI path of normalization.py:121-139 — image 0 only, like the

@@ -154,6 +154,14 @@ int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* 
 int chb_generator_forward_host(chb_generator* g, const uint8_t* labels_host, const float* codes_host,
                                const float* noise_host, uint64_t seed, float* out_host, int B, int impl,
                                void* stream);
+/* Streamed form of chb_generator_forward_host for callers that render many batches (validation_in_train.py:28-33,
+ * script_find_direction.py:55-74 loop gen_img): returns once the work is enqueued.  The H2D copies run on an internal
+ * stream and overlap the previous batch's kernels, the D2H copy of the image overlaps the next batch's kernels; inputs
+ * and output are double buffered inside the workspace.  Host buffers should be pinned and must stay valid until
+ * chb_generator_host_sync() returns; noise is drawn on the device from `seed`. */
+int chb_generator_forward_host_async(chb_generator* g, const uint8_t* labels_host, const float* codes_host,
+                                     uint64_t seed, float* out_host, int B, void* stream);
+int chb_generator_host_sync(chb_generator* g);
 /* Same as chb_generator_forward (tcgen05 path) with a CUDA event recorded on `stream` between consecutive conv
  * launches: fills ms[i] / flops[i] (tensor-core FLOPs issued) for launch i and returns the number of launches
  * (or a negative error).  Synchronises on the last event.  Used by bench.py for the live roofline figure. */

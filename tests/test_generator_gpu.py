@@ -92,6 +92,23 @@ def test_host_entry_point_equals_device_entry_point(gen64):
     assert torch.equal(a, b)
 
 
+def test_streamed_host_entry_point_equals_device_entry_point(gen64):
+    """forward_host_async double-buffers H2D / compute / D2H across calls: five different batches in flight through
+    two buffer sets must each come back equal to the device entry point with the same seed."""
+    B, n = 3, 5
+    ins = [(synth.make_labels(B, 64, "blocky", seed=40 + i).pin_memory(), synth.make_codes(B, seed=50 + i).pin_memory())
+           for i in range(n)]
+    outs = [torch.empty((B, 3, 64, 64)).pin_memory() for _ in range(n)]
+    for i, (lab, cod) in enumerate(ins):
+        gen64.forward_host_async(lab, cod, outs[i], seed=7 + i)
+    gen64.host_sync()
+    for i, (lab, cod) in enumerate(ins):
+        want = gen64.forward_labels(lab.cuda(), cod.cuda(), seed=7 + i).cpu()
+        assert torch.equal(outs[i], want), i
+    with pytest.raises(_lib.ChbError):
+        gen64.forward_host_async(ins[0][0].cuda(), ins[0][1], outs[0])
+
+
 def test_full_size_batch_properties(gen256):
     """Size-independent properties at 256x256: an image's result does not depend on its batch-mates or its slot,
     and device noise is seed-deterministic."""
