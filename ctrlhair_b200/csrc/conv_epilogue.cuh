@@ -342,10 +342,12 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // 32 accumulator columns of the PLAIN epilogue through the staging block (channels-last output, full block valid).
 // ro / oo4 / oo8: per-tile row offsets (16-byte units) of the residual and of the output in the 8- and 4-lanes-per-row
 // arrangements; bi = image of this lane's own row (for per-image bias).
+// breg (fast geometry only): this block's 32 bias values, one per lane, fetched before the accumulator wait; they
+// are broadcast with warp shuffles instead of being re-loaded (and waited for) inside the block.
 template <int ACT, bool FAST>
 __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uint32_t stg, int lane, int n, int bi,
                                               const RowOff<8, FAST>& ro, const RowOff<4, FAST>& oo4,
-                                              const RowOff<8, FAST>& oo8) {
+                                              const RowOff<8, FAST>& oo8, float breg = 0.f) {
   float v[32];
   tmem_ld<32>(taddr, v);
   uint4 rr[8];
@@ -355,7 +357,10 @@ __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uin
     gather_commit<8>(stg, lane, g, rr);
   }
   tmem_ld_fence(v);
-  if (e.bias) {
+  if (FAST) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, breg, i);
+  } else if (e.bias) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)bi * e.nrows : 0) + n);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -558,11 +563,22 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
           }
         }
         const int bi = b < p.B ? b : p.B - 1;
+        float breg[4] = {0.f, 0.f, 0.f, 0.f};
+        if (FAST && e.bias) {
+          const float* bp = e.bias + (e.bias_per_image ? (long long)bi * e.nrows : 0) + n0 + j + lane;
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk)
+            if (32 * blk < ch) breg[blk] = __ldg(bp + 32 * blk);
+        }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
         if (FAST) {
-          for (; j < jend; j += 32) plain_block32<ACT, FAST>(e, taddr + (uint32_t)j, stg, lane, n0 + j, bi, ro, oo4, oo8);
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk)
+            if (32 * blk < ch)
+              plain_block32<ACT, FAST>(e, taddr + (uint32_t)(j + 32 * blk), stg, lane, n0 + j + 32 * blk, bi, ro, oo4, oo8,
+                                       breg[blk]);
         } else {
           for (; j + 32 <= jend; j += 32) {
             if (staged && n0 + j + 32 <= p.N) {
