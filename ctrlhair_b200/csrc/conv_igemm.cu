@@ -310,7 +310,9 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   }
   const int halo_buf = kc_max == 64 ? kHaloBufBytes : kHaloBufBytes / 2;
   const int kRegion = 193 * 1024;  // 227 KB - align slack - barriers - epilogue staging
-  if (wbytes_total + 2LL * halo_buf > kRegion || d.Nrows / d.BN > device_sm_count()) wstat_ok = false;
+  int wstat_min_halo = 2;
+  if (const char* mv = getenv("CHB_WSTAT_MINHALO")) wstat_min_halo = atoi(mv);
+  if (wbytes_total + (long long)wstat_min_halo * halo_buf > kRegion || d.Nrows / d.BN > device_sm_count()) wstat_ok = false;
   k.wstat = wstat_ok ? 1 : 0;
   k.halo_any = 0;
   k.halo_bo = 0;
@@ -333,6 +335,12 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   } else {
     k.wstat_bytes = 0;
     k.nhalo = k.halo_any ? 2 : 0;
+    if (k.halo_any) {
+      if (const char* nv = getenv(d.BN <= 64 ? "CHB_NHALO64" : (d.BN <= 128 ? "CHB_NHALO128" : "CHB_NHALO256"))) {
+        const int n = atoi(nv);
+        if (n >= 2 && n <= kMaxHalo) k.nhalo = n;
+      }
+    }
     k.stage_bytes = k.a_region + ((d.BN * 128 * k.hg + 1023) / 1024) * 1024;
     const int budget = kSmemBudget - k.nhalo * halo_buf;
     k.nstages = budget / k.stage_bytes;

@@ -171,6 +171,18 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
               tc_fence_after();
               sb = stage_base + stage * stage_bytes + a_region;
             }
+            if (tg == 3) {
+              // a whole kernel row (kx = 0, 1, 2) in one asm block
+              const uint64_t adesc = umma_desc_make(hiA, hb + voff);
+              const uint64_t bdesc = umma_desc_make(hiB, sb);
+              if (elect_one()) {
+                if (k64) umma_f16_ss_row3<4>(d_tmem, adesc, bdesc, row_bytes >> 4, bstep >> 4, idesc, accumulate);
+                else umma_f16_ss_row3<2>(d_tmem, adesc, bdesc, row_bytes >> 4, bstep >> 4, idesc, accumulate);
+              }
+              __syncwarp();
+              accumulate = 1;
+              voff += row_step;
+            } else
             for (int g = 0; g < tg; ++g) {
               const uint64_t adesc = umma_desc_make(hiA, hb + voff);
               const uint64_t bdesc = umma_desc_make(hiB, sb);

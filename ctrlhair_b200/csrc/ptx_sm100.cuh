@@ -154,6 +154,97 @@ __device__ __forceinline__ void umma_f16_ss_k<2>(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One kernel row of a 3x3 tap group (taps kx = 0, 1, 2 of one ky) issued from a single asm block: 3 x KS MMAs.
+// The A view advances by a_step16 (= row_bytes >> 4: one pixel to the right inside the halo tile) and the weight slab by
+// b_step16 per tap, both in descriptor address units (16 bytes).  For narrow N tiles (N <= 128: 32-64 tensor-core
+// cycles per MMA) the per-tap loop overhead of the issuing warp, not the tensor core, sets the pace otherwise.
+template <int KS>
+__device__ __forceinline__ void umma_f16_ss_row3(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a_step16,
+                                                 uint32_t b_step16, uint32_t idesc, uint32_t accumulate);
+template <>
+__device__ __forceinline__ void umma_f16_ss_row3<4>(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a_step16,
+                                                    uint32_t b_step16, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b64 a, b, as, bs, ta, tb;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 pt, %6, %6;\n\t"
+      "cvt.u64.u32 as, %3;\n\t"
+      "cvt.u64.u32 bs, %4;\n\t"
+      "mov.b64 a, %1;\n\t"
+      "mov.b64 b, %2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, p;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(a_step16), "r"(b_step16), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void umma_f16_ss_row3<2>(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a_step16,
+                                                    uint32_t b_step16, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b64 a, b, as, bs, ta, tb;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 pt, %6, %6;\n\t"
+      "cvt.u64.u32 as, %3;\n\t"
+      "cvt.u64.u32 bs, %4;\n\t"
+      "mov.b64 a, %1;\n\t"
+      "mov.b64 b, %2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, p;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %5, pt;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(a_step16), "r"(b_step16), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Descriptor from a precomputed high word (stride / version / layout) and a shared-memory address.
 __device__ __forceinline__ uint32_t umma_desc_hi(uint32_t row_bytes, uint32_t sbo_bytes) {
   return (sbo_bytes >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);

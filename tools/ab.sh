@@ -4,11 +4,12 @@
 R=${ROUNDS:-3}
 mkdir -p gpurun_out; rm -f gpurun_out/ab_*.log
 for r in $(seq 1 $R); do
-  i=0
-  for L in "$@"; do
+  n=$#
+  for j in $(seq 0 $((n-1))); do
+    i=$j; [ $((r % 2)) -eq 0 ] && i=$((n-1-j))   # even rounds run the builds in reverse order
+    L=${@:$((i+1)):1}
     CHB_LIB_PATH=$L timeout 300 python tools/gpu_quick_bench.py --steps 6 --warmup 2 --table > gpurun_out/ab_${i}_$r.log 2>&1
     echo "[$i] round $r: $(grep -E '^best' gpurun_out/ab_${i}_$r.log | cut -c1-40)  | $(grep -E 'per-launch' gpurun_out/ab_${i}_$r.log | sed 's/.*total/total/')"
-    i=$((i+1))
   done
 done
 python - "$@" <<'PY'
