@@ -162,6 +162,17 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
           const uint32_t hb = halo_base + hs * halo_bytes;
           uint32_t voff = ntaps == 9 ? 0u : row_step + row_bytes;  // view offset of the current tap
           uint32_t kx = 0;
+          if (WSTAT && ntaps == 9) {
+            // resident weights: nothing to wait for between taps, all 9 x KS MMAs of the chunk go out in one asm block
+            const uint64_t adesc = umma_desc_make(hiA, hb);
+            const uint64_t bdesc = umma_desc_make(hiB, wstat_base + (uint32_t)sg.wofs + (uint32_t)c * wbytes);
+            if (elect_one()) {
+              if (k64) umma_f16_ss_tile9<4>(d_tmem, adesc, bdesc, row_bytes >> 4, row_step >> 4, bstep >> 4, idesc, accumulate);
+              else umma_f16_ss_tile9<2>(d_tmem, adesc, bdesc, row_bytes >> 4, row_step >> 4, bstep >> 4, idesc, accumulate);
+            }
+            __syncwarp();
+            accumulate = 1;
+          } else
           for (int t0 = 0; t0 < ntaps; t0 += tg) {
             uint32_t sb;
             if (WSTAT) {

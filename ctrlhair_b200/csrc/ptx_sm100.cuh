@@ -245,6 +245,214 @@ __device__ __forceinline__ void umma_f16_ss_row3<2>(uint32_t tmem_d, uint64_t ad
       "l"(adesc), "l"(bdesc), "r"(a_step16), "r"(b_step16), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// All nine taps of a 3x3 segment chunk from one asm block (weight-stationary mode: no per-tap barrier): tap (ky, kx)
+// reads the halo view at ky * row_step16 + kx * a_step16 and the weight slab at (ky*3 + kx) * b_step16 (16-byte units).
+template <int KS>
+__device__ __forceinline__ void umma_f16_ss_tile9(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a_step16,
+                                                  uint32_t row_step16, uint32_t b_step16, uint32_t idesc,
+                                                  uint32_t accumulate);
+template <>
+__device__ __forceinline__ void umma_f16_ss_tile9<4>(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a_step16,
+                                                     uint32_t row_step16, uint32_t b_step16, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b64 a, b, ar, as, rs, bs, ta, tb;\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.eq.b32 pt, %7, %7;\n\t"
+      "cvt.u64.u32 as, %3;\n\t"
+      "cvt.u64.u32 rs, %4;\n\t"
+      "cvt.u64.u32 bs, %5;\n\t"
+      "mov.b64 ar, %1;\n\t"
+      "mov.b64 b, %2;\n\t"
+      "mov.b64 a, ar;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, p;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ar, ar, rs;\n\t"
+      "mov.b64 a, ar;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ar, ar, rs;\n\t"
+      "mov.b64 a, ar;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 4;\n\t"
+      "add.u64 tb, b, 4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ta, a, 6;\n\t"
+      "add.u64 tb, b, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(a_step16), "r"(row_step16), "r"(b_step16), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void umma_f16_ss_tile9<2>(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a_step16,
+                                                     uint32_t row_step16, uint32_t b_step16, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pt;\n\t"
+      ".reg .b64 a, b, ar, as, rs, bs, ta, tb;\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.eq.b32 pt, %7, %7;\n\t"
+      "cvt.u64.u32 as, %3;\n\t"
+      "cvt.u64.u32 rs, %4;\n\t"
+      "cvt.u64.u32 bs, %5;\n\t"
+      "mov.b64 ar, %1;\n\t"
+      "mov.b64 b, %2;\n\t"
+      "mov.b64 a, ar;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, p;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ar, ar, rs;\n\t"
+      "mov.b64 a, ar;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 ar, ar, rs;\n\t"
+      "mov.b64 a, ar;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "add.u64 a, a, as;\n\t"
+      "add.u64 b, b, bs;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %6, pt;\n\t"
+      "add.u64 ta, a, 2;\n\t"
+      "add.u64 tb, b, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ta, tb, %6, pt;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(a_step16), "r"(row_step16), "r"(b_step16), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Descriptor from a precomputed high word (stride / version / layout) and a shared-memory address.
 __device__ __forceinline__ uint32_t umma_desc_hi(uint32_t row_bytes, uint32_t sbo_bytes) {
   return (sbo_bytes >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
