@@ -291,7 +291,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   k.N = d.N;
   // Halo path (on by default; CHB_HALO=0 turns it off for A/B comparisons): 3x3 segments with 64-channel chunks on
   // 8-wide single-image tiles load a (TH+2)x(TW+2) halo tile once per channel chunk and feed all nine taps from it.
-  int halo_mode = 1, wstat_mode = 1;
+  int halo_mode = 1, wstat_mode = 2;
   if (const char* hv = getenv("CHB_HALO")) halo_mode = atoi(hv);
   if (const char* wv = getenv("CHB_WSTAT")) wstat_mode = atoi(wv);
   const bool halo_geo = d.TW == 8 && d.TB == 1 && d.TH <= 16;
@@ -305,7 +305,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     const int kc = g.C == 32 ? 32 : 64;
     if (kc > kc_max) kc_max = kc;
     if (g.per_image) wstat_ok = false;
-    if (kc == 32 && wstat_mode < 2) wstat_ok = false;  // measured on B200: one-hot (64-byte row) layers run faster streamed
+    if (kc == 32 && wstat_mode < 2) wstat_ok = false;  // CHB_WSTAT=1: one-hot (64-byte row) layers streamed (slower since the nine taps of a resident chunk go out in one asm block)
     wbytes_total += (long long)g.taps * g.C * d.BN * 2;
   }
   const int halo_buf = kc_max == 64 ? kHaloBufBytes : kHaloBufBytes / 2;
