@@ -13,6 +13,7 @@ constexpr int kMaxLevels = 8;
 struct PyramidParams {
   const uint8_t* labels;
   int B, S, nlevels, nclass;
+  int ones_ch0, ones_n;  // channels [ones_ch0, ones_ch0 + ones_n) are written as 1.0 at every pixel (bias carriers)
   int shift[kMaxLevels];
   __half* out[kMaxLevels];
   long long first_pix[kMaxLevels + 1];  // prefix sum of B*r*r per level
@@ -42,6 +43,12 @@ __global__ void onehot_pyramid_kernel(const PyramidParams p) {
 #pragma unroll
       for (int k = 0; k < 16; ++k)
         if (k == (lab >> 1)) w[k] = (lab & 1) ? (one << 16) : one;
+    }
+    for (int c = p.ones_ch0; c < p.ones_ch0 + p.ones_n; ++c) {
+      const uint32_t one = 0x3C00u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k == (c >> 1)) w[k] |= (c & 1) ? (one << 16) : one;
     }
     uint4* o = reinterpret_cast<uint4*>(p.out[l] + pix * 32);
     o[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -135,11 +142,16 @@ int codes_cast_transpose(const float* in, void* out, int B, int NC, int L, cudaS
 
 }  // namespace chb
 
-extern "C" {
-
-int chb_onehot_pyramid(const uint8_t* labels, int B, int S, int nlevels, const int* shifts, void* const* outs,
-                       int nclass, void* stream) {
-  using namespace chb;
+namespace chb {
+// Same, with channels [ones_ch0, ones_ch0 + ones_n) set to 1.0 at every pixel.  The generator uses two such channels
+// to carry conv biases through the GEMM: sum_j one_hot[p][j] = 1, and the centre tap of a zero-padded 3x3 conv never
+// leaves the image, so weight[n][centre tap][ones channel] = bias[n] (split hi + lo in fp16) adds the bias exactly.
+int onehot_pyramid_ones(const uint8_t* labels, int B, int S, int nlevels, const int* shifts, void* const* outs,
+                             int nclass, int ones_ch0, int ones_n, void* stream) {
+  if (ones_n < 0 || (ones_n > 0 && (ones_ch0 < nclass || ones_ch0 + ones_n > 32))) {
+    set_error("onehot_pyramid: constant channels must lie in [nclass, 32)");
+    return CHB_ERR_ARG;
+  }
   if (!labels || !shifts || !outs || B <= 0 || S <= 0 || nlevels <= 0 || nlevels > kMaxLevels || nclass <= 0 ||
       nclass > 32) {
     set_error("chb_onehot_pyramid: bad arguments (need 1..8 levels, 1..32 classes)");
@@ -147,6 +159,7 @@ int chb_onehot_pyramid(const uint8_t* labels, int B, int S, int nlevels, const i
   }
   PyramidParams p;
   p.labels = labels; p.B = B; p.S = S; p.nlevels = nlevels; p.nclass = nclass;
+  p.ones_ch0 = ones_ch0; p.ones_n = ones_n;
   p.first_pix[0] = 0;
   for (int l = 0; l < nlevels; ++l) {
     if (shifts[l] < 0 || (S >> shifts[l]) <= 0 || ((S >> shifts[l]) << shifts[l]) != S || !outs[l]) {
@@ -160,6 +173,15 @@ int chb_onehot_pyramid(const uint8_t* labels, int B, int S, int nlevels, const i
   }
   onehot_pyramid_kernel<<<grid_for(p.first_pix[nlevels], 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("onehot_pyramid");
+}
+
+}  // namespace chb
+
+extern "C" {
+
+int chb_onehot_pyramid(const uint8_t* labels, int B, int S, int nlevels, const int* shifts, void* const* outs,
+                       int nclass, void* stream) {
+  return chb::onehot_pyramid_ones(labels, B, S, nlevels, shifts, outs, nclass, 0, 0, stream);
 }
 
 int chb_noise_fill(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {

@@ -358,8 +358,10 @@ __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uin
   }
   tmem_ld_fence(v);
   if (FAST) {
+    if (e.bias) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, breg, i);
+      for (int i = 0; i < 32; ++i) v[i] += __shfl_sync(0xffffffffu, breg, i);
+    }
   } else if (e.bias) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (e.bias_per_image ? (long long)bi * e.nrows : 0) + n);
 #pragma unroll

@@ -340,7 +340,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     d.seg[0] = make_seg(ws + g->ws_onehot[0], g->sw, 32, 0, 32, 9, blobp(g, g->t_fcw));
     d.N = d.Nrows = 16 * nf; d.BN = 256;
     d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
-    d.bias = reinterpret_cast<const float*>(blobp(g, g->t_fcb));
+    d.bias = nullptr;  // carried by the constant one-hot channels (fc.w centre tap); fc.b stays in the blob for checkers
     nhwc_out(&d, ws + g->ws_x0, CHB_F32, g->sw, 16 * nf);
     if ((rc = push_step(steps, d, "fc")) != CHB_OK) return rc;
   }
@@ -358,7 +358,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.seg[0] = make_seg(onehot, r, 32, 0, 32, 9, blobp(g, b.t_shw));
       d.N = d.Nrows = actvC; d.BN = actvC == 384 ? 192 : 256;  // one-hot A tile is re-read per N tile: keep N tiles few
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_RELU;
-      d.bias = reinterpret_cast<const float*>(blobp(g, b.t_shb));
+      d.bias = nullptr;  // carried by the constant one-hot channels (sh.w centre tap)
       nhwc_out(&d, ws + g->ws_actv, CHB_F16, r, actvC);
       if ((rc = push_step(steps, d, b.name + ".mlp_shared")) != CHB_OK) return rc;
     }
@@ -452,11 +452,11 @@ int chb_generator_create(const chb_gen_config* cfg, chb_generator** out) {
     set_error("chb_generator_create: NULL argument");
     return CHB_ERR_ARG;
   }
-  if (cfg->ngf <= 0 || cfg->ngf % 64 != 0 || cfg->label_nc <= 0 || cfg->label_nc > 32 || cfg->crop < 32 ||
+  if (cfg->ngf <= 0 || cfg->ngf % 64 != 0 || cfg->label_nc <= 0 || cfg->label_nc > 30 || cfg->crop < 32 ||
       cfg->crop % 32 != 0 || (cfg->crop & (cfg->crop - 1)) != 0 || cfg->style_len <= 0 || cfg->style_len % 64 != 0 ||
       cfg->max_batch <= 0) {
     set_error(
-        "chb_generator_create: need ngf % 64 == 0, label_nc in 1..32, crop a power of two >= 32, style_len % 64 == 0, "
+        "chb_generator_create: need ngf % 64 == 0, label_nc in 1..30, crop a power of two >= 32, style_len % 64 == 0, "
         "max_batch > 0");
     return CHB_ERR_ARG;
   }
@@ -605,7 +605,8 @@ static int forward_impl(chb_generator* g, const uint8_t* labels, const float* co
     shifts[l] = 5 - l;
     outs[l] = ws + g->ws_onehot[l];
   }
-  rc = chb_onehot_pyramid(labels, B, c.crop, 6, shifts, outs, c.label_nc, stream);
+  // channels label_nc, label_nc + 1 are constant 1: they carry the fc / mlp_shared biases through the GEMM (packer.py)
+  rc = onehot_pyramid_ones(labels, B, c.crop, 6, shifts, outs, c.label_nc, c.label_nc, 2, stream);
   if (rc != CHB_OK) return rc;
   float* nz = reinterpret_cast<float*>(ws + g->ws_noise);
   if (noise) {

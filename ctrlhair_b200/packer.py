@@ -30,11 +30,19 @@ def _k_major(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
 
-def _k_major_onehot(w):
-    """[N, 19, 3, 3] -> [N, 9*32], label channels zero-padded to 32."""
+def _k_major_onehot(w, bias=None):
+    """[N, 19, 3, 3] -> [N, 9*32], label channels zero-padded to 32.  With `bias`: the two channels after the labels
+    are constant 1 in the device one-hot maps (csrc/aux_kernels.cu), and the centre tap of a zero-padded 3x3 conv
+    never leaves the image, so bias[n] placed on that tap of those channels (fp16 hi + lo split: exact to 2^-22) is
+    added by the GEMM itself and the epilogue has no bias to fetch."""
     n, c = w.shape[0], w.shape[1]
     out = torch.zeros((n, 3, 3, ONEHOT_PAD), dtype=w.dtype)
     out[..., :c] = w.permute(0, 2, 3, 1)
+    if bias is not None:
+        assert c + 2 <= ONEHOT_PAD
+        hi = bias.float().to(torch.float16).float()
+        out[:, 1, 1, c] = hi
+        out[:, 1, 1, c + 1] = (bias.float() - hi).to(torch.float16).float()
     return out.reshape(n, 9 * ONEHOT_PAD)
 
 
@@ -61,14 +69,15 @@ def pack_generator(sd, ngf=64, label_nc=19, weight_dtype=torch.float16):
     """Returns {blob tensor name: CPU tensor} for every tensor chb_generator_tensor_info enumerates."""
     out = {}
     wd = weight_dtype
-    out["fc.w"] = _k_major_onehot(sd["fc.weight"].float()).to(wd)
+    out["fc.w"] = _k_major_onehot(sd["fc.weight"].float(), sd["fc.bias"]).to(wd)
     out["fc.b"] = sd["fc.bias"].float()
     fcmu_w, fcmu_b = [], []
     for name, fi, fo, styled in BLOCKS:
         fin, fout = fi * ngf, fo * ngf
         aces = ace_list(fin, fout)
         out[name + ".sh.w"] = torch.cat(
-            [_k_major_onehot(sd["%s.%s.Spade.mlp_shared.0.weight" % (name, a)].float()) for a, _ in aces]).to(wd)
+            [_k_major_onehot(sd["%s.%s.Spade.mlp_shared.0.weight" % (name, a)].float(),
+                             sd["%s.%s.Spade.mlp_shared.0.bias" % (name, a)]) for a, _ in aces]).to(wd)
         out[name + ".sh.b"] = torch.cat([sd["%s.%s.Spade.mlp_shared.0.bias" % (name, a)].float() for a, _ in aces])
         for a, C in aces:
             p = "%s.%s" % (name, a)

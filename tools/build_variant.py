@@ -29,7 +29,8 @@ def main():
     objs = []
     for f in b.SOURCES:
         o = os.path.join(src, f.replace(".cu", ".o"))
-        subprocess.check_call([b._nvcc()] + b.NVCC_FLAGS + ["-c", os.path.join(src, f), "-o", o])
+        extra = os.environ.get("VARIANT_FLAGS", "").split()   # e.g. VARIANT_FLAGS="-DCHB_EXP_NOSTG"
+        subprocess.check_call([b._nvcc()] + b.NVCC_FLAGS + extra + ["-c", os.path.join(src, f), "-o", o])
         objs.append(o)
     os.makedirs(os.path.join(ROOT, "variants"), exist_ok=True)
     out = os.path.join(ROOT, "variants", "lib%s.so" % name)
