@@ -158,6 +158,20 @@ SYMBOLS = [
     ("chb_cttrain_step", C.c_int, [C.c_void_p, C.c_int, C.POINTER(CtTrainBatch), C.c_void_p, C.c_void_p]),
     ("chb_cttrain_adam", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_cttrain_launches", C.c_int, [C.c_void_p, C.c_int]),
+    ("chb_image_to_u8", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("chb_blend_mask", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("chb_poisson_blend", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("chb_postprocess_workspace_bytes", C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    ("chb_postprocess_blending", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+      C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("chb_rgb_to_hsv", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("chb_hsv_to_rgb", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("chb_onehot_to_label", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
+    ("chb_label_to_onehot", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
 ]
 
 

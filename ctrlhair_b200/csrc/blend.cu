@@ -1,0 +1,558 @@
+// Post-processing either side of the generator, device resident:
+//   * Poisson blending of the generated image into the input face (poisson_blending.py:29-87, hair_editor.py:257-308):
+//     blend mask (hair union + elliptical dilations), the sparse system solved by conjugate gradients in fp64 with the
+//     whole state of one (image, channel) system resident in the shared memory of an 8-CTA cluster (halo rows and the
+//     two dot products per iteration travel through distributed shared memory, no HBM traffic inside the loop);
+//   * 8-bit RGB <-> HSV (cv2.cvtColor at ui/backend.py:98-101,108-125) and label map <-> one-hot
+//     (shape_branch/shape_util.py:6-20), which remove the host round trips of Backend.parse_img / output.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdint>
+#include <string>
+
+#include "../../include/ctrlhair_b200.h"
+#include "conv_igemm.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace chb {
+
+namespace {
+
+int blend_check(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+int blend_grid(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+constexpr int kHair = 13;        // global_value_utils.py:49-52
+constexpr int kBackground = 0;   // PARSING_LABEL_LIST.index('background')
+
+// ndarray.astype('uint8') of an in-range float: truncation toward zero (x86 numpy wraps out-of-range values modulo 256)
+__device__ __forceinline__ uint8_t f32_to_u8_trunc(float v) { return (uint8_t)(((int)truncf(v)) & 0xFF); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// hair_editor.py:273-288: generator output [B,3,H,W] in [-1,1] -> cv2 layout uint8 [B,H,W,3], (x*127.5+127.5).astype(uint8)
+__global__ void image_to_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, int B, int H, int W) {
+  const long long hw = (long long)H * W, total = (long long)B * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, pix = i - b * hw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = img[(b * 3 + c) * hw + pix];
+      out[i * 3 + c] = f32_to_u8_trunc(__fadd_rn(__fmul_rn(v, 127.5f), 127.5f));  // numpy: two roundings, no FMA
+    }
+  }
+}
+
+// hair_editor.py:297-306.  cv2.getStructuringElement(MORPH_ELLIPSE): half-width of each row of the 13x13 / 5x5 element.
+__constant__ int kEll13[13] = {0, 3, 4, 5, 6, 6, 6, 6, 6, 5, 4, 3, 0};
+__constant__ int kEll5[5] = {0, 2, 2, 2, 0};
+
+__global__ void blend_mask_kernel(const uint8_t* __restrict__ target_parsing, const uint8_t* __restrict__ face_parsing,
+                                  uint8_t* __restrict__ res_mask_dilated, uint8_t* __restrict__ solve_mask, int B, int H,
+                                  int W) {
+  const long long hw = (long long)H * W, total = (long long)B * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw;
+    const int pix = (int)(i - b * hw), y = pix / W, x = pix - y * W;
+    const uint8_t* tp = target_parsing + b * hw;
+    const uint8_t* fp = face_parsing + b * hw;
+    const bool bg = tp[pix] == kBackground;
+    const int k = bg ? 5 : 13, r = k >> 1;
+    int hit = 0;
+    for (int dy = -r; dy <= r && !hit; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;  // pixels outside the image never win a dilation
+      const int hwid = bg ? kEll5[dy + r] : kEll13[dy + r];
+      const int x0 = max(0, x - hwid), x1 = min(W - 1, x + hwid);
+      for (int xx = x0; xx <= x1; ++xx) {
+        if (tp[yy * W + xx] == kHair || fp[yy * W + xx] == kHair) { hit = 1; break; }
+      }
+    }
+    if (res_mask_dilated) res_mask_dilated[i] = (uint8_t)hit;
+    if (solve_mask) solve_mask[i] = (uint8_t)(1 - hit);  // the `1 - res_mask_dilated` handed to poisson_blending
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Poisson solve.  The reference assembles (poisson_blending.py:45-76), per channel, the H*W x H*W system
+//   row k = identity             for interior pixels with mask == 0            (f = target)
+//   row k = 5-point Laplacian    for every other pixel (mask != 0, or on the image border), truncated at the border
+//   b[k]  = Laplacian(source)[k] where mask != 0, target[k] where mask == 0
+// and calls spsolve.  Eliminating the identity rows leaves a symmetric positive definite system on the set U of
+// Laplacian-row pixels:  4 f_i - sum_{j in N(i), j in U} f_j = b_i + sum_{j in N(i), j not in U} target_j,
+// which is solved here by conjugate gradients in fp64.
+constexpr int kPoiCluster = 8;     // CTAs per system (portable cluster size)
+constexpr int kPoiThreads = 1024;
+constexpr int kPoiPx = 8;          // pixels per thread -> up to 8 * 1024 * 8 = 65536 pixels per system
+
+struct PoissonParams {
+  const uint8_t* source;   // [B,H,W,3]
+  const uint8_t* target;   // [B,H,W,3]
+  const uint8_t* mask;     // [B,H,W], non-zero = solve
+  uint8_t* out;            // [B,H,W,3]
+  float* stats;            // [B*3][2] = iterations, final relative residual; may be null
+  const double* lut_fwd;   // [256] v ** (1/2.2) as the caller's host computes it, or null (device pow)
+  const uint8_t* lut_known;// [256] uint8((v ** (1/2.2)) ** 2.2) on the caller's host, or null
+  int B, H, W, R;          // R = rows per CTA
+  int with_gamma, max_iter;
+  double tol2;             // squared relative residual target
+};
+
+struct PoissonSmem {
+  double lut[256];                 // v ** (1/gamma)
+  double warp_part[32];
+  double slots[2][kPoiCluster];    // per-CTA partial sums of the two alternating cluster reductions
+};
+
+__device__ __forceinline__ double poisson_cluster_sum(cg::cluster_group& cluster, double v, PoissonSmem* sm, int set,
+                                                      unsigned rank) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) sm->warp_part[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double s = sm->warp_part[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (lane < kPoiCluster) {
+      double* remote = cluster.map_shared_rank(&sm->slots[set][0], lane);   // CTA `lane` of the cluster
+      remote[rank] = s;
+    }
+  }
+  cluster.sync();  // release/acquire across the cluster: every CTA now holds all eight partials
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < kPoiCluster; ++k) tot += sm->slots[set][k];  // same order in every CTA: bitwise identical sums
+  return tot;
+}
+
+__global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoiThreads, 1)
+    poisson_cg_kernel(const PoissonParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int sys = blockIdx.x / kPoiCluster;     // (image, channel)
+  const int b = sys / 3, ch = sys - b * 3;
+  const int H = p.H, W = p.W, R = p.R;
+  const int row0 = (int)rank * R;
+  const int n_own = max(0, min(R, H - row0));   // rows of this CTA
+  const int n_next = max(0, min(R, H - (row0 + R)));
+
+  PoissonSmem* sm = reinterpret_cast<PoissonSmem*>(smem_raw);
+  double* pbuf = reinterpret_cast<double*>(smem_raw + sizeof(PoissonSmem));  // [(R + 2) rows][W]: search direction + halos
+  double* xbuf = pbuf + (size_t)(R + 2) * W;                                  // [R rows][W]: iterate
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (R + 2) * W; i += kPoiThreads) pbuf[i] = 0.0;
+  if (tid < 256)
+    sm->lut[tid] = p.with_gamma ? (p.lut_fwd ? p.lut_fwd[tid] : pow((double)tid, 1.0 / 2.2)) : (double)tid;
+  if (tid < 2 * kPoiCluster) sm->slots[tid / kPoiCluster][tid % kPoiCluster] = 0.0;
+  cluster.sync();  // nobody pushes a halo row into a buffer that is still being cleared
+
+  const long long img_off = (long long)b * H * W;
+  const uint8_t* src = p.source + img_off * 3 + ch;
+  const uint8_t* tgt = p.target + img_off * 3 + ch;
+  const uint8_t* msk = p.mask + img_off;
+
+  // per-pixel flags: bit 0 = in U, bit 1 = has a left neighbour, bit 2 = has a right neighbour
+  unsigned flags = 0;
+  double r[kPoiPx], q[kPoiPx];
+  double bb_local = 0.0;
+#pragma unroll
+  for (int j = 0; j < kPoiPx; ++j) {
+    r[j] = 0.0;
+    const int li = tid + j * kPoiThreads;
+    if (li >= n_own * W) continue;
+    const int lr = li / W, x = li - lr * W, y = row0 + lr;
+    const int g = y * W + x;
+    const bool m = msk[g] != 0;
+    const bool border = (y == 0) | (y == H - 1) | (x == 0) | (x == W - 1);
+    const bool inU = m | border;
+    const double s = sm->lut[src[3 * g]], t = sm->lut[tgt[3 * g]];
+    double rhs = m ? 4.0 * s : t;
+    // neighbours inside the image: source Laplacian where mask != 0; known targets move to the right-hand side
+    const int ny[4] = {y - 1, y + 1, y, y};
+    const int nx[4] = {x, x, x - 1, x + 1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = ny[k], xx = nx[k];
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const int gn = yy * W + xx;
+      if (m) rhs -= sm->lut[src[3 * gn]];
+      const bool nborder = (yy == 0) | (yy == H - 1) | (xx == 0) | (xx == W - 1);
+      if (!(nborder || msk[gn] != 0)) rhs += sm->lut[tgt[3 * gn]];
+    }
+    unsigned f = 0;
+    if (inU) f |= 1u;
+    if (x > 0) f |= 2u;
+    if (x < W - 1) f |= 4u;
+    flags |= f << (3 * j);
+    if (inU) {
+      r[j] = rhs;
+      bb_local += rhs * rhs;
+      const double x0 = m ? s : t;  // initial guess: the source where its gradients are kept, the target elsewhere
+      pbuf[(lr + 1) * W + x] = x0;
+      xbuf[li] = x0;
+    } else {
+      xbuf[li] = t;                 // known pixel: f = target (pbuf stays 0 there)
+    }
+  }
+  __syncthreads();
+
+  auto push_halos = [&]() {
+    // first owned row -> bottom halo (row R + 1) of the CTA above; last owned row -> top halo (row 0) of the CTA below
+    if (n_own > 0) {
+      if (rank > 0 && tid < W) {
+        double* remote = cluster.map_shared_rank(pbuf, rank - 1);
+        remote[(R + 1) * W + tid] = pbuf[W + tid];
+      }
+      if (n_next > 0 && tid >= 512 && tid - 512 < W) {
+        double* remote = cluster.map_shared_rank(pbuf, rank + 1);
+        remote[tid - 512] = pbuf[n_own * W + (tid - 512)];
+      }
+    }
+  };
+  auto apply = [&](int j) -> double {  // (A p)_i for pixel j of this thread (p == 0 outside U and outside the image)
+    const unsigned f = (flags >> (3 * j)) & 7u;
+    if (!(f & 1u)) return 0.0;
+    const int li = tid + j * kPoiThreads;
+    const int idx = li + W;  // (lr + 1) * W + x
+    double v = 4.0 * pbuf[idx] - pbuf[idx - W] - pbuf[idx + W];
+    if (f & 2u) v -= pbuf[idx - 1];
+    if (f & 4u) v -= pbuf[idx + 1];
+    return v;
+  };
+
+  push_halos();
+  const double bb = poisson_cluster_sum(cluster, bb_local, sm, 0, rank);  // its cluster.sync also publishes the halos
+  // r = rhs - A x0
+  double rr_local = 0.0;
+#pragma unroll
+  for (int j = 0; j < kPoiPx; ++j) {
+    r[j] -= apply(j);
+    rr_local += r[j] * r[j];
+  }
+  cluster.sync();  // every CTA has finished reading x0 (own rows and halos) before p = r overwrites it
+#pragma unroll
+  for (int j = 0; j < kPoiPx; ++j)
+    if ((flags >> (3 * j)) & 1u) pbuf[tid + j * kPoiThreads + W] = r[j];
+  __syncthreads();
+  push_halos();
+  double rr = poisson_cluster_sum(cluster, rr_local, sm, 1, rank);
+  const double thresh = p.tol2 * bb;
+
+  int it = 0;
+  while (it < p.max_iter && rr > thresh) {
+    double pq = 0.0;
+#pragma unroll
+    for (int j = 0; j < kPoiPx; ++j) {
+      q[j] = apply(j);
+      if ((flags >> (3 * j)) & 1u) pq += q[j] * pbuf[tid + j * kPoiThreads + W];
+    }
+    const double pAp = poisson_cluster_sum(cluster, pq, sm, 0, rank);
+    const double alpha = rr / pAp;
+    double rn_local = 0.0;
+#pragma unroll
+    for (int j = 0; j < kPoiPx; ++j) {
+      if ((flags >> (3 * j)) & 1u) {
+        const int li = tid + j * kPoiThreads;
+        xbuf[li] += alpha * pbuf[li + W];
+        r[j] -= alpha * q[j];
+        rn_local += r[j] * r[j];
+      }
+    }
+    const double rn = poisson_cluster_sum(cluster, rn_local, sm, 1, rank);
+    ++it;
+    const double beta = rn / rr;
+    rr = rn;
+    if (!(rr > thresh) || it >= p.max_iter) break;  // identical in every CTA of the cluster (same sums, same order)
+#pragma unroll
+    for (int j = 0; j < kPoiPx; ++j) {
+      if ((flags >> (3 * j)) & 1u) {
+        const int idx = tid + j * kPoiThreads + W;
+        pbuf[idx] = r[j] + beta * pbuf[idx];
+      }
+    }
+    __syncthreads();
+    push_halos();
+    cluster.sync();
+  }
+
+  // poisson_blending.py:81-86: back through the gamma curve, clip to [0, 255], truncate to uint8
+  uint8_t* out = p.out + img_off * 3 + ch;
+#pragma unroll
+  for (int j = 0; j < kPoiPx; ++j) {
+    const int li = tid + j * kPoiThreads;
+    if (li >= n_own * W) continue;
+    const int g = row0 * W + li;
+    if (p.with_gamma && p.lut_known && !((flags >> (3 * j)) & 1u)) {
+      // f == target here: pow(pow(v, 1/2.2), 2.2) lands within an ulp of the integer v and truncates to v or v - 1
+      // depending on the host's pow; the caller's table reproduces its own host exactly
+      out[3 * g] = p.lut_known[tgt[3 * g]];
+      continue;
+    }
+    double v = xbuf[li];
+    if (p.with_gamma) v = v > 0.0 ? pow(v, 2.2) : 0.0;  // numpy: negative ** 2.2 = nan -> 0 after astype
+    v = v > 255.0 ? 255.0 : (v < 0.0 ? 0.0 : v);
+    out[3 * g] = (uint8_t)(int)v;
+  }
+  if (p.stats && rank == 0 && tid == 0) {
+    p.stats[2 * sys] = (float)it;
+    p.stats[2 * sys + 1] = bb > 0.0 ? (float)sqrt(rr / bb) : 0.0f;
+  }
+  cluster.sync();  // no CTA leaves while a peer may still address its shared memory
+}
+
+static size_t poisson_smem_bytes(int R, int W) {
+  return sizeof(PoissonSmem) + (size_t)(R + 2) * W * sizeof(double) + (size_t)R * W * sizeof(double);
+}
+
+static int poisson_launch(const uint8_t* source, const uint8_t* target, const uint8_t* mask, uint8_t* out, int B, int H,
+                          int W, int with_gamma, double tol, int max_iter, float* stats, const double* lut_fwd,
+                          const uint8_t* lut_known, cudaStream_t stream) {
+  if (!source || !target || !mask || !out || B <= 0 || H < 3 || W < 3) {
+    set_error("chb_poisson_blend: bad arguments (need B > 0, H, W >= 3)");
+    return CHB_ERR_ARG;
+  }
+  const int R = (H + kPoiCluster - 1) / kPoiCluster;
+  if ((long long)R * W > (long long)kPoiPx * kPoiThreads || W > 512) {
+    set_error("chb_poisson_blend: image too large for the cluster-resident solver (ceil(H/8)*W <= 8192, W <= 512)");
+    return CHB_ERR_ARG;
+  }
+  if (!(tol > 0.0) || max_iter < 0) {
+    set_error("chb_poisson_blend: need tol > 0 and max_iter >= 0");
+    return CHB_ERR_ARG;
+  }
+  int rc = chb_check_device();
+  if (rc != CHB_OK) return rc;
+  const size_t smem = poisson_smem_bytes(R, W);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(poisson_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error(std::string("poisson smem attribute: ") + cudaGetErrorString(e));
+      return CHB_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  PoissonParams p;
+  p.source = source; p.target = target; p.mask = mask; p.out = out; p.stats = stats;
+  p.lut_fwd = lut_fwd; p.lut_known = lut_known;
+  p.B = B; p.H = H; p.W = W; p.R = R;
+  p.with_gamma = with_gamma ? 1 : 0; p.max_iter = max_iter; p.tol2 = tol * tol;
+  poisson_cg_kernel<<<dim3((unsigned)(B * 3 * kPoiCluster)), kPoiThreads, smem, stream>>>(p);
+  return blend_check("poisson_cg");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 8-bit colour space, one thread per triple.
+// RGB -> HSV: OpenCV's RGB2HSV_b (fixed point, hsv_shift 12, H range 180), as cv2.cvtColor(uint8, COLOR_RGB2HSV).
+__device__ __forceinline__ int round_half_even_div(long long num, long long den) {  // cvRound(num / den), num, den > 0
+  long long qd = num / den, rem = num - qd * den;
+  if (2 * rem > den || (2 * rem == den && (qd & 1))) ++qd;
+  return (int)qd;
+}
+
+__global__ void rgb_to_hsv_kernel(const float* __restrict__ rgb_f, const uint8_t* __restrict__ rgb_u8,
+                                  uint8_t* __restrict__ hsv, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int r, g, b;
+    if (rgb_f) {  // ui/backend.py:98-99: the float colour is cast with astype('uint8') first
+      r = f32_to_u8_trunc(rgb_f[3 * i]); g = f32_to_u8_trunc(rgb_f[3 * i + 1]); b = f32_to_u8_trunc(rgb_f[3 * i + 2]);
+    } else {
+      r = rgb_u8[3 * i]; g = rgb_u8[3 * i + 1]; b = rgb_u8[3 * i + 2];
+    }
+    const int v = max(r, max(g, b)), vmin = min(r, min(g, b)), diff = v - vmin;
+    const int sdiv = v ? round_half_even_div(255LL << 12, v) : 0;
+    const int hdiv = diff ? round_half_even_div(180LL << 12, 6LL * diff) : 0;
+    const int s = (diff * sdiv + (1 << 11)) >> 12;
+    int h = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
+    h = (h * hdiv + (1 << 11)) >> 12;   // arithmetic shift of a possibly negative value, as in OpenCV
+    if (h < 0) h += 180;
+    hsv[3 * i] = (uint8_t)h; hsv[3 * i + 1] = (uint8_t)s; hsv[3 * i + 2] = (uint8_t)v;
+  }
+}
+
+// HSV -> RGB: OpenCV's scalar HSV2RGB_b path (what a one-pixel cv2.cvtColor call runs): float32 HSV2RGB_native with
+// hscale 6/180 on (h, s/255, v/255); the shipped binary fuses `1 - s*h` and `1 - s*(1-h)` (pinned exhaustively).
+__global__ void hsv_to_rgb_kernel(const uint8_t* __restrict__ hsv, uint8_t* __restrict__ rgb, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float h = (float)hsv[3 * i];
+    const float s = __fmul_rn((float)hsv[3 * i + 1], 1.f / 255.f), v = __fmul_rn((float)hsv[3 * i + 2], 1.f / 255.f);
+    float bb, gg, rr;
+    if (hsv[3 * i + 1] == 0) {
+      bb = gg = rr = v;
+    } else {
+      h = __fmul_rn(h, 6.f / 180.f);
+      h = fmodf(h, 6.f);
+      int sector = (int)floorf(h);
+      h = __fsub_rn(h, (float)sector);
+      if ((unsigned)sector >= 6u) { sector = 0; h = 0.f; }
+      float tab[4];
+      tab[0] = v;
+      tab[1] = __fmul_rn(v, __fsub_rn(1.f, s));
+      tab[2] = __fmul_rn(v, __fmaf_rn(-s, h, 1.f));
+      tab[3] = __fmul_rn(v, __fmaf_rn(-s, __fsub_rn(1.f, h), 1.f));
+      const int sd[6][3] = {{1, 3, 0}, {1, 0, 2}, {3, 0, 1}, {0, 2, 1}, {0, 1, 3}, {2, 1, 0}};
+      bb = tab[sd[sector][0]]; gg = tab[sd[sector][1]]; rr = tab[sd[sector][2]];
+    }
+    const float o[3] = {rr, gg, bb};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int q = __float2int_rn(__fmul_rn(o[c], 255.f));  // saturate_cast<uchar>: round half to even, clamp
+      rgb[3 * i + c] = (uint8_t)min(255, max(0, q));
+    }
+  }
+}
+
+// shape_util.py:17-20: label = argmax over channels (first maximum wins), 255 where every channel is 0.
+__global__ void onehot_to_label_kernel(const float* __restrict__ one_hot, uint8_t* __restrict__ labels, int B, int C,
+                                       long long hw) {
+  const long long total = (long long)B * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, pix = i - b * hw;
+    const float* src = one_hot + b * C * hw + pix;
+    float best = src[0];
+    int arg = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = src[c * hw];
+      if (v > best) { best = v; arg = c; }
+    }
+    labels[i] = (best == 0.f) ? (uint8_t)255 : (uint8_t)arg;
+  }
+}
+
+// shape_util.py:6-14: uint8 labels (255 = none) -> float32 one-hot [B,C,H,W]; out-of-range labels give an all-zero pixel.
+__global__ void label_to_onehot_kernel(const uint8_t* __restrict__ labels, float* __restrict__ out, int B, int C,
+                                       long long hw) {
+  const long long total = (long long)B * C * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw, bc = i / hw;
+    const int c = (int)(bc % C);
+    const long long b = bc / C;
+    out[i] = labels[b * hw + pix] == c ? 1.f : 0.f;
+  }
+}
+
+}  // namespace chb
+
+extern "C" {
+
+int chb_image_to_u8(const float* img, uint8_t* out, int B, int H, int W, void* stream) {
+  using namespace chb;
+  if (!img || !out || B <= 0 || H <= 0 || W <= 0) {
+    set_error("chb_image_to_u8: bad arguments");
+    return CHB_ERR_ARG;
+  }
+  image_to_u8_kernel<<<blend_grid((long long)B * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      img, out, B, H, W);
+  return blend_check("image_to_u8");
+}
+
+int chb_blend_mask(const uint8_t* target_parsing, const uint8_t* face_parsing, uint8_t* res_mask_dilated,
+                   uint8_t* solve_mask, int B, int H, int W, void* stream) {
+  using namespace chb;
+  if (!target_parsing || !face_parsing || (!res_mask_dilated && !solve_mask) || B <= 0 || H <= 0 || W <= 0) {
+    set_error("chb_blend_mask: bad arguments");
+    return CHB_ERR_ARG;
+  }
+  blend_mask_kernel<<<blend_grid((long long)B * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      target_parsing, face_parsing, res_mask_dilated, solve_mask, B, H, W);
+  return blend_check("blend_mask");
+}
+
+int chb_poisson_blend(const uint8_t* source, const uint8_t* target, const uint8_t* mask, uint8_t* out, int B, int H,
+                      int W, int with_gamma, double tol, int max_iter, float* stats, const double* lut_fwd,
+                      const uint8_t* lut_known, void* stream) {
+  return chb::poisson_launch(source, target, mask, out, B, H, W, with_gamma, tol, max_iter, stats, lut_fwd, lut_known,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int64_t chb_postprocess_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (int64_t)B * H * W * 4;  // uint8 generated image [B,H,W,3] + solve mask [B,H,W]
+}
+
+int chb_postprocess_blending(const uint8_t* face_img, const float* res_img, const uint8_t* face_parsing,
+                             const uint8_t* target_parsing, uint8_t* out, uint8_t* res_mask_dilated, void* workspace,
+                             int B, int H, int W, int blending, double tol, int max_iter, float* stats,
+                             const double* lut_fwd, const uint8_t* lut_known, void* stream) {
+  using namespace chb;
+  if (!res_img || !out || B <= 0 || H <= 0 || W <= 0) {
+    set_error("chb_postprocess_blending: bad arguments");
+    return CHB_ERR_ARG;
+  }
+  if (!blending) return chb_image_to_u8(res_img, out, B, H, W, stream);  // hair_editor.py:307-308
+  if (!face_img || !face_parsing || !target_parsing || !workspace) {
+    set_error("chb_postprocess_blending: blending needs the face image, both parsings and a workspace");
+    return CHB_ERR_ARG;
+  }
+  uint8_t* gen_u8 = reinterpret_cast<uint8_t*>(workspace);
+  uint8_t* solve_mask = gen_u8 + (size_t)B * H * W * 3;
+  int rc = chb_image_to_u8(res_img, gen_u8, B, H, W, stream);
+  if (rc != CHB_OK) return rc;
+  rc = chb_blend_mask(target_parsing, face_parsing, res_mask_dilated, solve_mask, B, H, W, stream);
+  if (rc != CHB_OK) return rc;
+  return chb_poisson_blend(face_img, gen_u8, solve_mask, out, B, H, W, 1, tol, max_iter, stats, lut_fwd, lut_known,
+                           stream);
+}
+
+int chb_rgb_to_hsv(const float* rgb_f32, const uint8_t* rgb_u8, uint8_t* hsv, int64_t n, void* stream) {
+  using namespace chb;
+  if ((!rgb_f32 == !rgb_u8) || !hsv || n <= 0) {
+    set_error("chb_rgb_to_hsv: pass exactly one of rgb_f32 / rgb_u8, and n > 0");
+    return CHB_ERR_ARG;
+  }
+  rgb_to_hsv_kernel<<<blend_grid(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rgb_f32, rgb_u8, hsv, n);
+  return blend_check("rgb_to_hsv");
+}
+
+int chb_hsv_to_rgb(const uint8_t* hsv, uint8_t* rgb, int64_t n, void* stream) {
+  using namespace chb;
+  if (!hsv || !rgb || n <= 0) {
+    set_error("chb_hsv_to_rgb: bad arguments");
+    return CHB_ERR_ARG;
+  }
+  hsv_to_rgb_kernel<<<blend_grid(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hsv, rgb, n);
+  return blend_check("hsv_to_rgb");
+}
+
+int chb_onehot_to_label(const float* one_hot, uint8_t* labels, int B, int C, int64_t hw, void* stream) {
+  using namespace chb;
+  if (!one_hot || !labels || B <= 0 || C <= 0 || C > 255 || hw <= 0) {
+    set_error("chb_onehot_to_label: bad arguments");
+    return CHB_ERR_ARG;
+  }
+  onehot_to_label_kernel<<<blend_grid((long long)B * hw, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      one_hot, labels, B, C, hw);
+  return blend_check("onehot_to_label");
+}
+
+int chb_label_to_onehot(const uint8_t* labels, float* one_hot, int B, int C, int64_t hw, void* stream) {
+  using namespace chb;
+  if (!one_hot || !labels || B <= 0 || C <= 0 || C > 255 || hw <= 0) {
+    set_error("chb_label_to_onehot: bad arguments");
+    return CHB_ERR_ARG;
+  }
+  label_to_onehot_kernel<<<blend_grid((long long)B * C * hw, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      labels, one_hot, B, C, hw);
+  return blend_check("label_to_onehot");
+}
+
+}  // extern "C"

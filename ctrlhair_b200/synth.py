@@ -326,3 +326,23 @@ def make_shape_inputs(B, S=256, seed=1261):
     labels = make_labels(B, S, "blocky", seed).long()
     oh = torch.zeros((B, 19, S, S)).scatter_(1, labels[:, None], 1.0)
     return oh[:, [13]], torch.cat([oh[:, :13], oh[:, 14:]], 1)
+
+
+def make_blend_case(H, W, seed):
+    """Synthetic post-processing inputs (hair_editor.py:257-308): a smooth 'input face' uint8 [H,W,3], a 'generated
+    image' that differs from it by a smooth offset + noise, and two label maps [H,W] (background frame touching the
+    border, skin, a mouth patch, and a hair blob that moves between the input parsing and the target parsing)."""
+    import numpy as np
+    g = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    base = 120 + 60 * np.sin(xx / W * 5.0)[..., None] * np.cos(yy / H * 4.0)[..., None] + g.normal(0, 12, (H, W, 3))
+    face = np.clip(base, 0, 255).astype(np.uint8)
+    gen = np.clip(base * 0.9 + 25 + g.normal(0, 10, (H, W, 3)), 0, 255).astype(np.uint8)
+
+    def parsing(cx, cy, rx, ry):
+        p = np.full((H, W), 1, np.uint8)
+        p[(yy < H * 0.15) | (xx < W * 0.08) | (xx > W * 0.92)] = 0
+        p[((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 < 1.0] = 13
+        p[(np.abs(xx - W * 0.5) < W * 0.1) & (np.abs(yy - H * 0.7) < H * 0.05)] = 11
+        return p
+    return face, gen, parsing(W * 0.45, H * 0.25, W * 0.3, H * 0.2), parsing(W * 0.55, H * 0.3, W * 0.33, H * 0.26)

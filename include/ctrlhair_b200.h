@@ -296,6 +296,43 @@ int chb_cttrain_step(chb_cttrain* t, int which, const chb_cttrain_batch* batch, 
 int chb_cttrain_adam(chb_cttrain* t, int which, void* stream);
 int chb_cttrain_launches(const chb_cttrain* t, int which);
 
+/* ------------------------------------------------------------------------------------------
+ * Operator 8: post-processing either side of the generator.  Device pointers; integer
+ * results are bit exact, the Poisson solve is fp64 conjugate gradients to a relative residual `tol`.
+ * ------------------------------------------------------------------------------------------ */
+/* hair_editor.py:273-288: generator output float [B,3,H,W] in [-1,1] -> uint8 [B,H,W,3] = (x*127.5+127.5).astype(uint8). */
+int chb_image_to_u8(const float* img, uint8_t* out, int B, int H, int W, void* stream);
+/* hair_editor.py:297-306: res_mask = (target_parsing == 13) | (face_parsing == 13), dilated by cv2's 13x13 ellipse
+ * (5x5 where target_parsing is background).  Parsings uint8 [B,H,W].  Writes res_mask_dilated (0/1) and/or
+ * solve_mask = 1 - res_mask_dilated (what poisson_blending receives); either may be NULL. */
+int chb_blend_mask(const uint8_t* target_parsing, const uint8_t* face_parsing, uint8_t* res_mask_dilated,
+                   uint8_t* solve_mask, int B, int H, int W, void* stream);
+/* poisson_blending.py:29-87 (replaces the lil_matrix assembly + three spsolve calls).  source, target, out uint8
+ * [B,H,W,3]; mask uint8 [B,H,W], non-zero = keep the source's gradients.  ceil(H/8)*W <= 8192, W <= 512.
+ * stats (optional) float [B*3][2] = CG iterations, final relative residual per (image, channel).
+ * lut_fwd (optional, device, double[256]) = v**(1/2.2) and lut_known (optional, device, uint8[256]) =
+ * uint8((v**(1/2.2))**2.2) as the CALLER's host computes them: pow() differs by an ulp between libm / SVML builds of
+ * numpy, which decides whether an untouched pixel v comes back as v or v-1; NULL = the device's pow. */
+int chb_poisson_blend(const uint8_t* source, const uint8_t* target, const uint8_t* mask, uint8_t* out, int B, int H,
+                      int W, int with_gamma, double tol, int max_iter, float* stats, const double* lut_fwd,
+                      const uint8_t* lut_known, void* stream);
+/* hair_editor.py:257-308 HairEditor.postprocess_blending in one call: face_img uint8 [B,H,W,3], res_img float
+ * [B,3,H,W] (generator output), parsings uint8 [B,H,W] -> out uint8 [B,H,W,3] (+ res_mask_dilated [B,H,W], optional).
+ * blending == 0: out = uint8 image of res_img only.  workspace: chb_postprocess_workspace_bytes(B,H,W) device bytes. */
+int64_t chb_postprocess_workspace_bytes(int B, int H, int W);
+int chb_postprocess_blending(const uint8_t* face_img, const float* res_img, const uint8_t* face_parsing,
+                             const uint8_t* target_parsing, uint8_t* out, uint8_t* res_mask_dilated, void* workspace,
+                             int B, int H, int W, int blending, double tol, int max_iter, float* stats,
+                             const double* lut_fwd, const uint8_t* lut_known, void* stream);
+/* ui/backend.py:98-101,117-125 (cv2.cvtColor(c.astype('uint8'), COLOR_RGB2HSV)) and :108-115 (COLOR_HSV2RGB) on n
+ * colour triples: OpenCV's 8-bit algorithms (H in 0..179), bit exact.  Pass exactly one of rgb_f32 / rgb_u8. */
+int chb_rgb_to_hsv(const float* rgb_f32, const uint8_t* rgb_u8, uint8_t* hsv, int64_t n, void* stream);
+int chb_hsv_to_rgb(const uint8_t* hsv, uint8_t* rgb, int64_t n, void* stream);
+/* shape_branch/shape_util.py:17-20 mask_one_hot_to_label: float [B,C,hw] -> uint8 [B,hw] (first maximum, 255 if all 0)
+ * and :6-14 mask_label_to_one_hot: uint8 [B,hw] (255 = none) -> float [B,C,hw]. */
+int chb_onehot_to_label(const float* one_hot, uint8_t* labels, int B, int C, int64_t hw, void* stream);
+int chb_label_to_onehot(const uint8_t* labels, float* one_hot, int B, int C, int64_t hw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

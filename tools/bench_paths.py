@@ -10,6 +10,7 @@ pipeline       config 3: encode -> edit -> decode chain with every network call 
 train     a12  config 5: one train.py loop iteration (D sub-step + G sub-step + both Adam updates), steps/s;
                world size > 1 adds the flat gradient all-reduce (NCCL)
 gen512         config 4 per-GPU share: generator forward at 512x512, images/s
+blend     8f.2 postprocess_blending (blend mask + Poisson solve) at 256x256, images/s, next to the CPU oracle
 All timings: CUDA events on the launching stream, W warm-up + K timed iterations, inputs resident on the device.
 """
 import argparse
@@ -177,6 +178,38 @@ def bench_train(a):
         torch.distributed.destroy_process_group()
 
 
+def bench_blend(a):
+    """HairEditor.postprocess_blending (hair_editor.py:257-308) for B images, device resident, next to
+    the oracle port (vectorised assembly + spsolve; the reference's own Python pixel loop is slower still) on the CPU."""
+    import time
+    import numpy as np
+    from ctrlhair_b200 import blend
+    from oracle import blend_oracle as bo
+    B = a.B
+    cases = [synth.make_blend_case(256, 256, 900 + i) for i in range(B)]
+    face = torch.from_numpy(np.stack([c[0] for c in cases])).cuda()
+    res = torch.from_numpy(np.stack([c[1] for c in cases])).cuda().permute(0, 3, 1, 2).float().div(127.5).sub(1).contiguous()
+    fp = torch.from_numpy(np.stack([c[2] for c in cases])).cuda()
+    tp = torch.from_numpy(np.stack([c[3] for c in cases])).cuda()
+    ms = timed(lambda: blend.postprocess_blending(face, res, fp, tp), a.steps, a.warmup)
+    src_u8 = blend.image_to_u8(res)
+    mask = 1 - blend.blend_mask(tp, fp)
+    _, stats = blend.poisson_blending(face, src_u8, mask, return_stats=True)
+    ms_solve = timed(lambda: blend.poisson_blending(face, src_u8, mask), a.steps, a.warmup)
+    n_cpu = 2
+    t0 = time.time()
+    for i in range(n_cpu):
+        bo.postprocess_blending(cases[i][0], res[i].cpu().numpy(), cases[i][2], cases[i][3])
+    cpu_s = (time.time() - t0) / n_cpu
+    it = float(stats[..., 0].mean())
+    emit({"path": "8f.2 postprocess_blending 256x256 (mask + fp64 CG Poisson solve, 3 channels)", "B": B, "ms": ms,
+          "images_per_s": B / ms * 1e3, "poisson_kernel_ms": ms_solve, "cg_iterations_mean": it,
+          "cg_iterations_max": float(stats[..., 0].max()), "residual_max": float(stats[..., 1].max()),
+          "us_per_iteration_per_wave": ms_solve * 1e3 / it / max(1.0, B * 3 / 16.0),
+          "unknown_fraction": float(torch.as_tensor(mask).float().mean()),
+          "cpu_oracle_images_per_s": 1.0 / cpu_s, "cpu_sample": "%d images, scipy spsolve, 1 thread" % n_cpu})
+
+
 def bench_gen512(a, sd):
     from ctrlhair_b200 import flops as flopmodel
     from ctrlhair_b200.generator import SeanGeneratorB200
@@ -212,6 +245,8 @@ def main():
         bench_pipeline(a, sd)
     if "gen512" in what:
         bench_gen512(a, sd)
+    if "blend" in what:
+        bench_blend(a)
     if "train" in what:
         bench_train(a)
 
