@@ -7,6 +7,7 @@ stays where it is in the reference.
   HairEditorB200.gen_img          hair_editor.py:159-179
   HairEditorB200.generate_by_sean hair_editor.py:181-206
   HairEditorB200.load_average_feature  hair_editor.py:131-147
+  HairEditorB200.gen_img_batch    batched gen_img for the validation / direction-finding callers
 """
 import glob
 import os
@@ -68,8 +69,8 @@ class Pix2PixModelB200:
 class HairEditorB200:
     """The slice of HairEditor that touches the generator and the style encoder."""
 
-    def __init__(self, state_dict, median_codes=None, median_dir=None, img_size=256, device=None):
-        self.sean_model = Pix2PixModelB200(state_dict, crop=img_size, device=device)
+    def __init__(self, state_dict, median_codes=None, median_dir=None, img_size=256, device=None, max_batch=1):
+        self.sean_model = Pix2PixModelB200(state_dict, crop=img_size, device=device, max_batch=max_batch)
         self.img_size = img_size
         self.device = self.sean_model.device
         if median_codes is None and median_dir is not None:
@@ -110,6 +111,26 @@ class HairEditorB200:
         data = {"label": torch.as_tensor(parsing, dtype=torch.float32), "instance": torch.tensor(0),
                 "image": torch.zeros((0, 3, self.img_size, self.img_size)), "obj_dic": obj_dic, "noise": noise}
         return self.sean_model(data, mode="UI_mode")[0]
+
+    def gen_img_batch(self, codes, parsing, noise=None):
+        """gen_img for B (code, parsing) pairs in one generator call (validation_in_train.py:87-288 and
+        script_find_direction.py:55-74 render hundreds of images one gen_img at a time).  codes [B,19,512]; all-zero
+        rows take the median code of their class (hair_editor.py:165-168), which is cached on the device instead of
+        being re-read from 19 .npy files per call (:131-147).  parsing uint8 [B,S,S] -> images [B,3,S,S] (CUDA)."""
+        if self.median is None:
+            raise _lib.ChbError("median style codes were not provided (hair_editor.py:134 reads them from disk)")
+        netG = self.sean_model.netG
+        codes = torch.as_tensor(codes).to(self.device, torch.float32)
+        B = codes.shape[0]
+        if B > netG.max_batch:
+            raise _lib.ChbError("batch %d exceeds the generator's max_batch %d" % (B, netG.max_batch))
+        if getattr(self, "_median_dev", None) is None:
+            self._median_dev = self.median.to(self.device)
+        empty = (codes == 0).all(dim=2, keepdim=True)
+        codes = torch.where(empty, self._median_dev[None].expand_as(codes), codes).contiguous()
+        labels = torch.as_tensor(parsing).to(self.device).to(torch.uint8).reshape(B, self.img_size, self.img_size)
+        self.sean_model.seed += 1
+        return netG.forward_labels(labels.contiguous(), codes, noise=noise, seed=self.sean_model.seed)
 
     def generate_by_sean(self, face_img_code, hair_code, target_seg, noise=None):
         face_img_code = torch.as_tensor(face_img_code).float().cpu()

@@ -42,3 +42,27 @@ def test_style_code_mode_and_invalid_mode(synthetic_sd, editor):
     assert float((codes - ref).norm() / ref.norm()) < 2e-3
     with pytest.raises(ValueError):
         ed.sean_model({"label": labels[:, None].float(), "image": img}, mode="generator")
+
+
+def test_gen_img_batch_equals_looped_gen_img(synthetic_sd):
+    """one batched call == B separate gen_img calls (same noise), zero rows -> median."""
+    from ctrlhair_b200.editor import HairEditorB200
+    gen = torch.Generator().manual_seed(78)
+    median = torch.randn((19, 512), generator=gen) * 0.135
+    B = 3
+    ed = HairEditorB200(synthetic_sd, median_codes=median, img_size=64, max_batch=B)
+    labels = synth.make_labels(B, 64, "blocky", seed=5)
+    codes = synth.make_codes(B)
+    codes[1, 13] = 0
+    codes[2, 0] = 0
+    noise = synth.make_noise(B, 64)
+    batch = ed.gen_img_batch(codes, labels, noise=synth.flatten_noise(noise).cuda()).cpu()
+    assert batch.shape == (B, 3, 64, 64)
+    for i in range(B):
+        one = ed.gen_img(codes[i:i + 1], labels[i:i + 1, None].numpy(),
+                         noise=synth.flatten_noise([p[i:i + 1] for p in noise])).cpu()
+        assert torch.equal(one, batch[i]), i           # same kernels, same inputs: bitwise identical
+    eff = codes.clone()
+    eff[1, 13], eff[2, 0] = median[13], median[0]
+    ref = so.generator_forward(synthetic_sd, labels, eff, noise)
+    assert float((batch - ref).norm() / ref.norm()) < 1e-3

@@ -10,6 +10,7 @@ pipeline       config 3: encode -> edit -> decode chain with every network call 
 train     a12  config 5: one train.py loop iteration (D sub-step + G sub-step + both Adam updates), steps/s;
                world size > 1 adds the flat gradient all-reduce (NCCL)
 gen512         config 4 per-GPU share: generator forward at 512x512, images/s
+backend   8f.1 config 3 through BackendB200 (batched Backend.set_input_img + output incl. blending), images/s
 blend     8f.2 postprocess_blending (blend mask + Poisson solve) at 256x256, images/s, next to the CPU oracle
 All timings: CUDA events on the launching stream, W warm-up + K timed iterations, inputs resident on the device.
 """
@@ -210,6 +211,32 @@ def bench_blend(a):
           "cpu_oracle_images_per_s": 1.0 / cpu_s, "cpu_sample": "%d images, scipy spsolve, 1 thread" % n_cpu})
 
 
+def bench_backend(a, sd):
+    """Config 3 through BackendB200: set_input_img (shape encode/decode, style encode, colour predictor, RGB->HSV, code
+    encoder) + output (HSV->RGB, feature generator, generator, blend mask + Poisson blending), host buffers in and out,
+    nothing but the parsing network (BiSeNet, out of scope) missing from ui/backend.py's chain."""
+    import numpy as np
+    from ctrlhair_b200.backend import BackendB200
+    B = a.B
+    cases = [synth.make_blend_case(256, 256, 700 + i) for i in range(B)]
+    img_h = torch.from_numpy(np.stack([c[0] for c in cases])).pin_memory()
+    lab_h = torch.from_numpy(np.stack([c[2] for c in cases])).pin_memory()
+    out_h = torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory()
+    be = BackendB200(sd, synth.make_shape_state_dict(), synth.make_ct_state_dicts(),
+                     median_codes=synth.make_codes(1, seed=4321)[0], max_batch=B, blending=True)
+
+    def chain():
+        be.set_input_img(img_h.cuda(non_blocking=True), lab_h.cuda(non_blocking=True))
+        out_h.copy_(be.output(), non_blocking=True)
+    ms = timed(chain, a.steps, a.warmup)
+    be.blending = False
+    ms_nb = timed(chain, a.steps, a.warmup)
+    emit({"path": "config 3 via BackendB200: set_input_img + output incl. Poisson blending (parsing network excluded)",
+          "B": B, "ms": ms, "images_per_s": B / ms * 1e3, "ms_without_blending": ms_nb,
+          "images_per_s_without_blending": B / ms_nb * 1e3,
+          "h2d_bytes": int(img_h.numel() + lab_h.numel()), "d2h_bytes": int(out_h.numel())})
+
+
 def bench_gen512(a, sd):
     from ctrlhair_b200 import flops as flopmodel
     from ctrlhair_b200.generator import SeanGeneratorB200
@@ -234,7 +261,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     what = a.what.split(",")
-    sd = synth.make_state_dict() if any(w in what for w in ("zencoder", "pipeline", "gen512")) else None
+    sd = synth.make_state_dict() if any(w in what for w in ("zencoder", "pipeline", "gen512", "backend")) else None
     if "zencoder" in what:
         bench_zencoder(a, sd)
     if "shape" in what:
@@ -247,6 +274,8 @@ def main():
         bench_gen512(a, sd)
     if "blend" in what:
         bench_blend(a)
+    if "backend" in what:
+        bench_backend(a, sd)
     if "train" in what:
         bench_train(a)
 
