@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/ctrlhair_b200.h"
@@ -319,6 +320,242 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoiThread
   cluster.sync();  // no CTA leaves while a peer may still address its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Second generation of the solver (the default when the image fits it): Chronopoulos-Gear conjugate gradients, whose two
+// dot products (r.r and r.Ar) come out of ONE cluster reduction per iteration, with the per-pixel state in registers.
+//   * 512 threads; a thread owns a 16-row strip of one column, so the vertical neighbours of the 5-point stencil are
+//     its own registers and only left / right (and the two strip ends) are read from shared memory;
+//   * r, p = search direction and s = A p live in registers (96 of the 128 available), x and w = A r in shared memory
+//     (touched once per iteration each), r additionally in a haloed shared buffer for the neighbours;
+//   * per iteration: one halo exchange + one two-value reduction through distributed shared memory (2 cluster
+//     barriers instead of 3, one block reduction instead of 2) and 7 shared-memory accesses per pixel instead of 11.
+// x_{i+1} = x_i + a_i p_i, r_{i+1} = r_i - a_i s_i, w = A r_{i+1}, g = (r,r), d = (r,w), b = g/g_old,
+// a = g / (d - b g / a_old), p = r + b p, s = w + b s.
+constexpr int kPoi2Threads = 512;
+constexpr int kPoi2Rows = 16;   // rows per thread
+
+struct Poisson2Smem {
+  double lut[256];
+  double warp_part[2][kPoi2Threads / 32];
+  double slots[2][2][kPoiCluster];   // [parity][value][CTA]
+};
+
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void poisson_cluster_sum2(cg::cluster_group& cluster, double& a, double& b, Poisson2Smem* sm,
+                                                     int set, unsigned rank) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) { sm->warp_part[0][warp] = a; sm->warp_part[1][warp] = b; }
+  __syncthreads();
+  if (warp == 0) {
+    // lanes 0..15 hold the 16 warp partials of value 0, lanes 16..31 those of value 1
+    double v = sm->warp_part[lane >> 4][lane & 15];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, 16);
+    const double v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 16);
+    if (lane < 2 * kPoiCluster) {
+      const int which = lane / kPoiCluster, dst = lane % kPoiCluster;
+      double* remote = cluster.map_shared_rank(&sm->slots[set][which][0], dst);
+      remote[rank] = which ? v1 : v0;
+    }
+  }
+  cluster.sync();
+  double ta = 0.0, tb = 0.0;
+#pragma unroll
+  for (int k = 0; k < kPoiCluster; ++k) { ta += sm->slots[set][0][k]; tb += sm->slots[set][1][k]; }
+  a = ta; b = tb;
+}
+
+template <int W, int R>
+__global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoi2Threads, 1)
+    poisson_cg2_kernel(const PoissonParams p) {
+  // compile-time geometry (the reference's 256 x 256 images: 8 CTAs x 32 rows): every shared-memory offset below is
+  // an immediate, which is what lets r, p and s stay in registers.  The inner loop is branch free: pixels outside U
+  // (and rows beyond the image in a partial CTA) keep r = p = s = 0 because their stencil value is selected to 0,
+  // and the haloed buffer has a zero column on either side so that column 0 / W-1 need no special case.
+  static_assert(R % kPoi2Rows == 0 && (R / kPoi2Rows) * W == kPoi2Threads, "one thread per (16-row strip, column)");
+  constexpr int P = W + 2;   // pitch of the haloed residual buffer
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int sys = blockIdx.x / kPoiCluster;
+  const int b = sys / 3, ch = sys - b * 3;
+  const int H = p.H;
+  const int row0 = (int)rank * R;
+  const int n_own = max(0, min(R, H - row0));
+  const int n_next = max(0, min(R, H - (row0 + R)));
+
+  Poisson2Smem* sm = reinterpret_cast<Poisson2Smem*>(smem_raw);
+  double* rbuf = reinterpret_cast<double*>(smem_raw + sizeof(Poisson2Smem));  // [(R + 2)][P] residual + halo ring
+  double* xbuf = rbuf + (R + 2) * P;                                           // [R][W] iterate
+  double* wbuf = xbuf + R * W;                                                 // [R][W] A r
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (R + 2) * P; i += kPoi2Threads) rbuf[i] = 0.0;
+  if (tid < 256)
+    sm->lut[tid] = p.with_gamma ? (p.lut_fwd ? p.lut_fwd[tid] : pow((double)tid, 1.0 / 2.2)) : (double)tid;
+  if (tid < 4 * kPoiCluster) (&sm->slots[0][0][0])[tid] = 0.0;
+  cluster.sync();
+
+  const long long img_off = (long long)b * H * W;
+  const uint8_t* src = p.source + img_off * 3 + ch;
+  const uint8_t* tgt = p.target + img_off * 3 + ch;
+  const uint8_t* msk = p.mask + img_off;
+
+  // this thread: column `col`, local rows lr0 .. lr0 + 15
+  const int strip = tid / W, col = tid - strip * W;
+  const int lr0 = strip * kPoi2Rows;
+  unsigned umask = 0, vmask = 0;              // bit j: pixel j is in U / exists
+  double bb_local = 0.0;
+  // assembly of the right-hand side (parked in wbuf), the initial guess (rbuf, xbuf) and the masks: a rolled loop
+#pragma unroll 1
+  for (int j = 0; j < kPoi2Rows; ++j) {
+    const int lr = lr0 + j;
+    double x0 = 0.0, rhs = 0.0;
+    if (lr < n_own) {
+      vmask |= 1u << j;
+      const int x = col, y = row0 + lr;
+      const int g = y * W + x;
+      const bool m = msk[g] != 0;
+      const bool border = (y == 0) | (y == H - 1) | (x == 0) | (x == W - 1);
+      const bool inU = m | border;
+      const double sv = sm->lut[src[3 * g]], tv = sm->lut[tgt[3 * g]];
+      rhs = m ? 4.0 * sv : tv;
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        const int yy = y + (k == 0 ? -1 : (k == 1 ? 1 : 0)), xx = x + (k == 2 ? -1 : (k == 3 ? 1 : 0));
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const int gn = yy * W + xx;
+        if (m) rhs -= sm->lut[src[3 * gn]];
+        const bool nborder = (yy == 0) | (yy == H - 1) | (xx == 0) | (xx == W - 1);
+        if (!(nborder || msk[gn] != 0)) rhs += sm->lut[tgt[3 * gn]];
+      }
+      x0 = tv;
+      if (inU) {
+        umask |= 1u << j;
+        bb_local += rhs * rhs;
+        x0 = m ? sv : tv;
+        rbuf[(lr + 1) * P + 1 + col] = x0;
+      } else {
+        rhs = 0.0;
+      }
+    }
+    xbuf[lr * W + col] = x0;
+    wbuf[lr * W + col] = rhs;
+  }
+
+  double* rc = rbuf + (lr0 + 1) * P + 1 + col;   // this thread's first pixel in the haloed buffer
+  double* xc = xbuf + lr0 * W + col;
+  double* wc = wbuf + lr0 * W + col;
+  // boundary rows travel straight from the owning thread into the neighbour CTA's halo row
+  double* halo_up = (strip == 0 && rank > 0 && n_own > 0)
+                        ? cluster.map_shared_rank(rbuf, rank - 1) + (R + 1) * P + 1 + col : nullptr;
+  double* halo_dn = (strip == R / kPoi2Rows - 1 && n_next > 0)
+                        ? cluster.map_shared_rank(rbuf, rank + 1) + 1 + col : nullptr;
+
+  if (halo_up) *halo_up = rc[0];
+  if (halo_dn) *halo_dn = rc[(kPoi2Rows - 1) * P];
+  cluster.sync();
+  // r = rhs - A x0 (all five points from shared memory: rbuf holds x0 here)
+  double r[kPoi2Rows], pd[kPoi2Rows], s[kPoi2Rows];
+#pragma unroll
+  for (int j = 0; j < kPoi2Rows; ++j) {
+    pd[j] = 0.0; s[j] = 0.0;
+    const double v = 4.0 * rc[j * P] - rc[(j - 1) * P] - rc[(j + 1) * P] - rc[j * P - 1] - rc[j * P + 1];
+    r[j] = ((umask >> j) & 1u) ? wc[j * W] - v : 0.0;
+  }
+  double zero = 0.0;
+  poisson_cluster_sum2(cluster, bb_local, zero, sm, 0, rank);  // also: every CTA is done reading x0 from rbuf
+  const double bb = bb_local;
+  const double thresh = p.tol2 * bb;
+
+  int it = 0, parity = 1;
+  double gamma = 1.0, alpha = 1.0;
+  bool first = true;
+  while (true) {
+    // publish r: own pixels, and the strip-end rows into the neighbours' halos
+#pragma unroll
+    for (int j = 0; j < kPoi2Rows; ++j) rc[j * P] = r[j];
+    if (halo_up) *halo_up = r[0];
+    if (halo_dn) *halo_dn = r[kPoi2Rows - 1];
+    __syncthreads();            // the CTA's own rows are visible: rows 1..14 of every strip can start
+    cluster_arrive_release();   // ... while the halo rows of the neighbour CTAs are still in flight
+    // w = A r, g = (r, r), d = (r, w); vertical neighbours from registers, the rest from shared memory
+    double g_l = 0.0, d_l = 0.0;
+    auto row = [&](int j, double up, double dn) {
+      const double c = r[j];
+      double v = 4.0 * c - up - dn - rc[j * P - 1] - rc[j * P + 1];
+      v = ((umask >> j) & 1u) ? v : 0.0;
+      wc[j * W] = v;
+      g_l += c * c;
+      d_l += c * v;
+    };
+#pragma unroll
+    for (int j = 1; j < kPoi2Rows - 1; ++j) row(j, r[j - 1], r[j + 1]);
+    cluster_wait_acquire();
+    row(0, rc[-P], r[1]);
+    row(kPoi2Rows - 1, r[kPoi2Rows - 2], rc[kPoi2Rows * P]);
+    poisson_cluster_sum2(cluster, g_l, d_l, sm, parity, rank);
+    parity ^= 1;
+    const double gamma_new = g_l, delta = d_l;
+    if (!(gamma_new > thresh) || it >= p.max_iter) { gamma = gamma_new; break; }
+    double beta;
+    if (first) { beta = 0.0; alpha = gamma_new / delta; first = false; }
+    else {
+      // a = g / (d - b g / a_old) with b = g / g_old, as one division: a = g g_old a_old / (d g_old a_old - g g)
+      beta = gamma_new / gamma;
+      const double ga = gamma * alpha;
+      alpha = gamma_new * ga / (delta * ga - gamma_new * gamma_new);
+    }
+    gamma = gamma_new;
+#pragma unroll
+    for (int j = 0; j < kPoi2Rows; ++j) {
+      pd[j] = r[j] + beta * pd[j];
+      s[j] = wc[j * W] + beta * s[j];
+      xc[j * W] += alpha * pd[j];
+      r[j] -= alpha * s[j];
+    }
+    ++it;
+  }
+
+  uint8_t* out = p.out + img_off * 3 + ch;
+#pragma unroll 1
+  for (int j = 0; j < kPoi2Rows; ++j) {
+    if (!((vmask >> j) & 1u)) continue;
+    const int lr = lr0 + j;
+    const int g = (row0 + lr) * W + col;
+    if (p.with_gamma && p.lut_known && !((umask >> j) & 1u)) {
+      out[3 * g] = p.lut_known[tgt[3 * g]];
+      continue;
+    }
+    double v = xbuf[lr * W + col];
+    if (p.with_gamma) v = v > 0.0 ? pow(v, 2.2) : 0.0;
+    v = v > 255.0 ? 255.0 : (v < 0.0 ? 0.0 : v);
+    out[3 * g] = (uint8_t)(int)v;
+  }
+  if (p.stats && rank == 0 && tid == 0) {
+    p.stats[2 * sys] = (float)it;
+    p.stats[2 * sys + 1] = bb > 0.0 ? (float)sqrt(gamma / bb) : 0.0f;
+  }
+  cluster.sync();
+}
+
+constexpr int kPoi2W = 256, kPoi2R = 32;   // the instantiated geometry: 256 columns, H in 249..256
+static size_t poisson2_smem_bytes(int R, int W) {
+  return sizeof(Poisson2Smem) + (size_t)(R + 2) * (W + 2) * sizeof(double) + 2 * (size_t)R * W * sizeof(double);
+}
+static bool poisson2_fits(int R, int W) { return W == kPoi2W && R == kPoi2R; }
+
 static size_t poisson_smem_bytes(int R, int W) {
   return sizeof(PoissonSmem) + (size_t)(R + 2) * W * sizeof(double) + (size_t)R * W * sizeof(double);
 }
@@ -341,10 +578,16 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
   }
   int rc = chb_check_device();
   if (rc != CHB_OK) return rc;
-  const size_t smem = poisson_smem_bytes(R, W);
+  static const bool force_v1 = [] { const char* v = getenv("CHB_POISSON_V1"); return v && atoi(v) != 0; }();
+  // second generation for the reference's image size; first generation for any other W <= 512, ceil(H/8)*W <= 8192
+  const bool v2 = !force_v1 && poisson2_fits(R, W);
+  const size_t smem = v2 ? poisson2_smem_bytes(R, W) : poisson_smem_bytes(R, W);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(poisson_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)poisson2_smem_bytes(kPoi2R, kPoi2W));
     if (e != cudaSuccess) {
       set_error(std::string("poisson smem attribute: ") + cudaGetErrorString(e));
       return CHB_ERR_CUDA;
@@ -356,7 +599,10 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
   p.lut_fwd = lut_fwd; p.lut_known = lut_known;
   p.B = B; p.H = H; p.W = W; p.R = R;
   p.with_gamma = with_gamma ? 1 : 0; p.max_iter = max_iter; p.tol2 = tol * tol;
-  poisson_cg_kernel<<<dim3((unsigned)(B * 3 * kPoiCluster)), kPoiThreads, smem, stream>>>(p);
+  if (v2)
+    poisson_cg2_kernel<kPoi2W, kPoi2R><<<dim3((unsigned)(B * 3 * kPoiCluster)), kPoi2Threads, smem, stream>>>(p);
+  else
+    poisson_cg_kernel<<<dim3((unsigned)(B * 3 * kPoiCluster)), kPoiThreads, smem, stream>>>(p);
   return blend_check("poisson_cg");
 }
 
