@@ -582,17 +582,13 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
   // second generation for the reference's image size; first generation for any other W <= 512, ceil(H/8)*W <= 8192
   const bool v2 = !force_v1 && poisson2_fits(R, W);
   const size_t smem = v2 ? poisson2_smem_bytes(R, W) : poisson_smem_bytes(R, W);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(poisson_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)poisson2_smem_bytes(kPoi2R, kPoi2W));
-    if (e != cudaSuccess) {
-      set_error(std::string("poisson smem attribute: ") + cudaGetErrorString(e));
-      return CHB_ERR_CUDA;
-    }
-    attr_done = true;
+  // (set on every call: the attribute is per device, and a process may drive several)
+  cudaError_t e = v2 ? cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                     : cudaFuncSetAttribute(poisson_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error(std::string("poisson smem attribute: ") + cudaGetErrorString(e));
+    return CHB_ERR_CUDA;
   }
   PoissonParams p;
   p.source = source; p.target = target; p.mask = mask; p.out = out; p.stats = stats;
