@@ -331,13 +331,13 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoiThread
 //     barriers instead of 3, one block reduction instead of 2) and 7 shared-memory accesses per pixel instead of 11.
 // x_{i+1} = x_i + a_i p_i, r_{i+1} = r_i - a_i s_i, w = A r_{i+1}, g = (r,r), d = (r,w), b = g/g_old,
 // a = g / (d - b g / a_old), p = r + b p, s = w + b s.
-constexpr int kPoi2Threads = 512;
+constexpr int kPoi2MaxCluster = 16;
 constexpr int kPoi2Rows = 16;   // rows per thread
 
 struct Poisson2Smem {
   double lut[256];
-  double warp_part[2][kPoi2Threads / 32];
-  double slots[2][2][kPoiCluster];   // [parity][value][CTA]
+  double warp_part[2][16];
+  double slots[2][2][kPoi2MaxCluster];   // [parity][value][CTA]
 };
 
 __device__ __forceinline__ void cluster_arrive_release() {
@@ -347,6 +347,7 @@ __device__ __forceinline__ void cluster_wait_acquire() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+template <int CL, int NW>   // CTAs per cluster, warps per CTA (<= 16)
 __device__ __forceinline__ void poisson_cluster_sum2(cg::cluster_group& cluster, double& a, double& b, Poisson2Smem* sm,
                                                      int set, unsigned rank) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -358,13 +359,13 @@ __device__ __forceinline__ void poisson_cluster_sum2(cg::cluster_group& cluster,
   if (lane == 0) { sm->warp_part[0][warp] = a; sm->warp_part[1][warp] = b; }
   __syncthreads();
   if (warp == 0) {
-    // lanes 0..15 hold the 16 warp partials of value 0, lanes 16..31 those of value 1
-    double v = sm->warp_part[lane >> 4][lane & 15];
+    // lanes 0..15 hold the warp partials of value 0, lanes 16..31 those of value 1
+    double v = (lane & 15) < NW ? sm->warp_part[lane >> 4][lane & 15] : 0.0;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, 16);
     const double v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 16);
-    if (lane < 2 * kPoiCluster) {
-      const int which = lane / kPoiCluster, dst = lane % kPoiCluster;
+    if (lane < 2 * CL) {
+      const int which = lane / CL, dst = lane % CL;
       double* remote = cluster.map_shared_rank(&sm->slots[set][which][0], dst);
       remote[rank] = which ? v1 : v0;
     }
@@ -372,23 +373,24 @@ __device__ __forceinline__ void poisson_cluster_sum2(cg::cluster_group& cluster,
   cluster.sync();
   double ta = 0.0, tb = 0.0;
 #pragma unroll
-  for (int k = 0; k < kPoiCluster; ++k) { ta += sm->slots[set][0][k]; tb += sm->slots[set][1][k]; }
+  for (int k = 0; k < CL; ++k) { ta += sm->slots[set][0][k]; tb += sm->slots[set][1][k]; }
   a = ta; b = tb;
 }
 
-template <int W, int R>
-__global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoi2Threads, 1)
+template <int W, int R, int CL>   // columns, rows per CTA, CTAs per cluster (cluster shape comes from the launch attribute)
+__global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * W))
     poisson_cg2_kernel(const PoissonParams p) {
+  constexpr int kPoi2Threads = (R / kPoi2Rows) * W;
   // compile-time geometry (the reference's 256 x 256 images: 8 CTAs x 32 rows): every shared-memory offset below is
   // an immediate, which is what lets r, p and s stay in registers.  The inner loop is branch free: pixels outside U
   // (and rows beyond the image in a partial CTA) keep r = p = s = 0 because their stencil value is selected to 0,
   // and the haloed buffer has a zero column on either side so that column 0 / W-1 need no special case.
-  static_assert(R % kPoi2Rows == 0 && (R / kPoi2Rows) * W == kPoi2Threads, "one thread per (16-row strip, column)");
+  static_assert(R % kPoi2Rows == 0 && kPoi2Threads <= 512 && CL <= kPoi2MaxCluster, "one thread per (16-row strip, column)");
   constexpr int P = W + 2;   // pitch of the haloed residual buffer
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
-  const int sys = blockIdx.x / kPoiCluster;
+  const int sys = blockIdx.x / CL;
   const int b = sys / 3, ch = sys - b * 3;
   const int H = p.H;
   const int row0 = (int)rank * R;
@@ -404,7 +406,7 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoi2Threa
   for (int i = tid; i < (R + 2) * P; i += kPoi2Threads) rbuf[i] = 0.0;
   if (tid < 256)
     sm->lut[tid] = p.with_gamma ? (p.lut_fwd ? p.lut_fwd[tid] : pow((double)tid, 1.0 / 2.2)) : (double)tid;
-  if (tid < 4 * kPoiCluster) (&sm->slots[0][0][0])[tid] = 0.0;
+  if (tid < 4 * kPoi2MaxCluster) (&sm->slots[0][0][0])[tid] = 0.0;
   cluster.sync();
 
   const long long img_off = (long long)b * H * W;
@@ -475,7 +477,7 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoi2Threa
     r[j] = ((umask >> j) & 1u) ? wc[j * W] - v : 0.0;
   }
   double zero = 0.0;
-  poisson_cluster_sum2(cluster, bb_local, zero, sm, 0, rank);  // also: every CTA is done reading x0 from rbuf
+  poisson_cluster_sum2<CL, kPoi2Threads / 32>(cluster, bb_local, zero, sm, 0, rank);  // also: every CTA is done reading x0 from rbuf
   const double bb = bb_local;
   const double thresh = p.tol2 * bb;
 
@@ -505,7 +507,7 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoi2Threa
     cluster_wait_acquire();
     row(0, rc[-P], r[1]);
     row(kPoi2Rows - 1, r[kPoi2Rows - 2], rc[kPoi2Rows * P]);
-    poisson_cluster_sum2(cluster, g_l, d_l, sm, parity, rank);
+    poisson_cluster_sum2<CL, kPoi2Threads / 32>(cluster, g_l, d_l, sm, parity, rank);
     parity ^= 1;
     const double gamma_new = g_l, delta = d_l;
     if (!(gamma_new > thresh) || it >= p.max_iter) { gamma = gamma_new; break; }
@@ -551,6 +553,8 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoi2Threa
 }
 
 constexpr int kPoi2W = 256, kPoi2R = 32;   // the instantiated geometry: 256 columns, H in 249..256
+// ... and the same image on 16-CTA clusters (non-portable size) of 256-thread CTAs, two CTAs per SM
+constexpr int kPoi2R16 = 16;
 static size_t poisson2_smem_bytes(int R, int W) {
   return sizeof(Poisson2Smem) + (size_t)(R + 2) * (W + 2) * sizeof(double) + 2 * (size_t)R * W * sizeof(double);
 }
@@ -581,13 +585,28 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
   static const bool force_v1 = [] { const char* v = getenv("CHB_POISSON_V1"); return v && atoi(v) != 0; }();
   // second generation for the reference's image size; first generation for any other W <= 512, ceil(H/8)*W <= 8192
   const bool v2 = !force_v1 && poisson2_fits(R, W);
-  const size_t smem = v2 ? poisson2_smem_bytes(R, W) : poisson_smem_bytes(R, W);
+  size_t smem = v2 ? poisson2_smem_bytes(R, W) : poisson_smem_bytes(R, W);
+  // 16-CTA clusters (non-portable size, 256-thread CTAs) halve the rows per CTA: 20 % lower latency while at most 8
+  // clusters are in flight (interactive B <= 2, the reference's own use), same throughput as 8-CTA clusters beyond
+  // that (measured, profiles/r1_s_poisson_solver.txt).  CHB_POISSON_CL16 = 0 / 1 overrides the choice.
+  static const int force_cl16 = [] { const char* v = getenv("CHB_POISSON_CL16"); return v ? (atoi(v) != 0 ? 1 : 0) : -1; }();
+  const bool cl16 = v2 && (force_cl16 >= 0 ? force_cl16 == 1 : B * 3 <= 8);
+  if (cl16) smem = poisson2_smem_bytes(kPoi2R16, W);
   // (set on every call: the attribute is per device, and a process may drive several)
-  cudaError_t e = v2 ? cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                     : cudaFuncSetAttribute(poisson_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e;
+  if (cl16) {
+    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R16, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  } else if (v2) {
+    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+  } else {
+    e = cudaFuncSetAttribute(poisson_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   if (e != cudaSuccess) {
-    set_error(std::string("poisson smem attribute: ") + cudaGetErrorString(e));
+    set_error(std::string("poisson kernel attribute: ") + cudaGetErrorString(e));
     return CHB_ERR_CUDA;
   }
   PoissonParams p;
@@ -595,10 +614,29 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
   p.lut_fwd = lut_fwd; p.lut_known = lut_known;
   p.B = B; p.H = H; p.W = W; p.R = R;
   p.with_gamma = with_gamma ? 1 : 0; p.max_iter = max_iter; p.tol2 = tol * tol;
-  if (v2)
-    poisson_cg2_kernel<kPoi2W, kPoi2R><<<dim3((unsigned)(B * 3 * kPoiCluster)), kPoi2Threads, smem, stream>>>(p);
-  else
+  if (v2) {
+    const int cl = cl16 ? 16 : kPoiCluster;
+    const int threads = (cl16 ? kPoi2R16 : kPoi2R) / kPoi2Rows * kPoi2W;
+    if (cl16) p.R = kPoi2R16;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * 3 * cl));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cl16 ? cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R16, 16>, p)
+             : cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster>, p);
+    if (e != cudaSuccess) {
+      set_error(std::string("poisson_cg2 launch: ") + cudaGetErrorString(e));
+      return CHB_ERR_CUDA;
+    }
+  } else {
     poisson_cg_kernel<<<dim3((unsigned)(B * 3 * kPoiCluster)), kPoiThreads, smem, stream>>>(p);
+  }
   return blend_check("poisson_cg");
 }
 
