@@ -1,6 +1,6 @@
 """GPU parity probe of the whole generator against the CPU oracle (and the golden fixtures), with per-block taps.
 
-python tools/gpu_gen_check.py [crop] [B] [kind]
+python tests/_gpu_gen_check.py [crop] [B] [kind]
 """
 import os
 import sys

@@ -34,6 +34,9 @@ def face_like_case(H, W, seed):
     return synth.make_blend_case(H, W, seed)   # same construction as oracle/make_golden_blend.py
 
 
+synth_case = face_like_case
+
+
 def assert_close_u8(got, want, what, mask=None):
     """mask: the [H, W] solve mask of the call; untouched pixels (outside bo.unknown_set(mask)) are not counted."""
     got, want = np.asarray(got).astype(int), np.asarray(want).astype(int)
@@ -221,3 +224,40 @@ def test_poisson_argument_errors():
     z = np.zeros((2, 8, 3), np.uint8)
     with pytest.raises(_lib.ChbError):
         blend.poisson_blending(z, z, np.ones((2, 8), np.uint8))         # H < 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,B", [(250, 256, 1), (250, 256, 3), (249, 256, 1), (136, 200, 2), (128, 512, 1), (64, 64, 1)])
+def test_poisson_ragged_sizes_match_oracle(H, W, B):
+    """Partial last CTA of both cluster shapes of the 256-column kernel (H = 249, 250; B = 1 takes 16-CTA clusters,
+    B = 3 takes 8-CTA clusters), and sizes that take the general kernel."""
+    from ctrlhair_b200 import blend
+    cases = [synth_case(H, W, 600 + 7 * i) for i in range(B)]
+    src = np.stack([c[0] for c in cases])
+    tgt = np.stack([c[1] for c in cases])
+    masks = np.stack([1 - bo.blend_mask(c[3], c[2]) for c in cases])
+    out, stats = blend.poisson_blending(src, tgt, masks, return_stats=True)
+    assert float(stats[..., 1].max()) <= 1.01e-11
+    for i in range(B):
+        assert_close_u8(out[i].cpu().numpy(), bo.poisson_blending(src[i], tgt[i], masks[i][..., None]),
+                        "%dx%d image %d" % (H, W, i), masks[i])
+
+
+@pytest.mark.gpu
+def test_poisson_extreme_masks():
+    """mask == 1 everywhere (every row is a Laplacian row with the source's Laplacian on the right: the exact solution
+    is the source itself, which sits on the truncation boundary of every pixel, so only |out - source| <= 1 is
+    meaningful) and a mask whose solved region touches all four borders."""
+    from ctrlhair_b200 import blend
+    face, gen, fp, tp = synth_case(96, 256, 11)
+    ones = np.ones((96, 256), np.uint8)
+    out, stats = blend.poisson_blending(face, gen, ones, return_stats=True)
+    assert float(stats[..., 1].max()) <= 1.01e-11
+    assert np.abs(out.cpu().numpy().astype(int) - face.astype(int)).max() <= 1
+    m = np.zeros((96, 256), np.uint8)
+    m[:, :40] = 1
+    m[:30, :] = 1
+    m[-5:, :] = 1
+    m[:, -1] = 1
+    out = blend.poisson_blending(face, gen, m).cpu().numpy()
+    assert_close_u8(out, bo.poisson_blending(face, gen, m[..., None]), "border-touching mask", m)

@@ -11,7 +11,7 @@ train     a12  config 5: one train.py loop iteration (D sub-step + G sub-step + 
                world size > 1 adds the flat gradient all-reduce (NCCL)
 gen512         config 4 per-GPU share: generator forward at 512x512, images/s
 backend   8f.1 config 3 through BackendB200 (batched Backend.set_input_img + output incl. blending), images/s
-blend     8f.2 postprocess_blending (blend mask + Poisson solve) at 256x256, images/s, next to the CPU oracle
+blend     8f.2 postprocess_blending (blend mask + Poisson solve) at 256x256, images/s
 All timings: CUDA events on the launching stream, W warm-up + K timed iterations, inputs resident on the device.
 """
 import argparse
@@ -180,12 +180,11 @@ def bench_train(a):
 
 
 def bench_blend(a):
-    """HairEditor.postprocess_blending (hair_editor.py:257-308) for B images, device resident, next to
-    the oracle port (vectorised assembly + spsolve; the reference's own Python pixel loop is slower still) on the CPU."""
-    import time
+    """HairEditor.postprocess_blending (hair_editor.py:257-308) for B images, device resident.
+    (The CPU figure beside it comes from tests/_cpu_baselines.py, which times the oracle port: nothing outside tests/,
+    smoke() and bench.py's cpu_baseline leg touches oracle/.)"""
     import numpy as np
     from ctrlhair_b200 import blend
-    from oracle import blend_oracle as bo
     B = a.B
     cases = [synth.make_blend_case(256, 256, 900 + i) for i in range(B)]
     face = torch.from_numpy(np.stack([c[0] for c in cases])).cuda()
@@ -197,18 +196,12 @@ def bench_blend(a):
     mask = 1 - blend.blend_mask(tp, fp)
     _, stats = blend.poisson_blending(face, src_u8, mask, return_stats=True)
     ms_solve = timed(lambda: blend.poisson_blending(face, src_u8, mask), a.steps, a.warmup)
-    n_cpu = 2
-    t0 = time.time()
-    for i in range(n_cpu):
-        bo.postprocess_blending(cases[i][0], res[i].cpu().numpy(), cases[i][2], cases[i][3])
-    cpu_s = (time.time() - t0) / n_cpu
     it = float(stats[..., 0].mean())
     emit({"path": "8f.2 postprocess_blending 256x256 (mask + fp64 CG Poisson solve, 3 channels)", "B": B, "ms": ms,
           "images_per_s": B / ms * 1e3, "poisson_kernel_ms": ms_solve, "cg_iterations_mean": it,
           "cg_iterations_max": float(stats[..., 0].max()), "residual_max": float(stats[..., 1].max()),
           "us_per_iteration_per_wave": ms_solve * 1e3 / it / max(1.0, B * 3 / 16.0),
-          "unknown_fraction": float(torch.as_tensor(mask).float().mean()),
-          "cpu_oracle_images_per_s": 1.0 / cpu_s, "cpu_sample": "%d images, scipy spsolve, 1 thread" % n_cpu})
+          "unknown_fraction": float(torch.as_tensor(mask).float().mean())})
 
 
 def bench_backend(a, sd):
