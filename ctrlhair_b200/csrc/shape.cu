@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -44,45 +45,65 @@ __global__ void shape_pos_kernel(__half* pos, int S) {
   }
 }
 
-// layer-0 encoder input: mask fp32 NCHW [B,Cm,S,S] ++ pos -> space-to-depth fp16 [B, S/2, S/2, Cpad],
-// channel = (py*2+px) * (Cm+40) + c; channels >= 4*(Cm+40) are zero padding.
-__global__ void shape_prep_kernel(const float* __restrict__ mask, const __half* __restrict__ pos, __half* __restrict__ out,
-                                  int B, int Cm, int S, int Cpad) {
+// Encoder input: concat [mask | positional map] (model.py:96-101) in the space-to-depth layout the first conv reads:
+// out[b, by, bx, par * Cin + c] = in[c][2 by + par / 2][2 bx + par % 2], channels >= 4 Cin zero.  One block per
+// (32 output pixels of a row, row, image): the gather runs with the pixel index across the lanes (coalesced reads of
+// the NCHW mask planes), a padded shared tile turns it into contiguous 16-byte stores.  HBM-bound: 4 B read per mask
+// element + 2 B written per output element.
+constexpr int kPrepBx = 32;
+__global__ void __launch_bounds__(256) shape_prep_kernel(const float* __restrict__ mask, const __half* __restrict__ pos,
+                                                         __half* __restrict__ out, int B, int Cm, int S, int Cpad) {
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  __half* tile = reinterpret_cast<__half*>(prep_smem);   // [kPrepBx][Cpad + 2]
+  const int pitch = Cpad + 2;
   const int Cin = Cm + kPosCh, Hh = S / 2;
-  const long long total = (long long)B * Hh * Hh * Cpad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % Cpad);
-    long long p = i / Cpad;
-    const int bx = (int)(p % Hh);
-    p /= Hh;
-    const int by = (int)(p % Hh);
-    const int b = (int)(p / Hh);
+  const int bx0 = blockIdx.x * kPrepBx, by = blockIdx.y, b = blockIdx.z;
+  for (int idx = threadIdx.x; idx < Cpad * kPrepBx; idx += 256) {
+    const int ch = idx / kPrepBx, bxl = idx - ch * kPrepBx;
+    const int bx = bx0 + bxl;
     __half v = __float2half_rn(0.f);
-    if (ch < 4 * Cin) {
-      const int par = ch / Cin, c = ch % Cin;
+    if (ch < 4 * Cin && bx < Hh) {
+      const int par = ch / Cin, c = ch - par * Cin;
       const int y = 2 * by + (par >> 1), x = 2 * bx + (par & 1);
-      v = c < Cm ? __float2half_rn(mask[(((long long)b * Cm + c) * S + y) * S + x])
+      v = c < Cm ? __float2half_rn(__ldg(mask + (((long long)b * Cm + c) * S + y) * S + x))
                  : pos[((long long)y * S + x) * kPosCh + (c - Cm)];
     }
-    out[i] = v;
+    tile[bxl * pitch + ch] = v;
+  }
+  __syncthreads();
+  const int c8 = Cpad / 8;
+  __half* orow = out + (((long long)b * Hh + by) * Hh + bx0) * Cpad;
+  for (int idx = threadIdx.x; idx < kPrepBx * c8; idx += 256) {
+    const int bxl = idx / c8, k = idx - bxl * c8;
+    if (bx0 + bxl >= Hh) continue;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tile + bxl * pitch + k * 8);   // pitch is even: 4-byte aligned
+    *reinterpret_cast<uint4*>(orow + (long long)bxl * Cpad + k * 8) = make_uint4(src[0], src[1], src[2], src[3]);
   }
 }
 
-// per-sample sum / sum of squares over all n elements (double)
-__global__ void ln_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, long long n) {
+// Sum and sum of squares of each image (the custom LayerNorm of my_torchlib/module.py:177-205 normalises over C*H*W).
+// 16-byte loads, four in flight per thread, fp32 partials flushed to double every 64 values, one atomic per warp.
+__global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
+                                                       long long n) {
   const int b = blockIdx.y;
-  const float* xb = x + (long long)b * n;
+  const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * n);
+  const long long n4 = n >> 2;   // n = H*W*C is a multiple of 8
   double d1 = 0.0, d2 = 0.0;
-  float s1 = 0.f, s2 = 0.f;
-  int cnt = 0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = xb[i];
-    s1 += v;
-    s2 = fmaf(v, v, s2);
-    if (++cnt == 32) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      v[u] = (i + u * stride < n4) ? __ldg(xb + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s1 += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+      s2 = fmaf(v[u].x, v[u].x, s2); s2 = fmaf(v[u].y, v[u].y, s2);
+      s2 = fmaf(v[u].z, v[u].z, s2); s2 = fmaf(v[u].w, v[u].w, s2);
+    }
+    d1 += s1; d2 += s2;
   }
-  d1 += s1; d2 += s2;
   for (int o = 16; o > 0; o >>= 1) {
     d1 += __shfl_xor_sync(0xffffffffu, d1, o);
     d2 += __shfl_xor_sync(0xffffffffu, d2, o);
@@ -93,42 +114,67 @@ __global__ void ln_stats_kernel(const float* __restrict__ x, double* __restrict_
   }
 }
 
-// y = lrelu(((x - mean) / (std + eps)) * gamma_c + beta_c)   (norm = 1)   or   y = x  (norm = 0, the decoder fc output)
-// x fp32 NHWC [B,H,W,C] -> fp16:  mode 0 plain [B,H,W,C];  mode 1 space-to-depth [B,H/2,W/2,4C];
-//                                 mode 2 nearest upsample x2 [B,2H,2W,C]
-__global__ void ln_apply_kernel(const float* __restrict__ x, const double* __restrict__ sums,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out,
-                                int B, int H, int W, int C, int mode, int norm) {
-  const long long n = (long long)H * W * C;
-  const long long total = (long long)B * n;
+// per image {1 / (std + eps), -mean / (std + eps)}: unbiased std, eps added to the std (module.py:189-199)
+__global__ void ln_finalize_kernel(const double* __restrict__ sums, float2* __restrict__ ss, int B, double n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double mean = sums[b * 2] / n;
+  const double var = (sums[b * 2 + 1] - n * mean * mean) / (n - 1.0);
+  const double inv = 1.0 / (sqrt(var > 0.0 ? var : 0.0) + 1e-5);
+  ss[b] = make_float2((float)inv, (float)(-mean * inv));
+}
+
+// LayerNorm apply (+ per-channel affine + LeakyReLU 0.2) and relayout to the fp16 tensor the next conv reads.
+// mode 0: same layout; mode 1: space-to-depth (next conv is 4x4 stride 2); mode 2: nearest 2x upsample.
+// norm 0: plain fp32 -> fp16 conversion.  One thread per 8 channels of a pixel: 16-byte loads and stores.
+__global__ void __launch_bounds__(256) ln_apply_kernel(const float* __restrict__ x, const float2* __restrict__ ss,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       __half* __restrict__ out, int B, int H, int W, int C, int mode,
+                                                       int norm) {
+  const int c8 = C >> 3;
+  const unsigned per_img = (unsigned)H * W * c8;
+  const long long total = (long long)B * per_img;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long p = i / C;
-    const int xx = (int)(p % W);
-    p /= W;
-    const int yy = (int)(p % H);
-    const int b = (int)(p / H);
-    float v = x[i];
+    const int b = (int)(i / per_img);
+    unsigned p = (unsigned)(i - (long long)b * per_img);
+    const int c = (int)(p % c8) * 8;
+    p /= c8;
+    const int xx = (int)(p % W), yy = (int)(p / W);
+    const float4* src = reinterpret_cast<const float4*>(x + i * 8);
+    const float4 a = __ldg(src), bq = __ldg(src + 1);
+    float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
     if (norm) {
-      const double mean = sums[b * 2] / (double)n;
-      const double var = (sums[b * 2 + 1] - (double)n * mean * mean) / (double)(n - 1);  // unbiased (torch.std)
-      const float inv = (float)(1.0 / (sqrt(var > 0.0 ? var : 0.0) + 1e-5));
-      v = (v - (float)mean) * inv * gamma[c] + beta[c];
-      v = v > 0.f ? v : 0.2f * v;
+      const float2 s = __ldg(ss + b);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t = fmaf(fmaf(v[k], s.x, s.y), g[k], be[k]);
+        v[k] = t > 0.f ? t : 0.2f * t;
+      }
     }
-    const __half h = __float2half_rn(v);
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+      pk[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    const uint4 q = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     if (mode == 0) {
-      out[i] = h;
+      *reinterpret_cast<uint4*>(out + i * 8) = q;
     } else if (mode == 1) {
       const int par = (yy & 1) * 2 + (xx & 1);
-      out[(((long long)b * (H / 2) + (yy >> 1)) * (W / 2) + (xx >> 1)) * (4LL * C) + (long long)par * C + c] = h;
+      *reinterpret_cast<uint4*>(out + (((long long)b * (H / 2) + (yy >> 1)) * (W / 2) + (xx >> 1)) * (4LL * C) +
+                                (long long)par * C + c) = q;
     } else {
-      const long long o = (((long long)b * 2 * H + 2 * yy) * 2 * W + 2 * xx) * C + c;
-      out[o] = h;
-      out[o + C] = h;
-      out[o + 2LL * W * C] = h;
-      out[o + 2LL * W * C + C] = h;
+      __half* o = out + (((long long)b * 2 * H + 2 * yy) * 2 * W + 2 * xx) * C + c;
+      *reinterpret_cast<uint4*>(o) = q;
+      *reinterpret_cast<uint4*>(o + C) = q;
+      *reinterpret_cast<uint4*>(o + 2LL * W * C) = q;
+      *reinterpret_cast<uint4*>(o + 2LL * W * C + C) = q;
     }
   }
 }
@@ -277,6 +323,16 @@ static chb_conv_desc conv_desc(int B, int H, int W, const void* a, int C, const 
   d.TW = W < 8 ? W : 8;
   d.TH = H < 16 ? H : 16;
   d.TB = 1;
+  static const bool batch_tiles = [] { const char* v = getenv("CHB_SHAPE_TB"); return !v || atoi(v) != 0; }();
+  if (batch_tiles && d.TW * d.TH <= 64) {
+    // tiny maps (2x2 .. 8x8): several images share one 128-row MMA tile, so the 2048 x 36864 weight matrices of the
+    // deep layers are streamed once per N tile instead of once per image ...
+    d.TB = 128 / (d.TW * d.TH);
+    if (d.TB > B) d.TB = B;
+    // ... and the N tile shrinks until there are enough tiles to spread that stream over the SMs
+    const int m_tiles = ((B + d.TB - 1) / d.TB) * ((H + d.TH - 1) / d.TH) * ((W + d.TW - 1) / d.TW);
+    while (BN > 32 && N % (BN / 2) == 0 && m_tiles * (N / BN) < 96) BN /= 2;
+  }
   d.nseg = 1;
   chb_conv_seg& s = d.seg[0];
   s.a = a; s.Ca = C; s.C = C; s.taps = 9; s.w = w;
@@ -348,14 +404,18 @@ static void ln(chb_shape* z, cudaStream_t st, int B, int H, int W, int C, const 
   const float* x = reinterpret_cast<const float*>(z->ws + (norm == 2 ? z->ws_fcout : z->ws_conv));
   double* sums = reinterpret_cast<double*>(z->ws + z->ws_sums);
   const long long n = (long long)H * W * C;
+  float2* ss = reinterpret_cast<float2*>(sums + (size_t)z->cfg.max_batch * 2);
   if (norm == 1) {
     cudaMemsetAsync(sums, 0, (size_t)B * 2 * sizeof(double), st);
-    long long blocks = (n + 256 * 64 - 1) / (256 * 64);
-    if (blocks > 256) blocks = 256;
+    long long blocks = (n / 4 + 256 * 16 - 1) / (256 * 16);
+    const long long want = ((long long)device_sm_count() * 8 + B - 1) / B;
+    if (blocks > want) blocks = want;
+    if (blocks < 1) blocks = 1;
     ln_stats_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, st>>>(x, sums, n);
+    ln_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(sums, ss, B, (double)n);
   }
-  ln_apply_kernel<<<sgrid((long long)B * n, 256), 256, 0, st>>>(x, sums, gamma, beta, out, B, H, W, C, mode,
-                                                                norm == 1 ? 1 : 0);
+  ln_apply_kernel<<<sgrid((long long)B * (n / 8), 256), 256, 0, st>>>(x, ss, gamma, beta, out, B, H, W, C, mode,
+                                                                      norm == 1 ? 1 : 0);
 }
 }  // namespace chb
 
@@ -409,7 +469,7 @@ int chb_shape_create(const chb_shape_config* cfg, chb_shape** out) {
   z->ws_code16 = sws(z, B * 1088 * 2);
   z->ws_logit[0] = sws(z, B * S * S * 16 * 4);
   z->ws_logit[1] = sws(z, B * S * S * 32 * 4);
-  z->ws_sums = sws(z, B * 2 * 8);
+  z->ws_sums = sws(z, B * 2 * 8 + B * 8);   // double moments [B][2] + float2 {1/(std+eps), shift} [B]
   z->ws_io = sws(z, B * 19 * S * S * 4);
   *out = z;
   return CHB_OK;
@@ -472,7 +532,8 @@ int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B
   }
   const std::vector<ConvPlan>& pl = it->second;
   const int S = z->cfg.crop;
-  shape_prep_kernel<<<sgrid((long long)B * (S / 2) * (S / 2) * kEncPad0[net], 256), 256, 0, st>>>(
+  shape_prep_kernel<<<dim3((unsigned)((S / 2 + kPrepBx - 1) / kPrepBx), (unsigned)(S / 2), (unsigned)B), 256,
+                      (size_t)kPrepBx * (kEncPad0[net] + 2) * sizeof(__half), st>>>(
       mask, reinterpret_cast<const __half*>(z->ws + z->ws_pos), reinterpret_cast<__half*>(z->ws + z->ws_in), B,
       kEncCm[net], S, kEncPad0[net]);
   for (int i = 0; i < 7; ++i) {

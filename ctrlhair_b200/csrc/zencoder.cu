@@ -67,53 +67,92 @@ __global__ void zenc_conv1_kernel(const float* __restrict__ img, const float* __
 }
 
 // ---------------------------------------------------------------- InstanceNorm statistics
-// x fp32 NHWC [B, Hs, Ws, C]; the normalised map is the sub-grid (y*s, x*s), y < H, x < W.  Accumulates sum and
-// sum of squares per (b, c) in double.  grid = (slabs, B), block = 256; thread t owns channel t % C.
-__global__ void in_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int H, int W, int C, int s,
-                                long long row_stride, long long img_stride) {
+// x fp32 NHWC [B, Hs, Ws, C]; the normalised map is the sub-grid (y*s, x*s), y < H, x < W.  Per (b, c) sum and sum of
+// squares in double.  grid = (slabs, B), block = 256: a thread owns 4 consecutive channels (one 16-byte load per
+// pixel), 256 / (C/4) pixels are in flight per block step; the block combines its lanes in shared memory and issues
+// ONE atomic per (channel, moment) — HBM-bound: algorithmic bytes = 4 B per element of the sub-grid.
+__global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int H,
+                                                       int W, int C, int s, long long row_stride,
+                                                       long long img_stride) {
+  __shared__ double part[256 * 8];   // [lane][channel][2], lanes * C = 1024 entries
   const int b = blockIdx.y;
-  const int c = threadIdx.x % C;
-  const int lanes = blockDim.x / C;  // pixels processed in parallel by the block
-  const int pl = threadIdx.x / C;
-  const long long npix = (long long)H * W;
-  float s1 = 0.f, s2 = 0.f;
-  double d1 = 0.0, d2 = 0.0;
+  const int c4 = C >> 2;
+  const int lanes = 256 / c4;
+  const int cg = threadIdx.x % c4, pl = threadIdx.x / c4;
+  const int npix = H * W;
+  const float* xb = x + (long long)b * img_stride + cg * 4;
+  double d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int cnt = 0;
-  if (pl < lanes) {
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes) {
-      const int yy = (int)(p / W), xx = (int)(p % W);
-      const float v = x[(long long)b * img_stride + (long long)(yy * s) * row_stride + (long long)(xx * s) * C + c];
-      s1 += v;
-      s2 = fmaf(v, v, s2);
-      if (++cnt == 64) {  // flush to double regularly: fp32 running sums stay short
-        d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0;
+  const int step = gridDim.x * lanes;
+  for (int p = blockIdx.x * lanes + pl; p < npix; p += 4 * step) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = p + u * step;
+      if (q < npix) {
+        const int yy = q / W, xx = q - yy * W;
+        v[u] = __ldg(reinterpret_cast<const float4*>(xb + (long long)(yy * s) * row_stride + (long long)(xx * s) * C));
+      } else {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    d1 += s1; d2 += s2;
-    atomicAdd(&sums[((long long)b * C + c) * 2], d1);
-    atomicAdd(&sums[((long long)b * C + c) * 2 + 1], d2);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      f[0] += v[u].x; f[1] = fmaf(v[u].x, v[u].x, f[1]);
+      f[2] += v[u].y; f[3] = fmaf(v[u].y, v[u].y, f[3]);
+      f[4] += v[u].z; f[5] = fmaf(v[u].z, v[u].z, f[5]);
+      f[6] += v[u].w; f[7] = fmaf(v[u].w, v[u].w, f[7]);
+    }
+    if (++cnt == 16) {  // flush to double regularly: fp32 running sums stay short (64 pixels)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { d[k] += f[k]; f[k] = 0.f; }
+      cnt = 0;
+    }
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[(pl * c4 + cg) * 8 + k] = d[k] + (double)f[k];
+  __syncthreads();
+  // thread t < 2C: (channel, moment) = (t / 2, t % 2); part index of lane l = (l * c4 + ch / 4) * 8 + (ch % 4) * 2 + m
+  for (int t = threadIdx.x; t < 2 * C; t += 256) {
+    const int ch = t >> 1, m = t & 1;
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += part[(l * c4 + (ch >> 2)) * 8 + (ch & 3) * 2 + m];
+    atomicAdd(&sums[((long long)b * C + ch) * 2 + m], acc);
+  }
+}
+
+// (b, c): {rstd, -mean * rstd} in fp32 from the double moments (biased variance, eps 1e-5, as nn.InstanceNorm2d)
+__global__ void in_finalize_kernel(const double* __restrict__ sums, float2* __restrict__ ss, int n, double inv_n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = sums[2 * i] * inv_n;
+  const double var = sums[2 * i + 1] * inv_n - mean * mean;
+  const double r = 1.0 / sqrt(var + 1e-5);
+  ss[i] = make_float2((float)r, (float)(-mean * r));
 }
 
 // ---------------------------------------------------------------- InstanceNorm apply + LeakyReLU + relayout (fp16 out)
 // mode 0: out[b, y, x]       = f(in[y, x])                        out extent H x W
 // mode 1: zero insertion     out[b, 2y, 2x] = f(in[y, x]), else 0  out extent 2H x 2W   (ConvTranspose s2 as a conv)
 // mode 2: reflection pad 1   out[b, y, x] = f(in[refl(y-1), refl(x-1)])  out extent (H+2) x (W+2)
-__global__ void in_apply_kernel(const float* __restrict__ x, const double* __restrict__ sums, __half* __restrict__ out,
-                                int B, int H, int W, int C, int s, long long row_stride, long long img_stride, int mode) {
+// One thread per 8 channels of an output pixel: two 16-byte loads, one 16-byte store, 8 FMAs (HBM-bound: 4 B read +
+// 2 B written per element).
+__global__ void __launch_bounds__(256) in_apply_kernel(const float* __restrict__ x, const float2* __restrict__ ss,
+                                                       __half* __restrict__ out, int B, int H, int W, int C, int s,
+                                                       long long row_stride, long long img_stride, int mode) {
   const int OH = mode == 1 ? 2 * H : (mode == 2 ? H + 2 : H);
   const int OW = mode == 1 ? 2 * W : (mode == 2 ? W + 2 : W);
   const int c8 = C / 8;
-  const long long total = (long long)B * OH * OW * c8;
-  const double inv_n = 1.0 / ((double)H * W);
+  const unsigned per_img = (unsigned)OH * OW * c8;
+  const long long total = (long long)B * per_img;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c8);
-    long long p = i / c8;
-    const int ox = (int)(p % OW);
-    p /= OW;
-    const int oy = (int)(p % OH);
-    const int b = (int)(p / OH);
+    const int b = (int)(i / per_img);
+    unsigned p = (unsigned)(i - (long long)b * per_img);
+    const int cg = (int)(p % c8);
+    p /= c8;
+    const int ox = (int)(p % OW), oy = (int)(p / OW);
     int iy = oy, ix = ox;
     bool zero = false;
     if (mode == 1) {
@@ -127,17 +166,16 @@ __global__ void in_apply_kernel(const float* __restrict__ x, const double* __res
     uint32_t pk[4] = {0u, 0u, 0u, 0u};
     if (!zero) {
       const float* src = x + (long long)b * img_stride + (long long)(iy * s) * row_stride + (long long)(ix * s) * C + cg * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src), bq = *reinterpret_cast<const float4*>(src + 4);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), bq = __ldg(reinterpret_cast<const float4*>(src + 4));
       const float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+      const float4* sp = reinterpret_cast<const float4*>(ss + (long long)b * C + cg * 8);
       float o[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const double* sp = sums + ((long long)b * C + cg * 8 + k) * 2;
-        const double mean = sp[0] * inv_n;
-        const double var = sp[1] * inv_n - mean * mean;  // biased variance, as nn.InstanceNorm2d
-        const float r = (float)(1.0 / sqrt(var + 1e-5));
-        const float t = (v[k] - (float)mean) * r;
-        o[k] = t > 0.f ? t : 0.2f * t;
+      for (int k = 0; k < 4; ++k) {
+        const float4 q = __ldg(sp + k);   // {rstd, shift} of channels 2k, 2k + 1
+        const float t0 = fmaf(v[2 * k], q.x, q.y), t1 = fmaf(v[2 * k + 1], q.z, q.w);
+        o[2 * k] = t0 > 0.f ? t0 : 0.2f * t0;
+        o[2 * k + 1] = t1 > 0.f ? t1 : 0.2f * t1;
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -151,26 +189,64 @@ __global__ void in_apply_kernel(const float* __restrict__ x, const double* __res
 
 // ---------------------------------------------------------------- region pooling
 // codes fp32 NHWC [B, R, R, C]; labels u8 [B, S, S], class of code pixel (y,x) = labels[y << sh][x << sh]
-// (F.interpolate nearest, architecture.py:181).  grid = (slabs, B), block = 256, C <= 512, classes <= 32.
-__global__ void region_pool_kernel(const float* __restrict__ codes, const uint8_t* __restrict__ labels,
-                                   float* __restrict__ sums /*[B][NC][C]*/, int* __restrict__ counts /*[B][NC]*/, int R,
-                                   int C, int S, int sh, int NC, int pix_per_block) {
+// (F.interpolate nearest, architecture.py:181).  grid = (slabs, B), block = C / 4 threads (one float4 of channels each).
+// A block walks its pixels in order with 8 loads in flight and keeps the running sum of the current label run in
+// registers; a run is flushed into the block's [NC][C] shared accumulator when the label changes (label maps are
+// piecewise constant along a row), and the accumulator goes out with one atomic per touched entry.  HBM-bound: 4 B per
+// code element.
+__global__ void __launch_bounds__(128) region_pool_kernel(const float* __restrict__ codes,
+                                                          const uint8_t* __restrict__ labels,
+                                                          float* __restrict__ sums /*[B][NC][C]*/,
+                                                          int* __restrict__ counts /*[B][NC]*/, int R, int C, int S,
+                                                          int sh, int NC, int pix_per_block) {
   extern __shared__ float acc[];  // [NC][C]
   __shared__ int cnt[32];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < NC * C; i += blockDim.x) acc[i] = 0.f;
   if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
   __syncthreads();
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  const long long p1 = min((long long)R * R, p0 + pix_per_block);
-  for (long long p = p0; p < p1; ++p) {
-    const int y = (int)(p / R), x = (int)(p % R);
-    const int lab = labels[((long long)b * S + ((long long)y << sh)) * S + ((long long)x << sh)];
-    if (lab >= NC) continue;
-    const float* src = codes + (((long long)b * R + y) * R + x) * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) acc[lab * C + c] += src[c];  // thread-private columns
-    if (threadIdx.x == 0) cnt[lab]++;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(R * R, p0 + pix_per_block);
+  const int c = threadIdx.x * 4;
+  const uint8_t* lb = labels + (long long)b * S * S;
+  const float* cb = codes + (long long)b * R * R * C + c;
+  int cur = -1, run = 0;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto flush = [&]() {
+    if (cur >= 0 && cur < NC) {   // thread-private columns of the accumulator: no conflicts
+      float* d = acc + cur * C + c;
+      d[0] += a.x; d[1] += a.y; d[2] += a.z; d[3] += a.w;
+      if (threadIdx.x == 0) cnt[cur] += run;
+    }
+  };
+  for (int p = p0; p < p1; p += 8) {
+    float4 v[8];
+    int lab[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int q = p + u;
+      if (q < p1) {
+        const int y = q / R, x = q - y * R;
+        lab[u] = lb[((long long)y << sh) * S + ((long long)x << sh)];
+        v[u] = __ldg(reinterpret_cast<const float4*>(cb + (long long)q * C));
+      } else {
+        lab[u] = -2;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (lab[u] == -2) continue;
+      if (lab[u] != cur) {
+        flush();
+        cur = lab[u]; run = 0;
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
+      ++run;
+    }
   }
+  flush();
   __syncthreads();
   for (int i = threadIdx.x; i < NC * C; i += blockDim.x) {
     const float v = acc[i];
@@ -299,7 +375,7 @@ int chb_zencoder_create(const chb_zenc_config* cfg, chb_zencoder** out) {
   z->ws_c4 = zws(z, B * S2 * S2 * 256 * 4);
   z->ws_a4 = zws(z, B * (S2 + 2) * (S2 + 2) * 256 * 2);
   z->ws_codes = zws(z, B * S2 * S2 * 512 * 4);
-  z->ws_sums = zws(z, B * 256 * 2 * 8);
+  z->ws_sums = zws(z, B * 256 * 2 * 8 + B * 256 * 8);   // double moments [B][256][2] + float2 {rstd, shift} [B][256]
   z->ws_psum = zws(z, B * NC * 512 * 4);
   z->ws_pcnt = zws(z, B * NC * 4);
   (void)S4;
@@ -365,12 +441,17 @@ int chb_zencoder_forward(chb_zencoder* z, const float* img, const uint8_t* label
   auto norm = [&](const float* x, int H, int W, int C, int s, long long row_stride, long long img_stride, __half* y,
                   int mode) {
     cudaMemsetAsync(sums, 0, (size_t)B * C * 2 * sizeof(double), st);
-    const int lanes = 256 / C > 0 ? 256 / C : 1;
+    const int lanes = 256 / (C / 4);
+    // enough blocks to fill the machine (B * slabs >= ~8 per SM), each with >= 64 pixels per lane where possible
     long long slabs = ((long long)H * W + lanes * 64 - 1) / (lanes * 64);
-    if (slabs > 512) slabs = 512;
+    const long long want = ((long long)device_sm_count() * 8 + B - 1) / B;
+    if (slabs > want) slabs = want;
+    if (slabs < 1) slabs = 1;
     in_stats_kernel<<<dim3((unsigned)slabs, (unsigned)B), 256, 0, st>>>(x, sums, H, W, C, s, row_stride, img_stride);
+    float2* ss = reinterpret_cast<float2*>(sums + (size_t)B * 256 * 2);   // second half of the statistics buffer
+    in_finalize_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(sums, ss, B * C, 1.0 / ((double)H * W));
     const int OH = mode == 1 ? 2 * H : (mode == 2 ? H + 2 : H), OW = mode == 1 ? 2 * W : (mode == 2 ? W + 2 : W);
-    in_apply_kernel<<<zgrid((long long)B * OH * OW * (C / 8), 256), 256, 0, st>>>(x, sums, y, B, H, W, C, s, row_stride,
+    in_apply_kernel<<<zgrid((long long)B * OH * OW * (C / 8), 256), 256, 0, st>>>(x, ss, y, B, H, W, C, s, row_stride,
                                                                                 img_stride, mode);
   };
   // L1
@@ -397,7 +478,7 @@ int chb_zencoder_forward(chb_zencoder* z, const float* img, const uint8_t* label
   cudaMemsetAsync(pcnt, 0, (size_t)B * NC * 4, st);
   int sh = 0;
   while ((S2 << sh) < S) ++sh;
-  const int ppb = 512;
+  const int ppb = 256;
   const int slabs = (S2 * S2 + ppb - 1) / ppb;
   const size_t smem = (size_t)NC * 512 * 4;
   static bool attr_set = false;
@@ -405,7 +486,7 @@ int chb_zencoder_forward(chb_zencoder* z, const float* img, const uint8_t* label
     cudaFuncSetAttribute(region_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 512 * 4);
     attr_set = true;
   }
-  region_pool_kernel<<<dim3((unsigned)slabs, (unsigned)B), 256, smem, st>>>(F(z->ws_codes), labels, psum, pcnt, S2, 512,
+  region_pool_kernel<<<dim3((unsigned)slabs, (unsigned)B), 128, smem, st>>>(F(z->ws_codes), labels, psum, pcnt, S2, 512,
                                                                            S, sh, NC, ppb);
   region_finalize_kernel<<<zgrid((long long)B * NC * 512, 256), 256, 0, st>>>(psum, pcnt, out, (long long)B * NC * 512,
                                                                              512);

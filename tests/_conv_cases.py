@@ -171,6 +171,13 @@ def make_cases(device="cuda"):
                act=ops.ACT_RELU, seed=11)
     plain_case("plain_tb4_rows", 6, 1, 19, [(512, 0, 512, 1, False)], 256, 256, tile=(32, 1, 4), use_bias=False,
                layout="nchw", seed=12)
+    # batch-tiled 3x3 convs at tiny resolutions (shape nets: several images share one 128-row MMA tile), narrow N tiles
+    plain_case("plain_tb8_3x3_r4_c512_bn64", 11, 4, 4, [(512, 0, 512, 9, False)], 256, 64, tile=(4, 4, 8),
+               out_dtype=torch.float32, seed=13)
+    plain_case("plain_tb32_3x3_r2_c1024_bn16", 33, 2, 2, [(1024, 0, 1024, 9, False)], 128, 16, tile=(2, 2, 32),
+               out_dtype=torch.float32, seed=14)
+    plain_case("plain_tb2_3x3_r8_c256_bn32", 5, 8, 8, [(256, 0, 256, 9, False)], 128, 32, tile=(8, 8, 2),
+               out_dtype=torch.float32, seed=15)
     mod_case("mod_styled_c128_bn256_up", 2, 32, 32, 128, 256, True, x_shift=1, seed=1)
     mod_case("mod_unstyled_c64_bn128", 2, 32, 32, 64, 128, False, seed=2)
     mod_case("mod_styled_c256_two_ntiles_nonoise", 2, 16, 16, 256, 256, True, act=ops.ACT_NONE, use_noise=False,
