@@ -58,17 +58,40 @@ __global__ void __launch_bounds__(256) shape_prep_kernel(const float* __restrict
   const int pitch = Cpad + 2;
   const int Cin = Cm + kPosCh, Hh = S / 2;
   const int bx0 = blockIdx.x * kPrepBx, by = blockIdx.y, b = blockIdx.z;
-  for (int idx = threadIdx.x; idx < Cpad * kPrepBx; idx += 256) {
-    const int ch = idx / kPrepBx, bxl = idx - ch * kPrepBx;
+  // mask planes: pixel index across the lanes (8-byte stride in x), one 4-byte load per element
+  for (int idx = threadIdx.x; idx < 4 * Cm * kPrepBx; idx += 256) {
+    const int chm = idx / kPrepBx, bxl = idx - chm * kPrepBx;
+    const int par = chm / Cm, c = chm - par * Cm;
     const int bx = bx0 + bxl;
     __half v = __float2half_rn(0.f);
-    if (ch < 4 * Cin && bx < Hh) {
-      const int par = ch / Cin, c = ch - par * Cin;
+    if (bx < Hh) {
       const int y = 2 * by + (par >> 1), x = 2 * bx + (par & 1);
-      v = c < Cm ? __float2half_rn(__ldg(mask + (((long long)b * Cm + c) * S + y) * S + x))
-                 : pos[((long long)y * S + x) * kPosCh + (c - Cm)];
+      v = __float2half_rn(__ldg(mask + (((long long)b * Cm + c) * S + y) * S + x));
     }
-    tile[bxl * pitch + ch] = v;
+    tile[bxl * pitch + par * Cin + c] = v;
+  }
+  // positional map: 40 contiguous halves per source pixel = five 16-byte loads
+  static_assert(kPosCh % 8 == 0, "positional channels are read in 16-byte pieces");
+  constexpr int kQ = kPosCh / 8;
+  for (int idx = threadIdx.x; idx < 4 * kPrepBx * kQ; idx += 256) {
+    const int q = idx % kQ, t = idx / kQ;
+    const int bxl = t % kPrepBx, par = t / kPrepBx;
+    const int bx = bx0 + bxl;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (bx < Hh) {
+      const int y = 2 * by + (par >> 1), x = 2 * bx + (par & 1);
+      v = __ldg(reinterpret_cast<const uint4*>(pos + ((long long)y * S + x) * kPosCh) + q);
+    }
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    __half* dst = tile + bxl * pitch + par * Cin + Cm + q * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = h[j];
+  }
+  // zero padding channels
+  const int npad = Cpad - 4 * Cin;
+  for (int idx = threadIdx.x; idx < npad * kPrepBx; idx += 256) {
+    const int bxl = idx / npad, k = idx - bxl * npad;
+    tile[bxl * pitch + 4 * Cin + k] = __float2half_rn(0.f);
   }
   __syncthreads();
   const int c8 = Cpad / 8;
@@ -83,7 +106,10 @@ __global__ void __launch_bounds__(256) shape_prep_kernel(const float* __restrict
 
 // Sum and sum of squares of each image (the custom LayerNorm of my_torchlib/module.py:177-205 normalises over C*H*W).
 // 16-byte loads, four in flight per thread, fp32 partials flushed to double every 64 values, one atomic per warp.
+// The last block of an image to finish turns the moments into {1 / (std + eps), -mean / (std + eps)} (unbiased std, eps
+// added to the std: module.py:189-199), so no separate finalize launch is needed.
 __global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
+                                                       unsigned* __restrict__ done, float2* __restrict__ ss,
                                                        long long n) {
   const int b = blockIdx.y;
   const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * n);
@@ -112,16 +138,20 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const float* __restrict__
     atomicAdd(&sums[b * 2], d1);
     atomicAdd(&sums[b * 2 + 1], d2);
   }
-}
-
-// per image {1 / (std + eps), -mean / (std + eps)}: unbiased std, eps added to the std (module.py:189-199)
-__global__ void ln_finalize_kernel(const double* __restrict__ sums, float2* __restrict__ ss, int B, double n) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const double mean = sums[b * 2] / n;
-  const double var = (sums[b * 2 + 1] - n * mean * mean) / (n - 1.0);
-  const double inv = 1.0 / (sqrt(var > 0.0 ? var : 0.0) + 1e-5);
-  ss[b] = make_float2((float)inv, (float)(-mean * inv));
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&done[b], 1u);
+    if (t == gridDim.x - 1) {   // every other block's atomics are visible: it fenced before it counted
+      __threadfence();
+      const double m1 = atomicAdd(&sums[b * 2], 0.0), m2 = atomicAdd(&sums[b * 2 + 1], 0.0);
+      const double dn = (double)n;
+      const double mean = m1 / dn;
+      const double var = (m2 - dn * mean * mean) / (dn - 1.0);
+      const double inv = 1.0 / (sqrt(var > 0.0 ? var : 0.0) + 1e-5);
+      ss[b] = make_float2((float)inv, (float)(-mean * inv));
+    }
+  }
 }
 
 // LayerNorm apply (+ per-channel affine + LeakyReLU 0.2) and relayout to the fp16 tensor the next conv reads.
@@ -404,15 +434,16 @@ static void ln(chb_shape* z, cudaStream_t st, int B, int H, int W, int C, const 
   const float* x = reinterpret_cast<const float*>(z->ws + (norm == 2 ? z->ws_fcout : z->ws_conv));
   double* sums = reinterpret_cast<double*>(z->ws + z->ws_sums);
   const long long n = (long long)H * W * C;
-  float2* ss = reinterpret_cast<float2*>(sums + (size_t)z->cfg.max_batch * 2);
+  const size_t mb = (size_t)z->cfg.max_batch;
+  unsigned* done = reinterpret_cast<unsigned*>(sums + mb * 2);             // [max_batch] block counters (8 B slots)
+  float2* ss = reinterpret_cast<float2*>(sums + mb * 3);
   if (norm == 1) {
-    cudaMemsetAsync(sums, 0, (size_t)B * 2 * sizeof(double), st);
+    cudaMemsetAsync(sums, 0, mb * 3 * sizeof(double), st);                 // moments and counters
     long long blocks = (n / 4 + 256 * 16 - 1) / (256 * 16);
     const long long want = ((long long)device_sm_count() * 8 + B - 1) / B;
     if (blocks > want) blocks = want;
     if (blocks < 1) blocks = 1;
-    ln_stats_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, st>>>(x, sums, n);
-    ln_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(sums, ss, B, (double)n);
+    ln_stats_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, st>>>(x, sums, done, ss, n);
   }
   ln_apply_kernel<<<sgrid((long long)B * (n / 8), 256), 256, 0, st>>>(x, ss, gamma, beta, out, B, H, W, C, mode,
                                                                       norm == 1 ? 1 : 0);
@@ -469,7 +500,7 @@ int chb_shape_create(const chb_shape_config* cfg, chb_shape** out) {
   z->ws_code16 = sws(z, B * 1088 * 2);
   z->ws_logit[0] = sws(z, B * S * S * 16 * 4);
   z->ws_logit[1] = sws(z, B * S * S * 32 * 4);
-  z->ws_sums = sws(z, B * 2 * 8 + B * 8);   // double moments [B][2] + float2 {1/(std+eps), shift} [B]
+  z->ws_sums = sws(z, B * 2 * 8 + B * 8 + B * 8);   // double moments [B][2], block counters [B], float2 constants [B]
   z->ws_io = sws(z, B * 19 * S * S * 4);
   *out = z;
   return CHB_OK;
