@@ -23,11 +23,18 @@
 namespace chb {
 
 // ---------------------------------------------------------------- L1: 3 -> 32, reflection pad, fp32
-__global__ void zenc_conv1_kernel(const float* __restrict__ img, const float* __restrict__ w /*[32][27]: co, (ky,kx,ci)*/,
-                                  const float* __restrict__ bias, float* __restrict__ out, int B, int S) {
-  __shared__ float sw[32 * 27];
+__global__ void __launch_bounds__(128) zenc_conv1_kernel(const float* __restrict__ img,
+                                                         const float* __restrict__ w /*[32][27]: co, (ky,kx,ci)*/,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                         int S) {
+  // weights padded to 28 per output channel so that four taps come with one 16-byte shared-memory load: the kernel was
+  // bound by one broadcast LDS per FMA (864 per pixel), now 224 LDS.128 per pixel
+  __shared__ __align__(16) float sw[32 * 28];
   __shared__ float sb[32];
-  for (int i = threadIdx.x; i < 32 * 27; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 32 * 28; i += blockDim.x) {
+    const int co = i / 28, k = i - co * 28;
+    sw[i] = k < 27 ? w[co * 27 + k] : 0.f;
+  }
   if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const long long total = (long long)B * S * S;
@@ -36,7 +43,8 @@ __global__ void zenc_conv1_kernel(const float* __restrict__ img, const float* __
     const int x = (int)(i % S);
     const int y = (int)((i / S) % S);
     const int b = (int)(i / ((long long)S * S));
-    float in[27];
+    float in[28];
+    in[27] = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       int yy = y + ky - 1;
@@ -46,7 +54,7 @@ __global__ void zenc_conv1_kernel(const float* __restrict__ img, const float* __
         int xx = x + kx - 1;
         xx = xx < 0 ? -xx : (xx >= S ? 2 * S - 2 - xx : xx);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) in[(ky * 3 + kx) * 3 + c] = img[(((long long)b * 3 + c) * S + yy) * S + xx];
+        for (int c = 0; c < 3; ++c) in[(ky * 3 + kx) * 3 + c] = __ldg(img + (((long long)b * 3 + c) * S + yy) * S + xx);
       }
     }
     float4* o = reinterpret_cast<float4*>(out + i * 32);
@@ -56,9 +64,16 @@ __global__ void zenc_conv1_kernel(const float* __restrict__ img, const float* __
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int co = g * 4 + j;
+        const float4* wr = reinterpret_cast<const float4*>(sw + co * 28);
         float acc = sb[co];
 #pragma unroll
-        for (int k = 0; k < 27; ++k) acc = fmaf(in[k], sw[co * 27 + k], acc);
+        for (int q = 0; q < 7; ++q) {   // same accumulation order as before: k = 0 .. 26 (the 28th term is 0 * 0)
+          const float4 wv = wr[q];
+          acc = fmaf(in[4 * q], wv.x, acc);
+          acc = fmaf(in[4 * q + 1], wv.y, acc);
+          acc = fmaf(in[4 * q + 2], wv.z, acc);
+          acc = fmaf(in[4 * q + 3], wv.w, acc);
+        }
         v[j] = acc;
       }
       o[g] = make_float4(v[0], v[1], v[2], v[3]);
