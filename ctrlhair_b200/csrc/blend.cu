@@ -14,6 +14,7 @@
 
 #include "../../include/ctrlhair_b200.h"
 #include "conv_igemm.cuh"
+#include "ptx_sm100.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -327,8 +328,9 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoiThread
 //     its own registers and only left / right (and the two strip ends) are read from shared memory;
 //   * r, p = search direction and s = A p live in registers (96 of the 128 available), x and w = A r in shared memory
 //     (touched once per iteration each), r additionally in a haloed shared buffer for the neighbours;
-//   * per iteration: one halo exchange + one two-value reduction through distributed shared memory (2 cluster
-//     barriers instead of 3, one block reduction instead of 2) and 7 shared-memory accesses per pixel instead of 11.
+//   * per iteration: one halo exchange (split cluster barrier, overlapped with the interior rows) + one two-value
+//     reduction signalled through transaction barriers (st.async into the peers' shared memory, no cluster
+//     rendezvous), one block reduction instead of 2, and 7 shared-memory accesses per pixel instead of 11.
 // x_{i+1} = x_i + a_i p_i, r_{i+1} = r_i - a_i s_i, w = A r_{i+1}, g = (r,r), d = (r,w), b = g/g_old,
 // a = g / (d - b g / a_old), p = r + b p, s = w + b s.
 constexpr int kPoi2MaxCluster = 16;
@@ -338,7 +340,21 @@ struct Poisson2Smem {
   double lut[256];
   double warp_part[2][16];
   double slots[2][2][kPoi2MaxCluster];   // [parity][value][CTA]
+  uint64_t red_bar[2];                   // one transaction barrier per parity: 16 * CL bytes of partial sums per phase
 };
+
+// The address of `saddr` (a shared::cta address of this CTA) in CTA `cta` of the cluster.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+  return r;
+}
+// 8-byte store into a peer CTA's shared memory that signals 8 bytes on that CTA's transaction barrier when it lands.
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_bar)
+               : "memory");
+}
 
 __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -347,9 +363,15 @@ __device__ __forceinline__ void cluster_wait_acquire() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int CL, int NW>   // CTAs per cluster, warps per CTA (<= 16)
-__device__ __forceinline__ void poisson_cluster_sum2(cg::cluster_group& cluster, double& a, double& b, Poisson2Smem* sm,
-                                                     int set, unsigned rank) {
+// Cluster-wide sum of two values per iteration without a cluster barrier: every CTA sends its two partials to every
+// CTA of the cluster with st.async, each store completing 8 bytes on the RECEIVER's transaction barrier; a CTA waits on
+// its own barrier only (CL = CTAs per cluster, NW = warps per CTA <= 16).
+// No cluster-wide rendezvous and no fence: the latency is one DSMEM store.  Two barriers / slot sets alternate; a CTA can
+// only be one reduction ahead of any other (it needs everyone's partials to finish the current one), so a set is
+// never overwritten while somebody still reads it.
+template <int CL, int NW>
+__device__ __forceinline__ void poisson_cluster_sum2_async(double& a, double& b, Poisson2Smem* sm, int set,
+                                                           uint32_t phase, unsigned rank) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -359,18 +381,18 @@ __device__ __forceinline__ void poisson_cluster_sum2(cg::cluster_group& cluster,
   if (lane == 0) { sm->warp_part[0][warp] = a; sm->warp_part[1][warp] = b; }
   __syncthreads();
   if (warp == 0) {
-    // lanes 0..15 hold the warp partials of value 0, lanes 16..31 those of value 1
     double v = (lane & 15) < NW ? sm->warp_part[lane >> 4][lane & 15] : 0.0;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, 16);
     const double v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 16);
+    if (lane == 0) mbar_arrive_expect_tx(&sm->red_bar[set], 16u * CL);
     if (lane < 2 * CL) {
       const int which = lane / CL, dst = lane % CL;
-      double* remote = cluster.map_shared_rank(&sm->slots[set][which][0], dst);
-      remote[rank] = which ? v1 : v0;
+      st_async_f64(mapa_u32(smem_u32(&sm->slots[set][which][rank]), (uint32_t)dst), which ? v1 : v0,
+                   mapa_u32(smem_u32(&sm->red_bar[set]), (uint32_t)dst));
     }
   }
-  cluster.sync();
+  mbar_wait(&sm->red_bar[set], phase);
   double ta = 0.0, tb = 0.0;
 #pragma unroll
   for (int k = 0; k < CL; ++k) { ta += sm->slots[set][0][k]; tb += sm->slots[set][1][k]; }
@@ -407,6 +429,11 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
   if (tid < 256)
     sm->lut[tid] = p.with_gamma ? (p.lut_fwd ? p.lut_fwd[tid] : pow((double)tid, 1.0 / 2.2)) : (double)tid;
   if (tid < 4 * kPoi2MaxCluster) (&sm->slots[0][0][0])[tid] = 0.0;
+  if (tid == 0) {
+    mbar_init(&sm->red_bar[0], 1);
+    mbar_init(&sm->red_bar[1], 1);
+    fence_mbar_init();
+  }
   cluster.sync();
 
   const long long img_off = (long long)b * H * W;
@@ -477,7 +504,10 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
     r[j] = ((umask >> j) & 1u) ? wc[j * W] - v : 0.0;
   }
   double zero = 0.0;
-  poisson_cluster_sum2<CL, kPoi2Threads / 32>(cluster, bb_local, zero, sm, 0, rank);  // also: every CTA is done reading x0 from rbuf
+  uint32_t red_phase[2] = {0u, 0u};
+  poisson_cluster_sum2_async<CL, kPoi2Threads / 32>(bb_local, zero, sm, 0, red_phase[0], rank);
+  red_phase[0] ^= 1u;
+  cluster.sync();   // every CTA is done reading x0 from rbuf (own rows and halos) before r overwrites it
   const double bb = bb_local;
   const double thresh = p.tol2 * bb;
 
@@ -507,7 +537,8 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
     cluster_wait_acquire();
     row(0, rc[-P], r[1]);
     row(kPoi2Rows - 1, r[kPoi2Rows - 2], rc[kPoi2Rows * P]);
-    poisson_cluster_sum2<CL, kPoi2Threads / 32>(cluster, g_l, d_l, sm, parity, rank);
+    poisson_cluster_sum2_async<CL, kPoi2Threads / 32>(g_l, d_l, sm, parity, red_phase[parity], rank);
+    red_phase[parity] ^= 1u;
     parity ^= 1;
     const double gamma_new = g_l, delta = d_l;
     if (!(gamma_new > thresh) || it >= p.max_iter) { gamma = gamma_new; break; }
