@@ -13,11 +13,20 @@ intermediate left on the GPU:
                                   of wrap_codes/, out of scope: pass the warped parsing with shape_from_mask)
   tensor_hsv_to_rgb / tensor_rgb_to_hsv / interpolate_hsv   ui/backend.py:108-125,323-332
   gen_img_batch(codes, parsing)   hair_editor.py:159-179 for B codes at once, median codes cached on the device
+  change_curliness / change_color / change_shape / change_texture / continue_change_with_direction,
+  get_*_be2fe, interpolate / interpolate_triple / interpolate_each_att, get_random_*, directly_change_hair_mask
+                                  ui/backend.py:177-262,334-394,409-459: the latent edits of the UI, applied to every
+                                  image of the batch (or to `index` only) without leaving the device
+  DistTranslation                 util/color_from_hsv_to_gaussian.py:15-34 (slider value <-> HSV through the data set's
+                                  sorted HSV table)
 
 There is no CPU path: every network and every pre/post-processing step is a kernel of libctrlhair_b200.so.
 """
 import copy
+from bisect import bisect_left, bisect_right
+from statistics import NormalDist
 
+import numpy as np
 import torch
 
 from . import _lib, blend
@@ -48,9 +57,30 @@ class LatentRepresentation:
         return out
 
 
+class DistTranslation:
+    """util/color_from_hsv_to_gaussian.py:15-34 with the table passed in (the reference unpickles
+    dataset_info_ctrlhair/hsv_stat_dict_ordered.pkl: uint8 [N,3], each column sorted).  scipy.stats.norm.cdf / ppf are
+    the standard normal's; statistics.NormalDist gives the same values without the dependency."""
+
+    def __init__(self, cols_hsv):
+        self.cols_hsv = np.asarray(cols_hsv)
+        self._n = NormalDist()
+
+    def gaussian_to_val(self, dim, val):
+        return self.cols_hsv[int(self._n.cdf(float(val)) * self.cols_hsv.shape[0])][dim]
+
+    def val_to_gaussian(self, dim, val):
+        col = self.cols_hsv[:, dim]
+        left_v, right_v = bisect_left(col, val), bisect_right(col, val)
+        q = (left_v + right_v) / 2 / self.cols_hsv.shape[0]
+        if q <= 0.0 or q >= 1.0:            # scipy's ppf returns -inf / inf here
+            return float("-inf") if q <= 0.0 else float("inf")
+        return self._n.inv_cdf(q)
+
+
 class BackendB200:
     def __init__(self, sean_sd, shape_sd, ct_sds, median_codes=None, max_batch=1, blending=True, img_size=256,
-                 device=None):
+                 device=None, maximum_value_fe=2.5, hsv_table=None, shape_dirs=None, texture_dirs=None):
         g_sd, d_sd, p_sd = ct_sds
         self.netG = SeanGeneratorB200(crop=img_size, max_batch=max_batch, device=device).load_state_dict(sean_sd)
         self.zencoder = ZencoderB200(crop=img_size, max_batch=max_batch, device=device).load_state_dict(sean_sd)
@@ -65,6 +95,11 @@ class BackendB200:
         self.seed = 0
         # hair_editor.py:131-147 reads 19 ACE.npy files on every gen_img; here they are uploaded once
         self.median = None if median_codes is None else torch.as_tensor(median_codes).float().to(self.device)
+        self.maximum_value_fe = maximum_value_fe
+        self.dist_translation = None if hsv_table is None else DistTranslation(hsv_table)
+        self.shape_dirs = None if shape_dirs is None else [torch.as_tensor(d).float().to(self.device) for d in shape_dirs]
+        self.texture_dirs = (None if texture_dirs is None
+                             else [torch.as_tensor(d).float().to(self.device) for d in texture_dirs])
         self.input_img = self.input_mask = self.cur_mask = self.cur_latent = None
         self.input_sean_code = self.input_hair_feature = None
         self.target_img = self.target_mask = self.target_latent = self.target_hair_feature = None
@@ -201,3 +236,110 @@ class BackendB200:
             self.refresh_cur_mask()
         if flag == "texture":
             self.transfer_latent_representation("curliness")
+
+    # ------------------------------------------------------------------ latent edits (ui/backend.py:177-262,334-459)
+    @staticmethod
+    def _rows(t, index):
+        return t if index is None else t[index:index + 1]
+
+    def change_curliness(self, val, index=None):
+        self._rows(self.cur_latent.curliness, index)[:] = val
+
+    def change_color(self, val, idx, index=None):
+        """idx 0 / 1 / 2 = hue / saturation / brightness through the data set's HSV distribution, idx 3 = variance in
+        [-maximum_value_fe, maximum_value_fe] (ui/backend.py:196-209)."""
+        if idx == 3:
+            val = (val + self.maximum_value_fe) / 2 / self.maximum_value_fe
+            self._rows(self.cur_latent.color["pca_std"], index)[:] = val * 100 + 20
+        else:
+            if self.dist_translation is None:
+                raise _lib.ChbError("change_color needs the HSV table (hsv_table=...; the reference unpickles it)")
+            self._rows(self.cur_latent.color["hsv"], index)[:, idx] = int(self.dist_translation.gaussian_to_val(idx, val))
+
+    def continue_change_with_direction(self, att_name, direction, val, index=None):
+        """att <- att + (val - <att, direction>) * direction, per image (ui/backend.py:450-459)."""
+        direction = torch.as_tensor(direction).float().to(self.device)
+        att = getattr(self.cur_latent, att_name)
+        new = att + (val - att @ direction)[:, None] * direction[None]
+        if index is not None:
+            keep = torch.ones((att.shape[0], 1), device=att.device, dtype=torch.bool)
+            keep[index] = False
+            new = torch.where(keep, att, new)
+        setattr(self.cur_latent, att_name, new)
+        if att_name == "shape":
+            self.refresh_cur_mask()
+
+    def change_shape(self, val, idx, index=None):
+        self.continue_change_with_direction("shape", self.shape_dirs[idx], val, index)
+
+    def change_texture(self, val, idx, index=None):
+        self.continue_change_with_direction("texture", self.texture_dirs[idx], val, index)
+
+    def get_curliness_be2fe(self, index=0):
+        return self.cur_latent.curliness[index]
+
+    def get_color_be2fe(self, index=0):
+        c_hsv = self.cur_latent.color["hsv"][index].cpu().numpy()
+        color = [self.dist_translation.val_to_gaussian(k, c_hsv[k]) for k in range(3)]
+        var_fe = ((self.cur_latent.color["pca_std"][index] - 20) / 100 * 2 * self.maximum_value_fe -
+                  self.maximum_value_fe)
+        return color[0], color[1], color[2], var_fe
+
+    def get_shape_be2fe(self, index=0):
+        return [torch.dot(self.cur_latent.shape[index], self.shape_dirs[i]) for i in range(len(self.shape_dirs))]
+
+    def get_texture_be2fe(self, index=0):
+        return [torch.dot(self.cur_latent.texture[index], self.texture_dirs[i]) for i in range(len(self.texture_dirs))]
+
+    def interpolate(self, latent1, latent2, alpha):
+        out = LatentRepresentation()
+        for att in ("curliness", "shape", "texture"):
+            setattr(out, att, getattr(latent1, att) * (1 - alpha) + getattr(latent2, att) * alpha)
+        out.color = {"pca_std": latent1.color["pca_std"] * (1 - alpha) + latent2.color["pca_std"] * alpha,
+                     "hsv": self.interpolate_hsv(latent1.color["hsv"], latent2.color["hsv"], alpha)}
+        out.face = self.cur_latent.face
+        return out
+
+    def interpolate_triple(self, latent1, latent2, latent3, alpha1, alpha2, alpha3):
+        latent12 = self.interpolate(latent1, latent2, alpha2 / (alpha1 + alpha2))
+        return self.interpolate(latent12, latent3, alpha3)
+
+    def interpolate_each_att(self, latent1, latent2, alpha, att_name):
+        out = LatentRepresentation()
+        for att in ("curliness", "shape", "texture"):
+            setattr(out, att, getattr(self.cur_latent, att).clone())
+        keep_color = {k: self.cur_latent.color[k].clone() for k in ("hsv", "pca_std")}
+        if att_name == "shape":
+            out.shape = latent1.shape * (1 - alpha) + latent2.shape * alpha
+            out.color = keep_color
+        elif att_name in ("curliness", "texture"):
+            out.curliness = latent1.curliness * (1 - alpha) + latent2.curliness * alpha
+            out.texture = latent1.texture * (1 - alpha) + latent2.texture * alpha
+            out.color = keep_color
+        else:
+            out.color = {"pca_std": latent1.color["pca_std"] * (1 - alpha) + latent2.color["pca_std"] * alpha,
+                         "hsv": self.interpolate_hsv(latent1.color["hsv"], latent2.color["hsv"], alpha)}
+        out.face = self.cur_latent.face
+        return out
+
+    def _random_like(self, t, generator=None):
+        return torch.randn(t.shape, generator=generator).to(self.device)    # common generate_noise: standard normal
+
+    def get_random_texture(self, generator=None):
+        self.cur_latent.texture = self._random_like(self.cur_latent.texture, generator)
+
+    def get_random_shape(self, generator=None):
+        self.cur_latent.shape = self._random_like(self.cur_latent.shape, generator)
+        self.refresh_cur_mask()
+
+    def get_random_curliness(self, generator=None):
+        self.cur_latent.curliness = self._random_like(self.cur_latent.curliness, generator)
+
+    def directly_change_hair_mask(self, hair_mask):
+        """ui/backend.py:409-420: paste a hair region (label map [B,S,S], HAIR_IDX where hair) over the decoded face."""
+        hair = torch.as_tensor(hair_mask).to(self.device) == HAIR_IDX
+        face_logit = self.mask_generator.forward_face_decoder(self.cur_latent.face)
+        hair_logit = hair.reshape(-1, 1, self.img_size, self.img_size).to(face_logit.dtype)
+        hair_logit = hair_logit * (face_logit.max() - face_logit.min() + 2) + face_logit.min() - 1
+        self.cur_mask = blend.mask_one_hot_to_label(self.mask_generator.forward_decoder(hair_logit, face_logit))
+        return self.cur_mask
