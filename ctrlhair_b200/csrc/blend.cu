@@ -1,8 +1,10 @@
 // Post-processing either side of the generator, device resident:
 //   * Poisson blending of the generated image into the input face (poisson_blending.py:29-87, hair_editor.py:257-308):
 //     blend mask (hair union + elliptical dilations), the sparse system solved by conjugate gradients in fp64 with the
-//     whole state of one (image, channel) system resident in the shared memory of an 8-CTA cluster (halo rows and the
-//     two dot products per iteration travel through distributed shared memory, no HBM traffic inside the loop);
+//     whole state of one (image, channel) system resident in the registers and shared memory of an 8- or 16-CTA
+//     thread-block cluster (halo rows and the dot products of an iteration travel through distributed shared memory,
+//     no HBM traffic inside the loop).  Two kernels: poisson_cg2_kernel for the reference's 256-column images,
+//     poisson_cg_kernel (first generation, classic CG, 1024 threads) for every other size;
 //   * 8-bit RGB <-> HSV (cv2.cvtColor at ui/backend.py:98-101,108-125) and label map <-> one-hot
 //     (shape_branch/shape_util.py:6-20), which remove the host round trips of Backend.parse_img / output.
 #include <cooperative_groups.h>
@@ -97,6 +99,9 @@ __global__ void blend_mask_kernel(const uint8_t* __restrict__ target_parsing, co
 // and calls spsolve.  Eliminating the identity rows leaves a symmetric positive definite system on the set U of
 // Laplacian-row pixels:  4 f_i - sum_{j in N(i), j in U} f_j = b_i + sum_{j in N(i), j not in U} target_j,
 // which is solved here by conjugate gradients in fp64.
+//
+// First-generation kernel (general sizes: W <= 512, ceil(H/8) * W <= 8192): classic CG, 8 pixels per thread addressed
+// through per-pixel flags, x / p in shared memory, three cluster barriers and two reductions per iteration.
 constexpr int kPoiCluster = 8;     // CTAs per system (portable cluster size)
 constexpr int kPoiThreads = 1024;
 constexpr int kPoiPx = 8;          // pixels per thread -> up to 8 * 1024 * 8 = 65536 pixels per system
@@ -324,7 +329,7 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoiThread
 // ------------------------------------------------------------------------------------------------------------------
 // Second generation of the solver (the default when the image fits it): Chronopoulos-Gear conjugate gradients, whose two
 // dot products (r.r and r.Ar) come out of ONE cluster reduction per iteration, with the per-pixel state in registers.
-//   * 512 threads; a thread owns a 16-row strip of one column, so the vertical neighbours of the 5-point stencil are
+//   * 512 threads (256 in the 16-CTA shape); a thread owns a 16-row strip of one column, so the vertical neighbours of the 5-point stencil are
 //     its own registers and only left / right (and the two strip ends) are read from shared memory;
 //   * r, p = search direction and s = A p live in registers (96 of the 128 available), x and w = A r in shared memory
 //     (touched once per iteration each), r additionally in a haloed shared buffer for the neighbours;
