@@ -45,13 +45,21 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.stop_flag = False
         self.err = None
-
-    def run(self):
-        try:
+        self.nv = self.h = None
+        self.max_mhz = 0
+        try:  # NVML is initialised here, before the timed region, so that the thread samples from its first instant
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:
+            self.err = repr(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        try:
+            nv, h = self.nv, self.h
             while not self.stop_flag:
                 mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
@@ -174,7 +182,9 @@ def run_ours(args):
     for i in range(args.warmup):
         gen.forward_labels(labels_d, codes_d, seed=i, out=out_d)
     barrier()
+    labels_iid = synth.make_labels(B, crop, "iid", seed=2234 + rank).to(dev)   # second label distribution (below)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
     if sampler:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -185,15 +195,11 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    if sampler:
-        sampler.stop_flag = True
-        sampler.join(timeout=3)
     finite = bool(torch.isfinite(out_d).all())
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # SURVEY 8d asks for both label distributions: the same timed loop on iid-uniform per-pixel labels (no spatial
     # coherence, every class present at every scale).  The kernels are dense, so this is a check, not a second headline.
-    labels_iid = synth.make_labels(B, crop, "iid", seed=2234 + rank).to(dev)
     gen.forward_labels(labels_iid, codes_d, seed=50, out=out_d)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -203,6 +209,9 @@ def run_ours(args):
     e3.record()
     barrier()
     value_iid = world * B * args.steps / (max_over_ranks(e2.elapsed_time(e3)) * 1e-3)
+    if sampler:  # sampled over both timed loops (same step, same load)
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
     finite = finite and bool(torch.isfinite(out_d).all())
 
     # ---------------- end to end through the host-buffer entry point (`e2e`): every step copies its labels + codes
