@@ -151,3 +151,15 @@ def test_errors_are_loud(gen64):
         gen64.forward_labels(torch.zeros((1, 32, 32), dtype=torch.uint8).cuda(), synth.make_codes(1).cuda())
     with pytest.raises(_lib.ChbError):
         gen64.forward_labels(torch.zeros((1, 64, 64), dtype=torch.uint8), synth.make_codes(1))
+
+
+def test_generator_512_vs_oracle(synthetic_sd):
+    """Config 4's resolution (512x512): one image against the oracle (dense reference algorithm, fp32)."""
+    g = SeanGeneratorB200(crop=512, max_batch=1)
+    g.load_state_dict(synthetic_sd)
+    labels, codes, noise = synth.make_labels(1, 512, "blocky", seed=21), synth.make_codes(1, seed=22), synth.make_noise(1, 512)
+    ref = so.generator_forward(synthetic_sd, labels, codes, noise)
+    out = g.forward_labels(labels.cuda(), codes.cuda(), noise=synth.flatten_noise(noise).cuda()).cpu()
+    assert tuple(out.shape) == (1, 3, 512, 512) and torch.isfinite(out).all()
+    l2, mx = _errs(out, ref)
+    assert l2 < L2_TOL and mx < MAX_TOL, (l2, mx)
