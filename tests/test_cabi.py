@@ -60,3 +60,23 @@ def test_no_cpu_fallback():
         pass
     lib = _lib.load()
     assert lib.chb_check_device() != 0
+
+
+def test_postprocessing_entry_points_validate_arguments(lib):
+    """Argument errors of the post-processing entry points are reported before anything touches the device."""
+    assert lib.chb_postprocess_workspace_bytes(2, 256, 256) == 2 * 256 * 256 * 4
+    assert lib.chb_postprocess_workspace_bytes(0, 256, 256) == 0
+    assert lib.chb_image_to_u8(None, None, 1, 8, 8, None) == -1
+    assert lib.chb_blend_mask(None, None, None, None, 1, 8, 8, None) == -1
+    assert lib.chb_rgb_to_hsv(None, None, None, 1, None) == -1
+    assert b"exactly one" in lib.chb_last_error()
+    assert lib.chb_hsv_to_rgb(None, None, 1, None) == -1
+    assert lib.chb_onehot_to_label(None, None, 1, 19, 64, None) == -1
+    assert lib.chb_label_to_onehot(None, None, 1, 19, 64, None) == -1
+    dummy = C.c_void_p(16)   # never dereferenced: the size checks come first
+    assert lib.chb_poisson_blend(dummy, dummy, dummy, dummy, 1, 300, 300, 1, 1e-11, 100, None, None, None, None) == -1
+    assert b"too large" in lib.chb_last_error()
+    assert lib.chb_poisson_blend(dummy, dummy, dummy, dummy, 1, 2, 8, 1, 1e-11, 100, None, None, None, None) == -1
+    assert lib.chb_poisson_blend(dummy, dummy, dummy, dummy, 1, 64, 64, 1, 0.0, 100, None, None, None, None) == -1
+    assert lib.chb_postprocess_blending(None, None, None, None, None, None, None, 1, 8, 8, 1, 1e-11, 10, None, None,
+                                        None, None) == -1
