@@ -143,6 +143,7 @@ SYMBOLS = [
     ("chb_shape_workspace_bytes", C.c_int64, [C.c_void_p]),
     ("chb_shape_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("chb_shape_encode", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_shape_encode_labels", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_shape_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_shape_decode_logits", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_shape_softmax", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

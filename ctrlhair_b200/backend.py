@@ -132,11 +132,7 @@ class BackendB200:
     # ------------------------------------------------------------------ encode half (ui/backend.py:67-106)
     def shape_from_mask(self, mask_batch):
         """mask [B,1,S,S] uint8 -> (hair_code, face_code) (ui/backend.py:81-86)."""
-        one_hot = blend.mask_label_to_one_hot(mask_batch)
-        hair, face = blend.split_hair_face(one_hot)
-        hair_code = self.mask_generator.forward_hair_encoder(hair.contiguous(), testing=True)
-        face_code = self.mask_generator.forward_face_encoder(face.contiguous())
-        return hair_code, face_code
+        return self.mask_generator.encode_labels(mask_batch)   # one-hot + hair / face split happen inside the gather
 
     def get_code(self, img, mask_batch):
         """hair_editor.py:149-157: style codes [B,19,512] of the image under its parsing."""

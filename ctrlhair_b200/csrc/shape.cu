@@ -51,8 +51,13 @@ __global__ void shape_pos_kernel(__half* pos, int S) {
 // the NCHW mask planes), a padded shared tile turns it into contiguous 16-byte stores.  HBM-bound: 4 B read per mask
 // element + 2 B written per output element.
 constexpr int kPrepBx = 32;
-__global__ void __launch_bounds__(256) shape_prep_kernel(const float* __restrict__ mask, const __half* __restrict__ pos,
-                                                         __half* __restrict__ out, int B, int Cm, int S, int Cpad) {
+// With `labels` (uint8 [B,S,S], 255 = none) instead of `mask`, the one-hot channels are synthesised on the fly
+// (shape_util.py:6-26: channel c of the hair net is class 13, of the face net class c + (c >= 13)), so a caller that
+// holds a label map needs neither the [B,19,S,S] one-hot tensor nor the hair / face split.
+__global__ void __launch_bounds__(256) shape_prep_kernel(const float* __restrict__ mask,
+                                                         const uint8_t* __restrict__ labels,
+                                                         const __half* __restrict__ pos, __half* __restrict__ out, int B,
+                                                         int Cm, int S, int Cpad) {
   extern __shared__ __align__(16) unsigned char prep_smem[];
   __half* tile = reinterpret_cast<__half*>(prep_smem);   // [kPrepBx][Cpad + 2]
   const int pitch = Cpad + 2;
@@ -66,7 +71,12 @@ __global__ void __launch_bounds__(256) shape_prep_kernel(const float* __restrict
     __half v = __float2half_rn(0.f);
     if (bx < Hh) {
       const int y = 2 * by + (par >> 1), x = 2 * bx + (par & 1);
-      v = __float2half_rn(__ldg(mask + (((long long)b * Cm + c) * S + y) * S + x));
+      if (labels) {
+        const int cls = Cm == 1 ? 13 : (c < 13 ? c : c + 1);
+        v = __float2half_rn(labels[((long long)b * S + y) * S + x] == cls ? 1.f : 0.f);
+      } else {
+        v = __float2half_rn(__ldg(mask + (((long long)b * Cm + c) * S + y) * S + x));
+      }
     }
     tile[bxl * pitch + par * Cin + c] = v;
   }
@@ -548,8 +558,28 @@ int chb_shape_bind(chb_shape* z, const void* blob, void* workspace) {
 }
 
 // net: 0 = hair encoder (mask [B,1,S,S] -> out [B,32] = mean(16) ++ |std|(16)), 1 = face encoder ([B,18,S,S] -> [B,1024])
+static int shape_encode_impl(chb_shape* z, int net, const float* mask, const uint8_t* labels, float* out, int B,
+                             void* stream_);
+
 int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B, void* stream_) {
-  if (!z || !mask || !out || !z->ws || net < 0 || net > 1 || B <= 0 || B > z->cfg.max_batch) {
+  if (!mask) {
+    chb::set_error("chb_shape_encode: bad arguments or unbound object");
+    return CHB_ERR_ARG;
+  }
+  return shape_encode_impl(z, net, mask, nullptr, out, B, stream_);
+}
+
+int chb_shape_encode_labels(chb_shape* z, int net, const uint8_t* labels, float* out, int B, void* stream_) {
+  if (!labels) {
+    chb::set_error("chb_shape_encode_labels: bad arguments or unbound object");
+    return CHB_ERR_ARG;
+  }
+  return shape_encode_impl(z, net, nullptr, labels, out, B, stream_);
+}
+
+static int shape_encode_impl(chb_shape* z, int net, const float* mask, const uint8_t* labels, float* out, int B,
+                             void* stream_) {
+  if (!z || !out || !z->ws || net < 0 || net > 1 || B <= 0 || B > z->cfg.max_batch) {
     set_error("chb_shape_encode: bad arguments or unbound object");
     return CHB_ERR_ARG;
   }
@@ -565,7 +595,7 @@ int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B
   const int S = z->cfg.crop;
   shape_prep_kernel<<<dim3((unsigned)((S / 2 + kPrepBx - 1) / kPrepBx), (unsigned)(S / 2), (unsigned)B), 256,
                       (size_t)kPrepBx * (kEncPad0[net] + 2) * sizeof(__half), st>>>(
-      mask, reinterpret_cast<const __half*>(z->ws + z->ws_pos), reinterpret_cast<__half*>(z->ws + z->ws_in), B,
+      mask, labels, reinterpret_cast<const __half*>(z->ws + z->ws_pos), reinterpret_cast<__half*>(z->ws + z->ws_in), B,
       kEncCm[net], S, kEncPad0[net]);
   for (int i = 0; i < 7; ++i) {
     int rc = launch_conv_plan(pl[i], CHB_IMPL_TCGEN05, st);

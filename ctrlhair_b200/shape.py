@@ -147,6 +147,23 @@ class ShapeGeneratorB200:
                                                  C.c_void_p(out.data_ptr()), B, self._stream()))
         return out
 
+    def encode_labels(self, labels):
+        """Both encoders straight from a label map uint8 [B,S,S] (or [B,1,S,S]): what Backend.parse_img computes with
+        mask_label_to_one_hot + split_hair_face + forward_hair_encoder(testing=True) + forward_face_encoder
+        (ui/backend.py:81-86), without materialising the one-hot tensors.  Returns (hair_code [B,16], face_code)."""
+        if not labels.is_cuda:
+            raise _lib.ChbError("shape nets take CUDA tensors (there is no CPU path)")
+        labels = labels.to(torch.uint8).reshape(-1, 256, 256).contiguous()
+        B = labels.shape[0]
+        outs = []
+        for net, width in ((0, 32), (1, 1024)):
+            out = torch.empty((B, width), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.chb_shape_encode_labels(self.handle, net, C.c_void_p(labels.data_ptr()),
+                                                            C.c_void_p(out.data_ptr()), B, self._stream()))
+            outs.append(out)
+        return outs[0][:, :16], outs[1]
+
     def forward_hair_encoder(self, hair, testing=False):
         out = self._encode(0, hair, 32)
         mean, std = out[:, :16], out[:, 16:].abs()

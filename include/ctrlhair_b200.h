@@ -224,6 +224,9 @@ int chb_shape_bind(chb_shape* z, const void* blob, void* workspace);
 /* net 0: hair encoder, mask [B,1,256,256] -> out [B,32] = mean(16) ++ raw std head(16) (model.py:102-107; the caller
  * takes |.| of the second half); net 1: face encoder, mask [B,18,256,256] -> out [B,1024]. */
 int chb_shape_encode(chb_shape* z, int net, const float* mask, float* out, int B, void* stream);
+/* The same from a label map uint8 [B,S,S] (255 = no label): the one-hot planes of mask_label_to_one_hot + split_hair_face
+ * (shape_branch/shape_util.py:6-26, ui/backend.py:81-84) are synthesised inside the input gather. */
+int chb_shape_encode_labels(chb_shape* z, int net, const uint8_t* labels, float* out, int B, void* stream);
 /* forward_decode_by_code (model.py:195-199): -> softmax mask fp32 [B,19,256,256]. */
 int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_code, float* mask_out, int B,
                      void* stream);

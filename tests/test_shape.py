@@ -97,3 +97,25 @@ def test_shape_split_decoders_and_directly_change_hair_mask(shape_sd):
     assert torch.equal(m2.argmax(1), ref2.argmax(1))
     with pytest.raises(ValueError):
         net.forward_decoder(hl[:, :, :128], fl)
+
+
+@pytest.mark.gpu
+def test_encode_from_label_map_equals_one_hot_path(shape_sd):
+    """chb_shape_encode_labels synthesises the one-hot planes inside the input gather: same codes as
+    mask_label_to_one_hot + split_hair_face + the two encoders (ui/backend.py:81-86), label 255 = no class."""
+    from ctrlhair_b200 import blend
+    from ctrlhair_b200.shape import ShapeGeneratorB200
+    B = 3
+    shp = ShapeGeneratorB200(max_batch=B).load_state_dict(shape_sd)
+    labels = synth.make_labels(B, 256, "blocky", seed=31)
+    labels[0, :40, :40] = 255
+    labels[1, 100:180, 60:200] = 13
+    lab = labels.cuda()
+    one_hot = blend.mask_label_to_one_hot(lab[:, None])
+    hair, face = blend.split_hair_face(one_hot)
+    want_h = shp.forward_hair_encoder(hair.contiguous(), testing=True)
+    want_f = shp.forward_face_encoder(face.contiguous())
+    got_h, got_f = shp.encode_labels(lab)
+    # identical fp16 inputs to identical kernels; only the LayerNorm statistics (double atomics) can differ in the last bit
+    assert float((got_h - want_h).abs().max()) <= 1e-5 * float(want_h.abs().max())
+    assert float((got_f - want_f).abs().max()) <= 1e-5 * float(want_f.abs().max())
