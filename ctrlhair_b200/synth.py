@@ -346,3 +346,76 @@ def make_blend_case(H, W, seed):
         p[(np.abs(xx - W * 0.5) < W * 0.1) & (np.abs(yy - H * 0.7) < H * 0.05)] = 11
         return p
     return face, gen, parsing(W * 0.45, H * 0.25, W * 0.3, H * 0.2), parsing(W * 0.55, H * 0.3, W * 0.33, H * 0.26)
+
+
+def bisenet_shapes(n_classes=19):
+    """Ordered {key: shape} of external_code/face_parsing/model.py::BiSeNet(n_classes).state_dict() (checked against the
+    real module by oracle/make_golden_bisenet.py): ResNet-18 context path, two attention refinement modules, feature
+    fusion, three output heads."""
+    s = {}
+
+    def bn(name, c):
+        s[name + ".weight"] = (c,)
+        s[name + ".bias"] = (c,)
+        s[name + ".running_mean"] = (c,)
+        s[name + ".running_var"] = (c,)
+        s[name + ".num_batches_tracked"] = ()
+
+    def cbr(name, ci, co, k):          # ConvBNReLU (model.py:12-35)
+        s[name + ".conv.weight"] = (co, ci, k, k)
+        bn(name + ".bn", co)
+
+    s["cp.resnet.conv1.weight"] = (64, 3, 7, 7)
+    bn("cp.resnet.bn1", 64)
+    cin = 64
+    for li, co in enumerate((64, 128, 256, 512), start=1):
+        for bi in range(2):
+            p = "cp.resnet.layer%d.%d" % (li, bi)
+            s[p + ".conv1.weight"] = (co, cin, 3, 3)
+            bn(p + ".bn1", co)
+            s[p + ".conv2.weight"] = (co, co, 3, 3)
+            bn(p + ".bn2", co)
+            if cin != co:                # stride-2 first block of layers 2-4 (resnet.py:31-36)
+                s[p + ".downsample.0.weight"] = (co, cin, 1, 1)
+                bn(p + ".downsample.1", co)
+            cin = co
+    for name, ci in (("cp.arm16", 256), ("cp.arm32", 512)):
+        cbr(name + ".conv", ci, 128, 3)
+        s[name + ".conv_atten.weight"] = (128, 128, 1, 1)
+        bn(name + ".bn_atten", 128)
+    cbr("cp.conv_head32", 128, 128, 3)
+    cbr("cp.conv_head16", 128, 128, 3)
+    cbr("cp.conv_avg", 512, 128, 1)
+    cbr("ffm.convblk", 256, 256, 1)
+    s["ffm.conv1.weight"] = (64, 256, 1, 1)
+    s["ffm.conv2.weight"] = (256, 64, 1, 1)
+    for name, ci, mid in (("conv_out", 256, 256), ("conv_out16", 128, 64), ("conv_out32", 128, 64)):
+        cbr(name + ".conv", ci, mid, 3)
+        s[name + ".conv_out.weight"] = (n_classes, mid, 1, 1)
+    return s
+
+
+def make_bisenet_state_dict(seed=1270, n_classes=19):
+    """Seeded BiSeNet checkpoint in the reference's format (face_parsing_79999_iter.pth is a download): He-scaled conv
+    weights so that activations stay O(1) through the 20-odd layers, BatchNorm with non-trivial statistics."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in bisenet_shapes(n_classes).items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.tensor(1000, dtype=torch.int64)
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(shp, generator=gen) * 1.0 + 0.5
+        elif k.endswith("running_mean"):
+            sd[k] = torch.randn(shp, generator=gen) * 0.2
+        elif k.endswith("bn2.weight"):     # residual branch: smaller gain, the trunk does not double per block
+            sd[k] = torch.rand(shp, generator=gen) * 0.3 + 0.25
+        elif k.endswith("bn.weight") or k.endswith("bn1.weight") or k.endswith("bn_atten.weight") or \
+                k.endswith("downsample.1.weight"):
+            sd[k] = torch.rand(shp, generator=gen) * 0.6 + 0.7
+        elif k.endswith(".bias"):
+            sd[k] = torch.randn(shp, generator=gen) * 0.1
+        else:                              # conv weights
+            fan_in = shp[1] * shp[2] * shp[3]
+            gain = 0.5 if k.endswith("conv_out.weight") else 1.0
+            sd[k] = torch.randn(shp, generator=gen) * math.sqrt(2.0 / fan_in) * gain
+    return sd
