@@ -10,7 +10,6 @@ per GPU (weak scaling: the image batch shards across ranks, no per-step collecti
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

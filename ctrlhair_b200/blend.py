@@ -9,8 +9,6 @@ Inputs may be numpy arrays or tensors on any device (they are moved to the GPU);
 reference's callers `.cpu().numpy()` them when they need to (hair_editor.py:275).  Every function accepts a leading
 batch dimension the reference does not have.  There is no CPU path.
 """
-import ctypes as C
-
 import numpy as np
 import torch
 

@@ -5,7 +5,6 @@ python tools/gpu_quick_bench.py [--B 64] [--crop 256] [--steps 5] [--warmup 2]
 import argparse
 import os
 import sys
-import time
 
 import torch
 
