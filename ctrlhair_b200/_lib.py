@@ -145,6 +145,7 @@ SYMBOLS = [
     ("chb_shape_encode", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_shape_encode_labels", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_shape_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_shape_decode_labels", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_shape_decode_logits", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_shape_softmax", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_cttrain_create", C.c_int, [C.POINTER(CtTrainConfig), C.POINTER(C.c_void_p)]),

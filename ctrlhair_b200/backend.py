@@ -148,7 +148,7 @@ class BackendB200:
         out_mask = None
         if not target_img:
             lr.shape, lr.face = self.shape_from_mask(mask_batch)
-            out_mask = blend.mask_one_hot_to_label(self.mask_generator.forward_decode_by_code(lr.shape, lr.face))
+            out_mask = self.mask_generator.forward_decode_labels(lr.shape, lr.face)   # softmax + argmax fused
         input_code = self.get_code(self.preprocess_img(img_ts), mask_batch)
         hair_feature = input_code[:, HAIR_IDX].contiguous()
         out_color = self.feature_rgb_predictor({"code": hair_feature})
@@ -173,8 +173,7 @@ class BackendB200:
         """ui/backend.py:304-315, label map stays on the device."""
         if target_latent is None:
             target_latent = self.cur_latent
-        out_mask = blend.mask_one_hot_to_label(
-            self.mask_generator.forward_decode_by_code(target_latent.shape, target_latent.face))
+        out_mask = self.mask_generator.forward_decode_labels(target_latent.shape, target_latent.face)
         self.cur_mask = out_mask
         return out_mask
 

@@ -235,8 +235,11 @@ __global__ void code_pad_kernel(const float* __restrict__ a, int Ka, const float
 }
 
 // mask = softmax([face[:13], hair, face[13:]])  (model.py:184-187) -> fp32 NCHW [B,19,S,S]
+// `labels` (optional): mask_one_hot_to_label of the same probabilities (shape_util.py:17-20: first maximum; a softmax
+// row is never all zero, so 255 cannot occur) — written next to, or instead of, the [B,19,S,S] probabilities.
 __global__ void shape_softmax_kernel(const float* __restrict__ hair /*[B,S,S,16]*/, const float* __restrict__ face
-                                     /*[B,S,S,32]*/, float* __restrict__ out, int B, int S) {
+                                     /*[B,S,S,32]*/, float* __restrict__ out, uint8_t* __restrict__ labels, int B,
+                                     int S) {
   const long long total = (long long)B * S * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -258,8 +261,20 @@ __global__ void shape_softmax_kernel(const float* __restrict__ hair /*[B,S,S,16]
     }
     const float inv = 1.f / s;
     const long long b = i / ((long long)S * S), pix = i % ((long long)S * S);
+    if (out) {
 #pragma unroll
-    for (int k = 0; k < 19; ++k) out[(b * 19 + k) * (long long)S * S + pix] = l[k] * inv;
+      for (int k = 0; k < 19; ++k) out[(b * 19 + k) * (long long)S * S + pix] = l[k] * inv;
+    }
+    if (labels) {   // argmax of the fp32 probabilities the reference would see (ties of the rounded products included)
+      float best = l[0] * inv;
+      int arg = 0;
+#pragma unroll
+      for (int k = 1; k < 19; ++k) {
+        const float v = l[k] * inv;
+        if (v > best) { best = v; arg = k; }
+      }
+      labels[i] = (uint8_t)arg;
+    }
   }
 }
 
@@ -665,8 +680,27 @@ int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_cod
   }
   shape_softmax_kernel<<<sgrid((long long)B * S * S, 256), 256, 0, st>>>(
       reinterpret_cast<const float*>(z->ws + z->ws_logit[0]), reinterpret_cast<const float*>(z->ws + z->ws_logit[1]),
-      mask_out, B, S);
+      mask_out, nullptr, B, S);
   return last_launch("chb_shape_decode");
+}
+
+// forward_decode_by_code + mask_one_hot_to_label (ui/backend.py:89-90,312-313) in one call: uint8 labels [B,S,S].
+int chb_shape_decode_labels(chb_shape* z, const float* hair_code, const float* face_code, uint8_t* labels_out, int B,
+                            void* stream_) {
+  if (!z || !hair_code || !face_code || !labels_out || !z->ws || B <= 0 || B > z->cfg.max_batch) {
+    set_error("chb_shape_decode_labels: bad arguments or unbound object");
+    return CHB_ERR_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  const int S = z->cfg.crop;
+  for (int net = 0; net < 2; ++net) {
+    int rc = run_decoder(z, net, hair_code, face_code, B, st);
+    if (rc != CHB_OK) return rc;
+  }
+  shape_softmax_kernel<<<sgrid((long long)B * S * S, 256), 256, 0, st>>>(
+      reinterpret_cast<const float*>(z->ws + z->ws_logit[0]), reinterpret_cast<const float*>(z->ws + z->ws_logit[1]),
+      nullptr, labels_out, B, S);
+  return last_launch("chb_shape_decode_labels");
 }
 
 // forward_hair_decoder (net 0, model.py:175-178) / forward_face_decoder (net 1, :180-182): logits fp32 NCHW,

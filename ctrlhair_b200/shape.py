@@ -186,6 +186,19 @@ class ShapeGeneratorB200:
                                                  self._stream()))
         return out
 
+    def forward_decode_labels(self, hair_code, face_code):
+        """forward_decode_by_code + shape_util.mask_one_hot_to_label in one call (ui/backend.py:89-90,312-313): uint8
+        label map [B,256,256], the [B,19,256,256] probabilities are never written."""
+        B = hair_code.shape[0]
+        hair_code = hair_code.to(device=self.device, dtype=torch.float32).contiguous()
+        face_code = face_code.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty((B, 256, 256), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.chb_shape_decode_labels(self.handle, C.c_void_p(hair_code.data_ptr()),
+                                                        C.c_void_p(face_code.data_ptr()), C.c_void_p(out.data_ptr()), B,
+                                                        self._stream()))
+        return out
+
     def _decode_logits(self, net, hair_code, face_code, channels):
         B = face_code.shape[0]
         face_code = face_code.to(device=self.device, dtype=torch.float32).contiguous()

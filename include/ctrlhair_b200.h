@@ -230,6 +230,10 @@ int chb_shape_encode_labels(chb_shape* z, int net, const uint8_t* labels, float*
 /* forward_decode_by_code (model.py:195-199): -> softmax mask fp32 [B,19,256,256]. */
 int chb_shape_decode(chb_shape* z, const float* hair_code, const float* face_code, float* mask_out, int B,
                      void* stream);
+/* forward_decode_by_code followed by mask_one_hot_to_label (ui/backend.py:89-90,312-313; shape_util.py:17-20) in one
+ * call: uint8 labels [B,S,S] = argmax of the softmax probabilities, without writing the [B,19,S,S] tensor. */
+int chb_shape_decode_labels(chb_shape* z, const float* hair_code, const float* face_code, uint8_t* labels_out, int B,
+                            void* stream);
 /* forward_hair_decoder (net 0, model.py:175-178; input cat([face_code, hair_code])) and forward_face_decoder (net 1,
  * model.py:180-182; hair_code ignored, may be NULL): logits fp32 NCHW, [B,1,256,256] / [B,18,256,256]
  * (ui/backend.py:416 directly_change_hair_mask reads the face logits). */

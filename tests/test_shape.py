@@ -119,3 +119,18 @@ def test_encode_from_label_map_equals_one_hot_path(shape_sd):
     # identical fp16 inputs to identical kernels; only the LayerNorm statistics (double atomics) can differ in the last bit
     assert float((got_h - want_h).abs().max()) <= 1e-5 * float(want_h.abs().max())
     assert float((got_f - want_f).abs().max()) <= 1e-5 * float(want_f.abs().max())
+
+
+@pytest.mark.gpu
+def test_decode_to_labels_equals_argmax_of_probabilities(shape_sd):
+    """chb_shape_decode_labels == mask_one_hot_to_label(forward_decode_by_code(...)) (ui/backend.py:89-90)."""
+    from ctrlhair_b200 import blend
+    from ctrlhair_b200.shape import ShapeGeneratorB200
+    B = 2
+    shp = ShapeGeneratorB200(max_batch=B).load_state_dict(shape_sd)
+    hair, face = synth.make_shape_inputs(B)
+    hc, fc = shp.forward_hair_encoder(hair.cuda(), testing=True), shp.forward_face_encoder(face.cuda())
+    want = blend.mask_one_hot_to_label(shp.forward_decode_by_code(hc, fc))
+    got = shp.forward_decode_labels(hc, fc)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (B, 256, 256)
+    assert float((got == want).float().mean()) > 0.9999     # two decoder runs: LN statistics use atomics
