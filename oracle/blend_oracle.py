@@ -228,6 +228,14 @@ def table_digest(arr):
     return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
 
 
+def table_digest_of(fn, triples, chunk=1 << 20):
+    """SHA-256 of fn(triples) evaluated in chunks (same digest as table_digest(fn(triples)), a fraction of the memory)."""
+    h = hashlib.sha256()
+    for i in range(0, len(triples), chunk):
+        h.update(np.ascontiguousarray(fn(triples[i:i + chunk])).tobytes())
+    return h.hexdigest()
+
+
 def all_rgb():
     v = np.arange(256, dtype=np.uint8)
     return np.stack(np.meshgrid(v, v, v, indexing="ij"), -1).reshape(-1, 3)

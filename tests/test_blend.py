@@ -68,9 +68,10 @@ def test_oracle_blend_mask_matches_cv2_golden(gold):
 
 def test_oracle_colour_space_matches_cv2_exhaustively(gold):
     rgb = bo.all_rgb()
-    assert bo.table_digest(bo.rgb_to_hsv_u8(rgb)) == str(gold["rgb2hsv_sha256"])
-    hsv = rgb[rgb[:, 0] < 180]
-    assert bo.table_digest(bo.hsv_to_rgb_u8(hsv)) == str(gold["hsv2rgb_sha256"])
+    assert bo.table_digest_of(bo.rgb_to_hsv_u8, rgb) == str(gold["rgb2hsv_sha256"])
+    hsv = rgb[:180 * 256 * 256]              # all_rgb() is ordered by the first component: exactly the H < 180 triples
+    assert int(hsv[:, 0].max()) == 179
+    assert bo.table_digest_of(bo.hsv_to_rgb_u8, hsv) == str(gold["hsv2rgb_sha256"])
     assert np.array_equal(bo.hsv_to_rgb_u8(gold["hsv_sample"]), gold["hsv_sample_rgb"])
 
 
