@@ -7,6 +7,9 @@ Iterations of (preconditioned) CG to a 1e-11 relative residual on the 256x256 be
     incomplete-Poisson  M^-1 = K K^T, K = I - L D^-1 (Ament et al.)       346
     the same + additive coarse correction on 16x16 aggregates (256 dof)   110
     the same + additive coarse correction on  8x8  aggregates (1024 dof)   75
+With the 256 x 256 coarse operator of the 16x16 variant inverted once per system (dense, np.linalg.inv; condition number
+125) the count stays 110 whether the inverse is kept in fp64 or rounded to fp32 (256 KB per system = 32 KB per CTA of
+an 8-CTA cluster), and the uint8 result still matches spsolve (1 byte of 65 536 differs, max |f - f_spsolve| 1.7e-9).
 """
 import os
 import sys
