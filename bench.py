@@ -1,7 +1,7 @@
 """Headline benchmark: SEAN-generator 256x256 images/s on N B200s (BASELINE.json configs[1]).
 
   python bench.py --gpus 1 --steps K --warmup W                 # this build (CUDA, sm_100a)
-  python bench.py --impl reference --gpus N --steps K --warmup W # the reference algorithm on the host cores (oracle port)
+  python bench.py --impl reference --gpus N --steps K --warmup W # the unmodified reference (baseline/_ref) on the host cores
   N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py ...
 
 One step = one generator forward over a batch of 64 synthetic 256x256 19-class label maps + random style codes
@@ -85,15 +85,32 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(s[2] for s in self.samples), "samples": len(self.samples)}
 
 
-def cpu_oracle_throughput(n_images, crop, warm=0):
-    """Times the oracle port (reference algorithm, dense form, fp32, B=1 loop like the reference's UI path)."""
+def _ref_runner():
+    """baseline/ref_runner.py when the unmodified reference tree is staged under baseline/_ref (make_ref.py), else None."""
+    try:
+        from baseline import ref_runner
+        return ref_runner if ref_runner.ref_root() else None
+    except Exception:
+        return None
+
+
+def cpu_reference_throughput(n_images, crop, warm=1):
+    """Times the reference's own CPU path on all host cores: the UNMODIFIED SPADEGenerator (UI_mode, B=1 per call,
+    generator.py:72-109) from baseline/_ref when staged (kind "reference"), else the oracle port (kind "port")."""
     import torch
-    from oracle import sean_oracle as so
     from ctrlhair_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.make_state_dict()
-    labels = synth.make_labels(max(n_images, 1), crop, "blocky")
-    codes = synth.make_codes(max(n_images, 1))
+    labels = synth.make_labels(max(n_images + warm, 1), crop, "blocky")
+    codes = synth.make_codes(max(n_images + warm, 1))
+    rr = _ref_runner()
+    if rr is not None:
+        v, per, finite = rr.time_generator(sd, labels, codes, crop, "cpu", n_images, warm)
+        return {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": "%d images of %dx%d, one per call: unmodified reference SPADEGenerator.forward, UI_mode, "
+                          "torch CPU fp32 (baseline/_ref, tree sha256 %s)" % (n_images, crop, crop, rr.ref_digest()),
+                "ms_per_image": per * 1e3, "finite": finite}
+    from oracle import sean_oracle as so
     noise = synth.make_noise(1, crop)
     for i in range(warm):
         so.generator_forward(sd, labels[:1], codes[:1], noise)
@@ -101,45 +118,79 @@ def cpu_oracle_throughput(n_images, crop, warm=0):
     for i in range(n_images):
         so.generator_forward(sd, labels[i:i + 1], codes[i:i + 1], noise)
     dt = time.perf_counter() - t0
-    return n_images / dt, torch.get_num_threads()
+    return {"value": n_images / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d images of %dx%d, B=1 loop, reference algorithm (dense form) in torch CPU fp32 "
+                      "(oracle/sean_oracle.py; baseline/_ref not staged)" % (n_images, crop, crop),
+            "ms_per_image": dt / n_images * 1e3}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
-    from oracle import sean_oracle as so
-    from ctrlhair_b200 import synth
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = synth.make_state_dict()
-    per_step = 1  # bounded sample: one 256x256 image per step (the reference's own UI path is B=1)
-    labels = synth.make_labels(args.steps + args.warmup, args.crop, "blocky")
-    codes = synth.make_codes(args.steps + args.warmup)
-    noise = synth.make_noise(1, args.crop)
-    for i in range(args.warmup):
-        so.generator_forward(sd, labels[i:i + 1], codes[i:i + 1], noise)
-    t0 = time.perf_counter()
-    for i in range(args.warmup, args.warmup + args.steps):
-        so.generator_forward(sd, labels[i:i + 1], codes[i:i + 1], noise)
-    dt = time.perf_counter() - t0
-    value = per_step * args.steps / dt
-    cores = torch.get_num_threads()
+    cpu = cpu_reference_throughput(args.steps, args.crop, warm=max(args.warmup, 1))
+    value = cpu["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": cpu["ms_per_image"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "SEAN generator fwd, 256x256, 19-class blocky masks + N(0,0.135^2) style codes, "
-                               "reference algorithm (dense form) on host cores, B=1 per step", "crop": args.crop,
-                   "images_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d images of %dx%d, B=1 loop, torch CPU fp32 (oracle/sean_oracle.py)" %
-                                   (args.steps, args.crop, args.crop)},
+                               "the reference's own CPU path on the host cores, one image per step (a bounded sample of "
+                               "the B=64 workload: the reference's UI path is B=1 only)", "crop": args.crop,
+                   "images_per_step": 1},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
     return 0
+
+
+def parity_sample(gen, labels_h, codes_h, crop, dev, picks):
+    """Outside the timed region: the headline-batch schedule with explicit ACE noise, images `picks` compared with the
+    unmodified reference (CPU fp32, same injected noise).  Returns {l2, max, ...} (max = max|d| / max|ref|)."""
+    import torch
+    from ctrlhair_b200 import synth
+    rr = _ref_runner()
+    B = labels_h.shape[0]
+    planes = synth.make_noise(B, crop)
+    out = gen.forward_labels(labels_h.to(dev), codes_h.to(dev), noise=synth.flatten_noise(planes).to(dev)).cpu()
+    res = {"batch": B, "images": list(picks), "l2": 0.0, "max": 0.0}
+    if rr is not None:
+        net = rr.build_generator(synth.make_state_dict(), crop, "cpu")
+        res["against"] = "unmodified reference SPADEGenerator (baseline/_ref), CPU fp32, same injected noise"
+        ref_of = lambda i: rr.forward_ui(net, labels_h[i], codes_h[i], "cpu", [p[i:i + 1] for p in planes])[0]
+    else:
+        from oracle import sean_oracle as so
+        sd = synth.make_state_dict()
+        res["against"] = "oracle/sean_oracle.py (baseline/_ref not staged)"
+        ref_of = lambda i: so.generator_forward(sd, labels_h[i:i + 1], codes_h[i:i + 1], [p[i:i + 1] for p in planes])[0]
+    for i in picks:
+        ref = ref_of(i)
+        d = out[i] - ref
+        res["l2"] = max(res["l2"], float(d.norm() / ref.norm()))
+        res["max"] = max(res["max"], float(d.abs().max() / ref.abs().max()))
+    res["tolerance"] = 1e-3
+    res["ok"] = bool(res["max"] <= 1e-3 and res["l2"] <= 1e-3)
+    return res
+
+
+def reference_on_gpu(crop, dev, n_images=8, warm=2):
+    """The unmodified reference module run eagerly on the same B200 (fp32, stock torch settings, nothing patched):
+    the usefulness baseline of SURVEY 8d."""
+    import torch
+    from ctrlhair_b200 import synth
+    rr = _ref_runner()
+    if rr is None:
+        return None
+    sd = synth.make_state_dict()
+    labels = synth.make_labels(n_images + warm, crop, "blocky")
+    codes = synth.make_codes(n_images + warm)
+    v, per, finite = rr.time_generator(sd, labels, codes, crop, dev, n_images, warm)
+    torch.cuda.empty_cache()
+    return {"value": v, "unit": UNIT, "ms_per_image": per * 1e3, "finite": finite,
+            "what": "unmodified reference SPADEGenerator.forward, UI_mode, B=1 per call, eager PyTorch %s fp32 on the "
+                    "same GPU (cuDNN/cuBLAS), %d images" % (torch.__version__, n_images)}
 
 
 def run_ours(args):
@@ -263,12 +314,14 @@ def run_ours(args):
                        peaks["tflops_burst"],
         "top_launches": [{"name": n, "ms": round(m, 4), "issued_tflops": f / (m * 1e-3) / 1e12} for m, n, f in top],
     }
-    cpu = None
+    cpu = parity = ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores = cpu_oracle_throughput(args.cpu_images, crop, warm=1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d images of %dx%d, B=1 loop, reference algorithm (dense form) in torch CPU fp32" %
-                         (args.cpu_images, crop, crop)}
+        cpu = cpu_reference_throughput(args.cpu_images, crop, warm=1)
+    if rank == 0 and not args.no_parity:
+        # the headline schedule (this B) checked against the reference on the first, middle and last image of the batch
+        parity = parity_sample(gen, labels_h, codes_h, crop, dev, sorted({0, B // 2, B - 1}))
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        ref_gpu = reference_on_gpu(crop, dev)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -288,6 +341,8 @@ def run_ours(args):
             "gpu_launches": gen.launches() * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity": parity,
+            "reference_gpu": ref_gpu,
         }
         emit(line)
     if world > 1:
@@ -325,6 +380,8 @@ def main():
     ap.add_argument("--crop", type=int, default=256)
     ap.add_argument("--cpu-images", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -84,11 +84,11 @@ class BackendB200:
         g_sd, d_sd, p_sd = ct_sds
         self.netG = SeanGeneratorB200(crop=img_size, max_batch=max_batch, device=device).load_state_dict(sean_sd)
         self.zencoder = ZencoderB200(crop=img_size, max_batch=max_batch, device=device).load_state_dict(sean_sd)
-        self.mask_generator = ShapeGeneratorB200(max_batch=max_batch).load_state_dict(shape_sd)
-        self.feature_generator = ct.EigenGeneratorB200().load_state_dict(g_sd)
-        self.feature_encoder = ct.CodeEncoderB200().load_state_dict(d_sd)
-        self.feature_rgb_predictor = ct.PredictorB200().load_state_dict(p_sd)
         self.device = self.netG.device
+        self.mask_generator = ShapeGeneratorB200(max_batch=max_batch, device=self.device).load_state_dict(shape_sd)
+        self.feature_generator = ct.EigenGeneratorB200(device=self.device).load_state_dict(g_sd)
+        self.feature_encoder = ct.CodeEncoderB200(device=self.device).load_state_dict(d_sd)
+        self.feature_rgb_predictor = ct.PredictorB200(device=self.device).load_state_dict(p_sd)
         self.img_size = img_size
         self.max_batch = max_batch
         self.blending = blending

@@ -46,6 +46,13 @@ def _device_luts(device, tables=None):
     return _LUTS[key]
 
 
+def _launch(device, fn, *args):
+    """Every launch runs with `device` current and on ITS current stream: a BackendB200(device='cuda:1') built while
+    cuda:0 is current must not launch on GPU 0 against GPU 1 pointers."""
+    with torch.cuda.device(device):
+        _lib.check(fn(*args, _stream_ptr(device)))
+
+
 def _dev(device=None):
     if not torch.cuda.is_available():
         raise _lib.ChbError("ctrlhair_b200.blend needs a CUDA device (there is no CPU path)")
@@ -68,7 +75,7 @@ def image_to_u8(res_img, device=None):
     t = (t[None] if single else t).contiguous()
     B, _, H, W = t.shape
     out = torch.empty((B, H, W, 3), device=device, dtype=torch.uint8)
-    _lib.check(lib.chb_image_to_u8(t.data_ptr(), out.data_ptr(), B, H, W, _stream_ptr()))
+    _launch(device, lib.chb_image_to_u8, t.data_ptr(), out.data_ptr(), B, H, W)
     return out[0] if single else out
 
 
@@ -82,8 +89,8 @@ def blend_mask(target_parsing, face_parsing, device=None):
         tp, fp = tp[None], fp[None]
     tp, fp = tp.reshape(-1, tp.shape[-2], tp.shape[-1]), fp.reshape(-1, fp.shape[-2], fp.shape[-1])
     out = torch.empty_like(tp)
-    _lib.check(lib.chb_blend_mask(tp.data_ptr(), fp.data_ptr(), out.data_ptr(), None, tp.shape[0], tp.shape[1],
-                                  tp.shape[2], _stream_ptr()))
+    _launch(device, lib.chb_blend_mask, tp.data_ptr(), fp.data_ptr(), out.data_ptr(), None, tp.shape[0], tp.shape[1],
+                                  tp.shape[2])
     return out[0] if single else out
 
 
@@ -105,9 +112,9 @@ def poisson_blending(source, target, mask, with_gamma=True, tol=DEFAULT_TOL, max
     out = torch.empty_like(s)
     stats = torch.zeros((B, 3, 2), device=device, dtype=torch.float32)
     fwd, known = _device_luts(device, gamma_tables)
-    _lib.check(lib.chb_poisson_blend(s.data_ptr(), t.data_ptr(), m.data_ptr(), out.data_ptr(), B, H, W,
+    _launch(device, lib.chb_poisson_blend, s.data_ptr(), t.data_ptr(), m.data_ptr(), out.data_ptr(), B, H, W,
                                      1 if with_gamma else 0, float(tol), int(max_iter), stats.data_ptr(),
-                                     fwd.data_ptr(), known.data_ptr(), _stream_ptr()))
+                                     fwd.data_ptr(), known.data_ptr())
     out = out[0] if single else out
     return (out, stats) if return_stats else out
 
@@ -124,8 +131,8 @@ def postprocess_blending(face_img, res_img, face_parsing, target_parsing, blendi
     B, _, H, W = res.shape
     out = torch.empty((B, H, W, 3), device=device, dtype=torch.uint8)
     if not blending:
-        _lib.check(lib.chb_postprocess_blending(None, res.data_ptr(), None, None, out.data_ptr(), None, None, B, H, W, 0,
-                                                float(tol), int(max_iter), None, None, None, _stream_ptr()))
+        _launch(device, lib.chb_postprocess_blending, None, res.data_ptr(), None, None, out.data_ptr(), None, None, B, H, W, 0,
+                                                float(tol), int(max_iter), None, None, None)
         return (out[0] if single else out), None
     face = _u8(face_img, device).reshape(B, H, W, 3)
     fp = _u8(face_parsing, device).reshape(B, H, W)
@@ -133,9 +140,9 @@ def postprocess_blending(face_img, res_img, face_parsing, target_parsing, blendi
     rmd = torch.empty((B, H, W), device=device, dtype=torch.uint8)
     ws = torch.empty((int(lib.chb_postprocess_workspace_bytes(B, H, W)),), device=device, dtype=torch.uint8)
     fwd, known = _device_luts(device, gamma_tables)
-    _lib.check(lib.chb_postprocess_blending(face.data_ptr(), res.data_ptr(), fp.data_ptr(), tp.data_ptr(),
+    _launch(device, lib.chb_postprocess_blending, face.data_ptr(), res.data_ptr(), fp.data_ptr(), tp.data_ptr(),
                                             out.data_ptr(), rmd.data_ptr(), ws.data_ptr(), B, H, W, 1, float(tol),
-                                            int(max_iter), None, fwd.data_ptr(), known.data_ptr(), _stream_ptr()))
+                                            int(max_iter), None, fwd.data_ptr(), known.data_ptr())
     rmd = rmd[..., None]
     return (out[0], rmd[0]) if single else (out, rmd)
 
@@ -151,10 +158,10 @@ def tensor_rgb_to_hsv(rgb, device=None):
     n = t.numel() // 3
     if t.dtype == torch.uint8:
         t = t.contiguous()
-        _lib.check(lib.chb_rgb_to_hsv(None, t.data_ptr(), out.data_ptr(), n, _stream_ptr()))
+        _launch(device, lib.chb_rgb_to_hsv, None, t.data_ptr(), out.data_ptr(), n)
     else:
         t = t.to(torch.float32).contiguous()
-        _lib.check(lib.chb_rgb_to_hsv(t.data_ptr(), None, out.data_ptr(), n, _stream_ptr()))
+        _launch(device, lib.chb_rgb_to_hsv, t.data_ptr(), None, out.data_ptr(), n)
     return out
 
 
@@ -167,7 +174,7 @@ def tensor_hsv_to_rgb(hsv, device=None):
         t = (torch.trunc(t.to(torch.float64)).to(torch.int64) & 0xFF).to(torch.uint8)
     t = t.contiguous()
     out = torch.empty_like(t)
-    _lib.check(lib.chb_hsv_to_rgb(t.data_ptr(), out.data_ptr(), t.numel() // 3, _stream_ptr()))
+    _launch(device, lib.chb_hsv_to_rgb, t.data_ptr(), out.data_ptr(), t.numel() // 3)
     return out
 
 
@@ -180,7 +187,8 @@ def mask_one_hot_to_label(one_hot):
     t = one_hot.to(torch.float32).contiguous()
     B, Cn, H, W = t.shape
     out = torch.empty((B, H, W), device=t.device, dtype=torch.uint8)
-    _lib.check(lib.chb_onehot_to_label(t.data_ptr(), out.data_ptr(), B, Cn, H * W, _stream_ptr()))
+    device = t.device
+    _launch(device, lib.chb_onehot_to_label, t.data_ptr(), out.data_ptr(), B, Cn, H * W)
     return out
 
 
@@ -192,7 +200,8 @@ def mask_label_to_one_hot(img, nc=19):
     t = img.to(torch.uint8).contiguous()
     B, _, H, W = t.shape
     out = torch.empty((B, nc, H, W), device=t.device, dtype=torch.float32)
-    _lib.check(lib.chb_label_to_onehot(t.data_ptr(), out.data_ptr(), B, nc, H * W, _stream_ptr()))
+    device = t.device
+    _launch(device, lib.chb_label_to_onehot, t.data_ptr(), out.data_ptr(), B, nc, H * W)
     return out
 
 

@@ -1,8 +1,10 @@
 """Builds the in-tree CUDA library (sm_100a only) with nvcc.  No GPU is needed to build."""
+import json
 import os
 import shutil
 import subprocess
 import sys
+import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -35,8 +37,14 @@ def _stale(out, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+LAST_BUILD = {}
+
+
 def build_library(force=False, verbose=False):
+    """Compiles stale objects and relinks.  What was compiled and what was reused (objects ship to the GPU box with the
+    snapshot, so a build there normally reuses everything) is returned in LAST_BUILD and written to lib/BUILD_INFO.json."""
     os.makedirs(LIBDIR, exist_ok=True)
+    compiled, reused, t_start = [], [], time.time()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "ctrlhair_b200.h"))
     objs = []
@@ -51,6 +59,9 @@ def build_library(force=False, verbose=False):
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed on %s" % src)
+            compiled.append(src)
+        else:
+            reused.append(src)
         objs.append(o)
     out = lib_path()
     if force or _stale(out, objs):
@@ -59,6 +70,15 @@ def build_library(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+        linked = True
+    else:
+        linked = False
+    LAST_BUILD.clear()
+    LAST_BUILD.update({"compiled": compiled, "reused": reused, "linked": linked, "seconds": round(time.time() - t_start, 1),
+                       "flags": NVCC_FLAGS, "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())})
+    if compiled or linked or not os.path.exists(os.path.join(LIBDIR, "BUILD_INFO.json")):
+        with open(os.path.join(LIBDIR, "BUILD_INFO.json"), "w") as f:
+            json.dump(LAST_BUILD, f)
     return out
 
 

@@ -618,14 +618,22 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
   }
   int rc = chb_check_device();
   if (rc != CHB_OK) return rc;
+#ifdef CHB_TUNING_ENV  // A/B switch, tuning builds only (tools/build_variant.py with VARIANT_FLAGS=-DCHB_TUNING_ENV)
   static const bool force_v1 = [] { const char* v = getenv("CHB_POISSON_V1"); return v && atoi(v) != 0; }();
+#else
+  const bool force_v1 = false;
+#endif
   // second generation for the reference's image size; first generation for any other W <= 512, ceil(H/8)*W <= 8192
   const bool v2 = !force_v1 && poisson2_fits(R, W);
   size_t smem = v2 ? poisson2_smem_bytes(R, W) : poisson_smem_bytes(R, W);
   // 16-CTA clusters (non-portable size, 256-thread CTAs) halve the rows per CTA: 20 % lower latency while at most 8
   // clusters are in flight (interactive B <= 2, the reference's own use), same throughput as 8-CTA clusters beyond
   // that (measured, profiles/r1_s_poisson_solver.txt).  CHB_POISSON_CL16 = 0 / 1 overrides the choice.
+#ifdef CHB_TUNING_ENV
   static const int force_cl16 = [] { const char* v = getenv("CHB_POISSON_CL16"); return v ? (atoi(v) != 0 ? 1 : 0) : -1; }();
+#else
+  const int force_cl16 = -1;
+#endif
   const bool cl16 = v2 && (force_cl16 >= 0 ? force_cl16 == 1 : B * 3 <= 8);
   if (cl16) smem = poisson2_smem_bytes(kPoi2R16, W);
   // (set on every call: the attribute is per device, and a process may drive several)

@@ -23,6 +23,17 @@
 
 namespace chb {
 
+// Planner switches for in-box A/B experiments (tools/ab_env.sh).  They exist only in builds made with
+// -DCHB_TUNING_ENV (tools/build_variant.py); the product library never reads the environment.
+#ifdef CHB_TUNING_ENV
+static inline int tuning_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+#else
+static inline int tuning_env(const char*, int dflt) { return dflt; }
+#endif
+
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error_cstr() { return g_err.c_str(); }
@@ -291,9 +302,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   k.N = d.N;
   // Halo path (on by default; CHB_HALO=0 turns it off for A/B comparisons): 3x3 segments with 64-channel chunks on
   // 8-wide single-image tiles load a (TH+2)x(TW+2) halo tile once per channel chunk and feed all nine taps from it.
-  int halo_mode = 1, wstat_mode = 2;
-  if (const char* hv = getenv("CHB_HALO")) halo_mode = atoi(hv);
-  if (const char* wv = getenv("CHB_WSTAT")) wstat_mode = atoi(wv);
+  const int halo_mode = tuning_env("CHB_HALO", 1), wstat_mode = tuning_env("CHB_WSTAT", 2);
   const bool halo_geo = d.TW == 8 && d.TB == 1 && d.TH <= 16;
   // Weight-stationary mode: every segment can take its A operand from halo tiles (3x3 or 1x1-as-centre-tap, 32- or
   // 64-channel chunks), weights are shared by all images and the [BN x K] slab fits next to the halo ring.
@@ -310,8 +319,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   }
   const int halo_buf = kc_max == 64 ? kHaloBufBytes : kHaloBufBytes / 2;
   const int kRegion = 193 * 1024;  // 227 KB - align slack - barriers - epilogue staging
-  int wstat_min_halo = 2;
-  if (const char* mv = getenv("CHB_WSTAT_MINHALO")) wstat_min_halo = atoi(mv);
+  const int wstat_min_halo = tuning_env("CHB_WSTAT_MINHALO", 2);
   if (wbytes_total + (long long)wstat_min_halo * halo_buf > kRegion || d.Nrows / d.BN > device_sm_count()) wstat_ok = false;
   k.wstat = wstat_ok ? 1 : 0;
   k.halo_any = 0;
@@ -336,10 +344,8 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     k.wstat_bytes = 0;
     k.nhalo = k.halo_any ? 2 : 0;
     if (k.halo_any) {
-      if (const char* nv = getenv(d.BN <= 64 ? "CHB_NHALO64" : (d.BN <= 128 ? "CHB_NHALO128" : "CHB_NHALO256"))) {
-        const int n = atoi(nv);
-        if (n >= 2 && n <= kMaxHalo) k.nhalo = n;
-      }
+      const int n = tuning_env(d.BN <= 64 ? "CHB_NHALO64" : (d.BN <= 128 ? "CHB_NHALO128" : "CHB_NHALO256"), 0);
+      if (n >= 2 && n <= kMaxHalo) k.nhalo = n;
     }
     k.stage_bytes = k.a_region + ((d.BN * 128 * k.hg + 1023) / 1024) * 1024;
     const int budget = kSmemBudget - k.nhalo * halo_buf;
@@ -408,7 +414,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     if (d.epi == CHB_EPI_MODULATE)
       fast = fast && d.out_dtype == CHB_F16 && d.x_sb % 4 == 0 && d.x_sy % 4 == 0 && d.x_sx % 4 == 0 &&
              (d.x_shift == 0 || d.x_shift == 1) && (reinterpret_cast<uintptr_t>(d.x) & 15) == 0;
-    if (const char* fv = getenv("CHB_FAST")) fast = fast && atoi(fv) != 0;
+    fast = fast && tuning_env("CHB_FAST", 1) != 0;
     k.fast = fast ? 1 : 0;
     k.tx_sh = ilog2(k.tiles_x);
     k.ty_sh = ilog2(k.tiles_y);

@@ -524,6 +524,10 @@ int chb_generator_bind(chb_generator* g, const void* blob, void* workspace) {
 }
 
 static int get_steps(chb_generator* g, int B, std::vector<Step>** out) {
+  if (B <= 0 || B > g->cfg.max_batch) {  // plans address the workspace, which is sized for max_batch
+    set_error("chb_generator: batch must be in 1..max_batch");
+    return CHB_ERR_ARG;
+  }
   auto it = g->plans.find(B);
   if (it == g->plans.end()) {
     std::vector<Step> steps;

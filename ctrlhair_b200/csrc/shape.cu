@@ -378,7 +378,11 @@ static chb_conv_desc conv_desc(int B, int H, int W, const void* a, int C, const 
   d.TW = W < 8 ? W : 8;
   d.TH = H < 16 ? H : 16;
   d.TB = 1;
+#ifdef CHB_TUNING_ENV
   static const bool batch_tiles = [] { const char* v = getenv("CHB_SHAPE_TB"); return !v || atoi(v) != 0; }();
+#else
+  const bool batch_tiles = true;
+#endif
   if (batch_tiles && d.TW * d.TH <= 64) {
     // tiny maps (2x2 .. 8x8): several images share one 128-row MMA tile, so the 2048 x 36864 weight matrices of the
     // deep layers are streamed once per N tile instead of once per image ...

@@ -73,10 +73,13 @@ class _FusedAdam:
 
     def step(self):
         s = self.solver
+        caller = torch.cuda.current_stream(s.device)
+        s.stream.wait_stream(caller)  # anything the caller queued (e.g. a state_dict load) is ordered before the step
         with torch.cuda.device(s.device), torch.cuda.stream(s.stream):
             if s.world > 1:
                 parallel.allreduce_mean_(s.region(1, self.which))
             _lib.check(s.lib.chb_cttrain_adam(s.handle, self.which, C.c_void_p(s.stream.cuda_stream)))
+        caller.wait_stream(s.stream)  # ... and the updated parameters are visible to what the caller does next
 
 
 def train(cfg, loss_dict, optimizers, step=0, writer=None, flag="", retain_graph=False, write_log=False):
@@ -105,8 +108,20 @@ class SolverB200:
         for k in DEFAULTS:
             if k.startswith("lambda_"):
                 setattr(c, k, _cfg_get(cfg, k))
-        # the reference wires lr_d to G's optimizer and lr_g to D's (solver.py:52-55); both are 2e-4
-        c.lr, c.beta1, c.beta2, c.eps = _cfg_get(cfg, "lr_d"), _cfg_get(cfg, "beta1"), _cfg_get(cfg, "beta2"), 1e-8
+        # the reference wires lr_d to G's optimizer and lr_g to D's (solver.py:52-55); both are 2e-4 in every shipped
+        # config.  The fused Adam kernel takes ONE learning rate: differing values are rejected instead of ignored.
+        lr_d, lr_g = _cfg_get(cfg, "lr_d"), _cfg_get(cfg, "lr_g")
+        if lr_d != lr_g:
+            raise _lib.ChbError("SolverB200: lr_d (%g) != lr_g (%g) is not supported by the fused Adam step" % (lr_d, lr_g))
+        # lambda_rec_img (045: 0 -> 1000 at step 600 000) needs no guard: forward_rec_img runs under no_grad
+        # (pix2pix_model.py:60), so it changes the logged loss only, never a gradient.  lambda_adv_noise would add a
+        # third network (Model_D_noise) that this fused step does not hold: reject it.
+        v = None if cfg is None else (cfg.get("lambda_adv_noise", None) if isinstance(cfg, dict)
+                                      else getattr(cfg, "lambda_adv_noise", None))
+        vals = list(v.values()) if isinstance(v, dict) else [v]
+        if any(x not in (None, {}, 0, 0.0) for x in vals):
+            raise _lib.ChbError("SolverB200: lambda_adv_noise != 0 (noise discriminator) is not implemented")
+        c.lr, c.beta1, c.beta2, c.eps = lr_d, _cfg_get(cfg, "beta1"), _cfg_get(cfg, "beta2"), 1e-8
         c.use_graph = 1 if use_graph else 0
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -214,6 +229,11 @@ class SolverB200:
         dev = self.device
         f32 = lambda t: t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()  # noqa: E731
         i32 = lambda p: torch.as_tensor(p, dtype=torch.int32).to(dev, non_blocking=True)  # noqa: E731
+        caller = torch.cuda.current_stream(dev)
+        # the step runs on a private stream (graph replay): order it after the caller's stream, on which device-resident
+        # batch tensors may still be being produced, and make the caller's stream wait for the losses afterwards so that
+        # a reference-style `loss_dict[k].item()` / NaN check never reads an unwritten buffer
+        self.stream.wait_stream(caller)
         with torch.cuda.device(dev), torch.cuda.stream(self.stream):
             keep = {k: f32(d[k]) for k in ("code", "rgb_mean", "pca_std", "noise", "noise_curliness", "curliness_label")}
             keep["p1"], keep["p2"], keep["p3"] = i32(r["p1"]), i32(r["p2"]), i32(r["p3"])
@@ -230,6 +250,11 @@ class SolverB200:
                                                  C.c_void_p(self.stream.cuda_stream)))
             for t in keep.values():
                 t.record_stream(self.stream)
+            for k in ("code", "rgb_mean", "pca_std", "noise", "noise_curliness", "curliness_label"):
+                if isinstance(d[k], torch.Tensor) and d[k].is_cuda:
+                    d[k].record_stream(self.stream)  # inputs already on the device pass through f32() as views
+        caller.wait_stream(self.stream)
+        losses.record_stream(caller)
         self._keep = keep
         self.losses = losses
         return losses

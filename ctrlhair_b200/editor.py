@@ -55,8 +55,13 @@ class Pix2PixModelB200:
                 obj_dic = data["obj_dic"]
                 codes = torch.stack([torch.as_tensor(obj_dic[str(j)]["ACE"]).float().reshape(-1)
                                      for j in range(self.label_nc)]).to(self.device)
-                # the reference styles image 0 only (normalization.py:124); a batch re-uses the same dictionary
-                codes = codes[None].expand(labels.shape[0], -1, -1).contiguous()
+                # The reference's UI_mode styles image 0 ONLY (`for i in range(1)`, normalization.py:124): images 1.. of a
+                # batch would get a zero style map.  No caller relies on that, so a batch is rejected loudly instead of
+                # being styled differently from the reference; batched callers use HairEditorB200.gen_img_batch.
+                if labels.shape[0] != 1:
+                    raise _lib.ChbError("UI_mode takes one image per call (the reference styles image 0 only, "
+                                        "normalization.py:124); use gen_img_batch / forward_labels for batches")
+                codes = codes[None].contiguous()
                 self.seed += 1
                 return self.netG.forward_labels(labels, codes, noise=data.get("noise"), seed=self.seed)
             if mode == "style_code":

@@ -29,6 +29,9 @@ class SeanGeneratorB200:
         self.workspace = None
         self.status = "test"  # the reference flips this attribute on every module (hair_editor.py:34-37)
         self.impl = _lib.IMPL_TCGEN05
+        # Parity hook for callers that cannot pass `noise=` (the reference's Pix2PixModel calls netG(seg, img, obj_dic=...)):
+        # flat fp32 ACE noise planes used by forward() when no explicit noise is given; None = drawn on the device.
+        self.fixed_noise = None
         self._layout = self._read_layout()
 
     def __del__(self):
@@ -156,7 +159,11 @@ class SeanGeneratorB200:
         nptr = None
         if noise is not None:
             noise = torch.as_tensor(noise).to(torch.float32).contiguous()
+            if noise.numel() != self.noise_floats(B):
+                raise _lib.ChbError("noise has %d floats, expected %d" % (noise.numel(), self.noise_floats(B)))
             nptr = C.c_void_p(noise.data_ptr())
+        if labels.shape[1:] != (self.crop, self.crop) or codes.shape != (B, self.label_nc, self.style_len):
+            raise _lib.ChbError("bad input shapes %s %s" % (tuple(labels.shape), tuple(codes.shape)))
         if out is None:
             out = torch.empty((B, 3, self.crop, self.crop), dtype=torch.float32)
         with torch.cuda.device(self.device):
@@ -204,6 +211,8 @@ class SeanGeneratorB200:
         else:
             raise _lib.ChbError("style encoding from an RGB image (Zencoder) is not part of this build; pass obj_dic "
                                 "or a [B,19,512] codes tensor")
+        if noise is None:
+            noise = self.fixed_noise
         return self.forward_labels(labels, codes, noise=noise, seed=seed)
 
     __call__ = forward

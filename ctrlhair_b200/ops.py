@@ -8,8 +8,8 @@ from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, EPI_MODULATE, EPI_PL
                    IMPL_TCGEN05, ConvDesc)
 
 
-def _stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _require_cuda(t, name, dtype=None):

@@ -163,3 +163,23 @@ def test_generator_512_vs_oracle(synthetic_sd):
     assert tuple(out.shape) == (1, 3, 512, 512) and torch.isfinite(out).all()
     l2, mx = _errs(out, ref)
     assert l2 < L2_TOL and mx < MAX_TOL, (l2, mx)
+
+
+def test_headline_batch64_vs_oracle(synthetic_sd):
+    """BASELINE.json configs[1] itself: B = 64 at 256x256.  The batch size changes the plan (fc_mu tile width, the N tile
+    of the Weff GEMMs, the tile schedule of every persistent launch), so the headline schedule is compared with the
+    oracle on the first, a middle and the last image, and image-by-image with the B = 1 schedule (bitwise)."""
+    B = 64
+    g = SeanGeneratorB200(crop=256, max_batch=B)
+    g.load_state_dict(synthetic_sd)
+    labels, codes = synth.make_labels(B, 256, "blocky"), synth.make_codes(B)
+    planes = synth.make_noise(B, 256)
+    out = g.forward_labels(labels.cuda(), codes.cuda(), noise=synth.flatten_noise(planes).cuda())
+    assert torch.isfinite(out).all()
+    for i in (0, 31, 63):
+        one = [p[i:i + 1] for p in planes]
+        ref = so.generator_forward(synthetic_sd, labels[i:i + 1], codes[i:i + 1], one)
+        l2, mx = _errs(out[i:i + 1].cpu(), ref)
+        assert l2 < L2_TOL and mx < MAX_TOL, (i, l2, mx)
+        solo = g.forward_labels(labels[i:i + 1].cuda(), codes[i:i + 1].cuda(), noise=synth.flatten_noise(one).cuda())
+        assert torch.equal(solo[0], out[i]), i

@@ -52,7 +52,7 @@ def emulate_sites(packed, labels, codes, noise_planes, rounded, ngf=64, label_nc
         prev_r = res
         aces = ace_list(fin, fout)
         oh = onehot_at(res)
-        actv_all = r(name + ".actv", F.relu(F.conv2d(oh, _unpack(r(name + ".gbw", packed[name + ".sh.w"].float()), 32),
+        actv_all = r(name + ".actv", F.relu(F.conv2d(oh, _unpack(r(name + ".shw", packed[name + ".sh.w"].float()), 32),
                                                      packed[name + ".sh.b"], padding=1)))
         hs = {}
 
@@ -67,7 +67,7 @@ def emulate_sites(packed, labels, codes, noise_planes, rounded, ngf=64, label_nc
             if styled:
                 mu = mu_all[:, :, style_idx * L:(style_idx + 1) * L]
                 style_idx += 1
-                weff = r(name + ".weff", torch.einsum("nk,bjk->bnj", r("fcmu", packed[p + ".style.w"].float()), mu))
+                weff = r(name + ".weff", torch.einsum("nk,bjk->bnj", r("stylew", packed[p + ".style.w"].float()), mu))
                 weff = weff.reshape(B, 2 * C, 3, 3, label_nc).permute(0, 1, 4, 2, 3)
                 gb = gb + torch.cat([F.conv2d(oh[b:b + 1, :label_nc], weff[b], padding=1) for b in range(B)])
             g, be = _untile(gb, bn)
