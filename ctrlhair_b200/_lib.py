@@ -24,6 +24,7 @@ class ConvSeg(C.Structure):
         ("per_image", C.c_int),
         ("w_sb", C.c_int64),
         ("a_pad", C.c_int),
+        ("w_dup", C.c_int),
     ]
 
 
@@ -32,7 +33,7 @@ class ConvDesc(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("TW", C.c_int), ("TH", C.c_int), ("TB", C.c_int),
         ("nseg", C.c_int),
-        ("seg", ConvSeg * 3),
+        ("seg", ConvSeg * 4),
         ("N", C.c_int), ("Nrows", C.c_int), ("BN", C.c_int),
         ("epi", C.c_int), ("act", C.c_int),
         ("bias", C.c_void_p), ("bias_per_image", C.c_int),
@@ -43,6 +44,7 @@ class ConvDesc(C.Structure):
         ("x", C.c_void_p), ("x_sb", C.c_int64), ("x_sy", C.c_int64), ("x_sx", C.c_int64), ("x_shift", C.c_int),
         ("noise", C.c_void_p),
         ("chan", C.c_void_p),
+        ("o_split", C.c_int), ("o_lo_off", C.c_int64),
     ]
 
 
@@ -54,7 +56,18 @@ class MlpLayer(C.Structure):
 
 class GenConfig(C.Structure):
     _fields_ = [("ngf", C.c_int), ("label_nc", C.c_int), ("crop", C.c_int), ("style_len", C.c_int),
-                ("max_batch", C.c_int)]
+                ("max_batch", C.c_int), ("precision", C.c_uint)]
+
+
+PREC_IMG, PREC_SHORTCUT = 1, 2
+
+
+def prec_h1(i):
+    return 1 << (8 + i)
+
+
+def prec_h0(i):
+    return 1 << (16 + i)
 
 
 class ZencConfig(C.Structure):
@@ -99,6 +112,7 @@ SYMBOLS = [
     ("chb_f32_to_f16", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("chb_mlp_forward", C.c_int,
      [C.POINTER(MlpLayer), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_struct_size", C.c_int, [C.c_int]),
     ("chb_generator_create", C.c_int, [C.POINTER(GenConfig), C.POINTER(C.c_void_p)]),
     ("chb_generator_destroy", None, [C.c_void_p]),
     ("chb_generator_num_tensors", C.c_int, [C.c_void_p]),
@@ -192,6 +206,11 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for which, mirror in ((0, ConvSeg), (1, ConvDesc), (2, GenConfig), (3, MlpLayer)):
+        if lib.chb_struct_size(which) != C.sizeof(mirror):
+            raise ChbError("ctrlhair_b200: %s was built from a different include/ctrlhair_b200.h than this binding "
+                           "(struct %s: %d vs %d bytes); rebuild with __graft_entry__.build()" %
+                           (path, mirror.__name__, lib.chb_struct_size(which), C.sizeof(mirror)))
     _LIB = lib
     return lib
 

@@ -134,6 +134,62 @@ static int grid_for(long long n, int threads) {
   return (int)g;
 }
 
+// image = tanh(bias + sum over the 3x3 neighbourhood of the per-tap partial sums)   (generator.py:107-108)
+//   y   fp32 [B,S,S,32]: y[p][tap*3 + co] = sum_ci x[p][ci] * W[co][ci][tap]  (the 1x1 GEMM "conv_img.taps")
+//   out fp32 [B,3,S,S]:  out[co][p] = tanh(bias[co] + sum_tap y[p + d(tap)][tap*3 + co]), zero outside the image
+// HBM-bound: 128 B read + 12 B written per pixel.  One CTA = 32 x 8 pixels; the (8+2) x (32+2) halo of y rows is staged
+// in shared memory with a 33-float row pitch so that the 27 reads per pixel are bank-conflict free.
+constexpr int kGatherTX = 32, kGatherTY = 8, kGatherPitch = 33;
+__global__ void __launch_bounds__(kGatherTX * kGatherTY) img_from_taps_kernel(const float* __restrict__ y,
+                                                                              const float* __restrict__ bias,
+                                                                              float* __restrict__ out, int S) {
+  __shared__ float t[(kGatherTY + 2) * (kGatherTX + 2) * kGatherPitch];
+  const int tiles_x = S / kGatherTX, tiles_y = S / kGatherTY;
+  int tile = blockIdx.x;
+  const int x0 = (tile % tiles_x) * kGatherTX;
+  tile /= tiles_x;
+  const int y0 = (tile % tiles_y) * kGatherTY;
+  const int b = tile / tiles_y;
+  const float* yb = y + (size_t)b * S * S * 32;
+  constexpr int HW = kGatherTX + 2, HP = (kGatherTY + 2) * HW;
+  for (int i = threadIdx.x; i < HP * 8; i += kGatherTX * kGatherTY) {
+    const int pix = i >> 3, q = i & 7;
+    const int py = pix / HW, px = pix - py * HW;
+    const int yy = y0 - 1 + py, xx = x0 - 1 + px;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < S && xx >= 0 && xx < S)
+      v = __ldg(reinterpret_cast<const float4*>(yb + ((size_t)yy * S + xx) * 32) + q);
+    float* d = t + pix * kGatherPitch + q * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & (kGatherTX - 1), ly = threadIdx.x / kGatherTX;
+  float a0 = __ldg(bias), a1 = __ldg(bias + 1), a2 = __ldg(bias + 2);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      // output pixel (ly, lx) reads the neighbour at offset (ky-1, kx-1), whose partial sum for THIS tap is its
+      // contribution to (ly, lx): conv zero padding == the zero rows staged for out-of-image neighbours
+      const float* r = t + ((ly + ky) * HW + lx + kx) * kGatherPitch + (ky * 3 + kx) * 3;
+      a0 += r[0]; a1 += r[1]; a2 += r[2];
+    }
+  const size_t plane = (size_t)S * S;
+  float* o = out + (size_t)b * 3 * plane + (size_t)(y0 + ly) * S + x0 + lx;
+  o[0] = tanhf(a0);
+  o[plane] = tanhf(a1);
+  o[2 * plane] = tanhf(a2);
+}
+
+int img_from_taps(const float* y, const float* bias, float* out, int B, int S, cudaStream_t stream) {
+  if (!y || !bias || !out || B <= 0 || S < kGatherTX || S % kGatherTX != 0) {
+    set_error("img_from_taps: bad arguments (S must be a multiple of 32)");
+    return CHB_ERR_ARG;
+  }
+  img_from_taps_kernel<<<B * (S / kGatherTX) * (S / kGatherTY), kGatherTX * kGatherTY, 0, stream>>>(y, bias, out, S);
+  return check_launch("img_from_taps");
+}
+
 int codes_cast_transpose(const float* in, void* out, int B, int NC, int L, cudaStream_t stream) {
   codes_cast_kernel<<<grid_for((long long)B * NC * L, 256), 256, 0, stream>>>(in, reinterpret_cast<__half*>(out), B,
                                                                              NC, L);

@@ -72,7 +72,9 @@ __device__ __forceinline__ void plain_store_elem(const EpiK& e, int b, int y, in
   v = act_t<ACT>(v);
   const long long off = out_offset(e, b, y, x, n);
   if (e.out_dtype == CHB_F16) {
-    reinterpret_cast<__half*>(e.out)[off] = __float2half_rn(v);
+    const __half hi = __float2half_rn(v);
+    reinterpret_cast<__half*>(e.out)[off] = hi;
+    if (e.split) reinterpret_cast<__half*>(e.out)[off + e.o_lo] = __float2half_rn(v - __half2float(hi));
   } else {
     reinterpret_cast<float*>(e.out)[off] = v;
   }
@@ -339,6 +341,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// fp16 hi + lo split of two fp32 values: hi = fp16(v), lo = fp16(v - hi)  (v is then known to ~2^-22 relative)
+__device__ __forceinline__ void pack_h2_split(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // 32 accumulator columns of the PLAIN epilogue through the staging block (channels-last output, full block valid).
 // ro / oo4 / oo8: per-tile row offsets (16-byte units) of the residual and of the output in the 8- and 4-lanes-per-row
 // arrangements; bi = image of this lane's own row (for per-image bias).
@@ -381,12 +392,26 @@ __device__ __forceinline__ void plain_block32(const EpiK& e, uint32_t taddr, uin
   for (int i = 0; i < 32; ++i) v[i] = act_t<ACT>(v[i]);
   const long long noff = e.o_ngroup > 0 ? (long long)(n / e.o_ngroup) * e.o_sgroup + (long long)(n % e.o_ngroup) : n;
   if (e.out_dtype == CHB_F16) {
-    uint4 pk[4];
+    char* obase = reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16;
+    if (e.split) {
+      uint4 pk[4], pl[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
-                         pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
-    scatter_o<4, FAST>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + noff) + (lane & 3) * 16, oo4, pk);
+      for (int i = 0; i < 4; ++i) {
+        pack_h2_split(v[8 * i], v[8 * i + 1], pk[i].x, pl[i].x);
+        pack_h2_split(v[8 * i + 2], v[8 * i + 3], pk[i].y, pl[i].y);
+        pack_h2_split(v[8 * i + 4], v[8 * i + 5], pk[i].z, pl[i].z);
+        pack_h2_split(v[8 * i + 6], v[8 * i + 7], pk[i].w, pl[i].w);
+      }
+      scatter_o<4, FAST>(stg, lane, obase, oo4, pk);
+      scatter_o<4, FAST>(stg, lane, obase + e.o_lo * 2, oo4, pl);
+    } else {
+      uint4 pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+      scatter_o<4, FAST>(stg, lane, obase, oo4, pk);
+    }
   } else {
     uint4 pk[8];
 #pragma unroll
@@ -435,15 +460,14 @@ __device__ __forceinline__ void plain_chunk(const ConvKParams& p, const EpiK& e,
     const long long off = out_offset(e, b, y, x, n);
     if (e.out_dtype == CHB_F16) {
       uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + off);
+      uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + off + e.o_lo);
 #pragma unroll
       for (int i = 0; i < NC / 8; ++i) {
-        uint32_t pk[4];
+        uint32_t pk[4], pl[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          __half2 h = __floats2half2_rn(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]);
-          pk[k] = *reinterpret_cast<uint32_t*>(&h);
-        }
+        for (int k = 0; k < 4; ++k) pack_h2_split(v[8 * i + 2 * k], v[8 * i + 2 * k + 1], pk[k], pl[k]);
         op[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (e.split) ol[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
       }
     } else {
       float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off);
@@ -464,13 +488,14 @@ __device__ __forceinline__ void plain_chunk(const ConvKParams& p, const EpiK& e,
 // pairs (FFMA2/FADD2/FMUL2), fp16 output.  g / be: accumulator columns, xr: 4 x uint4 of fp32 x values, cst: the
 // five per-channel constant vectors of these 16 channels.
 // ------------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, bool SPLIT>
 __device__ __forceinline__ void modulate16(const float (&g)[16], const float (&be)[16], const uint4* xr, float nz,
                                            const float4 (&bg)[4], const float4 (&bb)[4], const float4 (&av)[4],
-                                           const float4 (&cv)[4], const float4 (&nv)[4], uint4& h0, uint4& h1) {
+                                           const float4 (&cv)[4], const float4 (&nv)[4], uint4& h0, uint4& h1,
+                                           uint4& l0, uint4& l1) {
   const uint64_t nz2 = pk2(nz, nz);
   const uint64_t slope2 = pk2(0.2f, 0.2f);
-  uint32_t pk[8];
+  uint32_t pk[8], pl[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint4 xq = xr[i];
@@ -500,11 +525,20 @@ __device__ __forceinline__ void modulate16(const float (&g)[16], const float (&b
       upk2(o23, o2, o3);
       o0 = act_t<ACT>(o0); o1 = act_t<ACT>(o1); o2 = act_t<ACT>(o2); o3 = act_t<ACT>(o3);
     }
-    pk[2 * i] = pack_h2(o0, o1);
-    pk[2 * i + 1] = pack_h2(o2, o3);
+    if (SPLIT) {
+      pack_h2_split(o0, o1, pk[2 * i], pl[2 * i]);
+      pack_h2_split(o2, o3, pk[2 * i + 1], pl[2 * i + 1]);
+    } else {
+      pk[2 * i] = pack_h2(o0, o1);
+      pk[2 * i + 1] = pack_h2(o2, o3);
+    }
   }
   h0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   h1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  if (SPLIT) {
+    l0 = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    l1 = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -663,7 +697,8 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
             x_offsets(tn, xon);
             gather_issue_o<8, FAST>(reinterpret_cast<const char*>(e.x + ntn * half_n + chalf * cw) + cl8 * 16, xon, pf);
           }
-          uint4 hk[4];
+          constexpr bool split = EPI == kEpiModulateSplit;  // compile time: the lo half costs 16 more live registers
+          uint4 hk[4], lk[4];
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             const int jj = j + 16 * sub;
@@ -681,7 +716,8 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
             }
             tmem_ld_fence(g);
             tmem_ld_fence(be);
-            modulate16<ACT>(g, be, &xr[4 * sub], nz, bg, bb, av, cv, nv, hk[2 * sub], hk[2 * sub + 1]);
+            modulate16<ACT, split>(g, be, &xr[4 * sub], nz, bg, bb, av, cv, nv, hk[2 * sub], hk[2 * sub + 1],
+                                   lk[2 * sub], lk[2 * sub + 1]);
           }
           if (u + 1 == units) {
             // the accumulator has been fully read: hand the TMEM buffer back before the stores
@@ -689,7 +725,9 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          scatter_o<4, FAST>(stg, lane, reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + c0 + j) + cl4 * 16, oo, hk);
+          char* obase = reinterpret_cast<char*>(reinterpret_cast<__half*>(e.out) + c0 + j) + cl4 * 16;
+          scatter_o<4, FAST>(stg, lane, obase, oo, hk);
+          if constexpr (split) scatter_o<4, FAST>(stg, lane, obase + e.o_lo * 2, oo, lk);
         }
       }
     }

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 struct SimtSeg {
   const __half* a;
   long long a_sb, a_sy, a_sx;
-  int ch_off, C, taps, per_image, a_pad;
+  int ch_off, C, Cw, taps, per_image, a_pad;
   const __half* w;
   long long w_sb;
 };
@@ -152,15 +152,15 @@ __device__ float simt_dot(const SimtParams& p, int b, int y, int x, int nrow) {
   float acc = 0.f;
   for (int s = 0; s < p.nseg; ++s) {
     const SimtSeg& sg = p.seg[s];
-    const int K = sg.taps * sg.C;
+    const int K = sg.taps * sg.Cw;
     const __half* wrow = sg.w + (sg.per_image ? (long long)b * (sg.w_sb > 0 ? sg.w_sb : (long long)p.e.nrows * K) : 0) + (long long)nrow * K;
     for (int tap = 0; tap < sg.taps; ++tap) {
       const int yy = y + sg.a_pad + (sg.taps == 9 ? tap / 3 - 1 : 0);
       const int xx = x + sg.a_pad + (sg.taps == 9 ? tap % 3 - 1 : 0);
       if (yy < 0 || yy >= p.H + 2 * sg.a_pad || xx < 0 || xx >= p.W + 2 * sg.a_pad) continue;
       const __half* ap = sg.a + (long long)b * sg.a_sb + (long long)yy * sg.a_sy + (long long)xx * sg.a_sx + sg.ch_off;
-      const __half* wp = wrow + tap * sg.C;
-      for (int c = 0; c < sg.C; ++c) acc = fmaf(__half2float(ap[c]), __half2float(wp[c]), acc);
+      const __half* wp = wrow + tap * sg.Cw;
+      for (int c = 0; c < sg.C; ++c) acc = fmaf(__half2float(ap[c]), __half2float(wp[c >= sg.Cw ? c - sg.Cw : c]), acc);
     }
   }
   return acc;
@@ -191,8 +191,11 @@ __global__ void conv_simt_kernel(const SimtParams p) {
       const float* cp = reinterpret_cast<const float*>(p.e.chan);
       const float a = __ldg(cp + n), c = __ldg(cp + p.e.chan_stride + n), nvv = __ldg(cp + 2 * p.e.chan_stride + n);
       const float o = apply_act(fmaf(fmaf(xv, a, fmaf(nz, nvv, c)), 1.f + g, be), p.e.act);
-      reinterpret_cast<__half*>(p.e.out)[(long long)b * p.e.o_sb + (long long)y * p.e.o_sy + (long long)x * p.e.o_sx + n] =
-          __float2half_rn(o);
+      __half* op = reinterpret_cast<__half*>(p.e.out) + (long long)b * p.e.o_sb + (long long)y * p.e.o_sy +
+                   (long long)x * p.e.o_sx + n;
+      const __half hi = __float2half_rn(o);
+      *op = hi;
+      if (p.e.split) op[p.e.o_lo] = __float2half_rn(o - __half2float(hi));
     }
   }
 }
@@ -254,7 +257,7 @@ static int validate_desc(const chb_conv_desc& d) {
   CHB_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0, "B,H,W must be positive");
   CHB_REQUIRE(d.TW > 0 && d.TH > 0 && d.TB > 0 && d.TW * d.TH * d.TB <= 128, "tile must have 1..128 rows");
   CHB_REQUIRE(d.TW <= 256 && d.TH <= 256 && d.TB <= 256, "tile dims <= 256");
-  CHB_REQUIRE(d.nseg >= 1 && d.nseg <= kMaxSeg, "1..3 segments");
+  CHB_REQUIRE(d.nseg >= 1 && d.nseg <= kMaxSeg, "1..4 segments");
   CHB_REQUIRE(d.BN >= 16 && d.BN <= 256 && d.BN % 16 == 0, "BN in 16..256, multiple of 16");
   CHB_REQUIRE(d.Nrows > 0 && d.Nrows % d.BN == 0, "Nrows must be a positive multiple of BN");
   CHB_REQUIRE(d.N > 0 && d.N <= d.Nrows, "0 < N <= Nrows");
@@ -270,6 +273,8 @@ static int validate_desc(const chb_conv_desc& d) {
                 "activation strides must be multiples of 8 elements (16 B)");
     CHB_REQUIRE(!g.per_image || d.TB == 1, "per-image weights need TB == 1");
     CHB_REQUIRE(g.a_pad >= 0 && g.a_pad <= 8, "a_pad in 0..8");
+    CHB_REQUIRE(g.w_dup == 0 || g.w_dup == 1 || (g.w_dup == 2 && g.C % 128 == 0),
+                "w_dup is 0, 1 or 2; a hi+lo split segment needs C % 128 == 0");
     CHB_REQUIRE((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0,
                 "operands must be 16-byte aligned");
   }
@@ -278,6 +283,11 @@ static int validate_desc(const chb_conv_desc& d) {
     CHB_REQUIRE(d.BN % 128 == 0 && d.N == d.Nrows, "modulate epilogue needs BN % 128 == 0 and N == Nrows");
     CHB_REQUIRE(d.act != CHB_ACT_TANH, "modulate epilogue supports none / relu / lrelu");
     CHB_REQUIRE(d.o_sn == 1 || d.o_sn == 0, "modulate output is channels-last");
+  }
+  if (d.o_split) {
+    CHB_REQUIRE(d.out_dtype == CHB_F16 && d.o_sn <= 1 && d.o_ngroup <= 0 && d.o_lo_off > 0 && d.o_lo_off % 8 == 0 &&
+                    d.N == d.Nrows && d.BN % 64 == 0,
+                "o_split needs fp16 channels-last output, N == Nrows, BN % 64 == 0 and o_lo_off % 8 == 0");
   }
 #undef CHB_REQUIRE
   return CHB_OK;
@@ -315,7 +325,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     if (kc > kc_max) kc_max = kc;
     if (g.per_image) wstat_ok = false;
     if (kc == 32 && wstat_mode < 2) wstat_ok = false;  // CHB_WSTAT=1: one-hot (64-byte row) layers streamed (slower since the nine taps of a resident chunk go out in one asm block)
-    wbytes_total += (long long)g.taps * g.C * d.BN * 2;
+    wbytes_total += (long long)g.taps * (g.w_dup == 2 ? g.C / 2 : g.C) * d.BN * 2;
   }
   const int halo_buf = kc_max == 64 ? kHaloBufBytes : kHaloBufBytes / 2;
   const int kRegion = 193 * 1024;  // 227 KB - align slack - barriers - epilogue staging
@@ -354,18 +364,21 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   }
   plan->smem_bytes = k.nstages * k.stage_bytes + 1024 /*align slack*/ + 1024 /*barriers*/ + kEpilogueWarps * 4096 +
                      k.nhalo * halo_buf + k.wstat_bytes;
-  long long ktotal = 0;
+  long long ktotal = 0, wk_total = 0;
   for (int s = 0; s < d.nseg; ++s) {
     const chb_conv_seg& g = d.seg[s];
     const int kc = g.C == 32 ? 32 : 64;
     k.seg[s].taps = g.taps;
     k.seg[s].kc = kc;
     k.seg[s].nchunk = g.C / kc;
+    const int Cw = g.w_dup == 2 ? g.C / 2 : g.C;  // channels the weights span
+    k.seg[s].nchunk_w = Cw / kc;
     k.seg[s].ch_off = g.ch_off;
     k.seg[s].per_image = g.per_image;
     k.seg[s].xy_off = g.a_pad;
-    k.seg[s].wofs = (int)(ktotal * d.BN * 2);  // offset of this segment inside the resident weight slab
+    k.seg[s].wofs = (int)(wk_total * d.BN * 2);  // offset of this segment inside the resident weight slab
     ktotal += (long long)g.taps * g.C;
+    wk_total += (long long)g.taps * Cw;
     {
       cuuint64_t dims[4] = {(cuuint64_t)g.Ca, (cuuint64_t)(d.W + 2 * g.a_pad), (cuuint64_t)(d.H + 2 * g.a_pad),
                             (cuuint64_t)d.B};
@@ -380,7 +393,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
       }
     }
     {
-      const cuuint64_t K = (cuuint64_t)g.taps * g.C;
+      const cuuint64_t K = (cuuint64_t)g.taps * Cw;
       cuuint64_t dims[3] = {K, (cuuint64_t)d.Nrows, (cuuint64_t)(g.per_image ? d.B : 1)};
       const cuuint64_t img_stride = (g.per_image && g.w_sb > 0) ? (cuuint64_t)g.w_sb * 2 : K * 2 * (cuuint64_t)d.Nrows;
       cuuint64_t str[2] = {K * 2, img_stride};
@@ -394,6 +407,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   e.out = d.out; e.out_dtype = d.out_dtype;
   e.o_sb = d.o_sb; e.o_sy = d.o_sy; e.o_sx = d.o_sx; e.o_sn = d.o_sn;
   e.o_ngroup = d.o_ngroup; e.o_sgroup = d.o_sgroup;
+  e.split = d.o_split ? 1 : 0; e.o_lo = d.o_lo_off;
   e.res = d.res; e.r_sb = d.r_sb; e.r_sy = d.r_sy; e.r_sx = d.r_sx; e.r_shift = d.r_shift;
   e.x = d.x; e.x_sb = d.x_sb; e.x_sy = d.x_sy; e.x_sx = d.x_sx; e.x_shift = d.x_shift;
   e.noise = d.noise;
@@ -443,6 +457,13 @@ static ConvKernelFn pick_kernel_wf(int epi, int act) {
       default: return conv_igemm_kernel<CHB_EPI_PLAIN, CHB_ACT_NONE, WSTAT, FAST>;
     }
   }
+  if (epi == kEpiModulateSplit) {
+    switch (act) {
+      case CHB_ACT_LRELU: return conv_igemm_kernel<kEpiModulateSplit, CHB_ACT_LRELU, WSTAT, FAST>;
+      case CHB_ACT_RELU: return conv_igemm_kernel<kEpiModulateSplit, CHB_ACT_RELU, WSTAT, FAST>;
+      default: return conv_igemm_kernel<kEpiModulateSplit, CHB_ACT_NONE, WSTAT, FAST>;
+    }
+  }
   switch (act) {
     case CHB_ACT_LRELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_LRELU, WSTAT, FAST>;
     case CHB_ACT_RELU: return conv_igemm_kernel<CHB_EPI_MODULATE, CHB_ACT_RELU, WSTAT, FAST>;
@@ -458,7 +479,7 @@ static int ensure_smem_attr() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    for (int epi = 0; epi < 2 && err == cudaSuccess; ++epi)
+    for (int epi = 0; epi < 3 && err == cudaSuccess; ++epi)
       for (int act = 0; act < 4 && err == cudaSuccess; ++act)
         for (int w = 0; w < 4 && err == cudaSuccess; ++w)
           err = cudaFuncSetAttribute(pick_kernel(epi, act, w & 1, w >> 1), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -482,6 +503,7 @@ int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
       sp.seg[s].a = reinterpret_cast<const __half*>(d.seg[s].a);
       sp.seg[s].a_sb = d.seg[s].a_sb; sp.seg[s].a_sy = d.seg[s].a_sy; sp.seg[s].a_sx = d.seg[s].a_sx;
       sp.seg[s].ch_off = d.seg[s].ch_off; sp.seg[s].C = d.seg[s].C; sp.seg[s].taps = d.seg[s].taps;
+      sp.seg[s].Cw = d.seg[s].w_dup == 2 ? d.seg[s].C / 2 : d.seg[s].C;
       sp.seg[s].per_image = d.seg[s].per_image;
       sp.seg[s].a_pad = d.seg[s].a_pad;
       sp.seg[s].w = reinterpret_cast<const __half*>(d.seg[s].w);
@@ -491,7 +513,8 @@ int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
   } else {
     int rc = ensure_smem_attr();
     if (rc != CHB_OK) return rc;
-    pick_kernel(plan.desc.epi, plan.desc.act, plan.kp.wstat, plan.kp.fast)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
+    const int epi = (plan.desc.epi == CHB_EPI_MODULATE && plan.desc.o_split) ? kEpiModulateSplit : plan.desc.epi;
+    pick_kernel(epi, plan.desc.act, plan.kp.wstat, plan.kp.fast)<<<plan.grid, kConvThreads, plan.smem_bytes, stream>>>(plan.kp);
   }
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
@@ -506,6 +529,16 @@ int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
 extern "C" {
 
 int chb_version(void) { return 100; }
+
+int chb_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(chb_conv_seg);
+    case 1: return (int)sizeof(chb_conv_desc);
+    case 2: return (int)sizeof(chb_gen_config);
+    case 3: return (int)sizeof(chb_mlp_layer);
+    default: return -1;
+  }
+}
 const char* chb_last_error(void) { return chb::last_error_cstr(); }
 
 int chb_check_device(void) {

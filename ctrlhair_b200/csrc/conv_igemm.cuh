@@ -9,7 +9,8 @@
 
 namespace chb {
 
-constexpr int kMaxSeg = 3;
+constexpr int kMaxSeg = 4;
+constexpr int kEpiModulateSplit = 2;  // kernel-internal: CHB_EPI_MODULATE with chb_conv_desc.o_split (own instantiation)
 constexpr int kATileBytes = 16384;  // 128 rows x 128 B
 constexpr int kMaxStages = 8;
 constexpr int kMaxHalo = 6;
@@ -23,6 +24,8 @@ struct SegK {
   int xy_off;  // explicit input border (chb_conv_seg.a_pad): added to the TMA x / y coordinates
   int wofs;  // weight-stationary mode: byte offset of this segment inside the resident weight slab
   int halo;  // 1: the A operand of this 3x3 segment is loaded once per channel chunk as a (TH+2)x(TW+2) halo tile
+  int nchunk_w;  // channel chunks the WEIGHTS have per tap: nchunk, or nchunk / 2 for a hi+lo split activation
+                 // (chb_conv_seg.w_dup == 2: chunk c of the activation uses weight chunk c % nchunk_w)
 };
 
 struct EpiK {
@@ -36,6 +39,8 @@ struct EpiK {
   long long o_sb, o_sy, o_sx, o_sn;
   int o_ngroup;
   long long o_sgroup;
+  int split;           // fp16 hi+lo split output: lo = fp16(v - hi) goes o_lo elements after hi
+  long long o_lo;
   const float* res;
   long long r_sb, r_sy, r_sx;
   int r_shift;
@@ -88,6 +93,7 @@ int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream);
 int device_sm_count();
 int onehot_pyramid_ones(const uint8_t* labels, int B, int S, int nlevels, const int* shifts, void* const* outs,
                         int nclass, int ones_ch0, int ones_n, void* stream);
+int img_from_taps(const float* y, const float* bias, float* out, int B, int S, cudaStream_t stream);
 int codes_cast_transpose(const float* in, void* out, int B, int NC, int L, cudaStream_t stream);
 
 }  // namespace chb

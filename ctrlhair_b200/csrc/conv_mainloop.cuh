@@ -41,7 +41,7 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
     for (int s = 0; s < p.nseg; ++s) {
       const SegK sg = p.seg[s];
       const uint32_t wbytes = (uint32_t)p.BN * (uint32_t)sg.kc * 2u;
-      for (int i = 0; i < sg.taps * sg.nchunk; ++i) {
+      for (int i = 0; i < sg.taps * sg.nchunk_w; ++i) {
         if (elect_one())
           tma_load_3d(&p.tmW[s], sm.wstat_base + sg.wofs + (size_t)i * wbytes, sm.wbar, i * sg.kc, n0, 0);
         __syncwarp();
@@ -59,6 +59,7 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
         const uint32_t hbytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * (uint32_t)sg.kc * 2u;
         const int tg = sg.taps == 9 ? p.hg : 1;  // taps per weight stage
         for (int c = 0; c < sg.nchunk; ++c) {
+          const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;  // weight chunk (hi+lo split: both halves share it)
           mbar_wait(&sm.hempty[hs], hphase ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(&sm.hfull[hs], hbytes);
@@ -77,7 +78,7 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
             if (elect_one()) {
               mbar_arrive_expect_tx(&sm.full[stage], wbytes * (uint32_t)tg);
               for (int g = 0; g < tg; ++g)
-                tma_load_3d(&p.tmW[s], sb + (size_t)g * wbytes, &sm.full[stage], ((t0 + g) * sg.nchunk + c) * sg.kc,
+                tma_load_3d(&p.tmW[s], sb + (size_t)g * wbytes, &sm.full[stage], ((t0 + g) * sg.nchunk_w + cw) * sg.kc,
                             o.n0, sg.per_image ? o.b0 : 0);
             }
             __syncwarp();
@@ -93,13 +94,14 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
           const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
           const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;
           for (int c = 0; c < sg.nchunk; ++c) {
+            const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;
             mbar_wait(&sm.empty[stage], phase ^ 1u);
             uint8_t* sa = sm.stage_base + (size_t)stage * p.stage_bytes;
             if (elect_one()) {
               mbar_arrive_expect_tx(&sm.full[stage], bytes);
               tma_load_4d(&p.tmA[s], sa, &sm.full[stage], sg.ch_off + c * sg.kc, o.x0 + dx + sg.xy_off,
                           o.y0 + dy + sg.xy_off, o.b0);
-              tma_load_3d(&p.tmW[s], sa + p.a_region, &sm.full[stage], (tap * sg.nchunk + c) * sg.kc, o.n0,
+              tma_load_3d(&p.tmW[s], sa + p.a_region, &sm.full[stage], (tap * sg.nchunk_w + cw) * sg.kc, o.n0,
                           sg.per_image ? o.b0 : 0);
             }
             __syncwarp();
@@ -154,9 +156,10 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
         const uint32_t hiA = umma_desc_hi(row_bytes, hw * row_bytes);
         const int ntaps = sg.taps;
         const int tg = ntaps == 9 ? p.hg : 1;
-        const uint32_t bstep = WSTAT ? (uint32_t)sg.nchunk * wbytes : wbytes;  // weight slab of the next tap
+        const uint32_t bstep = WSTAT ? (uint32_t)sg.nchunk_w * wbytes : wbytes;  // weight slab of the next tap
         const uint32_t row_step = hw * row_bytes;
         for (int c = 0; c < sg.nchunk; ++c) {
+          const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;  // resident weight chunk of this activation chunk
           mbar_wait(&sm.hfull[hs], hphase);
           tc_fence_after();
           const uint32_t hb = halo_base + hs * halo_bytes;
@@ -165,7 +168,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
           if (WSTAT && ntaps == 9) {
             // resident weights: nothing to wait for between taps, all 9 x KS MMAs of the chunk go out in one asm block
             const uint64_t adesc = umma_desc_make(hiA, hb);
-            const uint64_t bdesc = umma_desc_make(hiB, wstat_base + (uint32_t)sg.wofs + (uint32_t)c * wbytes);
+            const uint64_t bdesc = umma_desc_make(hiB, wstat_base + (uint32_t)sg.wofs + (uint32_t)cw * wbytes);
             if (elect_one()) {
               if (k64) umma_f16_ss_tile9<4>(d_tmem, adesc, bdesc, row_bytes >> 4, row_step >> 4, bstep >> 4, idesc, accumulate);
               else umma_f16_ss_tile9<2>(d_tmem, adesc, bdesc, row_bytes >> 4, row_step >> 4, bstep >> 4, idesc, accumulate);
@@ -176,7 +179,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
           for (int t0 = 0; t0 < ntaps; t0 += tg) {
             uint32_t sb;
             if (WSTAT) {
-              sb = wstat_base + (uint32_t)sg.wofs + (uint32_t)(t0 * sg.nchunk + c) * wbytes;
+              sb = wstat_base + (uint32_t)sg.wofs + (uint32_t)(t0 * sg.nchunk_w + cw) * wbytes;
             } else {
               mbar_wait(&sm.full[stage], phase);
               tc_fence_after();

@@ -42,12 +42,14 @@ struct BlockInfo {
   int fin, fout, fmid, r, level, in_shift, shortcut, styled;
   AceInfo ace[3];  // order: s, 0, 1 (s unused when !shortcut)
   int n_ace;
-  int t_shw, t_shb, t_c0w, t_c0b, t_c1w, t_c1b, t_csw;
+  int t_shw, t_shb, t_c0w, t_c0b, t_c1w, t_c1b, t_csw, t_cswlo;
+  int split_hs, split_h0, split_h1;  // fp16 hi+lo split of the conv_s / conv_0 / conv_1 input (chb_gen_config.precision)
   int64_t ws_xout;  // workspace offset of the block output
 };
 
 struct Step {
   ConvPlan plan;
+  int kind = 0;  // 0: conv_igemm launch, 1: image from the per-tap partial sums (img_from_taps)
   std::string name;
   int noise_ace_block = -1, noise_ace = -1;  // modulate steps: which noise plane
   bool final_image = false;
@@ -66,7 +68,8 @@ struct chb_generator {
   int n_styled = 0;
   int64_t weff_rows = 0;      // rows per image of the Weff table (each row = 32 fp16)
   int64_t noise_pix = 0;      // noise floats per image
-  int t_fcw, t_fcb, t_imgw, t_imgb, t_fcmuw, t_fcmub;
+  int t_fcw, t_fcb, t_imgw, t_imgb, t_fcmuw, t_fcmub, t_imgwy = -1, t_imgwylo = -1;
+  int64_t ws_y = 0;  // CHB_PREC_IMG: per-tap partial sums of conv_img, fp32 [B,S,S,32]
   // workspace layout (byte offsets, sized for max_batch)
   int64_t ws_bytes = 0;
   int64_t ws_labels, ws_codes32, ws_out, ws_codes16, ws_noise, ws_mu, ws_weff, ws_x0;
@@ -128,6 +131,9 @@ static void build_layout(chb_generator* g) {
     prev_r = b.r;
     b.shortcut = b.fin != b.fout;
     b.styled = specs[i].styled;
+    b.split_hs = (b.shortcut && (c.precision & CHB_PREC_SHORTCUT)) ? 1 : 0;
+    b.split_h0 = (c.precision & CHB_PREC_H0(i)) ? 1 : 0;
+    b.split_h1 = (c.precision & CHB_PREC_H1(i)) ? 1 : 0;
     b.n_ace = b.shortcut ? 3 : 2;
     const char* an[3] = {"ace_s", "ace_0", "ace_1"};
     int actv_off = 0;
@@ -160,6 +166,7 @@ static void build_layout(chb_generator* g) {
     b.t_c1w = add_tensor(g, b.name + ".conv_1.w", (int64_t)b.fout * 9 * b.fmid * 2, CHB_F16);
     b.t_c1b = add_tensor(g, b.name + ".conv_1.b", (int64_t)b.fout * 4, CHB_F32);
     b.t_csw = b.shortcut ? add_tensor(g, b.name + ".conv_s.w", (int64_t)b.fout * b.fin * 2, CHB_F16) : -1;
+    b.t_cswlo = b.split_hs ? add_tensor(g, b.name + ".conv_s.wlo", (int64_t)b.fout * b.fin * 2, CHB_F16) : -1;
     g->blocks.push_back(b);
   }
   g->noise_pix = noise_pix;
@@ -176,6 +183,11 @@ static void build_layout(chb_generator* g) {
   g->t_fcmub = add_tensor(g, "fcmu.b", (int64_t)c.label_nc * g->n_styled * L * 4, CHB_F32);
   g->t_imgw = add_tensor(g, "conv_img.w", (int64_t)16 * 9 * nf * 2, CHB_F16);
   g->t_imgb = add_tensor(g, "conv_img.b", (int64_t)16 * 4, CHB_F32);
+  if (c.precision & CHB_PREC_IMG) {
+    // conv_img as a 1x1 GEMM onto 27 (tap, out channel) partial sums + a 9-neighbour gather: rows tap*3 + co
+    g->t_imgwy = add_tensor(g, "conv_img.wy", (int64_t)32 * nf * 2, CHB_F16);
+    g->t_imgwylo = add_tensor(g, "conv_img.wylo", (int64_t)32 * nf * 2, CHB_F16);
+  }
 
   // ---------------- workspace
   const int64_t S = c.crop;
@@ -195,20 +207,26 @@ static void build_layout(chb_generator* g) {
   }
   g->ws_x0 = ws_alloc(g, (int64_t)B * g->sw * g->sw * 16 * nf * 4);
   g->debug["x_fc"] = {g->ws_x0, CHB_F32};
-  int64_t m_actv = 0, m_hin = 0, m_h1 = 0, m_dx0 = 0;
+  int64_t m_actv = 0, m_hs = 0, m_hin = 0, m_h1 = 0, m_dx0 = 0;
   for (auto& b : g->blocks) {
     const int64_t px = (int64_t)B * b.r * b.r;
     m_actv = std::max<int64_t>(m_actv, px * 128 * b.n_ace * 2);
-    m_hin = std::max<int64_t>(m_hin, px * b.fin * 2);
-    m_h1 = std::max<int64_t>(m_h1, px * b.fmid * 2);
+    m_hs = std::max<int64_t>(m_hs, px * b.fin * 2 * (b.split_hs ? 2 : 1));
+    m_hin = std::max<int64_t>(m_hin, px * b.fin * 2 * (b.split_h0 ? 2 : 1));
+    m_h1 = std::max<int64_t>(m_h1, px * b.fmid * 2 * (b.split_h1 ? 2 : 1));
     m_dx0 = std::max<int64_t>(m_dx0, px * b.fmid * 4);
     const bool last = (&b == &g->blocks.back());
-    b.ws_xout = ws_alloc(g, px * b.fout * (last ? 2 : 4));
+    // the last block's output feeds conv_img as an fp16 operand ([hi | lo] with CHB_PREC_IMG)
+    b.ws_xout = ws_alloc(g, px * b.fout * (last ? ((c.precision & CHB_PREC_IMG) ? 4 : 2) : 4));
     g->debug["x_" + b.name] = {b.ws_xout, last ? CHB_F16 : CHB_F32};
   }
   g->ws_actv = ws_alloc(g, m_actv);
-  g->ws_hs = ws_alloc(g, m_hin);
+  g->ws_hs = ws_alloc(g, m_hs);
   g->ws_h0 = ws_alloc(g, m_hin);
+  if (c.precision & CHB_PREC_IMG) {
+    g->ws_y = ws_alloc(g, (int64_t)B * S * S * 32 * 4);
+    g->debug["y_img"] = {g->ws_y, CHB_F32};
+  }
   g->ws_h1 = ws_alloc(g, m_h1);
   g->ws_dx0 = ws_alloc(g, m_dx0);
   g->debug["actv"] = {g->ws_actv, CHB_F16};
@@ -362,7 +380,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       nhwc_out(&d, ws + g->ws_actv, CHB_F16, r, actvC);
       if ((rc = push_step(steps, d, b.name + ".mlp_shared")) != CHB_OK) return rc;
     }
-    auto modulate = [&](int a, const float* x, int x_r, int x_shift, int xC, void* hout, int act) -> int {
+    auto modulate = [&](int a, const float* x, int x_r, int x_shift, int xC, void* hout, int act, int split) -> int {
       const AceInfo& A = b.ace[a];
       chb_conv_desc d = base_desc(B, r);
       int ns = 0;
@@ -382,19 +400,22 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.x = x; d.x_shift = x_shift;
       d.x_sx = xC; d.x_sy = (int64_t)x_r * xC; d.x_sb = (int64_t)x_r * x_r * xC;
       d.noise = reinterpret_cast<const float*>(ws + g->ws_noise) + (int64_t)B * A.noise_pix0;
-      nhwc_out(&d, hout, CHB_F16, r, A.C);
+      nhwc_out(&d, hout, CHB_F16, r, A.C * (split ? 2 : 1));  // split: pixel row = [hi(C) | lo(C)]
+      d.o_split = split; d.o_lo_off = split ? A.C : 0;
       const char* an3[3] = {"ace_s", "ace_0", "ace_1"};
       return push_step(steps, d, b.name + "." + an3[a] + ".gamma_beta_mod", (int)bi, a);
     };
     if (b.shortcut) {
-      if ((rc = modulate(0, xin, xin_r, b.in_shift, b.fin, ws + g->ws_hs, CHB_ACT_NONE)) != CHB_OK) return rc;
+      if ((rc = modulate(0, xin, xin_r, b.in_shift, b.fin, ws + g->ws_hs, CHB_ACT_NONE, b.split_hs)) != CHB_OK) return rc;
     }
-    if ((rc = modulate(1, xin, xin_r, b.in_shift, b.fin, ws + g->ws_h0, CHB_ACT_LRELU)) != CHB_OK) return rc;
+    if ((rc = modulate(1, xin, xin_r, b.in_shift, b.fin, ws + g->ws_h0, CHB_ACT_LRELU, b.split_h0)) != CHB_OK) return rc;
     // dx = conv_0(lrelu(ace_0(x)))   (architecture.py:73-75)
     {
       chb_conv_desc d = base_desc(B, r);
       d.nseg = 1;
-      d.seg[0] = make_seg(ws + g->ws_h0, r, b.fin, 0, b.fin, 9, blobp(g, b.t_c0w));
+      const int m0 = b.split_h0 ? 2 : 1;  // [hi | lo] halves share conv_0's weights
+      d.seg[0] = make_seg(ws + g->ws_h0, r, b.fin * m0, 0, b.fin * m0, 9, blobp(g, b.t_c0w));
+      d.seg[0].w_dup = m0;
       d.N = d.Nrows = b.fmid; d.BN = b.fmid < 256 ? b.fmid : 256;
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c0b));
@@ -402,14 +423,21 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       if ((rc = push_step(steps, d, b.name + ".conv_0")) != CHB_OK) return rc;
     }
     if ((rc = modulate(2, reinterpret_cast<const float*>(ws + g->ws_dx0), r, 0, b.fmid, ws + g->ws_h1,
-                       CHB_ACT_LRELU)) != CHB_OK)
+                       CHB_ACT_LRELU, b.split_h1)) != CHB_OK)
       return rc;
     // out = x_s + conv_1(lrelu(ace_1(dx)))   (architecture.py:77-84); conv_s rides along as a 1x1 K-segment
     {
       chb_conv_desc d = base_desc(B, r);
       int ns = 0;
-      d.seg[ns++] = make_seg(ws + g->ws_h1, r, b.fmid, 0, b.fmid, 9, blobp(g, b.t_c1w));
-      if (b.shortcut) {
+      const int m1 = b.split_h1 ? 2 : 1;
+      d.seg[ns] = make_seg(ws + g->ws_h1, r, b.fmid * m1, 0, b.fmid * m1, 9, blobp(g, b.t_c1w));
+      d.seg[ns++].w_dup = m1;
+      if (b.shortcut && b.split_hs) {
+        // x_s = conv_s(h_s) to ~2^-22: (hs_hi + hs_lo) * ws_hi + hs_hi * ws_lo, three 1x1 K-segments' worth
+        d.seg[ns] = make_seg(ws + g->ws_hs, r, b.fin * 2, 0, b.fin * 2, 1, blobp(g, b.t_csw));
+        d.seg[ns++].w_dup = 2;
+        d.seg[ns++] = make_seg(ws + g->ws_hs, r, b.fin * 2, 0, b.fin, 1, blobp(g, b.t_cswlo));
+      } else if (b.shortcut) {
         d.seg[ns++] = make_seg(ws + g->ws_hs, r, b.fin, 0, b.fin, 1, blobp(g, b.t_csw));
       } else {
         d.res = xin; d.r_shift = b.in_shift;
@@ -420,14 +448,40 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.epi = CHB_EPI_PLAIN;
       d.act = last ? CHB_ACT_LRELU : CHB_ACT_NONE;  // generator.py:107 leaky_relu before conv_img
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c1b));
-      nhwc_out(&d, ws + b.ws_xout, last ? CHB_F16 : CHB_F32, r, b.fout);
+      const int lsplit = (last && (c.precision & CHB_PREC_IMG)) ? 1 : 0;
+      nhwc_out(&d, ws + b.ws_xout, last ? CHB_F16 : CHB_F32, r, b.fout * (lsplit ? 2 : 1));
+      d.o_split = lsplit; d.o_lo_off = lsplit ? b.fout : 0;
       if ((rc = push_step(steps, d, b.name + (b.shortcut ? ".conv_1+conv_s" : ".conv_1+res"))) != CHB_OK) return rc;
     }
     xin = reinterpret_cast<const float*>(ws + b.ws_xout);
     xin_r = r;
   }
   // ---- image = tanh(conv_img(lrelu(x)))   (generator.py:107-108), fp32 NCHW
-  {
+  if (c.precision & CHB_PREC_IMG) {
+    // conv_img has 3 output channels: as an implicit GEMM with N = 16 every MMA still reads a full 128-row A tile per
+    // K step (A-bandwidth bound).  Instead ONE 1x1 GEMM computes the 27 per-(tap, channel) partial sums
+    // Y[p][tap*3+co] = sum_ci x[p][ci] * W[co][ci][tap] (K = 64 instead of 576), on the hi+lo split input and weights
+    // (x_hi + x_lo) * w_hi + x_hi * w_lo, and a small gather kernel adds the nine neighbours' sums, the bias and tanh.
+    const BlockInfo& b = g->blocks.back();
+    const int r = b.r;
+    chb_conv_desc d = base_desc(B, r);
+    d.nseg = 2;
+    d.seg[0] = make_seg(ws + b.ws_xout, r, 2 * b.fout, 0, 2 * b.fout, 1, blobp(g, g->t_imgwy));
+    d.seg[0].w_dup = 2;
+    d.seg[1] = make_seg(ws + b.ws_xout, r, 2 * b.fout, 0, b.fout, 1, blobp(g, g->t_imgwylo));
+    d.N = d.Nrows = 32; d.BN = 32;
+    d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
+    nhwc_out(&d, ws + g->ws_y, CHB_F32, r, 32);
+    if ((rc = push_step(steps, d, "conv_img.taps")) != CHB_OK) return rc;
+    Step s;
+    s.name = "conv_img.gather+tanh";
+    s.kind = 1;
+    s.final_image = true;
+    memset(&s.plan.kp, 0, sizeof s.plan.kp);
+    memset(&s.plan.desc, 0, sizeof s.plan.desc);
+    s.plan.grid = 0; s.plan.smem_bytes = 0; s.plan.flops = 0;
+    steps.push_back(s);
+  } else {
     const BlockInfo& b = g->blocks.back();
     const int r = b.r;
     chb_conv_desc d = base_desc(B, r);
@@ -630,7 +684,10 @@ static int forward_impl(chb_generator* g, const uint8_t* labels, const float* co
   if (evs && iev < nev) cudaEventRecord(evs[iev++], stream);
   for (const Step& s : *steps) {
     if (g->step_limit >= 0 && nrun++ >= g->step_limit) break;
-    if (s.final_image && out != reinterpret_cast<float*>(ws + g->ws_out)) {
+    if (s.kind == 1) {
+      rc = img_from_taps(reinterpret_cast<const float*>(ws + g->ws_y),
+                         reinterpret_cast<const float*>(blobp(g, g->t_imgb)), out, B, c.crop, stream);
+    } else if (s.final_image && out != reinterpret_cast<float*>(ws + g->ws_out)) {
       ConvPlan p = s.plan;
       p.kp.e.out = out;
       p.desc.out = out;
@@ -768,7 +825,7 @@ int chb_generator_launches(const chb_generator* g) {
   if (g->n_styled > 0) n += 1 + g->n_styled;
   n += 1;  // fc
   for (auto& b : g->blocks) n += 1 + b.n_ace + 2;
-  return n + 1;  // conv_img
+  return n + ((g->cfg.precision & CHB_PREC_IMG) ? 2 : 1);  // conv_img (taps GEMM + gather, or one conv)
 }
 
 double chb_generator_flops(const chb_generator* g_, int B) {

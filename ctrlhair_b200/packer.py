@@ -25,6 +25,13 @@ def _sn(sd, p):
     return w / sigma
 
 
+def _lo(w, wd):
+    """fp16 hi+lo split: the part of fp32 `w` that rounding to fp16 drops (zeros when packing in fp32)."""
+    if wd != torch.float16:
+        return torch.zeros_like(w).to(wd)
+    return (w.float() - w.to(torch.float16).float()).to(torch.float16)
+
+
 def _k_major(w):
     """[N, C, kh, kw] -> [N, kh*kw*C] with k = tap*C + c."""
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
@@ -109,7 +116,9 @@ def pack_generator(sd, ngf=64, label_nc=19, weight_dtype=torch.float16):
         out[name + ".conv_1.w"] = _k_major(_sn(sd, name + ".conv_1")).to(wd)
         out[name + ".conv_1.b"] = sd[name + ".conv_1.bias"].float()
         if fin != fout:
-            out[name + ".conv_s.w"] = _k_major(_sn(sd, name + ".conv_s")).to(wd)
+            ws = _k_major(_sn(sd, name + ".conv_s"))
+            out[name + ".conv_s.w"] = ws.to(wd)
+            out[name + ".conv_s.wlo"] = _lo(ws, wd)  # optional (CHB_PREC_SHORTCUT): fp16 rounding residual of conv_s.w
     # fc_mu: [19][n_styled*512][512], class-major so that "image == class" in the grouped GEMM
     out["fcmu.w"] = torch.cat(fcmu_w, 1).to(wd)        # [19, n_styled*512, 512]
     out["fcmu.b"] = torch.cat(fcmu_b, 1)               # [19, n_styled*512]
@@ -119,4 +128,17 @@ def pack_generator(sd, ngf=64, label_nc=19, weight_dtype=torch.float16):
     bi[:3] = sd["conv_img.bias"].float()
     out["conv_img.w"] = wi.to(wd)
     out["conv_img.b"] = bi
+    # optional (CHB_PREC_IMG): conv_img as a 1x1 GEMM onto per-(tap, out channel) partial sums, rows tap*3 + co
+    wy = torch.zeros((32, ngf), dtype=torch.float32)
+    wy[:27] = sd["conv_img.weight"].float().permute(2, 3, 0, 1).reshape(27, ngf)   # [ky, kx, co, ci]
+    out["conv_img.wy"] = wy.to(wd)
+    out["conv_img.wylo"] = _lo(wy, wd)
     return out
+
+
+OPTIONAL = (".conv_s.wlo", "conv_img.wy", "conv_img.wylo")
+
+
+def is_optional(name):
+    """Tensors only some precision policies place in the blob (chb_gen_config.precision)."""
+    return name.endswith(OPTIONAL)

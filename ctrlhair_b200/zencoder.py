@@ -31,8 +31,12 @@ def pack_zencoder(sd, weight_dtype=torch.float16):
     return out
 
 
-class ZencoderB200:
+class ZencoderB200(torch.nn.Module):
+    """nn.Module for the same reason as SeanGeneratorB200: the reference reaches it as the child module
+    `netG.Zencoder` (pix2pix_model.py:71)."""
+
     def __init__(self, crop=256, label_nc=19, max_batch=1, device=None):
+        super().__init__()
         if not torch.cuda.is_available():
             raise _lib.ChbError("ZencoderB200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _lib.load()
@@ -99,8 +103,6 @@ class ZencoderB200:
                                                      C.c_void_p(labels.data_ptr()), C.c_void_p(out.data_ptr()), B,
                                                      C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         return out
-
-    __call__ = forward
 
     def forward_host(self, img, labels):
         img = torch.as_tensor(img).to(torch.float32).contiguous()

@@ -51,6 +51,9 @@ typedef struct {
   int64_t w_sb;       /* per_image: element stride between images (0 = dense Nrows*taps*C)       */
   int a_pad;          /* the A tensor carries an explicit border of a_pad pixels per side (e.g. a reflection
                          pad): its extent is (H+2*a_pad) x (W+2*a_pad); output (y,x) reads (y+a_pad+dy, x+a_pad+dx) */
+  int w_dup;          /* 0/1: weights span all C channels.  2: the C channels are [hi half | lo half] of an fp16
+                         hi+lo split activation (see o_split) and BOTH halves use the same weights
+                         [(B,) Nrows, taps*(C/2)] — the low half restores the bits fp16 rounding dropped */
 } chb_conv_seg;
 
 enum { CHB_EPI_PLAIN = 0, CHB_EPI_MODULATE = 1 };
@@ -61,7 +64,7 @@ typedef struct {
   int B, H, W;        /* images, rows, columns of the output (== input) grid                     */
   int TW, TH, TB;     /* pixel tile: TW*TH*TB <= 128 rows of the MMA                             */
   int nseg;
-  chb_conv_seg seg[3];
+  chb_conv_seg seg[4];
   int N;              /* valid output columns                                                    */
   int Nrows;          /* weight rows, multiple of BN                                             */
   int BN;             /* N tile: 16..256, multiple of 16                                         */
@@ -78,9 +81,16 @@ typedef struct {
   const float* x; int64_t x_sb, x_sy, x_sx; int x_shift;
   const float* noise; /* [B, W, H] — the reference's randn(B,W,H,1) plane, read transposed; may be NULL */
   const float* chan;  /* planar [3][C]: a = rstd | c = -mean*rstd | nv = noise_var*rstd (C = N/2)         */
+  /* fp16 hi+lo split output (out_dtype CHB_F16, channels-last): besides hi = fp16(v) at channel n, the rounding
+     residual lo = fp16(v - hi) is stored at channel n + o_lo_off, so that a consumer segment with w_dup = 2 sees
+     v to ~2^-22.  0 = off. */
+  int o_split; int64_t o_lo_off;
 } chb_conv_desc;
 
 enum { CHB_IMPL_TCGEN05 = 0, CHB_IMPL_SIMT_DEBUG = 1 };
+/* sizeof() of the ABI structs as this library was compiled: 0 chb_conv_seg, 1 chb_conv_desc, 2 chb_gen_config,
+ * 3 chb_mlp_layer (-1: unknown index).  A foreign-language binding checks its mirror against these at load time. */
+int chb_struct_size(int which);
 /* One-shot: encode tensor maps and launch. impl selects the tcgen05 kernel or the slow SIMT checker kernel. */
 int chb_conv_run(const chb_conv_desc* d, int impl, void* stream);
 
@@ -127,7 +137,14 @@ typedef struct {
   int crop;       /* 256 (or 512); multiple of 32                                                */
   int style_len;  /* 512                                                                         */
   int max_batch;  /* workspace is sized for this many images per forward                         */
+  unsigned precision; /* where fp16 operand rounding is compensated by an fp16 hi+lo split (0 = nowhere):
+                         CHB_PREC_IMG      conv_img input and weights (generator.py:107-108)
+                         CHB_PREC_SHORTCUT conv_s input and weights in every learned-shortcut block (architecture.py:86-93)
+                         CHB_PREC_H1(i) / CHB_PREC_H0(i)  the input of conv_1 / conv_0 of block i (0 = head_0 .. 6 = up_3) */
 } chb_gen_config;
+enum { CHB_PREC_IMG = 1u, CHB_PREC_SHORTCUT = 2u };
+#define CHB_PREC_H1(i) (1u << (8 + (i)))
+#define CHB_PREC_H0(i) (1u << (16 + (i)))
 
 typedef struct chb_generator chb_generator;
 

@@ -24,8 +24,24 @@ def _untile(t, bn):
     return v[:, :, 0].reshape(t.shape[0], N // 2, *t.shape[2:]), v[:, :, 1].reshape(t.shape[0], N // 2, *t.shape[2:])
 
 
-def emulate(packed, labels, codes, noise_planes, ngf=64, label_nc=19, round16=False):
+def _split16(t):
+    """what an fp16 hi+lo split operand carries: hi = fp16(t), lo = fp16(t - hi)."""
+    hi = t.half().float()
+    return hi, (t - hi).half().float()
+
+
+def emulate(packed, labels, codes, noise_planes, ngf=64, label_nc=19, round16=False, precision=0):
+    """precision: chb_gen_config.precision flags (only meaningful with round16): the sites whose fp16 rounding the
+    kernels compensate with an hi+lo split are modelled the same way here."""
     r16 = (lambda t: t.half().float()) if round16 else (lambda t: t)
+
+    def rsplit(t, on):  # activation stored as [hi | lo] when `on`: both halves meet the same (fp16) weights
+        if not (round16 and on):
+            return r16(t)
+        hi, lo = _split16(t)
+        return hi + lo
+
+    PREC_IMG, PREC_SHORTCUT = 1, 2
     B, S = labels.shape[0], labels.shape[1]
     sw = S // 32
     onehot_full = F.one_hot(labels.long(), 32).permute(0, 3, 1, 2).float()  # [B,32,S,S]
@@ -44,7 +60,10 @@ def emulate(packed, labels, codes, noise_planes, ngf=64, label_nc=19, round16=Fa
     style_idx = 0
     mults = (1, 2, 2, 4, 8, 16, 32)
     prev_r = sw
-    for (name, fi, fo, styled), mul in zip(BLOCKS, mults):
+    for bidx, ((name, fi, fo, styled), mul) in enumerate(zip(BLOCKS, mults)):
+        split_hs = bool(precision & PREC_SHORTCUT)
+        split_h1 = bool(precision & (1 << (8 + bidx)))
+        split_h0 = bool(precision & (1 << (16 + bidx)))
         fin, fout = fi * ngf, fo * ngf
         r = sw * mul
         if r != prev_r:
@@ -55,7 +74,7 @@ def emulate(packed, labels, codes, noise_planes, ngf=64, label_nc=19, round16=Fa
         actv_all = r16(F.relu(F.conv2d(oh, _unpack(packed[name + ".sh.w"], 32), packed[name + ".sh.b"], padding=1)))
         hs = {}
 
-        def modulate(ai, xin, act):
+        def modulate(ai, xin, act, split=False):
             nonlocal style_idx
             a, C = aces[ai]
             p = "%s.%s" % (name, a)
@@ -77,21 +96,32 @@ def emulate(packed, labels, codes, noise_planes, ngf=64, label_nc=19, round16=Fa
             h = xn * (1 + g) + be
             if act:
                 h = F.leaky_relu(h, 0.2)
-            return r16(h)
+            return h if split is None else rsplit(h, split)
 
         ai = 0
         if fin != fout:
-            hs["s"] = modulate(0, x, False)
+            hs["s"] = modulate(0, x, False, None)
             ai = 1
-        h0 = modulate(ai, x, True)
+        h0 = modulate(ai, x, True, split_h0)
         dx0 = F.conv2d(h0, _unpack(packed[name + ".conv_0.w"], fin), packed[name + ".conv_0.b"], padding=1)
-        h1 = modulate(ai + 1, dx0, True)
+        h1 = modulate(ai + 1, dx0, True, split_h1)
         out = F.conv2d(h1, _unpack(packed[name + ".conv_1.w"], min(fin, fout)), packed[name + ".conv_1.b"], padding=1)
         if fin != fout:
-            out = out + F.conv2d(hs["s"], _unpack(packed[name + ".conv_s.w"], fin, 1))
+            ws = _unpack(packed[name + ".conv_s.w"], fin, 1)
+            if round16 and split_hs:  # (hs_hi + hs_lo) * ws_hi + hs_hi * ws_lo
+                hi, lo = _split16(hs["s"])
+                out = out + F.conv2d(hi + lo, ws) + F.conv2d(hi, _unpack(packed[name + ".conv_s.wlo"], fin, 1))
+            else:
+                out = out + F.conv2d(r16(hs["s"]), ws)
         else:
             out = out + x
         x = out
-    x = r16(F.leaky_relu(x, 0.2))
-    img = F.conv2d(x, _unpack(packed["conv_img.w"], ngf)[:3], packed["conv_img.b"][:3], padding=1)
+    x = F.leaky_relu(x, 0.2)
+    if round16 and (precision & PREC_IMG):
+        hi, lo = _split16(x)
+        wy = packed["conv_img.wy"].float()[:27].reshape(3, 3, 3, ngf).permute(2, 3, 0, 1)      # [co, ci, ky, kx]
+        wl = packed["conv_img.wylo"].float()[:27].reshape(3, 3, 3, ngf).permute(2, 3, 0, 1)
+        img = F.conv2d(hi + lo, wy, packed["conv_img.b"][:3], padding=1) + F.conv2d(hi, wl, padding=1)
+    else:
+        img = F.conv2d(r16(x), _unpack(packed["conv_img.w"], ngf)[:3], packed["conv_img.b"][:3], padding=1)
     return torch.tanh(img)

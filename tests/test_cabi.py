@@ -26,9 +26,12 @@ def test_header_symbols_exported(lib):
 
 
 def test_struct_sizes_match_header(lib):
-    # chb_conv_seg: 2 pointers, 4 int64, 5 ints (+pad); guards against silent ABI drift of the ctypes mirror
-    assert C.sizeof(_lib.ConvSeg) == 80
-    assert C.sizeof(_lib.GenConfig) == 20
+    # guards against silent ABI drift of the ctypes mirror: the library reports sizeof() of its own structs
+    assert C.sizeof(_lib.ConvSeg) == lib.chb_struct_size(0) == 80
+    assert C.sizeof(_lib.ConvDesc) == lib.chb_struct_size(1)
+    assert C.sizeof(_lib.GenConfig) == lib.chb_struct_size(2) == 24
+    assert C.sizeof(_lib.MlpLayer) == lib.chb_struct_size(3)
+    assert lib.chb_struct_size(99) == -1
 
 
 def test_version_and_argument_errors(lib):

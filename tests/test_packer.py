@@ -35,14 +35,24 @@ def test_fp16_storage_forecast(synthetic_sd):
     """fp16 weights + fp16 MMA operands, fp32 everywhere else: the error budget the CUDA path is held to."""
     labels, codes, noise = synth.make_labels(2, 64, "iid"), synth.make_codes(2), synth.make_noise(2, 64)
     ref = so.generator_forward(synthetic_sd, labels, codes, noise)
-    out = pe.emulate(packer.pack_generator(synthetic_sd), labels, codes, noise, round16=True)
+    packed = packer.pack_generator(synthetic_sd)
+    out = pe.emulate(packed, labels, codes, noise, round16=True)
     assert float((out - ref).norm() / ref.norm()) < 1e-3
     assert float((out - ref).abs().max() / ref.abs().max()) < 3e-3
+    # with the hi+lo split policies (chb_gen_config.precision) the forecast falls under north_star's 1e-3 max-norm
+    from ctrlhair_b200.generator import PRECISION_POLICIES
+    errs = {}
+    for policy in ("shortcut", "parity", "full"):
+        o = pe.emulate(packed, labels, codes, noise, round16=True, precision=PRECISION_POLICIES[policy])
+        errs[policy] = float((o - ref).abs().max() / ref.abs().max())
+    assert errs["parity"] < 1e-3 and errs["full"] < 1e-3 and errs["full"] < errs["shortcut"], errs
 
 
-def test_packer_matches_library_layout(synthetic_sd, lib):
+@pytest.mark.parametrize("policy", ["fast", "shortcut", "parity", "full"])
+def test_packer_matches_library_layout(synthetic_sd, lib, policy):
     """Every tensor the library's blob layout names is produced by the packer with the right dtype and size."""
-    cfg = _lib.GenConfig(64, 19, 256, 512, 4)
+    from ctrlhair_b200.generator import PRECISION_POLICIES
+    cfg = _lib.GenConfig(64, 19, 256, 512, 4, PRECISION_POLICIES[policy])
     h = C.c_void_p()
     assert lib.chb_generator_create(C.byref(cfg), C.byref(h)) == 0
     try:
@@ -60,10 +70,11 @@ def test_packer_matches_library_layout(synthetic_sd, lib):
             assert off.value % 256 == 0 and off.value >= end
             end = off.value + nb.value
             seen.add(k)
-        assert seen == set(packed)
+        optional = {k for k in packed if packer.is_optional(k)}
+        assert seen == (set(packed) - optional if policy == "fast" else set(packed))
         assert lib.chb_generator_blob_bytes(h) >= end
         # 267 M reference parameters -> ~534 MB of fp16 (one-hot padding 19->32 adds a little)
         assert 5.0e8 < lib.chb_generator_blob_bytes(h) < 6.0e8
-        assert lib.chb_generator_launches(h) == 60
+        assert lib.chb_generator_launches(h) == (60 if policy == "fast" else 61)
     finally:
         lib.chb_generator_destroy(h)
