@@ -205,7 +205,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     B, crop = args.batch, args.crop
-    gen = SeanGeneratorB200(crop=crop, max_batch=B, device=dev)
+    gen = SeanGeneratorB200(crop=crop, max_batch=B, device=dev, precision=args.precision)
     # one weight-blob broadcast at start-up (rank 0 packs the reference-format checkpoint)
     blob = gen.build_blob(synth.make_state_dict()) if rank == 0 else None
     blob = parallel.broadcast_blob(blob, gen.blob_bytes(), src=0, device=dev)
@@ -314,6 +314,29 @@ def run_ours(args):
                        peaks["tflops_burst"],
         "top_launches": [{"name": n, "ms": round(m, 4), "issued_tflops": f / (m * 1e-3) / 1e12} for m, n, f in top],
     }
+    # ---------------- interactive latency: one image per call (the reference's only real call pattern, gen_img)
+    lat = None
+    if rank == 0:
+        l1, c1 = labels_d[:1].contiguous(), codes_d[:1].contiguous()
+        o1 = torch.empty((1, 3, crop, crop), dtype=torch.float32, device=dev)
+        res = {}
+        for mode, use_graph in (("graph", True), ("launches", False)):
+            for i in range(5):
+                gen.forward_labels(l1, c1, seed=i, out=o1, graph=use_graph)
+            torch.cuda.synchronize(dev)
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_lat = 50
+            t0 = time.perf_counter()
+            ea.record()
+            for i in range(n_lat):
+                gen.forward_labels(l1, c1, seed=10 + i, out=o1, graph=use_graph)
+            eb.record()
+            torch.cuda.synchronize(dev)
+            res[mode] = {"device_ms": ea.elapsed_time(eb) / n_lat, "wall_ms": (time.perf_counter() - t0) / n_lat * 1e3}
+        lat = {"batch": 1, "crop": crop, "ms": res["graph"]["device_ms"], "graph": res["graph"], "launches": res["launches"],
+               "weight_stream_floor_ms": gen.blob_bytes() / (load_peaks()["hbm_gbs"] * 1e9) * 1e3,
+               "what": "SeanGeneratorB200.forward_labels(B=1, graph=True): one captured CUDA graph per call, back to "
+                       "back; floor = packed weight bytes / measured HBM copy bandwidth"}
     cpu = parity = ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_throughput(args.cpu_images, crop, warm=1)
@@ -329,6 +352,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "SEAN generator fwd fp16 (fp32 accumulate), batch=64 per GPU, 256x256, synthetic "
                                    "19-class blocky masks + N(0,0.135^2) style codes, device-drawn ACE noise",
+                       "precision_policy": "%s (chb_gen_config.precision = 0x%x)" % (args.precision, gen.precision),
                        "batch_per_gpu": B, "crop": crop, "ngf": 64, "parallelism": "image-batch shard x%d" % world,
                        "l2": "per-step working set (weights 0.53 GB + activations > 10 GB) exceeds the 126 MB L2; "
                              "no explicit flush", "outputs_finite": finite,
@@ -343,6 +367,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "parity": parity,
             "reference_gpu": ref_gpu,
+            "latency_b1_ms": lat,
         }
         emit(line)
     if world > 1:
@@ -381,6 +406,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--precision", default="parity", help="precision policy of SeanGeneratorB200 (parity | fast | full | shortcut)")
     ap.add_argument("--no-reference-gpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -123,6 +123,8 @@ SYMBOLS = [
     ("chb_generator_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("chb_generator_forward", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("chb_generator_forward_graph", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_generator_forward_host", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("chb_generator_forward_host_async", C.c_int,

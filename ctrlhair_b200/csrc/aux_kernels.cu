@@ -67,7 +67,8 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
 }
 
 __global__ void noise_fill_kernel(float* out, long long n, uint64_t seed, uint64_t offset) {
-  const long long quads = (n + 3) / 4;
+  const long long quads = (n + 3) / 4;  // (`seed` is a plain kernel parameter: a captured CUDA graph re-seeds this node
+                                        //  with cudaGraphExecKernelNodeSetParams, see chb_generator_forward_graph)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < quads;
        i += (long long)gridDim.x * blockDim.x) {
     const uint64_t ctr = (uint64_t)i + offset;
@@ -239,6 +240,8 @@ int chb_onehot_pyramid(const uint8_t* labels, int B, int S, int nlevels, const i
                        int nclass, void* stream) {
   return chb::onehot_pyramid_ones(labels, B, S, nlevels, shifts, outs, nclass, 0, 0, stream);
 }
+
+const void* chb_noise_fill_kernel_address(void) { return reinterpret_cast<const void*>(&chb::noise_fill_kernel); }
 
 int chb_noise_fill(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
   using namespace chb;

@@ -492,6 +492,8 @@ static int ensure_smem_attr() {
   return CHB_OK;
 }
 
+int ensure_conv_kernels_ready() { return ensure_smem_attr(); }
+
 int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream) {
   if (impl == CHB_IMPL_SIMT_DEBUG) {
     SimtParams sp;

@@ -90,9 +90,11 @@ struct ConvPlan {
 void set_error(const std::string& msg);
 int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan);
 int launch_conv_plan(const ConvPlan& plan, int impl, cudaStream_t stream);
+int ensure_conv_kernels_ready();  // one-time cudaFuncSetAttribute of every instantiation (not legal inside a capture)
 int device_sm_count();
 int onehot_pyramid_ones(const uint8_t* labels, int B, int S, int nlevels, const int* shifts, void* const* outs,
                         int nclass, int ones_ch0, int ones_n, void* stream);
+extern "C" const void* chb_noise_fill_kernel_address(void);
 int img_from_taps(const float* y, const float* bias, float* out, int B, int S, cudaStream_t stream);
 int codes_cast_transpose(const float* in, void* out, int B, int NC, int L, cudaStream_t stream);
 

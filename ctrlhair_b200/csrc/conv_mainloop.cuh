@@ -56,15 +56,21 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
       const SegK sg = p.seg[s];
       const uint32_t wbytes = (uint32_t)p.BN * (uint32_t)sg.kc * 2u;
       if (WSTAT || sg.halo) {
-        const uint32_t hbytes = (uint32_t)((p.TW + 2) * (p.TH + 2)) * (uint32_t)sg.kc * 2u;
+        // a 1x1 segment needs no halo: its exact 128-row tile goes into the halo ring buffer instead (29 % fewer bytes)
+        const bool exact = sg.taps == 1;
+        const uint32_t hbytes = (exact ? (uint32_t)p.rows : (uint32_t)((p.TW + 2) * (p.TH + 2))) * (uint32_t)sg.kc * 2u;
         const int tg = sg.taps == 9 ? p.hg : 1;  // taps per weight stage
         for (int c = 0; c < sg.nchunk; ++c) {
           const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;  // weight chunk (hi+lo split: both halves share it)
           mbar_wait(&sm.hempty[hs], hphase ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(&sm.hfull[hs], hbytes);
-            tma_load_4d(&p.tmH[s], sm.halo_base + (size_t)hs * p.halo_buf_bytes, &sm.hfull[hs], sg.ch_off + c * sg.kc,
-                        o.x0 - 1 + sg.xy_off, o.y0 - 1 + sg.xy_off, o.b0);
+            if (exact)
+              tma_load_4d(&p.tmA[s], sm.halo_base + (size_t)hs * p.halo_buf_bytes, &sm.hfull[hs], sg.ch_off + c * sg.kc,
+                          o.x0 + sg.xy_off, o.y0 + sg.xy_off, o.b0);
+            else
+              tma_load_4d(&p.tmH[s], sm.halo_base + (size_t)hs * p.halo_buf_bytes, &sm.hfull[hs], sg.ch_off + c * sg.kc,
+                          o.x0 - 1 + sg.xy_off, o.y0 - 1 + sg.xy_off, o.b0);
           }
           __syncwarp();
           if (++hs == nh) {
@@ -153,8 +159,9 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
         // of the UMMA operand is one tile row, (TW+2)*row_bytes apart.  The swizzle is a function of the absolute
         // shared-memory address bits (verified on B200: base_offset must stay 0 for views that start off the
         // swizzle-atom boundary), so a shifted start address is all a tap needs.
-        const uint32_t hiA = umma_desc_hi(row_bytes, hw * row_bytes);
         const int ntaps = sg.taps;
+        // 3x3: 8-row core groups are tile rows of the halo tile, (TW+2) pixels apart; 1x1: the exact tile, 8 rows apart
+        const uint32_t hiA = umma_desc_hi(row_bytes, ntaps == 9 ? hw * row_bytes : 8u * row_bytes);
         const int tg = ntaps == 9 ? p.hg : 1;
         const uint32_t bstep = WSTAT ? (uint32_t)sg.nchunk_w * wbytes : wbytes;  // weight slab of the next tap
         const uint32_t row_step = hw * row_bytes;
@@ -163,7 +170,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
           mbar_wait(&sm.hfull[hs], hphase);
           tc_fence_after();
           const uint32_t hb = halo_base + hs * halo_bytes;
-          uint32_t voff = ntaps == 9 ? 0u : row_step + row_bytes;  // view offset of the current tap
+          uint32_t voff = 0u;  // view offset of the current tap (a 1x1 segment holds its exact tile)
           uint32_t kx = 0;
           if (WSTAT && ntaps == 9) {
             // resident weights: nothing to wait for between taps, all 9 x KS MMAs of the chunk go out in one asm block

@@ -83,6 +83,18 @@ struct chb_generator {
   const uint8_t* blob = nullptr;
   uint8_t* ws = nullptr;
   std::map<int, std::vector<Step>> plans;  // keyed by batch size
+  // chb_generator_forward_graph: the whole schedule of a batch size captured once (device-drawn noise; its seed node
+  // is re-parameterised per call), inputs / image staged through the first set of I/O buffers of the workspace
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t noise_node = nullptr;
+    cudaKernelNodeParams noise_params;
+    float* nz = nullptr;
+    long long nz_n = 0;
+    uint64_t seed = 0, offset = 0;
+    void* args[4];
+  };
+  std::map<int, GraphEntry*> graphs;
   std::map<std::string, std::pair<int64_t, int>> debug;  // name -> (ws offset, dtype)
   int step_limit = -1;  // debug: run only the first n conv steps
 };
@@ -264,6 +276,19 @@ static chb_conv_seg make_seg(const void* a, int r, int Ca, int ch_off, int C, in
   return s;
 }
 
+// N tile of a PLAIN conv.  256 (or the whole width) at production batch sizes; for a handful of images (interactive
+// B = 1: hair_editor.py:159-179) the 8x8 .. 32x32 layers have 1-8 pixel tiles, so the N tile narrows (down to 64) until
+// ~64 CTAs share the streaming of the layer's weight matrix (19 MB for a 1024 -> 1024 conv).  The K order inside a tile
+// does not depend on BN, so results stay bitwise identical across batch sizes.
+static int pick_bn(int N, int B, int r) {
+  int bn = N < 256 ? N : 256;
+  int tw, th;
+  tw = r < 8 ? r : 8; th = r < 16 ? r : 16;
+  const long long m_tiles = (long long)B * ((r + tw - 1) / tw) * ((r + th - 1) / th);
+  while (bn > 64 && bn % 128 == 0 && m_tiles * (N / bn) < 64) bn /= 2;
+  return bn;
+}
+
 static chb_conv_desc base_desc(int B, int r) {
   chb_conv_desc d;
   memset(&d, 0, sizeof d);
@@ -356,7 +381,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     chb_conv_desc d = base_desc(B, g->sw);
     d.nseg = 1;
     d.seg[0] = make_seg(ws + g->ws_onehot[0], g->sw, 32, 0, 32, 9, blobp(g, g->t_fcw));
-    d.N = d.Nrows = 16 * nf; d.BN = 256;
+    d.N = d.Nrows = 16 * nf; d.BN = pick_bn(16 * nf, B, g->sw);
     d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
     d.bias = nullptr;  // carried by the constant one-hot channels (fc.w centre tap); fc.b stays in the blob for checkers
     nhwc_out(&d, ws + g->ws_x0, CHB_F32, g->sw, 16 * nf);
@@ -416,7 +441,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       const int m0 = b.split_h0 ? 2 : 1;  // [hi | lo] halves share conv_0's weights
       d.seg[0] = make_seg(ws + g->ws_h0, r, b.fin * m0, 0, b.fin * m0, 9, blobp(g, b.t_c0w));
       d.seg[0].w_dup = m0;
-      d.N = d.Nrows = b.fmid; d.BN = b.fmid < 256 ? b.fmid : 256;
+      d.N = d.Nrows = b.fmid; d.BN = pick_bn(b.fmid, B, r);
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c0b));
       nhwc_out(&d, ws + g->ws_dx0, CHB_F32, r, b.fmid);
@@ -444,7 +469,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
         d.r_sx = b.fin; d.r_sy = (int64_t)xin_r * b.fin; d.r_sb = (int64_t)xin_r * xin_r * b.fin;
       }
       d.nseg = ns;
-      d.N = d.Nrows = b.fout; d.BN = b.fout < 256 ? b.fout : 256;
+      d.N = d.Nrows = b.fout; d.BN = pick_bn(b.fout, B, r);
       d.epi = CHB_EPI_PLAIN;
       d.act = last ? CHB_ACT_LRELU : CHB_ACT_NONE;  // generator.py:107 leaky_relu before conv_img
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c1b));
@@ -530,6 +555,10 @@ void chb_generator_destroy(chb_generator* g) {
   }
   if (g->h2d_stream) cudaStreamDestroy(g->h2d_stream);
   if (g->d2h_stream) cudaStreamDestroy(g->d2h_stream);
+  for (auto& kv : g->graphs) {
+    if (kv.second->exec) cudaGraphExecDestroy(kv.second->exec);
+    delete kv.second;
+  }
   delete g;
 }
 
@@ -567,6 +596,11 @@ int chb_generator_bind(chb_generator* g, const void* blob, void* workspace) {
   g->blob = reinterpret_cast<const uint8_t*>(blob);
   g->ws = reinterpret_cast<uint8_t*>(workspace);
   g->plans.clear();
+  for (auto& kv : g->graphs) {
+    if (kv.second->exec) cudaGraphExecDestroy(kv.second->exec);
+    delete kv.second;
+  }
+  g->graphs.clear();
   // mu rows 19..31 (class padding) are never written by the fc_mu GEMM and must read as zero, so that the
   // Weff columns they produce are exact zeros.
   cudaError_t err = cudaMemset(g->ws + g->ws_mu, 0, (size_t)g->n_styled * g->cfg.max_batch * 32 * g->cfg.style_len * 2);
@@ -697,6 +731,112 @@ static int forward_impl(chb_generator* g, const uint8_t* labels, const float* co
     }
     if (rc != CHB_OK) return rc;
     if (evs && iev < nev) cudaEventRecord(evs[iev++], stream);
+  }
+  return CHB_OK;
+}
+
+// One cudaGraphLaunch per forward: at B = 1 the ~64 launches of the schedule are a few microseconds of work each, so
+// launch gaps, not kernels, set the latency of the reference's only real call pattern (gen_img, one image at a time).
+int chb_generator_forward_graph(chb_generator* g, const uint8_t* labels, const float* codes, uint64_t seed, float* out,
+                                int B, void* stream_) {
+  if (!g || !labels || !codes || !out || !g->ws || !g->blob) {
+    set_error("chb_generator_forward_graph: NULL argument or unbound generator");
+    return CHB_ERR_ARG;
+  }
+  if (B <= 0 || B > g->cfg.max_batch) {
+    set_error("chb_generator_forward_graph: batch exceeds max_batch");
+    return CHB_ERR_ARG;
+  }
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const chb_gen_config& c = g->cfg;
+  uint8_t* ws = g->ws;
+  const size_t S2 = (size_t)c.crop * c.crop;
+  uint8_t* d_labels = ws + g->ws_labels;
+  float* d_codes = reinterpret_cast<float*>(ws + g->ws_codes32);
+  float* d_out = reinterpret_cast<float*>(ws + g->ws_out);
+  cudaError_t err = cudaSuccess;
+  if (g->d2h_stream && g->async_calls > 0) {
+    // the streamed host entry point shares these staging buffers: let its copies drain first
+    err = cudaStreamSynchronize(g->h2d_stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(g->d2h_stream);
+  }
+  auto it = g->graphs.find(B);
+  if (it == g->graphs.end()) {
+    std::vector<Step>* steps = nullptr;
+    int rc = get_steps(g, B, &steps);  // plans (tensor maps) are built outside the capture
+    if (rc != CHB_OK) return rc;
+    rc = ensure_conv_kernels_ready();
+    if (rc != CHB_OK) return rc;
+    chb_generator::GraphEntry* ge = new chb_generator::GraphEntry();
+    cudaStream_t cap = nullptr;
+    cudaGraph_t graph = nullptr;
+    err = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (err == cudaSuccess) {
+      rc = forward_impl(g, d_labels, d_codes, nullptr, seed, d_out, B, CHB_IMPL_TCGEN05, cap, nullptr, 0);
+      err = cudaStreamEndCapture(cap, &graph);
+      if (rc != CHB_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        delete ge;
+        return rc;
+      }
+    }
+    if (err == cudaSuccess) {
+      size_t n = 0;
+      err = cudaGraphGetNodes(graph, nullptr, &n);
+      std::vector<cudaGraphNode_t> nodes(n);
+      if (err == cudaSuccess) err = cudaGraphGetNodes(graph, nodes.data(), &n);
+      for (size_t i = 0; i < n && err == cudaSuccess; ++i) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+        if (kp.func == chb_noise_fill_kernel_address()) {
+          ge->noise_node = nodes[i];
+          ge->noise_params = kp;
+        }
+      }
+      if (err == cudaSuccess && !ge->noise_node) {
+        set_error("forward_graph: noise node not found in the captured graph");
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        delete ge;
+        return CHB_ERR_CUDA;
+      }
+    }
+    if (err == cudaSuccess) err = cudaGraphInstantiate(&ge->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (cap) cudaStreamDestroy(cap);
+    if (err != cudaSuccess) {
+      set_error(std::string("forward_graph: capture / instantiate failed: ") + cudaGetErrorString(err));
+      delete ge;
+      cudaGetLastError();
+      return CHB_ERR_CUDA;
+    }
+    ge->nz = reinterpret_cast<float*>(ws + g->ws_noise);
+    ge->nz_n = (long long)B * g->noise_pix;
+    ge->offset = 0;
+    ge->args[0] = &ge->nz; ge->args[1] = &ge->nz_n; ge->args[2] = &ge->seed; ge->args[3] = &ge->offset;
+    ge->noise_params.kernelParams = ge->args;
+    ge->noise_params.extra = nullptr;
+    it = g->graphs.emplace(B, ge).first;
+  }
+  chb_generator::GraphEntry* ge = it->second;
+  if (err == cudaSuccess && labels != d_labels)
+    err = cudaMemcpyAsync(d_labels, labels, (size_t)B * S2, cudaMemcpyDeviceToDevice, stream);
+  if (err == cudaSuccess && codes != d_codes)
+    err = cudaMemcpyAsync(d_codes, codes, (size_t)B * c.label_nc * c.style_len * 4, cudaMemcpyDeviceToDevice, stream);
+  if (err == cudaSuccess) {
+    ge->seed = seed;
+    err = cudaGraphExecKernelNodeSetParams(ge->exec, ge->noise_node, &ge->noise_params);
+  }
+  if (err == cudaSuccess) err = cudaGraphLaunch(ge->exec, stream);
+  if (err == cudaSuccess && out != d_out)
+    err = cudaMemcpyAsync(out, d_out, (size_t)B * 3 * S2 * 4, cudaMemcpyDeviceToDevice, stream);
+  if (err != cudaSuccess) {
+    set_error(std::string("forward_graph: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
   }
   return CHB_OK;
 }

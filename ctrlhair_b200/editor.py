@@ -63,7 +63,7 @@ class Pix2PixModelB200:
                                         "normalization.py:124); use gen_img_batch / forward_labels for batches")
                 codes = codes[None].contiguous()
                 self.seed += 1
-                return self.netG.forward_labels(labels, codes, noise=data.get("noise"), seed=self.seed)
+                return self.netG.forward_labels(labels, codes, noise=data.get("noise"), seed=self.seed, graph=True)
             if mode == "style_code":
                 return self.zencoder(image.to(self.device), labels)
         raise ValueError("|mode| is invalid")

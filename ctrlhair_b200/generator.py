@@ -122,9 +122,11 @@ class SeanGeneratorB200(torch.nn.Module):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def forward_labels(self, labels, codes, noise=None, seed=0, out=None):
+    def forward_labels(self, labels, codes, noise=None, seed=0, out=None, graph=False):
         """labels uint8 [B,S,S] (cuda), codes fp32 [B,19,512] (cuda), noise: flat fp32 of noise_floats(B) or None
-        (drawn on device from `seed`).  Returns fp32 [B,3,S,S] in [-1,1]."""
+        (drawn on device from `seed`).  Returns fp32 [B,3,S,S] in [-1,1].
+        graph=True (device-drawn noise only): replay the schedule from one captured CUDA graph per batch size — the
+        low-latency path for the reference's one-image-per-call callers; same result as graph=False."""
         if self.blob is None:
             raise _lib.ChbError("no weights loaded")
         if not (labels.is_cuda and codes.is_cuda):
@@ -143,9 +145,14 @@ class SeanGeneratorB200(torch.nn.Module):
         if out is None:
             out = torch.empty((B, 3, self.crop, self.crop), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.chb_generator_forward(self.handle, C.c_void_p(labels.data_ptr()),
-                                                      C.c_void_p(codes.data_ptr()), nptr, seed,
-                                                      C.c_void_p(out.data_ptr()), B, self.impl, self._stream()))
+            if graph and nptr is None and self.impl == _lib.IMPL_TCGEN05:
+                _lib.check(self.lib.chb_generator_forward_graph(self.handle, C.c_void_p(labels.data_ptr()),
+                                                                C.c_void_p(codes.data_ptr()), seed,
+                                                                C.c_void_p(out.data_ptr()), B, self._stream()))
+            else:
+                _lib.check(self.lib.chb_generator_forward(self.handle, C.c_void_p(labels.data_ptr()),
+                                                          C.c_void_p(codes.data_ptr()), nptr, seed,
+                                                          C.c_void_p(out.data_ptr()), B, self.impl, self._stream()))
         return out
 
     def forward_timed(self, labels, codes, seed=0, out=None):
@@ -239,7 +246,7 @@ class SeanGeneratorB200(torch.nn.Module):
                                 "or a [B,19,512] codes tensor")
         if noise is None:
             noise = self.fixed_noise
-        return self.forward_labels(labels, codes, noise=noise, seed=seed)
+        return self.forward_labels(labels, codes, noise=noise, seed=seed, graph=(B == 1))
 
     # ------------------------------------------------------------------ introspection
     def launches(self):

@@ -166,6 +166,12 @@ int chb_generator_bind(chb_generator* g, const void* blob, void* workspace);
  * out fp32 [B,3,crop,crop] NCHW in [-1,1]. */
 int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
                           uint64_t seed, float* out, int B, int impl, void* stream);
+/* Same with device-drawn noise, replayed from ONE captured CUDA graph per batch size: the latency path of the
+ * reference's interactive callers (HairEditor.gen_img, hair_editor.py:159-179, one image per call).  The first call
+ * for a batch size captures; later calls cost one cudaGraphLaunch.  Results are identical to chb_generator_forward
+ * with the same seed. */
+int chb_generator_forward_graph(chb_generator* g, const uint8_t* labels, const float* codes, uint64_t seed, float* out,
+                                int B, void* stream);
 /* Same, host buffers in and out (pinned or pageable); copies are issued on `stream` and the call returns
  * after the output has landed in `out_host`. */
 int chb_generator_forward_host(chb_generator* g, const uint8_t* labels_host, const float* codes_host,

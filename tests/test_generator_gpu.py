@@ -4,7 +4,9 @@ Tolerances (written out, as the task asks):
   * integer work (one-hot scatter / nearest pyramid): bit exact (tests/test_aux_gpu.py)
   * generator image, fp16 tensor-core operands with fp32 accumulation, vs the fp32 reference:
       rel-L2  ||d|| / ||ref||            <= 1e-3   (north_star's "1e-3 relative")
-      max-norm max|d| / max|ref|         <= MAX_TOL (numerics, for the per-stage error budget)
+      max-norm max|d| / max|ref|         <= 1e-3   (met by the default "parity" precision policy —
+                                                    fp16 hi+lo split of conv_img, conv_s and conv_1 inputs; the
+                                                    single-pass "fast" policy sits at 1.5-1.8e-3: DESIGN.md numerics)
 """
 import os
 
@@ -20,7 +22,7 @@ from ctrlhair_b200 import synth
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 L2_TOL = 1e-3
-MAX_TOL = 2.5e-3
+MAX_TOL = 1e-3
 
 
 def _errs(got, ref):
@@ -130,6 +132,20 @@ def test_full_size_batch_properties(gen256):
     b = gen256.forward_labels(labels, codes, seed=11)
     c = gen256.forward_labels(labels, codes, seed=12)
     assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_graph_replay_equals_plain_launches(gen64, gen256):
+    """chb_generator_forward_graph (one captured CUDA graph per batch size, seed re-parameterised per call) returns
+    exactly what the launch-by-launch entry point returns, call after call and for two batch sizes."""
+    for g, crop in ((gen64, 64), (gen256, 256)):
+        for B in (1, 2):
+            labels, codes = synth.make_labels(B, crop, "blocky", seed=3 + B).cuda(), synth.make_codes(B, seed=9).cuda()
+            for seed in (5, 6, 5):
+                a = g.forward_labels(labels, codes, seed=seed)
+                b = g.forward_labels(labels, codes, seed=seed, graph=True)
+                assert torch.equal(a, b), (crop, B, seed)
+            labels2 = synth.make_labels(B, crop, "iid", seed=77).cuda()   # new inputs through the same graph
+            assert torch.equal(g.forward_labels(labels2, codes, seed=8), g.forward_labels(labels2, codes, seed=8, graph=True))
 
 
 def test_absent_class_codes_ignored(gen64):
