@@ -74,6 +74,10 @@ class ZencConfig(C.Structure):
     _fields_ = [("crop", C.c_int), ("label_nc", C.c_int), ("max_batch", C.c_int)]
 
 
+class BisenetConfig(C.Structure):
+    _fields_ = [("size", C.c_int), ("n_classes", C.c_int), ("max_batch", C.c_int)]
+
+
 class ShapeConfig(C.Structure):
     _fields_ = [("crop", C.c_int), ("max_batch", C.c_int)]
 
@@ -140,6 +144,18 @@ SYMBOLS = [
     ("chb_generator_set_step_limit", C.c_int, [C.c_void_p, C.c_int]),
     ("chb_generator_debug_tensor", C.c_int64,
      [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    ("chb_bisenet_create", C.c_int, [C.POINTER(BisenetConfig), C.POINTER(C.c_void_p)]),
+    ("chb_bisenet_destroy", None, [C.c_void_p]),
+    ("chb_bisenet_num_tensors", C.c_int, [C.c_void_p]),
+    ("chb_bisenet_tensor_info", C.c_int,
+     [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    ("chb_bisenet_blob_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_bisenet_workspace_bytes", C.c_int64, [C.c_void_p]),
+    ("chb_bisenet_launches", C.c_int, [C.c_void_p]),
+    ("chb_bisenet_bind", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("chb_bisenet_forward", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    ("chb_bisenet_forward_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("chb_zencoder_create", C.c_int, [C.POINTER(ZencConfig), C.POINTER(C.c_void_p)]),
     ("chb_zencoder_destroy", None, [C.c_void_p]),
     ("chb_zencoder_num_tensors", C.c_int, [C.c_void_p]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libctrlhair_b200.so"
-SOURCES = ["conv_igemm.cu", "aux_kernels.cu", "generator.cu", "mlp.cu", "zencoder.cu", "shape.cu", "ct_train.cu", "blend.cu"]
+SOURCES = ["conv_igemm.cu", "aux_kernels.cu", "generator.cu", "mlp.cu", "zencoder.cu", "shape.cu", "ct_train.cu", "blend.cu", "bisenet.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

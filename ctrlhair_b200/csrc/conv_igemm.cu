@@ -327,7 +327,12 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     if (kc == 32 && wstat_mode < 2) wstat_ok = false;  // CHB_WSTAT=1: one-hot (64-byte row) layers streamed (slower since the nine taps of a resident chunk go out in one asm block)
     wbytes_total += (long long)g.taps * (g.w_dup == 2 ? g.C / 2 : g.C) * d.BN * 2;
   }
-  const int halo_buf = kc_max == 64 ? kHaloBufBytes : kHaloBufBytes / 2;
+  // ring buffer of the A operand: a (TH+2)x(TW+2) halo tile, or — when every segment is 1x1 — the exact 128-row tile,
+  // which lets a thin 1x1 GEMM (conv_img.taps: K = 192, N = 32) keep 3-4 pixel tiles in flight instead of 2
+  bool all_1x1 = true;
+  for (int s = 0; s < d.nseg; ++s) all_1x1 = all_1x1 && d.seg[s].taps == 1;
+  const int halo_buf = all_1x1 ? (kc_max == 64 ? kATileBytes : kATileBytes / 2)
+                               : (kc_max == 64 ? kHaloBufBytes : kHaloBufBytes / 2);
   const int kRegion = 193 * 1024;  // 227 KB - align slack - barriers - epilogue staging
   const int wstat_min_halo = tuning_env("CHB_WSTAT_MINHALO", 2);
   if (wbytes_total + (long long)wstat_min_halo * halo_buf > kRegion || d.Nrows / d.BN > device_sm_count()) wstat_ok = false;

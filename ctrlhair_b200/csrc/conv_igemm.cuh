@@ -13,7 +13,7 @@ constexpr int kMaxSeg = 4;
 constexpr int kEpiModulateSplit = 2;  // kernel-internal: CHB_EPI_MODULATE with chb_conv_desc.o_split (own instantiation)
 constexpr int kATileBytes = 16384;  // 128 rows x 128 B
 constexpr int kMaxStages = 8;
-constexpr int kMaxHalo = 6;
+constexpr int kMaxHalo = 12;
 constexpr int kHaloBufBytes = 24576;  // (16+2) x (8+2) rows x 128 B, rounded up to 1 KB
 constexpr int kSmemBudget = 192 * 1024;  // pipeline stages; + 32 KB epilogue staging + barriers <= 227 KB
 constexpr int kEpilogueWarps = 8;

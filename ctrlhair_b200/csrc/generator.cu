@@ -86,6 +86,7 @@ struct chb_generator {
   // chb_generator_forward_graph: the whole schedule of a batch size captured once (device-drawn noise; its seed node
   // is re-parameterised per call), inputs / image staged through the first set of I/O buffers of the workspace
   struct GraphEntry {
+    cudaGraph_t graph = nullptr;  // kept alive: node handles (noise_node) belong to it
     cudaGraphExec_t exec = nullptr;
     cudaGraphNode_t noise_node = nullptr;
     cudaKernelNodeParams noise_params;
@@ -557,6 +558,7 @@ void chb_generator_destroy(chb_generator* g) {
   if (g->d2h_stream) cudaStreamDestroy(g->d2h_stream);
   for (auto& kv : g->graphs) {
     if (kv.second->exec) cudaGraphExecDestroy(kv.second->exec);
+    if (kv.second->graph) cudaGraphDestroy(kv.second->graph);
     delete kv.second;
   }
   delete g;
@@ -598,6 +600,7 @@ int chb_generator_bind(chb_generator* g, const void* blob, void* workspace) {
   g->plans.clear();
   for (auto& kv : g->graphs) {
     if (kv.second->exec) cudaGraphExecDestroy(kv.second->exec);
+    if (kv.second->graph) cudaGraphDestroy(kv.second->graph);
     delete kv.second;
   }
   g->graphs.clear();
@@ -806,10 +809,11 @@ int chb_generator_forward_graph(chb_generator* g, const uint8_t* labels, const f
       }
     }
     if (err == cudaSuccess) err = cudaGraphInstantiate(&ge->exec, graph, 0);
-    if (graph) cudaGraphDestroy(graph);
     if (cap) cudaStreamDestroy(cap);
+    ge->graph = graph;
     if (err != cudaSuccess) {
       set_error(std::string("forward_graph: capture / instantiate failed: ") + cudaGetErrorString(err));
+      if (graph) cudaGraphDestroy(graph);
       delete ge;
       cudaGetLastError();
       return CHB_ERR_CUDA;

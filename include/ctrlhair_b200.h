@@ -227,6 +227,37 @@ int chb_zencoder_forward_host(chb_zencoder* z, const float* img_host, const uint
                               int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Face parsing: BiSeNet on a ResNet-18 context path (external_code/face_parsing/model.py:230-274, resnet.py:21-93),
+ * driven as FaceParsing.parsing_img + swap_parsing_label_to_celeba_mask + HairEditor.get_mask do it
+ * (my_parsing_util.py:31-54, hair_editor.py:331-335; the reference runs it on the CPU at 512x512 for every image).
+ * img u8 [B,size,size,3] RGB, already resized to the network size (the PIL bilinear resize stays on the host)
+ * -> label map u8 [B,out_size,out_size]: argmax of the bilinearly x8-upsampled logits sampled at every
+ * (size/out_size)-th pixel (cv2 INTER_NEAREST), mapped through the blob's 19-entry label LUT.
+ * Eval BatchNorm is folded into conv weights/bias by the host packer (ctrlhair_b200/bisenet.py).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int size;       /* 512 (my_parsing_util.py:35); a multiple of 128 */
+  int n_classes;  /* 19 */
+  int max_batch;
+} chb_bisenet_config;
+typedef struct chb_bisenet chb_bisenet;
+int chb_bisenet_create(const chb_bisenet_config* cfg, chb_bisenet** out);
+void chb_bisenet_destroy(chb_bisenet* n);
+int chb_bisenet_num_tensors(const chb_bisenet* n);
+int chb_bisenet_tensor_info(const chb_bisenet* n, int i, char* name, int name_cap, int64_t* offset, int64_t* nbytes,
+                            int* dtype);
+int64_t chb_bisenet_blob_bytes(const chb_bisenet* n);
+int64_t chb_bisenet_workspace_bytes(const chb_bisenet* n);
+int chb_bisenet_launches(const chb_bisenet* n);
+int chb_bisenet_bind(chb_bisenet* n, const void* blob, void* workspace);
+/* Device buffers.  logits_out (optional): the 1/8-resolution logits fp32 [B,size/8,size/8,32] (19 valid channels). */
+int chb_bisenet_forward(chb_bisenet* n, const uint8_t* img, uint8_t* mask, int out_size, float* logits_out, int B,
+                        void* stream);
+/* Host buffers in and out; returns after the label map has landed in mask_host. */
+int chb_bisenet_forward_host(chb_bisenet* n, const uint8_t* img_host, uint8_t* mask_host, int out_size, int B,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The shape branch generator (shape_branch/model.py:146-199; HairEditor.mask_generator, hair_editor.py:96;
  * call sites ui/backend.py:85-89,282-283,312,416-419).  Masks are fp32 NCHW one-hot planes as
  * shape_util.split_hair_face (shape_util.py:23-26) produces them; crop is fixed at 256 like the reference.

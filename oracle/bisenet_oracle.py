@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement (functional torch, fp32) of the reference's face-parsing network, the
-groundwork for SURVEY §8f row 3 (BiSeNet parsing on the GPU).  NO CUDA PATH EXISTS FOR THIS ROW YET: nothing in
+checker of SURVEY §8f row 3 (BiSeNet parsing on the GPU: csrc/bisenet.cu, ctrlhair_b200/bisenet.py).  Nothing in
 ctrlhair_b200/ uses it.  Only tests/ may import it.
 
   bisenet_forward      external_code/face_parsing/model.py:257-274 (first head only: parsing_img uses out[0]),
@@ -90,13 +90,17 @@ def feature_fusion(sd, fsp, fcp):
     return feat * atten + feat
 
 
+def bisenet_logits_lowres(sd, x):
+    """x float [B,3,H,W] (normalised) -> the main head's logits [B,19,H/8,W/8] BEFORE the bilinear upsample."""
+    feat_res8, feat_cp8, _ = context_path(sd, x)
+    feat_fuse = feature_fusion(sd, feat_res8, feat_cp8)
+    return F.conv2d(_cbr(sd, "conv_out.conv", feat_fuse), sd["conv_out.conv_out.weight"])
+
+
 def bisenet_forward(sd, x):
     """x float [B,3,H,W] (normalised) -> logits [B,19,H,W] of the main head (model.py:257-270, out[0])."""
     H, W = x.shape[2:]
-    feat_res8, feat_cp8, _ = context_path(sd, x)
-    feat_fuse = feature_fusion(sd, feat_res8, feat_cp8)
-    out = F.conv2d(_cbr(sd, "conv_out.conv", feat_fuse), sd["conv_out.conv_out.weight"])
-    return F.interpolate(out, (H, W), mode="bilinear", align_corners=True)
+    return F.interpolate(bisenet_logits_lowres(sd, x), (H, W), mode="bilinear", align_corners=True)
 
 
 def normalise_image(img_u8):

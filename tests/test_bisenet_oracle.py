@@ -52,3 +52,25 @@ def test_conv_bn_folding_reproduces_the_oracle():
         s = sd[bn + ".weight"] * torch.rsqrt(sd[bn + ".running_var"] + bno.BN_EPS)
         got = F.conv2d(x, w * s[:, None, None, None], sd[bn + ".bias"] - sd[bn + ".running_mean"] * s, stride, pad)
         assert float((got - want).abs().max()) < 1e-5 * float(want.abs().max()), conv
+
+
+def test_packed_schedule_is_exact_in_fp32():
+    """The blob the CUDA path consumes (BatchNorm folded, identity shortcuts as identity 1x1 K-segments, the FFM concat as
+    two K-segments, stride-2 convs at full resolution + phase pick) reproduces the oracle in fp32; with fp16 rounding at
+    the kernels' storage points the labels still agree on > 99.9 % of the pixels."""
+    import _bisenet_emulation as be
+    from ctrlhair_b200.bisenet import label_lut, pack_bisenet
+    g = np.load(GOLD)
+    sd = synth.make_bisenet_state_dict()
+    packed = {k: (v.float() if v.dtype == torch.float16 else v) for k, v in pack_bisenet(sd).items()}
+    img = g["img"][:, :256, :256]            # a 256x256 crop keeps the CPU test short; the network is fully convolutional
+    with torch.no_grad():
+        ref = bno.bisenet_logits_lowres(sd, bno.normalise_image(img))
+        got = be.emulate(packed, img)
+        got16 = be.emulate(packed, img, round16=True)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) < 2e-3 * scale      # fp16 WEIGHTS only (activations fp32)
+    up = lambda t: F.interpolate(t, (256, 256), mode="bilinear", align_corners=True).argmax(1)
+    assert float((up(got16) == up(ref)).float().mean()) > 0.999
+    lut = label_lut(True)
+    assert np.array_equal(lut, bno.swap_parsing_label_to_celeba_mask(np.arange(19)))
