@@ -175,6 +175,86 @@ def parity_sample(gen, labels_h, codes_h, crop, dev, picks):
     return res
 
 
+def other_configs(args, gen, rank, world, dev, barrier, max_over_ranks):
+    """BASELINE.json configs 3-5 as extra keys of the line, each measured as the config states it:
+      config4  generator fwd at 512x512, 64 images per GPU, image batch sharded over the ranks (B = 512 at N = 8)
+      config5  one color_texture_branch/train.py iteration (D + G sub-steps), 32 samples per GPU, NCCL gradient
+               all-reduce when N > 1 (global batch 256 at N = 8; fp32 arithmetic, wider than the bf16 the config names)
+      config3  (rank 0, N = 1 only) Backend encode -> edit -> decode over the reference's imgs/*.png, batch 32, face
+               parser included, host buffers in and out"""
+    import argparse as _ap
+    import torch
+    from ctrlhair_b200 import flops as flopmodel
+    from ctrlhair_b200 import synth
+    from ctrlhair_b200.generator import SeanGeneratorB200
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_paths as bp
+    bp.QUIET = True
+    out = {}
+    # ---- config 4 (collectives sit outside the try blocks: a rank that fails must still reach them)
+    B4, crop4, n4 = 64, 512, 3
+    g4 = o4 = None
+    err4, ms_local = None, -1.0
+    try:
+        g4 = SeanGeneratorB200(crop=crop4, max_batch=B4, device=dev, precision=args.precision)
+        g4.load_state_dict(synth.make_state_dict())
+        lab = synth.make_labels(B4, crop4, "blocky", seed=4234 + rank).to(dev)
+        cod = synth.make_codes(B4, seed=4235 + rank).to(dev)
+        o4 = torch.empty((B4, 3, crop4, crop4), dtype=torch.float32, device=dev)
+        for i in range(2):
+            g4.forward_labels(lab, cod, seed=i, out=o4)
+    except Exception as e:
+        err4 = repr(e)[:300]
+    barrier()
+    if err4 is None:
+        try:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n4):
+                g4.forward_labels(lab, cod, seed=10 + i, out=o4)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms_local = e0.elapsed_time(e1) / n4
+        except Exception as e:
+            err4 = repr(e)[:300]
+    barrier()
+    ms4 = max_over_ranks(ms_local)
+    failed = max_over_ranks(0.0 if err4 is None else 1.0)
+    if failed > 0:
+        out["config4"] = {"error": err4 or "another rank failed"}
+    else:
+        _, fact4 = flopmodel.generator_macs(crop4)
+        peaks = load_peaks()
+        out["config4"] = {"what": "SEAN generator fwd fp16, 512x512, %d images per GPU x %d GPU(s) = batch %d, image batch "
+                                  "sharded across ranks (one weight broadcast, no per-step collective)" % (B4, world, B4 * world),
+                          "images_per_s": world * B4 / (ms4 * 1e-3), "ms_per_step": ms4, "steps": n4,
+                          "tflops_algorithmic_per_gpu": 2 * fact4 * B4 / ms4 / 1e9,
+                          "frac_of_sustained_peak": 2 * fact4 * B4 / ms4 / 1e9 / peaks["tflops_sustained"],
+                          "finite": bool(torch.isfinite(o4).all())}
+    del g4, o4
+    torch.cuda.empty_cache()
+    # ---- config 5
+    try:
+        a5 = _ap.Namespace(train_batch=32, steps=10, warmup=3)
+        r5 = bp.bench_train(a5)
+        if r5 is not None:
+            r5["what"] = "color_texture_branch/train.py iteration, %d samples per GPU x %d GPU(s)%s" % (
+                32, world, ", flat-buffer NCCL gradient all-reduce per sub-step" if world > 1 else "")
+            out["config5"] = r5
+    except Exception as e:
+        out["config5"] = {"error": repr(e)[:300]}
+    barrier()
+    # ---- config 3
+    if rank == 0 and world == 1:
+        try:
+            a3 = _ap.Namespace(B=32, steps=5, warmup=2)
+            out["config3"] = bp.bench_config3(a3, synth.make_state_dict())
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out["config3"] = {"error": repr(e)[:300]}
+    return out
+
+
 def reference_on_gpu(crop, dev, n_images=8, warm=2):
     """The unmodified reference module run eagerly on the same B200 (fp32, stock torch settings, nothing patched):
     the usefulness baseline of SURVEY 8d."""
@@ -337,6 +417,11 @@ def run_ours(args):
                "weight_stream_floor_ms": gen.blob_bytes() / (load_peaks()["hbm_gbs"] * 1e9) * 1e3,
                "what": "SeanGeneratorB200.forward_labels(B=1, graph=True): one captured CUDA graph per call, back to "
                        "back; floor = packed weight bytes / measured HBM copy bandwidth"}
+    # ---------------- the other BASELINE.json configs, measured as stated (extra keys; the headline stays config 2)
+    extra = {}
+    if not args.no_extra_configs:
+        del out_d, labels_iid
+        extra = other_configs(args, gen, rank, world, dev, barrier, max_over_ranks)
     cpu = parity = ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_throughput(args.cpu_images, crop, warm=1)
@@ -369,6 +454,7 @@ def run_ours(args):
             "reference_gpu": ref_gpu,
             "latency_b1_ms": lat,
         }
+        line.update(extra)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -408,6 +494,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--precision", default="parity", help="precision policy of SeanGeneratorB200 (parity | fast | full | shortcut)")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config3 / config4 / config5 keys")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -80,7 +80,8 @@ class DistTranslation:
 
 class BackendB200:
     def __init__(self, sean_sd, shape_sd, ct_sds, median_codes=None, max_batch=1, blending=True, img_size=256,
-                 device=None, maximum_value_fe=2.5, hsv_table=None, shape_dirs=None, texture_dirs=None):
+                 device=None, maximum_value_fe=2.5, hsv_table=None, shape_dirs=None, texture_dirs=None,
+                 parsing_sd=None):
         g_sd, d_sd, p_sd = ct_sds
         self.netG = SeanGeneratorB200(crop=img_size, max_batch=max_batch, device=device).load_state_dict(sean_sd)
         self.zencoder = ZencoderB200(crop=img_size, max_batch=max_batch, device=device).load_state_dict(sean_sd)
@@ -89,6 +90,13 @@ class BackendB200:
         self.feature_generator = ct.EigenGeneratorB200(device=self.device).load_state_dict(g_sd)
         self.feature_encoder = ct.CodeEncoderB200(device=self.device).load_state_dict(d_sd)
         self.feature_rgb_predictor = ct.PredictorB200(device=self.device).load_state_dict(p_sd)
+        # face parsing (hair_editor.py:331-335 -> my_parsing_util.py:31-54): BiSeNet on the GPU when its checkpoint
+        # (face_parsing_79999_iter.pth format) is given; otherwise callers pass the parsing themselves
+        self.face_parser = None
+        if parsing_sd is not None:
+            from .bisenet import BiSeNetB200
+            self.face_parser = BiSeNetB200(max_batch=max_batch, device=self.device,
+                                           swap_labels=True).load_state_dict(parsing_sd)
         self.img_size = img_size
         self.max_batch = max_batch
         self.blending = blending
@@ -138,11 +146,23 @@ class BackendB200:
         """hair_editor.py:149-157: style codes [B,19,512] of the image under its parsing."""
         return self.zencoder(img.to(self.device, torch.float32).contiguous(), mask_batch[:, 0].contiguous())
 
-    def parse_img(self, img_rgb, mask, target_img=False):
+    def get_mask(self, img_rgb):
+        """HairEditor.get_mask (hair_editor.py:331-335) for a batch: uint8 [B,S,S,3] -> uint8 label maps [B,S,S] on the
+        device (CelebAMask-HQ label order).  The PIL bilinear resize to the network's 512x512 stays on the host."""
+        if self.face_parser is None:
+            raise _lib.ChbError("no face-parsing checkpoint was given (BackendB200(parsing_sd=...)); pass the mask")
+        arr = torch.as_tensor(img_rgb).cpu().numpy()
+        net_in = np.stack([self.face_parser.resize_to_network(im, self.face_parser.size) for im in arr])
+        return self.face_parser(torch.from_numpy(net_in).to(self.device), out_size=self.img_size)
+
+    def parse_img(self, img_rgb, mask=None, target_img=False):
         """Returns (img, out_mask, latent, mask, input_code, hair_feature) like ui/backend.py:67-106; `mask` is the
-        parsing the reference gets from get_mask (BiSeNet, out of scope).  Everything is batched and on the device;
-        out_mask is the uint8 label map [B,S,S] decoded from the shape codes (None for a target image)."""
+        parsing the reference gets from get_mask — computed here by the GPU face parser when it is None.  Everything is
+        batched and on the device; out_mask is the uint8 label map [B,S,S] decoded from the shape codes (None for a
+        target image)."""
         img_ts = torch.as_tensor(img_rgb).to(self.device)
+        if mask is None:
+            mask = self.get_mask(img_rgb)
         mask_batch = self.preprocess_mask(mask)
         lr = LatentRepresentation()
         out_mask = None
@@ -158,12 +178,12 @@ class BackendB200:
         lr.texture = out_enc["noise"]
         return img_ts, out_mask, lr, mask_batch[:, 0], input_code, hair_feature
 
-    def set_input_img(self, img_rgb, mask):
+    def set_input_img(self, img_rgb, mask=None):
         (self.input_img, self.cur_mask, self.cur_latent, self.input_mask, self.input_sean_code,
          self.input_hair_feature) = self.parse_img(img_rgb, mask)
         return self.input_img, self.cur_mask
 
-    def set_target_img(self, img_rgb, mask):
+    def set_target_img(self, img_rgb, mask=None):
         (self.target_img, _, self.target_latent, self.target_mask, _,
          self.target_hair_feature) = self.parse_img(img_rgb, mask, target_img=True)
         return self.target_img, self.target_mask

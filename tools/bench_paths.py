@@ -50,8 +50,13 @@ def timed(fn, steps, warmup, stream=None):
     return e0.elapsed_time(e1) / steps
 
 
+QUIET = False   # bench.py imports these functions and folds their dicts into its single JSON line
+
+
 def emit(d):
-    print(json.dumps(d), flush=True)
+    if not QUIET:
+        print(json.dumps(d), flush=True)
+    return d
 
 
 def bench_zencoder(a, sd):
@@ -59,7 +64,7 @@ def bench_zencoder(a, sd):
     z = ZencoderB200(max_batch=a.B).load_state_dict(sd)
     img, lab = synth.make_image(a.B, 256).cuda(), synth.make_labels(a.B, 256, "blocky").cuda()
     ms = timed(lambda: z(img, lab), a.steps, a.warmup)
-    emit({"path": "zencoder (a8)", "B": a.B, "ms": ms, "images_per_s": a.B / ms * 1e3,
+    return emit({"path": "zencoder (a8)", "B": a.B, "ms": ms, "images_per_s": a.B / ms * 1e3,
           "tflops_algorithmic": ZENC_GFLOP * a.B / ms, "frac_of_sustained_peak": ZENC_GFLOP * a.B / ms / PEAK_TF})
 
 
@@ -71,7 +76,7 @@ def bench_shape(a):
     hc, fc = s.forward_hair_encoder(hair, testing=True), s.forward_face_encoder(face)
     ms_e = timed(lambda: (s.forward_hair_encoder(hair, testing=True), s.forward_face_encoder(face)), a.steps, a.warmup)
     ms_d = timed(lambda: s.forward_decode_by_code(hc, fc), a.steps, a.warmup)
-    emit({"path": "shape nets (a10)", "B": a.B, "encode_ms": ms_e, "decode_ms": ms_d,
+    return emit({"path": "shape nets (a10)", "B": a.B, "encode_ms": ms_e, "decode_ms": ms_d,
           "images_per_s": a.B / (ms_e + ms_d) * 1e3, "tflops_algorithmic": SHAPE_GFLOP * a.B / (ms_e + ms_d),
           "weights_mb_fp16": 482, "note": "241 M parameters: weight-bandwidth-bound at small B"})
 
@@ -87,7 +92,7 @@ def bench_ct(a):
         pred = P({"code": code})
         return ct.edit_infer(D, G, code, {"rgb_mean": pred["rgb_mean"], "pca_std": pred["pca_std"]})
     ms = timed(chain, a.steps * 5, a.warmup)
-    emit({"path": "colour/texture MLPs (a11): predictor + encoder + generator", "B": a.B, "ms": ms,
+    return emit({"path": "colour/texture MLPs (a11): predictor + encoder + generator", "B": a.B, "ms": ms,
           "codes_per_s": a.B / ms * 1e3, "launches": 3, "bound": "launch latency (0.93 M parameters)"})
 
 
@@ -123,13 +128,14 @@ def bench_pipeline(a, sd):
         out = gen.forward_labels(lab, codes, seed=1)
         out_h.copy_(out, non_blocking=True)
     ms = timed(chain, a.steps, a.warmup)
-    emit({"path": "config 3: Backend encode -> edit -> decode (network calls only; parsing/blending out of scope)",
+    return emit({"path": "config 3: Backend encode -> edit -> decode (network calls only; parsing/blending out of scope)",
           "B": B, "ms": ms, "images_per_s": B / ms * 1e3, "h2d_bytes": int(labels_h.numel() + img_h.numel() * 4),
           "d2h_bytes": int(out_h.numel() * 4)})
 
 
 def bench_train(a):
     from ctrlhair_b200 import ct_train
+    own_pg = not (torch.distributed.is_available() and torch.distributed.is_initialized())
     rank, local_rank, world = parallel.init_process_group()
     torch.cuda.set_device(local_rank)
     B = a.train_batch
@@ -169,14 +175,16 @@ def bench_train(a):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t)
     finite = bool(torch.isfinite(s.losses).all())
+    res = None
     if rank == 0:
-        emit({"path": "config 5: colour/texture train.py iteration (D + G sub-steps, 2 Adam updates)", "n_gpus": world,
+        res = emit({"path": "config 5: colour/texture train.py iteration (D + G sub-steps, 2 Adam updates)", "n_gpus": world,
               "batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms, "steps_per_s": 1e3 / ms,
               "samples_per_s": B * world / ms * 1e3, "launches_per_step": s.launches(0) + s.launches(1) + 2,
               "graph_launches_per_step": 2, "allreduce_per_step": 2 if world > 1 else 0, "dtype": "f32",
               "losses_finite": finite})
-    if world > 1:
+    if world > 1 and own_pg:
         torch.distributed.destroy_process_group()
+    return res
 
 
 def bench_blend(a):
@@ -197,7 +205,7 @@ def bench_blend(a):
     _, stats = blend.poisson_blending(face, src_u8, mask, return_stats=True)
     ms_solve = timed(lambda: blend.poisson_blending(face, src_u8, mask), a.steps, a.warmup)
     it = float(stats[..., 0].mean())
-    emit({"path": "8f.2 postprocess_blending 256x256 (mask + fp64 CG Poisson solve, 3 channels)", "B": B, "ms": ms,
+    return emit({"path": "8f.2 postprocess_blending 256x256 (mask + fp64 CG Poisson solve, 3 channels)", "B": B, "ms": ms,
           "images_per_s": B / ms * 1e3, "poisson_kernel_ms": ms_solve, "cg_iterations_mean": it,
           "cg_iterations_max": float(stats[..., 0].max()), "residual_max": float(stats[..., 1].max()),
           "us_per_iteration_per_wave": ms_solve * 1e3 / it / max(1.0, B * 3 / 16.0),
@@ -224,10 +232,70 @@ def bench_backend(a, sd):
     ms = timed(chain, a.steps, a.warmup)
     be.blending = False
     ms_nb = timed(chain, a.steps, a.warmup)
-    emit({"path": "config 3 via BackendB200: set_input_img + output incl. Poisson blending (parsing network excluded)",
+    return emit({"path": "config 3 via BackendB200: set_input_img + output incl. Poisson blending (parsing network excluded)",
           "B": B, "ms": ms, "images_per_s": B / ms * 1e3, "ms_without_blending": ms_nb,
           "images_per_s_without_blending": B / ms_nb * 1e3,
           "h2d_bytes": int(img_h.numel() + lab_h.numel()), "d2h_bytes": int(out_h.numel())})
+
+
+def load_example_faces(n):
+    """The reference's 50 example faces (imgs/*.png, all 256x256x3; staged by baseline/make_ref.py), RGB uint8 [n,256,256,3]
+    (cycled when n > 50).  None when the staged copy is absent."""
+    import glob
+    import numpy as np
+    d = os.path.join(ROOT, "baseline", "_ref", "imgs")
+    files = sorted(glob.glob(os.path.join(d, "*.png")))
+    if not files:
+        return None, 0
+    import cv2
+    imgs = [cv2.cvtColor(cv2.imread(f, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB) for f in files]
+    imgs = [cv2.resize(im, (256, 256)) if im.shape[:2] != (256, 256) else im for im in imgs]   # ui/backend.py:69
+    return np.stack([imgs[i % len(imgs)] for i in range(n)]), len(files)
+
+
+def bench_config3(a, sd):
+    """BASELINE.json config 3 as stated: Backend encode -> edit -> decode on imgs/*.png, batch 32, one B200 — every
+    network of ui/backend.py:67-106,147-175 on the GPU path INCLUDING the face parser (BiSeNet, my_parsing_util.py:31-47),
+    host uint8 images in, host uint8 images out.  Weights are the synthetic checkpoints (no trained ones ship with the
+    reference), so the masks are what the synthetic parser makes of the faces; the work per image is the same."""
+    from ctrlhair_b200.backend import BackendB200
+    B = a.B
+    faces, nfiles = load_example_faces(B)
+    if faces is None:
+        return emit({"path": "config 3 on imgs/*.png", "unavailable": "baseline/_ref/imgs not staged (baseline/make_ref.py)"})
+    img_h = torch.from_numpy(faces).pin_memory()
+    out_h = torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory()
+    be = BackendB200(sd, synth.make_shape_state_dict(), synth.make_ct_state_dicts(),
+                     median_codes=synth.make_codes(1, seed=4321)[0], max_batch=B, blending=True,
+                     parsing_sd=synth.make_bisenet_state_dict())
+
+    def chain():
+        be.set_input_img(img_h)                      # parses (PIL resize on the host + BiSeNet on the GPU), encodes
+        out_h.copy_(be.output(), non_blocking=True)  # edits, decodes, blends
+        torch.cuda.current_stream().synchronize()
+    import time as _t
+    for _ in range(a.warmup):
+        chain()
+    t0 = _t.perf_counter()
+    for _ in range(a.steps):
+        chain()
+    ms = (_t.perf_counter() - t0) / a.steps * 1e3
+    # where the time goes: the parser alone (device part), and the host-side PIL resize
+    net_in = torch.from_numpy(__import__("numpy").stack([be.face_parser.resize_to_network(im, 512) for im in faces])).cuda()
+    ms_parse = timed(lambda: be.face_parser(net_in, out_size=256), a.steps, a.warmup)
+    t0 = _t.perf_counter()
+    for im in faces:
+        be.face_parser.resize_to_network(im, 512)
+    ms_resize = (_t.perf_counter() - t0) * 1e3
+    be.blending = False
+    mask = be.get_mask(img_h)
+    ms_nb = timed(lambda: (be.set_input_img(img_h.cuda(non_blocking=True), mask), be.output()), a.steps, a.warmup)
+    return emit({"path": "config 3: Backend encode -> edit -> decode on the reference's imgs/*.png (parser included)",
+                 "B": B, "png_files": nfiles, "ms": ms, "images_per_s": B / ms * 1e3, "timing": "host wall clock, host buffers in/out",
+                 "face_parser_gpu_ms": ms_parse, "host_pil_resize_ms": ms_resize,
+                 "ms_without_parser_and_blending_device_timed": ms_nb,
+                 "h2d_bytes": int(img_h.numel() * 5), "d2h_bytes": int(out_h.numel()),
+                 "weights": "synthetic checkpoints (reference ships none); masks from the synthetic BiSeNet"})
 
 
 def bench_gen512(a, sd):
@@ -239,7 +307,7 @@ def bench_gen512(a, sd):
     out = torch.empty((B, 3, 512, 512), device="cuda")
     ms = timed(lambda: gen.forward_labels(labels, codes, seed=1, out=out), max(2, a.steps // 2), a.warmup)
     _, fact = flopmodel.generator_macs(512)
-    emit({"path": "config 4 per-GPU share: generator forward 512x512", "B": B, "ms": ms, "images_per_s": B / ms * 1e3,
+    return emit({"path": "config 4 per-GPU share: generator forward 512x512", "B": B, "ms": ms, "images_per_s": B / ms * 1e3,
           "tflops_algorithmic": 2 * fact * B / ms / 1e9, "frac_of_sustained_peak": 2 * fact * B / ms / 1e9 / PEAK_TF,
           "finite": bool(torch.isfinite(out).all())})
 
@@ -254,7 +322,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     what = a.what.split(",")
-    sd = synth.make_state_dict() if any(w in what for w in ("zencoder", "pipeline", "gen512", "backend")) else None
+    sd = synth.make_state_dict() if any(w in what for w in ("zencoder", "pipeline", "gen512", "backend", "config3")) else None
     if "zencoder" in what:
         bench_zencoder(a, sd)
     if "shape" in what:
@@ -265,6 +333,8 @@ def main():
         bench_pipeline(a, sd)
     if "gen512" in what:
         bench_gen512(a, sd)
+    if "config3" in what:
+        bench_config3(a, sd)
     if "blend" in what:
         bench_blend(a)
     if "backend" in what:
