@@ -156,6 +156,9 @@ SYMBOLS = [
     ("chb_bisenet_forward", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_bisenet_forward_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("chb_pil_resize_bilinear", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+      C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_zencoder_create", C.c_int, [C.POINTER(ZencConfig), C.POINTER(C.c_void_p)]),
     ("chb_zencoder_destroy", None, [C.c_void_p]),
     ("chb_zencoder_num_tensors", C.c_int, [C.c_void_p]),

@@ -148,12 +148,11 @@ class BackendB200:
 
     def get_mask(self, img_rgb):
         """HairEditor.get_mask (hair_editor.py:331-335) for a batch: uint8 [B,S,S,3] -> uint8 label maps [B,S,S] on the
-        device (CelebAMask-HQ label order).  The PIL bilinear resize to the network's 512x512 stays on the host."""
+        device (CelebAMask-HQ label order).  The PIL bilinear resize to the network's 512x512 (my_parsing_util.py:35) runs on
+        the GPU as well, bit exact (bisenet.resize_bilinear_u8)."""
         if self.face_parser is None:
             raise _lib.ChbError("no face-parsing checkpoint was given (BackendB200(parsing_sd=...)); pass the mask")
-        arr = torch.as_tensor(img_rgb).cpu().numpy()
-        net_in = np.stack([self.face_parser.resize_to_network(im, self.face_parser.size) for im in arr])
-        return self.face_parser(torch.from_numpy(net_in).to(self.device), out_size=self.img_size)
+        return self.face_parser.get_mask_device(img_rgb, self.img_size)
 
     def parse_img(self, img_rgb, mask=None, target_img=False):
         """Returns (img, out_mask, latent, mask, input_code, hair_feature) like ui/backend.py:67-106; `mask` is the

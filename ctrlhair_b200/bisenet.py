@@ -29,6 +29,65 @@ def label_lut(swap=True):
     return np.array([PARSING_LABEL_LIST.index(n) for n in BISENET_LABELS], dtype=np.uint8)
 
 
+def pil_bilinear_tables(in_size, out_size):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc (libImaging/Resample.c) for the BILINEAR filter: per output
+    index the input window (first index, count) and its 22-bit fixed-point weights.  Python floats are C doubles and
+    int() truncates like the C cast, so these are the very numbers Pillow computes."""
+    import math
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    coef = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        n = min(int(center + support + 0.5), in_size) - xmin
+        w = []
+        for x in range(n):
+            a = abs((x + xmin - center + 0.5) * ss)
+            w.append(1.0 - a if a < 1.0 else 0.0)
+        ww = 0.0
+        for v in w:   # same left-to-right double sum as the C loop
+            ww += v
+        for x in range(n):
+            v = w[x] / ww if ww != 0.0 else w[x]
+            coef[xx, x] = int(-0.5 + v * (1 << 22)) if v < 0 else int(0.5 + v * (1 << 22))
+        bounds[xx] = (xmin, n)
+    return bounds, coef, ksize
+
+
+_TABLES = {}
+
+
+def resize_bilinear_u8(img, out_h, out_w):
+    """PIL `Image.resize((out_w, out_h), Image.BILINEAR)` for a CUDA uint8 batch [B,H,W,C], bit exact."""
+    if not (isinstance(img, torch.Tensor) and img.is_cuda and img.dtype == torch.uint8 and img.dim() == 4):
+        raise _lib.ChbError("resize_bilinear_u8 takes a CUDA uint8 tensor [B,H,W,C] (there is no CPU path)")
+    lib = _lib.load()
+    img = img.contiguous()
+    B, H, W, Cn = img.shape
+    dev = img.device
+    tabs = []
+    for i, o in ((W, out_w), (H, out_h)):
+        key = (i, o, str(dev))
+        if key not in _TABLES:
+            b, c, ks = pil_bilinear_tables(i, o)
+            _TABLES[key] = (torch.from_numpy(b).to(dev), torch.from_numpy(c).to(dev), ks)
+        tabs.append(_TABLES[key])
+    tmp = torch.empty((B, H, out_w, Cn), dtype=torch.uint8, device=dev)
+    out = torch.empty((B, out_h, out_w, Cn), dtype=torch.uint8, device=dev)
+    (xb, xc, xks), (yb, yc, yks) = tabs
+    with torch.cuda.device(dev):
+        _lib.check(lib.chb_pil_resize_bilinear(
+            C.c_void_p(img.data_ptr()), C.c_void_p(tmp.data_ptr()), C.c_void_p(out.data_ptr()), B, H, W, Cn, out_h, out_w,
+            C.c_void_p(xb.data_ptr()), C.c_void_p(xc.data_ptr()), xks, C.c_void_p(yb.data_ptr()), C.c_void_p(yc.data_ptr()),
+            yks, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+
+
 def _fold(sd, conv, bn):
     """bias-free conv followed by eval BatchNorm -> (W', b'): W' = W * g/sqrt(var+eps), b' = beta - mean * g/sqrt(var+eps)."""
     w = sd[conv + ".weight"].double()
@@ -201,14 +260,20 @@ class BiSeNetB200(torch.nn.Module):
         lab = self.forward(torch.from_numpy(image[None].copy()).to(self.device))
         return lab[0].cpu().numpy().astype(np.int64), image
 
+    def get_mask_device(self, img_rgb, img_size=256):
+        """Batched HairEditor.get_mask on the device: uint8 [B,H,W,3] (host or CUDA) -> CUDA uint8 [B,img_size,img_size].
+        The PIL bilinear resize to the network size runs on the GPU too (bit exact, resize_bilinear_u8)."""
+        if not self.swap_labels:
+            raise _lib.ChbError("get_mask needs the label swap: build BiSeNetB200(swap_labels=True)")
+        img = torch.as_tensor(img_rgb).to(self.device).contiguous()
+        if img.shape[1] != self.size or img.shape[2] != self.size:
+            img = resize_bilinear_u8(img, self.size, self.size)
+        return self.forward(img, out_size=img_size)
+
     def get_mask(self, img_rgb, img_size=256):
         """HairEditor.get_mask (hair_editor.py:331-335): uint8 [H,W,3] -> uint8 [img_size,img_size], CelebAMask-HQ labels.
         Also takes a batch [B,H,W,3] (-> [B,img_size,img_size]), which the reference cannot."""
-        arr = np.asarray(img_rgb)
+        arr = np.ascontiguousarray(np.asarray(img_rgb))
         single = arr.ndim == 3
-        batch = arr[None] if single else arr
-        net_in = np.stack([self.resize_to_network(im, self.size) for im in batch])
-        if not self.swap_labels:
-            raise _lib.ChbError("get_mask needs the label swap: build BiSeNetB200(swap_labels=True)")
-        mask = self.forward(torch.from_numpy(net_in).to(self.device), out_size=img_size).cpu().numpy()
+        mask = self.get_mask_device(arr[None] if single else arr, img_size).cpu().numpy()
         return mask[0] if single else mask

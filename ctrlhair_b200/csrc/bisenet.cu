@@ -251,6 +251,33 @@ __global__ void __launch_bounds__(256) logits_to_mask_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------- Pillow's BILINEAR resize, 8 bits per channel, bit exact
+// my_parsing_util.py:35 resizes every image to 512x512 with PIL before the network.  Pillow resamples separably, first
+// along x then along y, with a triangle filter of support max(scale, 1), coefficients normalised in double precision and
+// rounded to 22-bit fixed point, an int32 accumulator started at 1 << 21 and the intermediate image rounded to uint8
+// between the passes (libImaging/Resample.c).  The host computes the coefficient tables with the same double arithmetic
+// (ctrlhair_b200/bisenet.py: pil_bilinear_tables); the passes below are pure integer work.
+//   one pass: out[.., o, ..] = clip8((2^21 + sum_{k < n[o]} in[.., lo[o] + k, ..] * coef[o][k]) >> 22)
+__global__ void __launch_bounds__(256) pil_resample_pass_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                                const int* __restrict__ bounds /*[O][2]: lo, n*/,
+                                                                const int* __restrict__ coef /*[O][ks]*/, int ks,
+                                                                long long outer, int I, int O, int inner) {
+  // tensor viewed as [outer][I][inner] -> [outer][O][inner]; x pass: outer = B*H, inner = 3; y pass: outer = B, inner = W*3
+  const long long total = outer * O * inner;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % inner);
+    const int o = (int)((i / inner) % O);
+    const long long q = i / ((long long)inner * O);
+    const int lo = __ldg(bounds + 2 * o), n = __ldg(bounds + 2 * o + 1);
+    const uint8_t* p = in + (q * I + lo) * inner + c;
+    int acc = 1 << 21;
+    for (int k = 0; k < n; ++k) acc += (int)__ldg(p + (long long)k * inner) * __ldg(coef + o * ks + k);
+    acc >>= 22;
+    out[i] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+  }
+}
+
 struct BTensor {
   std::string name;
   int64_t offset, nbytes;
@@ -580,6 +607,29 @@ int chb_bisenet_forward(chb_bisenet* n, const uint8_t* img, uint8_t* mask, int o
   if (err == cudaSuccess) err = cudaGetLastError();
   if (err != cudaSuccess) {
     set_error(std::string("bisenet launch failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
+}
+
+// Pillow-exact bilinear resize of uint8 [B,H,W,C] images on the device (see pil_resample_pass_kernel).  tmp holds the
+// x-resampled intermediate [B,H,OW,C]; the tables come from the host (double arithmetic identical to Pillow's).
+int chb_pil_resize_bilinear(const uint8_t* in, uint8_t* tmp, uint8_t* out, int B, int H, int W, int C, int OH, int OW,
+                            const int* xbounds, const int* xcoef, int xks, const int* ybounds, const int* ycoef, int yks,
+                            void* stream_) {
+  if (!in || !tmp || !out || !xbounds || !xcoef || !ybounds || !ycoef || B <= 0 || H <= 0 || W <= 0 || C <= 0 || OH <= 0 ||
+      OW <= 0 || xks <= 0 || yks <= 0) {
+    set_error("chb_pil_resize_bilinear: bad arguments");
+    return CHB_ERR_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  pil_resample_pass_kernel<<<bgrid((long long)B * H * OW * C, 256), 256, 0, st>>>(in, tmp, xbounds, xcoef, xks,
+                                                                                (long long)B * H, W, OW, C);
+  pil_resample_pass_kernel<<<bgrid((long long)B * OH * OW * C, 256), 256, 0, st>>>(tmp, out, ybounds, ycoef, yks, B, H,
+                                                                                 OH, OW * C);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error(std::string("pil_resize launch failed: ") + cudaGetErrorString(err));
     return CHB_ERR_CUDA;
   }
   return CHB_OK;

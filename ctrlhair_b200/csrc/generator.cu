@@ -352,14 +352,23 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
   // owns one Weff row and writes its 32 class columns as one contiguous 64-byte run.
   int gimg = 1;
   while (gimg < 8 && B % (gimg * 2) == 0) gimg *= 2;
-  for (auto& b : g->blocks)
-    for (int a = 0; a < 3; ++a) {
-      const AceInfo& A = b.ace[a];
-      if (!A.C || !A.styled) continue;
+  // Consecutive styled ACEs of equal width share ONE launch: their style weights lie back to back in the blob, their mu
+  // tables back to back in the workspace and their Weff rows back to back in the per-image table, so the ACE index is the
+  // operator's "image" dimension (15 launches -> 4: 8 x C=1024, 3 x 512, 3 x 256, 1 x 128).
+  {
+    std::vector<const AceInfo*> styled;
+    for (auto& b : g->blocks)
+      for (int a = 0; a < 3; ++a)
+        if (b.ace[a].C && b.ace[a].styled) styled.push_back(&b.ace[a]);
+    for (size_t i = 0; i < styled.size();) {
+      size_t j = i;
+      while (j < styled.size() && styled[j]->C == styled[i]->C) ++j;
+      const AceInfo& A = *styled[i];
+      const int n_grp = (int)(j - i);
       const int rows = 2 * A.C * 9;
       chb_conv_desc d;
       memset(&d, 0, sizeof d);
-      d.B = 1; d.H = 1; d.W = rows;
+      d.B = n_grp; d.H = 1; d.W = rows;
       d.TW = 128; d.TH = 1; d.TB = 1;
       d.nseg = 1;
       chb_conv_seg& s = d.seg[0];
@@ -368,15 +377,27 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       s.a_sx = L; s.a_sy = (int64_t)rows * L; s.a_sb = (int64_t)rows * L;
       s.Ca = L; s.C = L; s.taps = 1;
       s.w = ws + g->ws_mu + (int64_t)A.style_idx * B * 32 * L * 2;
+      s.per_image = 1;
+      s.w_sb = (int64_t)B * 32 * L;
       d.N = d.Nrows = B * 32;
       d.BN = 32 * gimg;
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
       d.out = ws + g->ws_weff + A.weff_row0 * 32 * 2; d.out_dtype = CHB_F16;
-      d.o_sb = 0; d.o_sy = 0; d.o_sx = 32; d.o_sn = 1;
+      d.o_sb = (int64_t)rows * 32; d.o_sy = 0; d.o_sx = 32; d.o_sn = 1;
       d.o_ngroup = 32; d.o_sgroup = g->weff_rows * 32;
-      const char* an3[3] = {"ace_s", "ace_0", "ace_1"};
-      if ((rc = push_step(steps, d, b.name + "." + an3[a] + ".weff")) != CHB_OK) return rc;
+      for (size_t k = i; k + 1 < j; ++k) {  // the layout facts this grouping relies on
+        if (styled[k + 1]->style_idx != styled[k]->style_idx + 1 || styled[k + 1]->weff_row0 != styled[k]->weff_row0 + rows ||
+            g->tensors[styled[k + 1]->t_stylew].offset != g->tensors[styled[k]->t_stylew].offset + (int64_t)rows * L * 2) {
+          set_error("generator: styled ACE tables are not contiguous");
+          return CHB_ERR_ARG;
+        }
+      }
+      char nm[64];
+      snprintf(nm, sizeof nm, "weff[%d ACEs x C=%d]", n_grp, A.C);
+      if ((rc = push_step(steps, d, nm)) != CHB_OK) return rc;
+      i = j;
     }
+  }
   // ---- x = fc(one_hot @ sw)   (generator.py:75-76)
   {
     chb_conv_desc d = base_desc(B, g->sw);
@@ -966,7 +987,16 @@ int chb_generator_host_sync(chb_generator* g) {
 int chb_generator_launches(const chb_generator* g) {
   if (!g) return 0;
   int n = 3;  // codes cast, one-hot pyramid, noise
-  if (g->n_styled > 0) n += 1 + g->n_styled;
+  if (g->n_styled > 0) {
+    n += 1;  // fc_mu
+    int prevC = -1;  // one weff launch per run of equal-width styled ACEs
+    for (auto& b : g->blocks)
+      for (int a = 0; a < 3; ++a)
+        if (b.ace[a].C && b.ace[a].styled) {
+          if (b.ace[a].C != prevC) ++n;
+          prevC = b.ace[a].C;
+        }
+  }
   n += 1;  // fc
   for (auto& b : g->blocks) n += 1 + b.n_ace + 2;
   return n + ((g->cfg.precision & CHB_PREC_IMG) ? 2 : 1);  // conv_img (taps GEMM + gather, or one conv)

@@ -253,6 +253,13 @@ int chb_bisenet_bind(chb_bisenet* n, const void* blob, void* workspace);
 /* Device buffers.  logits_out (optional): the 1/8-resolution logits fp32 [B,size/8,size/8,32] (19 valid channels). */
 int chb_bisenet_forward(chb_bisenet* n, const uint8_t* img, uint8_t* mask, int out_size, float* logits_out, int B,
                         void* stream);
+/* Pillow's Image.resize(..., BILINEAR) for uint8 [B,H,W,C] images, bit exact, on the device (my_parsing_util.py:35 resizes
+ * every image to 512x512 with PIL before parsing).  tmp: scratch of B*H*OW*C bytes.  The four tables are Pillow's
+ * per-output-pixel windows ([O][2] = first input index, count) and 22-bit fixed-point coefficients ([O][ks]) for the x and
+ * the y pass, computed on the host in double precision (ctrlhair_b200/bisenet.py: pil_bilinear_tables). */
+int chb_pil_resize_bilinear(const uint8_t* in, uint8_t* tmp, uint8_t* out, int B, int H, int W, int C, int OH, int OW,
+                            const int* xbounds, const int* xcoef, int xks, const int* ybounds, const int* ycoef, int yks,
+                            void* stream);
 /* Host buffers in and out; returns after the label map has landed in mask_host. */
 int chb_bisenet_forward_host(chb_bisenet* n, const uint8_t* img_host, uint8_t* mask_host, int out_size, int B,
                              void* stream);

@@ -78,3 +78,17 @@ def test_batch_and_host_entry_points(nets):
         swapped(torch.zeros((3, 512, 512, 3), dtype=torch.uint8).cuda())      # exceeds max_batch
     with pytest.raises(_lib.ChbError):
         swapped(torch.zeros((1, 256, 256, 3), dtype=torch.uint8).cuda())      # not the network size
+
+
+def test_get_mask_resizes_like_pil_on_the_device(nets):
+    """get_mask on a 256x256 face (what Backend.parse_img hands over, ui/backend.py:69-74) == parsing the image Pillow
+    resizes to 512x512 on the host (my_parsing_util.py:33-35): the device resize is bit exact, so the masks are equal."""
+    sd, raw, swapped = nets
+    g = np.load(GOLD)
+    small = np.ascontiguousarray(g["img"][0, ::2, ::2])                       # 256x256x3
+    big = swapped.resize_to_network(small, 512)                              # Pillow on the host
+    want = swapped(torch.from_numpy(big[None].copy()).cuda(), out_size=256)[0].cpu().numpy()
+    got = swapped.get_mask(small, img_size=256)
+    assert got.shape == (256, 256) and np.array_equal(got, want)
+    batch = swapped.get_mask(np.stack([small, small[::-1].copy()]), img_size=256)
+    assert np.array_equal(batch[0], want)
