@@ -195,6 +195,7 @@ SYMBOLS = [
     ("chb_cttrain_step", C.c_int, [C.c_void_p, C.c_int, C.POINTER(CtTrainBatch), C.c_void_p, C.c_void_p]),
     ("chb_cttrain_adam", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("chb_cttrain_launches", C.c_int, [C.c_void_p, C.c_int]),
+    ("chb_cttrain_schedule", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("chb_image_to_u8", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("chb_blend_mask", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -44,11 +44,9 @@ struct Gemm {
 // 32 x 32 output tile per CTA, K consumed in chunks of 128 so that every thread has 32 independent global loads in
 // flight per chunk: these GEMMs are a few MFLOP each and their duration is the dependent-load latency chain, not math.
 constexpr int kGemmKC = 128;
-__global__ void __launch_bounds__(256) gemm_kernel(const Gemm g) {
-  __shared__ float As[kGemmKC][33];
-  __shared__ float Bs[kGemmKC][33];
+__device__ __forceinline__ void gemm_tile(const Gemm& g, int bx, int by, float (*As)[33], float (*Bs)[33]) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int m0 = by * 32, n0 = bx * 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int k0 = 0; k0 < g.K; k0 += kGemmKC) {
     float av[16], bv[16];
@@ -93,17 +91,24 @@ __global__ void __launch_bounds__(256) gemm_kernel(const Gemm g) {
     __syncthreads();
   }
   const int n = n0 + tx;
-  if (n >= g.N) return;
+  if (n < g.N) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int m = m0 + ty + 8 * r;
-    if (m >= g.M) continue;
-    float v = acc[r];
-    if (g.bias) v += g.bias[n];
-    if (g.mask) v *= dlrelu(g.mask[(long)m * g.mask_sm + n]);
-    float* p = g.C + (long)m * g.c_sm + n;
-    *p = g.accumulate ? *p + v : v;
+    for (int r = 0; r < 4; ++r) {
+      const int m = m0 + ty + 8 * r;
+      if (m >= g.M) continue;
+      float v = acc[r];
+      if (g.bias) v += g.bias[n];
+      if (g.mask) v *= dlrelu(g.mask[(long)m * g.mask_sm + n]);
+      float* p = g.C + (long)m * g.c_sm + n;
+      *p = g.accumulate ? *p + v : v;
+    }
   }
+}
+
+__global__ void __launch_bounds__(256) gemm_kernel(const Gemm g) {
+  __shared__ float As[kGemmKC][33];
+  __shared__ float Bs[kGemmKC][33];
+  gemm_tile(g, blockIdx.x, blockIdx.y, As, Bs);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -145,9 +150,7 @@ struct PrepArgs {
   int B;
 };
 
-__global__ void prep_kernel(const PrepArgs a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+__device__ __forceinline__ void prep_row(const PrepArgs& a, int b) {
   const float* rb = a.r + (long)b * kDOut;
   float* xa = a.xinA + (long)b * kXinLd;
   xa[0] = rb[1 + kNoise];
@@ -170,6 +173,10 @@ __global__ void prep_kernel(const PrepArgs a) {
     a.LzA[l][b * kSub + k] = a.Lvec[l][k] * za;
     a.LzG[l][b * kSub + k] = a.Lvec[l][k] * zg;
   }
+}
+__global__ void prep_kernel(const PrepArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < a.B) prep_row(a, b);
 }
 
 __global__ void xhat_kernel(const float* __restrict__ code, const float* __restrict__ f, const float* __restrict__ alpha,
@@ -238,10 +245,17 @@ __device__ void common_losses(const LossArgs& a, float* red, float& info, float&
   ic = block_sum(s, red) / (float)B;
 }
 
-__global__ void __launch_bounds__(1024) loss_d_kernel(const LossArgs a) {
-  __shared__ float red[33];
-  __shared__ float nrm[kMaxBatch];
-  __shared__ float m1[1 + kNoise], m2[1 + kNoise];
+struct LossSmem {
+  float red[33];
+  float nrm[kMaxBatch];
+  float m1[1 + kNoise], m2[1 + kNoise];
+};
+
+__device__ void loss_d_body(const LossArgs& a, LossSmem& sm) {
+  float* red = sm.red;
+  float* nrm = sm.nrm;
+  float* m1 = sm.m1;
+  float* m2 = sm.m2;
   const int B = a.B, t = threadIdx.x, nt = blockDim.x, lane = t & 31, w = t >> 5, nw = nt >> 5;
   const float invB = 1.f / (float)B;
   // WGAN critic loss (solver.py:195-196)
@@ -271,12 +285,12 @@ __global__ void __launch_bounds__(1024) loss_d_kernel(const LossArgs a) {
   float info, rec, ic;
   common_losses(a, red, info, rec, ic);
   // moment losses on cat([noise_curliness, noise]) of the encoder outputs (solver.py:233-242)
-  if (w < 1 + kNoise) {
-    const int col = w == 0 ? 1 + kNoise : w;
+  for (int c = w; c < 1 + kNoise; c += nw) {   // one warp per column (the persistent form runs this with 8 warps)
+    const int col = c == 0 ? 1 + kNoise : c;
     float s1 = 0.f, s2 = 0.f;
     for (int b = lane; b < B; b += 32) { const float v = a.r[b * kDOut + col]; s1 += v; s2 += v * v; }
     s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if (lane == 0) { m1[w] = s1 * invB; m2[w] = s2 * invB; }
+    if (lane == 0) { m1[c] = s1 * invB; m2[c] = s2 * invB; }
   }
   __syncthreads();
   float M1 = 0.f, M2 = 0.f;
@@ -300,9 +314,13 @@ __global__ void __launch_bounds__(1024) loss_d_kernel(const LossArgs a) {
                          a.cfg.lambda_info_curliness * ic;
   }
 }
+__global__ void __launch_bounds__(1024) loss_d_kernel(const LossArgs a) {
+  __shared__ LossSmem sm;
+  loss_d_body(a, sm);
+}
 
-__global__ void __launch_bounds__(1024) loss_g_kernel(const LossArgs a) {
-  __shared__ float red[33];
+__device__ void loss_g_body(const LossArgs& a, LossSmem& sm) {
+  float* red = sm.red;
   const int B = a.B, t = threadIdx.x, nt = blockDim.x;
   const float invB = 1.f / (float)B;
   float s = 0.f;
@@ -368,6 +386,10 @@ __global__ void __launch_bounds__(1024) loss_g_kernel(const LossArgs a) {
                          a.cfg.lambda_cls_curliness * cls + a.cfg.lambda_orthogonal * orth;
   }
 }
+__global__ void __launch_bounds__(1024) loss_g_kernel(const LossArgs a) {
+  __shared__ LossSmem sm;
+  loss_g_body(a, sm);
+}
 
 // Gradients of the auto-encoder pass w.r.t. the generator's *inputs* that came out of the discriminator
 // (noise -> subspace coordinates, noise_curliness -> first input column): they continue into D's real-code pass.
@@ -377,10 +399,10 @@ struct GInArgs {
   const float* Lvec[kGLayers];
   const float* Win;  // [256,5]
   float* dR;
+  int B;
 };
-__global__ void __launch_bounds__(256) g_input_grads_kernel(const GInArgs a) {
-  __shared__ float red[33];
-  const int b = blockIdx.x, t = threadIdx.x;
+__device__ void g_input_grads_row(const GInArgs& a, int b, float* red) {
+  const int t = threadIdx.x;
   float v = a.ds[0][(long)b * kHid + t] * a.Win[t * kGIn + 0];
   v = block_sum(v, red);
   if (t == 0) a.dR[b * kDOut + 1 + kNoise] += v;
@@ -391,6 +413,10 @@ __global__ void __launch_bounds__(256) g_input_grads_kernel(const GInArgs a) {
       if (t == 0) a.dR[b * kDOut + 1 + l * kSub + k] += a.Lvec[l][k] * u;
     }
 }
+__global__ void __launch_bounds__(256) g_input_grads_kernel(const GInArgs a) {
+  __shared__ float red[33];
+  g_input_grads_row(a, blockIdx.x, red);
+}
 
 // dL[l][k] += sum_b z[b, 2l+k] * <ds_l[b,:], U_l[k,:]>   (SubspaceLayer.L, model_eigengan.py:24)
 struct LGradArgs {
@@ -399,14 +425,110 @@ struct LGradArgs {
   float* dL[kGLayers];
   const float* z; int ldz; int B;
 };
-__global__ void __launch_bounds__(256) subspace_l_grad_kernel(const LGradArgs a) {
-  __shared__ float red[33];
-  const int l = blockIdx.x / kSub, k = blockIdx.x % kSub, t = threadIdx.x;
+__device__ void subspace_l_grad_one(const LGradArgs& a, int idx, float* red) {
+  const int l = idx / kSub, k = idx % kSub, t = threadIdx.x;
   const float u = a.U[l][k * kHid + t];
   float s = 0.f;
   for (int b = 0; b < a.B; ++b) s += a.z[(long)b * a.ldz + l * kSub + k] * a.ds[l][(long)b * kHid + t] * u;
   s = block_sum(s, red);
   if (t == 0) a.dL[l][k] += s;
+}
+__global__ void __launch_bounds__(256) subspace_l_grad_kernel(const LGradArgs a) {
+  __shared__ float red[33];
+  subspace_l_grad_one(a, blockIdx.x, red);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent form of a sub-step (round 2): the same ~95 operations, in the same order and with the same per-tile
+// arithmetic, executed by ONE cooperative kernel that walks an operation list in device memory.  A grid-wide barrier
+// separates dependent operations only (the host analyses the read / write ranges when it builds the list), so the
+// cost of a dependency drops from a graph-node boundary (~7 us: drain, launch, fill) to an atomic barrier (~1.5 us),
+// and independent GEMMs (weight gradients next to the data path, the two generator passes) share a phase.
+enum { OP_GEMM = 0, OP_ZERO, OP_PREP, OP_XHAT, OP_LOSS_D, OP_LOSS_G, OP_GIN, OP_LGRAD };
+struct XhatArgs { const float *code, *f, *alpha; float* xh; int n; };
+struct ZeroArgs { float* p; long n; };
+struct Op {
+  int type, sync;   // sync: grid barrier before this operation
+  int rot, pad_;    // first CTA of this operation's tile loop (spreads the small GEMMs of one phase over the grid)
+  union {
+    Gemm gemm;
+    ZeroArgs zero;
+    PrepArgs prep;
+    XhatArgs xhat;
+    LossArgs loss;
+    GInArgs gin;
+    LGradArgs lgrad;
+  };
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                      // release: this CTA's writes are visible before it arrives
+    atomicAdd(bar, 1ull);
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory");
+    } while (seen < target);
+    __threadfence();                      // acquire: later (weak) loads of the CTA observe the other CTAs' writes
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) ctt_persistent_kernel(const Op* __restrict__ ops, int nops,
+                                                             unsigned long long* bar, unsigned long long base) {
+  __shared__ float As[kGemmKC][33];
+  __shared__ float Bs[kGemmKC][33];
+  __shared__ LossSmem lsm;
+  __shared__ Op op;
+  const int G = gridDim.x, cta = blockIdx.x;
+  unsigned long long target = base;
+  for (int i = 0; i < nops; ++i) {
+    __syncthreads();   // everyone is done with the previous descriptor
+    {
+      const int words = (int)(sizeof(Op) / 4);
+      const unsigned* src = reinterpret_cast<const unsigned*>(ops + i);
+      unsigned* dst = reinterpret_cast<unsigned*>(&op);
+      for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+    }
+    __syncthreads();
+    if (op.sync) {
+      target += (unsigned long long)G;
+      grid_barrier(bar, target);
+    }
+    switch (op.type) {
+      case OP_GEMM: {
+        const int ntx = (op.gemm.N + 31) / 32, nty = (op.gemm.M + 31) / 32;
+        for (int tile = (cta - op.rot + G) % G; tile < ntx * nty; tile += G)
+          gemm_tile(op.gemm, tile % ntx, tile / ntx, As, Bs);
+        break;
+      }
+      case OP_ZERO:
+        for (long j = (long)cta * blockDim.x + threadIdx.x; j < op.zero.n; j += (long)G * blockDim.x) op.zero.p[j] = 0.f;
+        break;
+      case OP_PREP:
+        for (int b = cta * blockDim.x + threadIdx.x; b < op.prep.B; b += G * blockDim.x) prep_row(op.prep, b);
+        break;
+      case OP_XHAT:
+        for (int j = cta * blockDim.x + threadIdx.x; j < op.xhat.n; j += G * blockDim.x) {
+          const float al = op.xhat.alpha[j / kCode];
+          op.xhat.xh[j] = al * op.xhat.code[j] + (1.f - al) * op.xhat.f[j];
+        }
+        break;
+      case OP_LOSS_D:
+        if (cta == 0) loss_d_body(op.loss, lsm);
+        break;
+      case OP_LOSS_G:
+        if (cta == 0) loss_g_body(op.loss, lsm);
+        break;
+      case OP_GIN:
+        for (int b = cta; b < op.gin.B; b += G) g_input_grads_row(op.gin, b, lsm.red);
+        break;
+      case OP_LGRAD:
+        for (int idx = cta; idx < kGLayers * kSub; idx += G) subspace_l_grad_one(op.lgrad, idx, lsm.red);
+        break;
+    }
+  }
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -453,6 +575,12 @@ struct chb_cttrain {
   long step_count[2] = {0, 0};
   cudaGraphExec_t exec[2] = {nullptr, nullptr};
   int launches[2] = {0, 0};
+  // persistent form (cfg.use_graph == 2): operation lists in library-owned device memory, one barrier counter
+  void* dev_ops[2] = {nullptr, nullptr};
+  int n_ops[2] = {0, 0}, n_sync[2] = {0, 0};
+  unsigned long long* dev_bar = nullptr;
+  unsigned long long bar_total = 0;
+  int persist_grid = 0;
   bool failed = false;
   // workspace pointers
   float *code, *rgb, *pca, *noise, *nc, *label, *alpha, *ones, *e0;
@@ -491,17 +619,32 @@ void build_mlp(chb_cttrain* t, Mlp& m, const char* prefix, int group, int in_dim
   }
 }
 
-struct Rec {  // records launches on a stream (plain or under capture)
+struct Rec {  // records launches on a stream (plain or under capture), or operations of the persistent form
   cudaStream_t s;
   int n = 0;
   cudaError_t err = cudaSuccess;
+  std::vector<Op>* ops = nullptr;
   void check() { if (err == cudaSuccess) err = cudaGetLastError(); }
 };
 
+Op new_op(int type) {
+  Op o;
+  memset(&o, 0, sizeof o);
+  o.type = type;
+  o.sync = 1;
+  return o;
+}
+
 void gemm(Rec& rc, const Gemm& g) {
+  rc.n++;
+  if (rc.ops) {
+    Op o = new_op(OP_GEMM);
+    o.gemm = g;
+    rc.ops->push_back(o);
+    return;
+  }
   dim3 grid((g.N + 31) / 32, (g.M + 31) / 32);
   gemm_kernel<<<grid, 256, 0, rc.s>>>(g);
-  rc.n++;
   rc.check();
 }
 
@@ -605,8 +748,14 @@ void gen_bwd(Rec& rc, chb_cttrain* t, const float* dcode, const float* xin, floa
     la.ds[l] = ds[l]; la.U[l] = P + t->g_U[l]; la.dL[l] = G + t->g_L[l];
   }
   la.z = z; la.ldz = ldz; la.B = B;
-  subspace_l_grad_kernel<<<kGLayers * kSub, 256, 0, rc.s>>>(la);
   rc.n++;
+  if (rc.ops) {
+    Op o = new_op(OP_LGRAD);
+    o.lgrad = la;
+    rc.ops->push_back(o);
+    return;
+  }
+  subspace_l_grad_kernel<<<kGLayers * kSub, 256, 0, rc.s>>>(la);
   rc.check();
 }
 
@@ -616,7 +765,14 @@ void record_step(chb_cttrain* t, int which, Rec& rc) {
   const float* PG = t->par(CHB_CTT_G);
   const float* PF = t->frozen();
   const int64_t ng = which == CHB_CTT_D ? t->nD : t->nG;
-  if (rc.err == cudaSuccess) rc.err = cudaMemsetAsync(t->grad(which), 0, ng * sizeof(float), rc.s);
+  if (rc.ops) {
+    Op o = new_op(OP_ZERO);
+    o.zero.p = t->grad(which);
+    o.zero.n = (long)ng;
+    rc.ops->push_back(o);
+  } else if (rc.err == cudaSuccess) {
+    rc.err = cudaMemsetAsync(t->grad(which), 0, ng * sizeof(float), rc.s);
+  }
   // ---- Solver.forward (solver.py:85-117)
   mlp_fwd(rc, t->D, PD, t->code, kCode, t->zR, t->r, B);
   PrepArgs pa{};
@@ -624,8 +780,15 @@ void record_step(chb_cttrain* t, int which, Rec& rc) {
   pa.p1 = t->p1; pa.p2 = t->p2; pa.p3 = t->p3; pa.flag = t->flag;
   pa.xinA = t->xinA; pa.xinG = t->xinG; pa.zG = t->zG; pa.labG = t->labG; pa.B = B;
   for (int l = 0; l < kGLayers; ++l) { pa.Lvec[l] = PG + t->g_L[l]; pa.LzA[l] = t->LzA[l]; pa.LzG[l] = t->LzG[l]; }
-  prep_kernel<<<(B + 127) / 128, 128, 0, rc.s>>>(pa);
-  rc.n++; rc.check();
+  rc.n++;
+  if (rc.ops) {
+    Op o = new_op(OP_PREP);
+    o.prep = pa;
+    rc.ops->push_back(o);
+  } else {
+    prep_kernel<<<(B + 127) / 128, 128, 0, rc.s>>>(pa);
+    rc.check();
+  }
   gen_fwd(rc, t, t->xinA, t->LzA, t->sA, t->ae);
   gen_fwd(rc, t, t->xinG, t->LzG, t->sG, t->f);
   mlp_fwd(rc, t->D, PD, t->f, kCode, t->zF, t->q, B);
@@ -638,12 +801,26 @@ void record_step(chb_cttrain* t, int which, Rec& rc) {
 
   if (which == CHB_CTT_D) {
     // ---- forward_general_dis: x_hat, D(x_hat), d out_hat / d x_hat with the graph kept (solver.py:198-216)
-    xhat_kernel<<<(B * kCode + 255) / 256, 256, 0, rc.s>>>(t->code, t->f, t->alpha, t->xh, B * kCode);
-    rc.n++; rc.check();
+    rc.n++;
+    if (rc.ops) {
+      Op o = new_op(OP_XHAT);
+      o.xhat.code = t->code; o.xhat.f = t->f; o.xhat.alpha = t->alpha; o.xhat.xh = t->xh; o.xhat.n = B * kCode;
+      rc.ops->push_back(o);
+    } else {
+      xhat_kernel<<<(B * kCode + 255) / 256, 256, 0, rc.s>>>(t->code, t->f, t->alpha, t->xh, B * kCode);
+      rc.check();
+    }
     mlp_fwd(rc, t->D, PD, t->xh, kCode, t->zH, nullptr, B, /*skip_last=*/true);
     mlp_bwd(rc, t->D, PD, nullptr, t->e0, t->xh, kCode, t->zH, t->uH, t->g, 0, B);
-    loss_d_kernel<<<1, 1024, 0, rc.s>>>(la);
-    rc.n++; rc.check();
+    rc.n++;
+    if (rc.ops) {
+      Op o = new_op(OP_LOSS_D);
+      o.loss = la;
+      rc.ops->push_back(o);
+    } else {
+      loss_d_kernel<<<1, 1024, 0, rc.s>>>(la);
+      rc.check();
+    }
     float* GD = t->grad(CHB_CTT_D);
     // D(fake) pass: parameter gradients only (the generator is not stepped here)
     mlp_bwd(rc, t->D, PD, GD, t->dQ, t->f, kCode, t->zF, t->dz, nullptr, 0, B);
@@ -651,9 +828,16 @@ void record_step(chb_cttrain* t, int which, Rec& rc) {
     gen_bwd(rc, t, t->dAE, t->xinA, t->LzA, nullptr, 0, t->sA, t->dsA, /*wg=*/false);
     GInArgs ga{};
     for (int l = 0; l < kGLayers; ++l) { ga.ds[l] = t->dsA[l]; ga.U[l] = PG + t->g_U[l]; ga.Lvec[l] = PG + t->g_L[l]; }
-    ga.Win = PG + t->g_win; ga.dR = t->dR;
-    g_input_grads_kernel<<<B, 256, 0, rc.s>>>(ga);
-    rc.n++; rc.check();
+    ga.Win = PG + t->g_win; ga.dR = t->dR; ga.B = B;
+    if (rc.ops) {
+      Op o = new_op(OP_GIN);
+      o.gin = ga;
+      rc.ops->push_back(o);
+    } else {
+      g_input_grads_kernel<<<B, 256, 0, rc.s>>>(ga);
+      rc.check();
+    }
+    rc.n++;
     mlp_bwd(rc, t->D, PD, GD, t->dR, t->code, kCode, t->zR, t->dz, nullptr, 0, B);
     // gradient penalty, second-order pass.  With u_l = lrelu'(z_l) * (u_{l+1} W_{l+1}) and g = u_1 W_1 the masks are
     // piecewise constant, so  dW_l += u_l^T dt_{l-1},  dt_l = (dt_{l-1} W_l^T) * lrelu'(z_l),  dt_0 = dGP/dg.
@@ -672,8 +856,15 @@ void record_step(chb_cttrain* t, int which, Rec& rc) {
   } else {
     mlp_fwd(rc, t->P, PF + t->off_P, t->f, kCode, t->zP, t->pout, B);
     mlp_fwd(rc, t->C, PF + t->off_C, t->f, kCode, t->zC, t->cout, B);
-    loss_g_kernel<<<1, 1024, 0, rc.s>>>(la);
-    rc.n++; rc.check();
+    rc.n++;
+    if (rc.ops) {
+      Op o = new_op(OP_LOSS_G);
+      o.loss = la;
+      rc.ops->push_back(o);
+    } else {
+      loss_g_kernel<<<1, 1024, 0, rc.s>>>(la);
+      rc.check();
+    }
     // d loss / d fake code: through D (adv, info, info_curliness), the rgb predictor and the curliness classifier
     mlp_bwd(rc, t->D, PD, nullptr, t->dQ, t->f, kCode, t->zF, t->dz, t->df, 0, B);
     mlp_bwd(rc, t->P, PF + t->off_P, nullptr, t->dP, t->f, kCode, t->zP, t->dz, t->df, 1, B);
@@ -681,6 +872,83 @@ void record_step(chb_cttrain* t, int which, Rec& rc) {
     gen_bwd(rc, t, t->df, t->xinG, t->LzG, t->zG, kNoise, t->sG, t->dsG, /*wg=*/true);
     gen_bwd(rc, t, t->dAE, t->xinA, t->LzA, t->r + 1, kDOut, t->sA, t->dsA, /*wg=*/true);
   }
+}
+
+// ---- persistent form: dependency analysis over byte ranges, then upload
+struct Range { const char* lo; const char* hi; };
+static void add_range(std::vector<Range>& v, const void* p, long floats) {
+  if (p && floats > 0) v.push_back({static_cast<const char*>(p), static_cast<const char*>(p) + floats * 4});
+}
+static bool overlaps(const std::vector<Range>& a, const std::vector<Range>& b) {
+  for (const Range& x : a)
+    for (const Range& y : b)
+      if (x.lo < y.hi && y.lo < x.hi) return true;
+  return false;
+}
+
+// Sets Op::sync / Op::rot.  GEMMs get exact (hull) read / write ranges; every other operation is a full fence.
+void schedule_ops(std::vector<Op>& ops, int G, int* n_sync) {
+  std::vector<Range> pr, pw;   // reads / writes of the current phase
+  bool fence = false;          // the phase holds an operation that conflicts with everything
+  long tiles_in_phase = 0;
+  *n_sync = 0;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    Op& o = ops[i];
+    std::vector<Range> r, w;
+    bool full = o.type != OP_GEMM;
+    long tiles = 1;
+    if (!full) {
+      const Gemm& g = o.gemm;
+      add_range(r, g.A, (long)(g.M - 1) * g.a_sm + (long)(g.K - 1) * g.a_sk + 1);
+      if (g.B) add_range(r, g.B, (long)(g.K - 1) * g.b_sk + (long)(g.N - 1) * g.b_sn + 1);
+      add_range(r, g.bias, g.N);
+      add_range(r, g.mask, (long)(g.M - 1) * g.mask_sm + g.N);
+      add_range(w, g.C, (long)(g.M - 1) * g.c_sm + g.N);
+      if (g.accumulate) add_range(r, g.C, (long)(g.M - 1) * g.c_sm + g.N);
+      tiles = (long)((g.N + 31) / 32) * ((g.M + 31) / 32);
+    }
+    const bool conflict = i > 0 && (fence || full || overlaps(r, pw) || overlaps(w, pr) || overlaps(w, pw));
+    if (conflict) {
+      o.sync = 1;
+      ++*n_sync;
+      pr.clear(); pw.clear();
+      fence = false;
+      tiles_in_phase = 0;
+    } else {
+      o.sync = 0;
+    }
+    o.rot = (int)(tiles_in_phase % G);
+    tiles_in_phase += tiles;
+    pr.insert(pr.end(), r.begin(), r.end());
+    pw.insert(pw.end(), w.begin(), w.end());
+    fence = fence || full;
+  }
+}
+
+cudaError_t build_persistent(chb_cttrain* t, int which) {
+  if (!t->persist_grid) {
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctt_persistent_kernel, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (!coop || per_sm < 1 || sms < 1) return cudaErrorNotSupported;
+    t->persist_grid = sms;   // one CTA per SM: every CTA is resident, the barrier cannot deadlock
+    e = cudaMalloc(&t->dev_bar, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(t->dev_bar, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+  }
+  std::vector<Op> ops;
+  Rec rc{nullptr};
+  rc.ops = &ops;
+  record_step(t, which, rc);
+  schedule_ops(ops, t->persist_grid, &t->n_sync[which]);
+  cudaError_t e = cudaMalloc(&t->dev_ops[which], ops.size() * sizeof(Op));
+  if (e == cudaSuccess) e = cudaMemcpy(t->dev_ops[which], ops.data(), ops.size() * sizeof(Op), cudaMemcpyHostToDevice);
+  t->n_ops[which] = (int)ops.size();
+  t->launches[which] = 2;   // stage kernel + the persistent kernel
+  return e;
 }
 
 }  // namespace
@@ -752,8 +1020,11 @@ int chb_cttrain_create(const chb_cttrain_config* cfg, chb_cttrain** out) {
 
 void chb_cttrain_destroy(chb_cttrain* t) {
   if (!t) return;
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (t->exec[i]) cudaGraphExecDestroy(t->exec[i]);
+    if (t->dev_ops[i]) cudaFree(t->dev_ops[i]);
+  }
+  if (t->dev_bar) cudaFree(t->dev_bar);
   delete t;
 }
 
@@ -833,8 +1104,20 @@ int chb_cttrain_step(chb_cttrain* t, int which, const chb_cttrain_batch* b, floa
   sa.B = t->B;
   stage_kernel<<<std::min(64, (t->B * kCode + 255) / 256), 256, 0, s>>>(sa);
   cudaError_t err = cudaGetLastError();
-  const bool graph = t->cfg.use_graph && s != nullptr && s != cudaStreamLegacy;
-  if (err == cudaSuccess && graph) {
+  const bool graph = t->cfg.use_graph == 1 && s != nullptr && s != cudaStreamLegacy;
+  if (err == cudaSuccess && t->cfg.use_graph == 2) {
+    if (!t->dev_ops[which]) err = build_persistent(t, which);
+    if (err == cudaSuccess) {
+      const Op* ops = static_cast<const Op*>(t->dev_ops[which]);
+      int nops = t->n_ops[which];
+      unsigned long long* bar = t->dev_bar;
+      unsigned long long base = t->bar_total;
+      void* args[4] = {&ops, &nops, &bar, &base};
+      err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(ctt_persistent_kernel), dim3(t->persist_grid), dim3(256),
+                                        args, 0, s);
+      t->bar_total += (unsigned long long)t->n_sync[which] * (unsigned long long)t->persist_grid;
+    }
+  } else if (err == cudaSuccess && graph) {
     if (!t->exec[which]) {
       Rec rc{s};
       err = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
@@ -886,6 +1169,14 @@ int chb_cttrain_adam(chb_cttrain* t, int which, void* stream) {
 
 int chb_cttrain_launches(const chb_cttrain* t, int which) {
   return (t && (which == 0 || which == 1)) ? t->launches[which] : 0;
+}
+
+/* Persistent form only: operations and grid barriers of one sub-step (0 before its first use). */
+int chb_cttrain_schedule(const chb_cttrain* t, int which, int* n_ops, int* n_barriers) {
+  if (!t || (which != 0 && which != 1)) return CHB_ERR_ARG;
+  if (n_ops) *n_ops = t->n_ops[which];
+  if (n_barriers) *n_barriers = t->n_sync[which];
+  return CHB_OK;
 }
 
 }  // extern "C"
