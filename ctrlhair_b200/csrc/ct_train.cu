@@ -462,15 +462,16 @@ struct Op {
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+  // release / acquire at gpu scope (no sequentially-consistent fence: MEMBAR.SC costs microseconds).  bar.sync orders
+  // the CTA's writes before thread 0's release (cumulativity); the acquire load is followed by an L1 invalidation
+  // (CCTL.IVALL in SASS), so the weak loads the CTA issues after the second bar.sync read the other CTAs' data from L2.
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();                      // release: this CTA's writes are visible before it arrives
-    atomicAdd(bar, 1ull);
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ull) : "memory");
     unsigned long long seen;
     do {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory");
     } while (seen < target);
-    __threadfence();                      // acquire: later (weak) loads of the CTA observe the other CTAs' writes
   }
   __syncthreads();
 }
@@ -480,18 +481,18 @@ __global__ void __launch_bounds__(256) ctt_persistent_kernel(const Op* __restric
   __shared__ float As[kGemmKC][33];
   __shared__ float Bs[kGemmKC][33];
   __shared__ LossSmem lsm;
-  __shared__ Op op;
+  __shared__ Op opbuf[2];   // descriptor i + 1 is fetched while operation i (and its barrier) run
   const int G = gridDim.x, cta = blockIdx.x;
   unsigned long long target = base;
+  constexpr int kWords = (int)(sizeof(Op) / 4);
+  if (threadIdx.x < kWords)
+    reinterpret_cast<unsigned*>(&opbuf[0])[threadIdx.x] = __ldg(reinterpret_cast<const unsigned*>(ops) + threadIdx.x);
   for (int i = 0; i < nops; ++i) {
-    __syncthreads();   // everyone is done with the previous descriptor
-    {
-      const int words = (int)(sizeof(Op) / 4);
-      const unsigned* src = reinterpret_cast<const unsigned*>(ops + i);
-      unsigned* dst = reinterpret_cast<unsigned*>(&op);
-      for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
-    }
-    __syncthreads();
+    __syncthreads();   // descriptor i has landed; everyone is done with descriptor i - 1 (the buffer refilled below)
+    const Op& op = opbuf[i & 1];
+    if (i + 1 < nops && threadIdx.x < kWords)
+      reinterpret_cast<unsigned*>(&opbuf[(i + 1) & 1])[threadIdx.x] =
+          __ldg(reinterpret_cast<const unsigned*>(ops + i + 1) + threadIdx.x);
     if (op.sync) {
       target += (unsigned long long)G;
       grid_barrier(bar, target);

@@ -48,16 +48,16 @@ def test_shape_cuda_matches_oracle_and_golden(shape_sd):
     hc = net.forward_hair_encoder(hair.cuda(), testing=True).cpu()
     fc = net.forward_face_encoder(face.cuda()).cpu()
     rh, rf = torch.from_numpy(g["hair_code"]), torch.from_numpy(g["face_code"])
-    # fp16 tensor-core operands through 7 LayerNorm'd conv layers
-    assert float((hc - rh).norm() / rh.norm()) < 3e-3, float((hc - rh).norm() / rh.norm())
-    assert float((fc - rf).norm() / rf.norm()) < 3e-3, float((fc - rf).norm() / rf.norm())
+    # fp16 tensor-core operands through 7 LayerNorm'd conv layers: 1e-3 relative (measured 7.6-7.7e-4)
+    assert float((hc - rh).norm() / rh.norm()) < 1e-3, float((hc - rh).norm() / rh.norm())
+    assert float((fc - rf).norm() / rf.norm()) < 1e-3, float((fc - rf).norm() / rf.norm())
     # decode from the *reference* codes so that encoder error does not leak into the decoder check
     m = net.forward_decode_by_code(rh.cuda(), rf.cuda()).cpu()
     ref = sho.forward_decode_by_code(shape_sd, rh, rf)
     assert float((m.sum(1) - 1).abs().max()) < 1e-5
-    assert float((m - ref).abs().max()) < 5e-3, float((m - ref).abs().max())
+    assert float((m - ref).abs().max()) < 1e-3, float((m - ref).abs().max())      # probabilities (measured 7.3e-4)
     agree = float((m.argmax(1) == ref.argmax(1)).float().mean())
-    assert agree > 0.995, agree
+    assert agree > 0.999, agree
     # VAE path returns (code, mean, std) like the reference (model.py:164-169)
     code, mean, std = net.forward_hair_encoder(hair.cuda())
     assert code.shape == (2, 16) and torch.equal(mean.cpu(), hc) and bool((std >= 0).all())
@@ -82,8 +82,8 @@ def test_shape_split_decoders_and_directly_change_hair_mask(shape_sd):
     assert hl.shape == (2, 1, 256, 256) and fl.shape == (2, 18, 256, 256)
     ref_h = sho.mask_decoder(shape_sd, "hair_decoder", torch.cat([rf, rh], 1))
     ref_f = sho.mask_decoder(shape_sd, "face_decoder", rf)
-    assert float((hl.cpu() - ref_h).norm() / ref_h.norm()) < 3e-3
-    assert float((fl.cpu() - ref_f).norm() / ref_f.norm()) < 3e-3
+    assert float((hl.cpu() - ref_h).norm() / ref_h.norm()) < 1e-3      # measured 6.7e-4 / 8.8e-4
+    assert float((fl.cpu() - ref_f).norm() / ref_f.norm()) < 1e-3
     # the pieces compose to forward_decode_by_code bit for bit (same kernels, same logits)
     m = net.forward_decoder(hl, fl)
     assert torch.equal(m, net.forward_decode_by_code(rh.cuda(), rf.cuda()))

@@ -36,9 +36,10 @@ def test_zencoder_cuda_matches_oracle_and_golden(synthetic_sd, name, S, B):
     ref = zo.zencoder_forward(synthetic_sd, img, labels)
     for want in (ref, gold):
         d = out - want
-        # fp16 tensor-core operands after four InstanceNorms: same budget as the generator
-        assert float(d.norm() / want.norm()) < 2e-3, float(d.norm() / want.norm())
-        assert float(d.abs().max() / want.abs().max()) < 5e-3, float(d.abs().max() / want.abs().max())
+        # fp16 tensor-core operands after four InstanceNorms: north_star's 1e-3 on both norms
+        # (measured on B200: rel-L2 2.5-3.2e-4, max-norm 4.1-5.6e-4)
+        assert float(d.norm() / want.norm()) < 1e-3, float(d.norm() / want.norm())
+        assert float(d.abs().max() / want.abs().max()) < 1e-3, float(d.abs().max() / want.abs().max())
     assert torch.equal(out.abs().sum(2) == 0, gold.abs().sum(2) == 0)  # absent classes: exactly zero rows
     # reference signature with a one-hot segmap, and the host-buffer entry point
     from oracle import sean_oracle as so
