@@ -3,11 +3,14 @@
 // (forward), :218-245 + :186-216 (forward_d / forward_general_dis), :119-166 (forward_g), my_torchlib/train_utils.py:
 // 54-89 (train), model_eigengan.py:14-89, model.py:86-127, predictor/predictor_model.py:14-41.
 //
-// The three nets are 256-wide MLPs and the per-rank batch is 16-256 rows, so a sub-step is ~100 dependent GEMMs of a few
-// MFLOP each: it is bound by launch latency, not by FLOPs or bytes.  The design answer is (a) no autograd tape - the
-// backward of every path is written out, with the leaky-ReLU masks re-derived from the stored pre-activations, (b) one
-// strided fp32 GEMM kernel for all three contraction shapes (X W^T, dY W, dY^T X), (c) the whole sub-step captured once
-// into a CUDA graph and replayed, so the host issues one graph launch instead of ~100 kernel launches and never syncs.
+// The three nets are 256-wide MLPs and the per-rank batch is 16-256 rows, so a sub-step is ~90 GEMMs of a few MFLOP
+// each: it is bound by the latency of its dependent chain, not by FLOPs or bytes.  The design answer is (a) no autograd
+// tape - the backward of every path is written out, with the leaky-ReLU masks re-derived from the stored
+// pre-activations, (b) one strided fp32 GEMM kernel for all three contraction shapes (X W^T, dY W, dY^T X) whose tile
+// is built for latency (register double-buffered staging, 4 x 4 register tiles), (c) the sub-step recorded as an
+// operation list whose read / write ranges give the REAL dependencies, and executed either as an explicit CUDA graph
+// (one node per operation, one edge per dependency: weight-gradient GEMMs, the two generator passes and the three
+// discriminator passes run beside the data path) or by one persistent cooperative kernel with grid barriers.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -41,15 +44,26 @@ struct Gemm {
   int a_act, b_act, accumulate;
 };
 
-// 32 x 32 output tile per CTA, K consumed in chunks of 128 so that every thread has 32 independent global loads in
-// flight per chunk: these GEMMs are a few MFLOP each and their duration is the dependent-load latency chain, not math.
+// 32 x 32 output tile per CTA, K consumed in chunks of 128.  These GEMMs are a few MFLOP each and sit on a dependent
+// chain, so what matters is the latency of one tile:
+//   * staging: every thread has 32 independent global loads in flight per chunk, and the loads of chunk c + 1 are
+//     issued before chunk c is computed (register double buffer);
+//   * compute: the 256 threads split the chunk's K range four ways (64 threads per quarter), each thread owning a
+//     4 x 4 register tile fed by two 16-byte shared-memory reads per k (the round-1 loop read five words per four FMAs
+//     and was bound by shared-memory issue: ~3 us per chunk); the four partial tiles are summed through shared memory.
 constexpr int kGemmKC = 128;
-__device__ __forceinline__ void gemm_tile(const Gemm& g, int bx, int by, float (*As)[33], float (*Bs)[33]) {
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+constexpr int kGemmLd = 36;   // row pitch of the staged operands (floats): a multiple of 4, so rows stay 16-byte aligned
+__device__ __forceinline__ void gemm_tile(const Gemm& g, int bx, int by, float (*As)[kGemmLd], float (*Bs)[kGemmLd]) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                       // staging / epilogue layout
+  const int slice = threadIdx.x >> 6, ty4 = (threadIdx.x & 63) >> 3, tx4 = threadIdx.x & 7;   // compute layout
   const int m0 = by * 32, n0 = bx * 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < g.K; k0 += kGemmKC) {
-    float av[16], bv[16];
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float av[16], bv[16];
+  auto load_chunk = [&](int k0) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       int m, k;
@@ -63,6 +77,10 @@ __device__ __forceinline__ void gemm_tile(const Gemm& g, int bx, int by, float (
       if (n0 + n < g.N && k0 + kb < g.K) w = g.B ? g.B[(long)(k0 + kb) * g.b_sk + (long)(n0 + n) * g.b_sn] : 1.f;
       bv[j] = w;
     }
+  };
+  load_chunk(0);
+  for (int k0 = 0; k0 < g.K; k0 += kGemmKC) {
+    __syncthreads();   // the previous chunk has been consumed
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       int m, k;
@@ -73,41 +91,45 @@ __device__ __forceinline__ void gemm_tile(const Gemm& g, int bx, int by, float (
       Bs[kb][n] = g.b_act ? lrelu(bv[j]) : bv[j];
     }
     __syncthreads();
-    const int kend = g.K - k0 < kGemmKC ? g.K - k0 : kGemmKC;
-    if (kend == kGemmKC) {
-#pragma unroll 16
-      for (int kk = 0; kk < kGemmKC; ++kk) {
-        const float b = Bs[kk][tx];
+    if (k0 + kGemmKC < g.K) load_chunk(k0 + kGemmKC);   // in flight while this chunk is computed
+    // rows / columns beyond K were staged as zeros: the quarter can always run its 32 steps
+#pragma unroll 8
+    for (int kk = slice * 32; kk < slice * 32 + 32; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty4 * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx4 * 4]);
+      const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[kk][ty + 8 * r], b, acc[r]);
-      }
-    } else {
-      for (int kk = 0; kk < kend; ++kk) {
-        const float b = Bs[kk][tx];
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[kk][ty + 8 * r], b, acc[r]);
-      }
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
-    __syncthreads();
   }
+  __syncthreads();
+  float* red = &As[0][0];   // 4 partial 32 x 33 tiles (4 224 floats) in the 4 608 floats of As
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(slice * 32 + ty4 * 4 + i) * 33 + tx4 * 4 + j] = acc[i][j];
+  __syncthreads();
   const int n = n0 + tx;
   if (n < g.N) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int m = m0 + ty + 8 * r;
+      const int ml = ty + 8 * r, m = m0 + ml;
       if (m >= g.M) continue;
-      float v = acc[r];
+      float v = (red[ml * 33 + tx] + red[(32 + ml) * 33 + tx]) + (red[(64 + ml) * 33 + tx] + red[(96 + ml) * 33 + tx]);
       if (g.bias) v += g.bias[n];
       if (g.mask) v *= dlrelu(g.mask[(long)m * g.mask_sm + n]);
       float* p = g.C + (long)m * g.c_sm + n;
       *p = g.accumulate ? *p + v : v;
     }
   }
+  __syncthreads();   // `red` aliases the staging buffer of the next tile
 }
 
 __global__ void __launch_bounds__(256) gemm_kernel(const Gemm g) {
-  __shared__ float As[kGemmKC][33];
-  __shared__ float Bs[kGemmKC][33];
+  __shared__ __align__(16) float As[kGemmKC][kGemmLd];
+  __shared__ __align__(16) float Bs[kGemmKC][kGemmLd];
   gemm_tile(g, blockIdx.x, blockIdx.y, As, Bs);
 }
 
@@ -478,8 +500,8 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
 
 __global__ void __launch_bounds__(256) ctt_persistent_kernel(const Op* __restrict__ ops, int nops,
                                                              unsigned long long* bar, unsigned long long base) {
-  __shared__ float As[kGemmKC][33];
-  __shared__ float Bs[kGemmKC][33];
+  __shared__ __align__(16) float As[kGemmKC][kGemmLd];
+  __shared__ __align__(16) float Bs[kGemmKC][kGemmLd];
   __shared__ LossSmem lsm;
   __shared__ Op opbuf[2];   // descriptor i + 1 is fetched while operation i (and its barrier) run
   const int G = gridDim.x, cta = blockIdx.x;
@@ -887,18 +909,12 @@ static bool overlaps(const std::vector<Range>& a, const std::vector<Range>& b) {
   return false;
 }
 
-// Sets Op::sync / Op::rot.  GEMMs get exact (hull) read / write ranges; every other operation is a full fence.
-void schedule_ops(std::vector<Op>& ops, int G, int* n_sync) {
-  std::vector<Range> pr, pw;   // reads / writes of the current phase
-  bool fence = false;          // the phase holds an operation that conflicts with everything
-  long tiles_in_phase = 0;
-  *n_sync = 0;
-  for (size_t i = 0; i < ops.size(); ++i) {
-    Op& o = ops[i];
-    std::vector<Range> r, w;
-    bool full = o.type != OP_GEMM;
-    long tiles = 1;
-    if (!full) {
+// Byte ranges an operation reads / writes (hulls of its strided accesses).  They drive both schedules: the grid
+// barriers of the persistent kernel and the edges of the explicit CUDA graph.
+static void op_ranges(const Op& o, int B, std::vector<Range>& r, std::vector<Range>& w) {
+  auto rw = [&](const void* p, long n) { add_range(r, p, n); add_range(w, p, n); };
+  switch (o.type) {
+    case OP_GEMM: {
       const Gemm& g = o.gemm;
       add_range(r, g.A, (long)(g.M - 1) * g.a_sm + (long)(g.K - 1) * g.a_sk + 1);
       if (g.B) add_range(r, g.B, (long)(g.K - 1) * g.b_sk + (long)(g.N - 1) * g.b_sn + 1);
@@ -906,14 +922,85 @@ void schedule_ops(std::vector<Op>& ops, int G, int* n_sync) {
       add_range(r, g.mask, (long)(g.M - 1) * g.mask_sm + g.N);
       add_range(w, g.C, (long)(g.M - 1) * g.c_sm + g.N);
       if (g.accumulate) add_range(r, g.C, (long)(g.M - 1) * g.c_sm + g.N);
-      tiles = (long)((g.N + 31) / 32) * ((g.M + 31) / 32);
+      break;
     }
-    const bool conflict = i > 0 && (fence || full || overlaps(r, pw) || overlaps(w, pr) || overlaps(w, pw));
+    case OP_ZERO:
+      add_range(w, o.zero.p, o.zero.n);
+      break;
+    case OP_PREP: {
+      const PrepArgs& a = o.prep;
+      add_range(r, a.r, (long)B * kDOut); add_range(r, a.rgb, (long)B * 3); add_range(r, a.pca, B);
+      add_range(r, a.noise, (long)B * kNoise); add_range(r, a.nc, B); add_range(r, a.label, B);
+      add_range(r, a.p1, B); add_range(r, a.p2, B); add_range(r, a.p3, B); add_range(r, a.flag, 1);
+      add_range(w, a.xinA, (long)B * kXinLd); add_range(w, a.xinG, (long)B * kXinLd);
+      add_range(w, a.zG, (long)B * kNoise); add_range(w, a.labG, B);
+      for (int l = 0; l < kGLayers; ++l) {
+        add_range(r, a.Lvec[l], kSub);
+        add_range(w, a.LzA[l], (long)B * kSub); add_range(w, a.LzG[l], (long)B * kSub);
+      }
+      break;
+    }
+    case OP_XHAT:
+      add_range(r, o.xhat.code, o.xhat.n); add_range(r, o.xhat.f, o.xhat.n); add_range(r, o.xhat.alpha, B);
+      add_range(w, o.xhat.xh, o.xhat.n);
+      break;
+    case OP_LOSS_D:
+    case OP_LOSS_G: {
+      const LossArgs& a = o.loss;
+      add_range(r, a.code, (long)B * kCode); add_range(r, a.r, (long)B * kDOut); add_range(r, a.q, (long)B * kDOut);
+      add_range(r, a.ae, (long)B * kCode); add_range(r, a.zG, (long)B * kNoise); add_range(r, a.xinG, (long)B * kXinLd);
+      add_range(r, a.labG, B); add_range(r, a.g, (long)B * kCode); add_range(r, a.pout, (long)B * kPOut);
+      add_range(r, a.cout, B);
+      rw(a.dR, (long)B * kDOut); rw(a.dQ, (long)B * kDOut); rw(a.dAE, (long)B * kCode); rw(a.Gt, (long)B * kCode);
+      rw(a.dP, (long)B * kPOut); rw(a.dC, B); rw(a.losses, 64);
+      for (int l = 0; l < kGLayers; ++l) {
+        add_range(r, a.U[l], (long)kSub * kHid);
+        if (o.type == OP_LOSS_G) rw(a.dU[l], (long)kSub * kHid);
+      }
+      break;
+    }
+    case OP_GIN: {
+      const GInArgs& a = o.gin;
+      for (int l = 0; l < kGLayers; ++l) {
+        add_range(r, a.ds[l], (long)B * kHid); add_range(r, a.U[l], (long)kSub * kHid); add_range(r, a.Lvec[l], kSub);
+      }
+      add_range(r, a.Win, (long)kHid * kGIn);
+      rw(a.dR, (long)B * kDOut);
+      break;
+    }
+    case OP_LGRAD: {
+      const LGradArgs& a = o.lgrad;
+      for (int l = 0; l < kGLayers; ++l) {
+        add_range(r, a.ds[l], (long)B * kHid); add_range(r, a.U[l], (long)kSub * kHid);
+        rw(a.dL[l], kSub);
+      }
+      add_range(r, a.z, (long)(B - 1) * a.ldz + kNoise);
+      break;
+    }
+  }
+}
+
+static bool ops_conflict(const std::vector<Range>& r1, const std::vector<Range>& w1, const std::vector<Range>& r2,
+                         const std::vector<Range>& w2) {
+  return overlaps(w1, r2) || overlaps(w1, w2) || overlaps(r1, w2);
+}
+
+// Sets Op::sync / Op::rot: a barrier before an operation that conflicts with anything since the last barrier.
+void schedule_ops(std::vector<Op>& ops, int G, int B, int* n_sync) {
+  std::vector<Range> pr, pw;   // reads / writes of the current phase
+  long tiles_in_phase = 0;
+  *n_sync = 0;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    Op& o = ops[i];
+    std::vector<Range> r, w;
+    op_ranges(o, B, r, w);
+    long tiles = 1;
+    if (o.type == OP_GEMM) tiles = (long)((o.gemm.N + 31) / 32) * ((o.gemm.M + 31) / 32);
+    const bool conflict = i > 0 && ops_conflict(pr, pw, r, w);
     if (conflict) {
       o.sync = 1;
       ++*n_sync;
       pr.clear(); pw.clear();
-      fence = false;
       tiles_in_phase = 0;
     } else {
       o.sync = 0;
@@ -922,8 +1009,81 @@ void schedule_ops(std::vector<Op>& ops, int G, int* n_sync) {
     tiles_in_phase += tiles;
     pr.insert(pr.end(), r.begin(), r.end());
     pw.insert(pw.end(), w.begin(), w.end());
-    fence = fence || full;
   }
+}
+
+// The same operation list as an explicit CUDA graph: one kernel (or memset) node per operation, an edge from every
+// earlier operation it conflicts with.  Stream capture (round 1) could only produce a linear chain of ~95 nodes;
+// with real dependencies the weight-gradient GEMMs, the two generator passes and the three discriminator passes run
+// beside the data path, and the dependent chain shrinks to the critical path.
+cudaError_t build_graph(chb_cttrain* t, int which) {
+  std::vector<Op> ops;
+  Rec rc{nullptr};
+  rc.ops = &ops;
+  record_step(t, which, rc);
+  const int B = t->B;
+  std::vector<std::vector<Range>> R(ops.size()), W(ops.size());
+  for (size_t i = 0; i < ops.size(); ++i) op_ranges(ops[i], B, R[i], W[i]);
+  cudaGraph_t gr = nullptr;
+  cudaError_t e = cudaGraphCreate(&gr, 0);
+  std::vector<cudaGraphNode_t> node(ops.size());
+  int edges = 0;
+  for (size_t i = 0; i < ops.size() && e == cudaSuccess; ++i) {
+    std::vector<cudaGraphNode_t> deps;
+    for (size_t j = 0; j < i; ++j)
+      if (ops_conflict(R[j], W[j], R[i], W[i])) deps.push_back(node[j]);
+    edges += (int)deps.size();
+    Op& o = ops[i];
+    if (o.type == OP_ZERO) {
+      cudaMemsetParams mp{};
+      mp.dst = o.zero.p; mp.value = 0; mp.elementSize = 4; mp.width = (size_t)o.zero.n; mp.height = 1; mp.pitch = 0;
+      e = cudaGraphAddMemsetNode(&node[i], gr, deps.data(), deps.size(), &mp);
+      continue;
+    }
+    cudaKernelNodeParams kp{};
+    void* args[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int xn = 0;
+    kp.blockDim = dim3(256);
+    kp.gridDim = dim3(1);
+    switch (o.type) {
+      case OP_GEMM:
+        kp.func = reinterpret_cast<void*>(gemm_kernel);
+        kp.gridDim = dim3((o.gemm.N + 31) / 32, (o.gemm.M + 31) / 32);
+        args[0] = &o.gemm;
+        break;
+      case OP_PREP:
+        kp.func = reinterpret_cast<void*>(prep_kernel);
+        kp.gridDim = dim3((B + 127) / 128); kp.blockDim = dim3(128);
+        args[0] = &o.prep;
+        break;
+      case OP_XHAT:
+        kp.func = reinterpret_cast<void*>(xhat_kernel);
+        kp.gridDim = dim3((o.xhat.n + 255) / 256);
+        xn = o.xhat.n;
+        args[0] = &o.xhat.code; args[1] = &o.xhat.f; args[2] = &o.xhat.alpha; args[3] = &o.xhat.xh; args[4] = &xn;
+        break;
+      case OP_LOSS_D:
+        kp.func = reinterpret_cast<void*>(loss_d_kernel); kp.blockDim = dim3(1024); args[0] = &o.loss;
+        break;
+      case OP_LOSS_G:
+        kp.func = reinterpret_cast<void*>(loss_g_kernel); kp.blockDim = dim3(1024); args[0] = &o.loss;
+        break;
+      case OP_GIN:
+        kp.func = reinterpret_cast<void*>(g_input_grads_kernel); kp.gridDim = dim3(B); args[0] = &o.gin;
+        break;
+      case OP_LGRAD:
+        kp.func = reinterpret_cast<void*>(subspace_l_grad_kernel); kp.gridDim = dim3(kGLayers * kSub); args[0] = &o.lgrad;
+        break;
+    }
+    kp.kernelParams = args;
+    e = cudaGraphAddKernelNode(&node[i], gr, deps.data(), deps.size(), &kp);
+  }
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&t->exec[which], gr, 0);
+  if (gr) cudaGraphDestroy(gr);
+  t->launches[which] = (int)ops.size() + 1;
+  t->n_ops[which] = (int)ops.size();
+  t->n_sync[which] = edges;
+  return e;
 }
 
 cudaError_t build_persistent(chb_cttrain* t, int which) {
@@ -944,7 +1104,7 @@ cudaError_t build_persistent(chb_cttrain* t, int which) {
   Rec rc{nullptr};
   rc.ops = &ops;
   record_step(t, which, rc);
-  schedule_ops(ops, t->persist_grid, &t->n_sync[which]);
+  schedule_ops(ops, t->persist_grid, t->B, &t->n_sync[which]);
   cudaError_t e = cudaMalloc(&t->dev_ops[which], ops.size() * sizeof(Op));
   if (e == cudaSuccess) e = cudaMemcpy(t->dev_ops[which], ops.data(), ops.size() * sizeof(Op), cudaMemcpyHostToDevice);
   t->n_ops[which] = (int)ops.size();
@@ -1119,19 +1279,7 @@ int chb_cttrain_step(chb_cttrain* t, int which, const chb_cttrain_batch* b, floa
       t->bar_total += (unsigned long long)t->n_sync[which] * (unsigned long long)t->persist_grid;
     }
   } else if (err == cudaSuccess && graph) {
-    if (!t->exec[which]) {
-      Rec rc{s};
-      err = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
-      if (err == cudaSuccess) {
-        record_step(t, which, rc);
-        cudaGraph_t gr = nullptr;
-        cudaError_t e2 = cudaStreamEndCapture(s, &gr);
-        err = rc.err != cudaSuccess ? rc.err : e2;
-        if (err == cudaSuccess) err = cudaGraphInstantiate(&t->exec[which], gr, 0);
-        if (gr) cudaGraphDestroy(gr);
-        t->launches[which] = rc.n + 1;
-      }
-    }
+    if (!t->exec[which]) err = build_graph(t, which);
     if (err == cudaSuccess) err = cudaGraphLaunch(t->exec[which], s);
   } else if (err == cudaSuccess) {
     Rec rc{s};
@@ -1172,7 +1320,7 @@ int chb_cttrain_launches(const chb_cttrain* t, int which) {
   return (t && (which == 0 || which == 1)) ? t->launches[which] : 0;
 }
 
-/* Persistent form only: operations and grid barriers of one sub-step (0 before its first use). */
+/* Operations and dependency edges (graph) / grid barriers (persistent kernel) of one sub-step (0 before first use). */
 int chb_cttrain_schedule(const chb_cttrain* t, int which, int* n_ops, int* n_barriers) {
   if (!t || (which != 0 && which != 1)) return CHB_ERR_ARG;
   if (n_ops) *n_ops = t->n_ops[which];

@@ -327,9 +327,10 @@ typedef struct {
   float lambda_adv, lambda_gp, lambda_info, lambda_info_curliness, lambda_rec, lambda_rgb, lambda_pca_std,
       lambda_moment_1, lambda_moment_2, lambda_cls_curliness, lambda_orthogonal; /* config.py:16-39,52-96   */
   float lr, beta1, beta2, eps;                                                      /* 2e-4, .5, .999, 1e-8    */
-  int use_graph;        /* 0: plain launches; 1: each sub-step captured into a CUDA graph on first use; 2: each sub-step as
-                           ONE persistent cooperative kernel walking an operation list with grid barriers between
-                           dependent operations only (same arithmetic; the default of the Python host)          */
+  int use_graph;        /* 0: plain launches; 1: each sub-step as an explicit CUDA graph built on first use, one node per
+                           operation and an edge per real data dependency (the default of the Python host); 2: each
+                           sub-step as ONE persistent cooperative kernel walking the operation list with grid barriers
+                           between dependent operations only.  Same arithmetic in all three.                       */
 } chb_cttrain_config;
 typedef struct {  /* device pointers, fp32 unless noted; rows = batch */
   const float* code;             /* [B,512]  data['code']                                   */
@@ -365,7 +366,8 @@ int chb_cttrain_step(chb_cttrain* t, int which, const chb_cttrain_batch* batch, 
 /* Adam update of one net from its grads region (after the optional all-reduce); advances that net's step count. */
 int chb_cttrain_adam(chb_cttrain* t, int which, void* stream);
 int chb_cttrain_launches(const chb_cttrain* t, int which);
-/* use_graph == 2: number of operations and of grid barriers in the persistent kernel of a sub-step (after first use). */
+/* After the first use of a sub-step: its number of operations and, for use_graph 1, of dependency edges in its graph,
+ * for use_graph 2, of grid barriers in its persistent kernel. */
 int chb_cttrain_schedule(const chb_cttrain* t, int which, int* n_ops, int* n_barriers);
 
 /* ------------------------------------------------------------------------------------------

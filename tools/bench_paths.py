@@ -139,7 +139,7 @@ def bench_train(a):
     rank, local_rank, world = parallel.init_process_group()
     torch.cuda.set_device(local_rank)
     B = a.train_batch
-    s = ct_train.SolverB200(None, "cuda:%d" % local_rank, batch_size=B, use_graph=getattr(a, "train_mode", "persistent"))
+    s = ct_train.SolverB200(None, "cuda:%d" % local_rank, batch_size=B, use_graph=getattr(a, "train_mode", "graph"))
     s.load_state_dicts(*synth.make_ct_train_state_dicts())
     batches = [synth.make_ct_train_batch(B, 5000 + 100 * rank + i) for i in range(4)]   # rank-distinct data
     batches = [{k: v.cuda() for k, v in b.items()} for b in batches]
@@ -180,8 +180,9 @@ def bench_train(a):
         res = emit({"path": "config 5: colour/texture train.py iteration (D + G sub-steps, 2 Adam updates)", "n_gpus": world,
               "batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms, "steps_per_s": 1e3 / ms,
               "samples_per_s": B * world / ms * 1e3, "launches_per_step": s.launches(0) + s.launches(1) + 2,
-              "mode": {2: "persistent cooperative kernel per sub-step", 1: "CUDA graph per sub-step", 0: "plain launches"}[s.mode],
-              "operations_and_barriers": [s.schedule(0), s.schedule(1)] if s.mode == 2 else None,
+              "mode": {2: "persistent cooperative kernel per sub-step", 1: "explicit dependency CUDA graph per sub-step", 0: "plain launches"}[s.mode],
+              "operations_and_%s" % ("barriers" if s.mode == 2 else "graph_edges"):
+                  [s.schedule(0), s.schedule(1)] if s.mode else None,
               "allreduce_per_step": 2 if world > 1 else 0, "dtype": "f32", "losses_finite": finite})
     if world > 1 and own_pg:
         torch.distributed.destroy_process_group()
@@ -320,7 +321,7 @@ def main():
     ap.add_argument("--B", type=int, default=32)
     ap.add_argument("--B512", type=int, default=16)
     ap.add_argument("--train-batch", type=int, default=32)
-    ap.add_argument("--train-mode", default="persistent", help="persistent | graph")
+    ap.add_argument("--train-mode", default="graph", help="graph | persistent")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
