@@ -376,17 +376,20 @@ def run_ours(args):
     peaks = load_peaks()
     achieved = algo_flops / (conv_ms * 1e-3) / 1e12
     top = sorted(zip(ms, names, fl), reverse=True)[:5]
-    traffic = None
+    traffic, traffic_note = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if B == 64 and crop == 256:
+        if B == 64 and crop == 256 and args.precision == "parity":
             traffic = tj["dram_bytes_per_launch_avg"]
+            traffic_note = ("DRAM bytes per conv launch, averaged over the %d conv launches of one step = %.1f GB per step "
+                            "(ncu dram__bytes_read.sum + dram__bytes_write.sum, %s)" %
+                            (tj["conv_launches_per_step"], tj["dram_bytes_per_step"] / 1e9, tj["source"].split(" ")[0]))
     except Exception:
         pass
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
-        "traffic_note": "DRAM bytes per conv launch, averaged over the 57 launches of one step (ncu, profiles/)",
+        "traffic_note": traffic_note,
         "kernel": "chb::conv_igemm_kernel (all %d conv launches of one step, CUDA events between launches)" % len(ms),
         "algorithmic_gflop_per_image": 2.0 * fact_macs / 1e9, "issued_gflop_per_image": sum(fl) / B / 1e9,
         "reference_dense_gflop_per_image": 2.0 * dense_macs / 1e9, "kernel_ms_per_step": conv_ms,

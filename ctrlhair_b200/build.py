@@ -65,7 +65,8 @@ def build_library(force=False, verbose=False):
         objs.append(o)
     out = lib_path()
     if force or _stale(out, objs):
-        cmd = [nvcc, "-shared", "-cudart", "static", "-o", out] + objs + ["-lpthread", "-ldl", "-lrt"]
+        cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + \
+              ["-lpthread", "-ldl", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
