@@ -34,25 +34,30 @@ static inline unsigned bgrid(long long n, int block) {
 }
 
 // ---------------------------------------------------------------- stem: normalise + conv 7x7 s2 p3 (3 -> 64) + BN + ReLU
-// img u8 [B,S,S,3] RGB (what cv2 / PIL hand over after the 512x512 resize); x = (img/255 - mean) / std is folded into a
-// per-channel affine (my_parsing_util.py:25-28).  One thread = one output pixel x 16 output channels; the 7x7x3 patch
-// lives in registers, weights [64][148] (147 padded) in shared memory read as broadcast float4.
+// img u8 [B,S,S,3] RGB (what cv2 / PIL hand over after the 512x512 resize); x = (img/255 - mean) / std
+// (my_parsing_util.py:25-28).  One thread = one output pixel x 16 output channels.  Consecutive threads own consecutive
+// pixels of the SAME channel group, so a warp's weight reads are pure shared-memory broadcasts (one 16-byte read feeds
+// four FMAs: rows of 21 weights are padded to 24) and its image reads walk along a row.
 __global__ void __launch_bounds__(256) bisenet_stem_kernel(const uint8_t* __restrict__ img,
                                                            const float* __restrict__ w /*[64][148]: co, (ky,kx,ci)*/,
                                                            const float* __restrict__ bias, __half* __restrict__ out,
                                                            int B, int S) {
-  __shared__ __align__(16) float sw[64 * 148];
+  __shared__ __align__(16) float sw[64 * 7 * 24];   // [co][ky][24]: 21 = 7 taps x 3 channels, zero padded
   __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 64 * 148; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 64 * 7 * 24; i += blockDim.x) {
+    const int co = i / 168, r = i - co * 168, ky = r / 24, k = r - ky * 24;
+    sw[i] = k < 21 ? w[co * 148 + ky * 21 + k] : 0.f;
+  }
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const int So = S / 2;
   const float nm[3] = {0.485f, 0.456f, 0.406f}, ns[3] = {0.229f, 0.224f, 0.225f};
-  const long long total = (long long)B * So * So * 4;   // 4 channel groups of 16 per pixel
+  const long long npix = (long long)B * So * So;
+  const long long total = npix * 4;   // 4 channel groups of 16 per pixel
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i & 3);
-    const long long pix = i >> 2;
+    const int cg = (int)(i / npix);
+    const long long pix = i - (long long)cg * npix;
     const int x = (int)(pix % So), y = (int)((pix / So) % So), b = (int)(pix / ((long long)So * So));
     float acc[16];
 #pragma unroll
@@ -72,10 +77,16 @@ __global__ void __launch_bounds__(256) bisenet_stem_kernel(const uint8_t* __rest
       in[21] = in[22] = in[23] = 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float* wr = sw + (cg * 16 + j) * 148 + ky * 21;
+        const float4* wr = reinterpret_cast<const float4*>(sw + ((cg * 16 + j) * 7 + ky) * 24);
         float a = acc[j];
 #pragma unroll
-        for (int k = 0; k < 21; ++k) a = fmaf(in[k], wr[k], a);
+        for (int q = 0; q < 6; ++q) {
+          const float4 wv = wr[q];
+          a = fmaf(in[4 * q], wv.x, a);
+          a = fmaf(in[4 * q + 1], wv.y, a);
+          a = fmaf(in[4 * q + 2], wv.z, a);
+          a = fmaf(in[4 * q + 3], wv.w, a);
+        }
         acc[j] = a;
       }
     }

@@ -45,6 +45,7 @@ struct BlockInfo {
   int t_shw, t_shb, t_c0w, t_c0b, t_c1w, t_c1b, t_csw, t_cswlo;
   int split_hs, split_h0, split_h1;  // fp16 hi+lo split of the conv_s / conv_0 / conv_1 input (chb_gen_config.precision)
   int64_t ws_xout;  // workspace offset of the block output
+  int64_t ws_actv;  // this block's mlp_shared output (own buffer: the mlp_shared launches of all blocks are independent)
 };
 
 struct Step {
@@ -96,6 +97,7 @@ struct chb_generator {
     void* args[4];
   };
   std::map<int, GraphEntry*> graphs;
+  std::vector<cudaStream_t> side;  // capture-time side streams of chb_generator_forward_graph
   std::map<std::string, std::pair<int64_t, int>> debug;  // name -> (ws offset, dtype)
   int step_limit = -1;  // debug: run only the first n conv steps
 };
@@ -220,10 +222,10 @@ static void build_layout(chb_generator* g) {
   }
   g->ws_x0 = ws_alloc(g, (int64_t)B * g->sw * g->sw * 16 * nf * 4);
   g->debug["x_fc"] = {g->ws_x0, CHB_F32};
-  int64_t m_actv = 0, m_hs = 0, m_hin = 0, m_h1 = 0, m_dx0 = 0;
+  int64_t m_hs = 0, m_hin = 0, m_h1 = 0, m_dx0 = 0;
   for (auto& b : g->blocks) {
     const int64_t px = (int64_t)B * b.r * b.r;
-    m_actv = std::max<int64_t>(m_actv, px * 128 * b.n_ace * 2);
+    b.ws_actv = ws_alloc(g, px * 128 * b.n_ace * 2);
     m_hs = std::max<int64_t>(m_hs, px * b.fin * 2 * (b.split_hs ? 2 : 1));
     m_hin = std::max<int64_t>(m_hin, px * b.fin * 2 * (b.split_h0 ? 2 : 1));
     m_h1 = std::max<int64_t>(m_h1, px * b.fmid * 2 * (b.split_h1 ? 2 : 1));
@@ -233,7 +235,7 @@ static void build_layout(chb_generator* g) {
     b.ws_xout = ws_alloc(g, px * b.fout * (last ? ((c.precision & CHB_PREC_IMG) ? 4 : 2) : 4));
     g->debug["x_" + b.name] = {b.ws_xout, last ? CHB_F16 : CHB_F32};
   }
-  g->ws_actv = ws_alloc(g, m_actv);
+  g->ws_actv = g->blocks.back().ws_actv;
   g->ws_hs = ws_alloc(g, m_hs);
   g->ws_h0 = ws_alloc(g, m_hin);
   if (c.precision & CHB_PREC_IMG) {
@@ -424,7 +426,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.N = d.Nrows = actvC; d.BN = actvC == 384 ? 192 : 256;  // one-hot A tile is re-read per N tile: keep N tiles few
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_RELU;
       d.bias = nullptr;  // carried by the constant one-hot channels (sh.w centre tap)
-      nhwc_out(&d, ws + g->ws_actv, CHB_F16, r, actvC);
+      nhwc_out(&d, ws + b.ws_actv, CHB_F16, r, actvC);
       if ((rc = push_step(steps, d, b.name + ".mlp_shared")) != CHB_OK) return rc;
     }
     auto modulate = [&](int a, const float* x, int x_r, int x_shift, int xC, void* hout, int act, int split) -> int {
@@ -437,7 +439,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
         d.seg[ns].w_sb = g->weff_rows * 32;
         ++ns;
       }
-      d.seg[ns++] = make_seg(ws + g->ws_actv, r, actvC, A.actv_off, 128, 9, blobp(g, A.t_gbw));
+      d.seg[ns++] = make_seg(ws + b.ws_actv, r, actvC, A.actv_off, 128, 9, blobp(g, A.t_gbw));
       d.nseg = ns;
       d.N = d.Nrows = 2 * A.C;
       d.BN = d.N < 256 ? d.N : 256;
@@ -582,6 +584,7 @@ void chb_generator_destroy(chb_generator* g) {
     if (kv.second->graph) cudaGraphDestroy(kv.second->graph);
     delete kv.second;
   }
+  for (cudaStream_t st : g->side) cudaStreamDestroy(st);
   delete g;
 }
 
@@ -652,7 +655,9 @@ static int get_steps(chb_generator* g, int B, std::vector<Step>** out) {
 }
 
 static int forward_impl(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
-                        uint64_t seed, float* out, int B, int impl, void* stream_, cudaEvent_t* evs, int nev);
+                        uint64_t seed, float* out, int B, int impl, void* stream_, cudaEvent_t* evs, int nev,
+                        bool dag = false);
+static int capture_steps_dag(chb_generator* g, std::vector<Step>& steps, int B, float* out, cudaStream_t cap);
 
 int chb_generator_forward(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
                           uint64_t seed, float* out, int B, int impl, void* stream_) {
@@ -694,7 +699,7 @@ int chb_generator_forward_timed(chb_generator* g, const uint8_t* labels, const f
 }
 
 static int forward_impl(chb_generator* g, const uint8_t* labels, const float* codes, const float* noise,
-                        uint64_t seed, float* out, int B, int impl, void* stream_, cudaEvent_t* evs, int nev) {
+                        uint64_t seed, float* out, int B, int impl, void* stream_, cudaEvent_t* evs, int nev, bool dag) {
   if (!g || !labels || !codes || !out) {
     set_error("chb_generator_forward: NULL argument");
     return CHB_ERR_ARG;
@@ -738,6 +743,7 @@ static int forward_impl(chb_generator* g, const uint8_t* labels, const float* co
     rc = chb_noise_fill(nz, (int64_t)B * g->noise_pix, seed, 0, stream);
     if (rc != CHB_OK) return rc;
   }
+  if (dag) return capture_steps_dag(g, *steps, B, out, stream);   // under capture: steps with their real dependencies
   int nrun = 0, iev = 0;
   if (evs && iev < nev) cudaEventRecord(evs[iev++], stream);
   for (const Step& s : *steps) {
@@ -755,6 +761,126 @@ static int forward_impl(chb_generator* g, const uint8_t* labels, const float* co
     }
     if (rc != CHB_OK) return rc;
     if (evs && iev < nev) cudaEventRecord(evs[iev++], stream);
+  }
+  return CHB_OK;
+}
+
+// ---- dependency-driven capture -------------------------------------------------------------------------------------
+// Byte ranges (hulls of the strided accesses) a step reads / writes inside the workspace.  Weights in the blob are
+// read-only and left out; per-image style tables (Weff) live in the workspace and are included.
+struct ByteRange { const char* lo; const char* hi; };
+static void add_br(std::vector<ByteRange>& v, const void* p, long long bytes) {
+  if (p && bytes > 0) v.push_back({static_cast<const char*>(p), static_cast<const char*>(p) + bytes});
+}
+static bool br_overlap(const std::vector<ByteRange>& a, const std::vector<ByteRange>& b) {
+  for (const ByteRange& x : a)
+    for (const ByteRange& y : b)
+      if (x.lo < y.hi && y.lo < x.hi) return true;
+  return false;
+}
+static void step_ranges(const chb_generator* g, const Step& s, int B, const float* out, std::vector<ByteRange>& r,
+                        std::vector<ByteRange>& w) {
+  const chb_gen_config& c = g->cfg;
+  if (s.kind == 1) {
+    add_br(r, g->ws + g->ws_y, (long long)B * c.crop * c.crop * 32 * 4);
+    add_br(w, out, (long long)B * 3 * c.crop * c.crop * 4);
+    return;
+  }
+  const chb_conv_desc& d = s.plan.desc;
+  for (int i = 0; i < d.nseg; ++i) {
+    const chb_conv_seg& q = d.seg[i];
+    add_br(r, q.a, ((long long)(d.B - 1) * q.a_sb + (long long)(d.H + 2 * q.a_pad - 1) * q.a_sy +
+                    (long long)(d.W + 2 * q.a_pad - 1) * q.a_sx + q.Ca) * 2);
+    if (q.per_image) {
+      const long long K = (long long)q.taps * (q.w_dup == 2 ? q.C / 2 : q.C);
+      const long long per = q.w_sb > 0 ? q.w_sb : (long long)d.Nrows * K;
+      add_br(r, q.w, ((long long)(d.B - 1) * per + (long long)d.Nrows * K) * 2);
+    }
+  }
+  const long long ob = d.out_dtype == CHB_F16 ? 2 : 4;
+  long long last = (long long)(d.B - 1) * d.o_sb + (long long)(d.H - 1) * d.o_sy + (long long)(d.W - 1) * d.o_sx;
+  if (d.o_ngroup > 0) last += (long long)((d.N - 1) / d.o_ngroup) * d.o_sgroup + (long long)(d.o_ngroup - 1) * d.o_sn;
+  else last += (long long)(d.N - 1) * d.o_sn;
+  if (d.o_split) last += d.o_lo_off;
+  add_br(w, s.final_image ? static_cast<const void*>(out) : d.out, (last + 1) * ob);
+  if (d.x)
+    add_br(r, d.x, ((long long)(d.B - 1) * d.x_sb + (long long)((d.H - 1) >> d.x_shift) * d.x_sy +
+                    (long long)((d.W - 1) >> d.x_shift) * d.x_sx + d.N / 2) * 4);
+  if (d.res)
+    add_br(r, d.res, ((long long)(d.B - 1) * d.r_sb + (long long)((d.H - 1) >> d.r_shift) * d.r_sy +
+                      (long long)((d.W - 1) >> d.r_shift) * d.r_sx + d.N) * 4);
+  if (d.noise) add_br(r, d.noise, (long long)d.B * d.W * d.H * 4);
+}
+
+// Captures the conv schedule into the graph being recorded on `cap` with its REAL dependencies: every step goes to a
+// side stream and waits for the events of the earlier steps it conflicts with (RAW / WAR / WAW on workspace ranges).  A
+// linear capture makes the 48 launches one chain; with dependencies the style path (fc_mu, weff), the mlp_shared launches
+// of all seven blocks and the two gamma/beta launches that read the same block input run beside the chain, which is
+// what the latency of a one-image forward consists of.
+static int capture_steps_dag(chb_generator* g, std::vector<Step>& steps, int B, float* out, cudaStream_t cap) {
+  const int kSide = 6;
+  cudaError_t err = cudaSuccess;
+  while ((int)g->side.size() < kSide && err == cudaSuccess) {
+    cudaStream_t st = nullptr;
+    err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (err == cudaSuccess) g->side.push_back(st);
+  }
+  const int n = (int)steps.size();
+  std::vector<std::vector<ByteRange>> R(n), W(n);
+  for (int i = 0; i < n; ++i) step_ranges(g, steps[i], B, out, R[i], W[i]);
+  std::vector<cudaEvent_t> ev(n + 1, nullptr);
+  for (auto& e : ev)
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  std::vector<int> stream_of(n, -1), tail(kSide, -1);
+  std::vector<char> joined(kSide, 0);
+  if (err == cudaSuccess) err = cudaEventRecord(ev[n], cap);   // root: the helper kernels recorded on `cap` so far
+  int rc = CHB_OK, rr = 0;
+  for (int i = 0; i < n && err == cudaSuccess && rc == CHB_OK; ++i) {
+    std::vector<int> deps;
+    for (int j = 0; j < i; ++j)
+      if (br_overlap(W[j], R[i]) || br_overlap(W[j], W[i]) || br_overlap(R[j], W[i])) deps.push_back(j);
+    // continue the chain of the latest dependency when it is still the tail of its stream, else take an idle stream
+    int k = -1;
+    for (int q = (int)deps.size() - 1; q >= 0 && k < 0; --q)
+      if (tail[stream_of[deps[q]]] == deps[q]) k = stream_of[deps[q]];
+    if (k < 0) {
+      for (int q = 0; q < kSide && k < 0; ++q)
+        if (tail[(rr + q) % kSide] < 0) k = (rr + q) % kSide;
+      if (k < 0) k = rr % kSide;
+      ++rr;
+    }
+    cudaStream_t st = g->side[k];
+    if (!joined[k]) {
+      err = cudaStreamWaitEvent(st, ev[n], 0);
+      joined[k] = 1;
+    }
+    for (int j : deps)
+      if (err == cudaSuccess && !(stream_of[j] == k)) err = cudaStreamWaitEvent(st, ev[j], 0);
+    if (err != cudaSuccess) break;
+    const Step& s = steps[i];
+    if (s.kind == 1) {
+      rc = img_from_taps(reinterpret_cast<const float*>(g->ws + g->ws_y),
+                         reinterpret_cast<const float*>(blobp(g, g->t_imgb)), out, B, g->cfg.crop, st);
+    } else if (s.final_image && out != reinterpret_cast<float*>(g->ws + g->ws_out)) {
+      ConvPlan p = s.plan;
+      p.kp.e.out = out;
+      p.desc.out = out;
+      rc = launch_conv_plan(p, CHB_IMPL_TCGEN05, st);
+    } else {
+      rc = launch_conv_plan(s.plan, CHB_IMPL_TCGEN05, st);
+    }
+    if (rc == CHB_OK) err = cudaEventRecord(ev[i], st);
+    stream_of[i] = k;
+    tail[k] = i;
+  }
+  for (int k = 0; k < kSide && err == cudaSuccess; ++k)   // join every side stream back into the capturing stream
+    if (tail[k] >= 0) err = cudaStreamWaitEvent(cap, ev[tail[k]], 0);
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+  if (rc != CHB_OK) return rc;
+  if (err != cudaSuccess) {
+    set_error(std::string("forward_graph: dependency capture failed: ") + cudaGetErrorString(err));
+    return CHB_ERR_CUDA;
   }
   return CHB_OK;
 }
@@ -797,7 +923,7 @@ int chb_generator_forward_graph(chb_generator* g, const uint8_t* labels, const f
     err = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (err == cudaSuccess) {
-      rc = forward_impl(g, d_labels, d_codes, nullptr, seed, d_out, B, CHB_IMPL_TCGEN05, cap, nullptr, 0);
+      rc = forward_impl(g, d_labels, d_codes, nullptr, seed, d_out, B, CHB_IMPL_TCGEN05, cap, nullptr, 0, /*dag=*/true);
       err = cudaStreamEndCapture(cap, &graph);
       if (rc != CHB_OK) {
         if (graph) cudaGraphDestroy(graph);
