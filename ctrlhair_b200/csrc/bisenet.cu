@@ -27,6 +27,7 @@
 
 namespace chb {
 
+constexpr int kPoolSlabs = 16;
 static inline unsigned bgrid(long long n, int block) {
   long long g = (n + block - 1) / block;
   const long long cap = (long long)device_sm_count() * 32;
@@ -35,17 +36,17 @@ static inline unsigned bgrid(long long n, int block) {
 
 // ---------------------------------------------------------------- stem: normalise + conv 7x7 s2 p3 (3 -> 64) + BN + ReLU
 // img u8 [B,S,S,3] RGB (what cv2 / PIL hand over after the 512x512 resize); x = (img/255 - mean) / std
-// (my_parsing_util.py:25-28).  One thread = one output pixel x 16 output channels.  Consecutive threads own consecutive
-// pixels of the SAME channel group, so a warp's weight reads are pure shared-memory broadcasts (one 16-byte read feeds
-// four FMAs: rows of 21 weights are padded to 24) and its image reads walk along a row.
-__global__ void __launch_bounds__(256) bisenet_stem_kernel(const uint8_t* __restrict__ img,
+// (my_parsing_util.py:25-28), evaluated in the reference's operation order (scale, subtract, divide).  One thread = one
+// output pixel x all 64 output channels: the 7 x 7 x 3 patch is fetched and normalised once, every weight read is a
+// shared-memory broadcast (a warp reads one 16-byte word for four FMAs; rows of 21 weights are padded to 24).
+__global__ void __launch_bounds__(128) bisenet_stem_kernel(const uint8_t* __restrict__ img,
                                                            const float* __restrict__ w /*[64][148]: co, (ky,kx,ci)*/,
                                                            const float* __restrict__ bias, __half* __restrict__ out,
                                                            int B, int S) {
-  __shared__ __align__(16) float sw[64 * 7 * 24];   // [co][ky][24]: 21 = 7 taps x 3 channels, zero padded
+  __shared__ __align__(16) float sw[7 * 64 * 24];   // [ky][co][24]: 21 = 7 taps x 3 channels, zero padded
   __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 64 * 7 * 24; i += blockDim.x) {
-    const int co = i / 168, r = i - co * 168, ky = r / 24, k = r - ky * 24;
+  for (int i = threadIdx.x; i < 7 * 64 * 24; i += blockDim.x) {
+    const int ky = i / (64 * 24), r = i - ky * 64 * 24, co = r / 24, k = r - co * 24;
     sw[i] = k < 21 ? w[co * 148 + ky * 21 + k] : 0.f;
   }
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
@@ -53,15 +54,12 @@ __global__ void __launch_bounds__(256) bisenet_stem_kernel(const uint8_t* __rest
   const int So = S / 2;
   const float nm[3] = {0.485f, 0.456f, 0.406f}, ns[3] = {0.229f, 0.224f, 0.225f};
   const long long npix = (long long)B * So * So;
-  const long long total = npix * 4;   // 4 channel groups of 16 per pixel
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i / npix);
-    const long long pix = i - (long long)cg * npix;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(pix % So), y = (int)((pix / So) % So), b = (int)(pix / ((long long)So * So));
-    float acc[16];
+    float acc[64];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = sb[cg * 16 + j];
+    for (int j = 0; j < 64; ++j) acc[j] = sb[j];
     for (int ky = 0; ky < 7; ++ky) {
       const int yy = 2 * y + ky - 3;
       float in[24];   // one kernel row: 7 taps x 3 channels (+ padding)
@@ -75,13 +73,13 @@ __global__ void __launch_bounds__(256) bisenet_stem_kernel(const uint8_t* __rest
           in[kx * 3 + c] = ok ? ((float)__ldg(p + c) * (1.f / 255.f) - nm[c]) / ns[c] : 0.f;
       }
       in[21] = in[22] = in[23] = 0.f;
+      const float4* wk = reinterpret_cast<const float4*>(sw + ky * 64 * 24);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4* wr = reinterpret_cast<const float4*>(sw + ((cg * 16 + j) * 7 + ky) * 24);
+      for (int j = 0; j < 64; ++j) {
         float a = acc[j];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-          const float4 wv = wr[q];
+          const float4 wv = wk[j * 6 + q];
           a = fmaf(in[4 * q], wv.x, a);
           a = fmaf(in[4 * q + 1], wv.y, a);
           a = fmaf(in[4 * q + 2], wv.z, a);
@@ -90,12 +88,15 @@ __global__ void __launch_bounds__(256) bisenet_stem_kernel(const uint8_t* __rest
         acc[j] = a;
       }
     }
-    __half2 h[8];
+    uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-    uint4* o = reinterpret_cast<uint4*>(out + pix * 64 + cg * 16);
-    o[0] = *reinterpret_cast<uint4*>(&h[0]);
-    o[1] = *reinterpret_cast<uint4*>(&h[4]);
+    for (int v = 0; v < 8; ++v) {
+      __half2 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        h[j] = __floats2half2_rn(fmaxf(acc[8 * v + 2 * j], 0.f), fmaxf(acc[8 * v + 2 * j + 1], 0.f));
+      o[v] = *reinterpret_cast<uint4*>(h);
+    }
   }
 }
 
@@ -143,17 +144,21 @@ __global__ void __launch_bounds__(256) subsample2_kernel(const __half* __restric
   }
 }
 
-// ---------------------------------------------------------------- global average pool: fp16 NHWC [B,HW,C] -> fp32 [B,C]
-// grid = B, block = 256; thread t owns channel pair (t % (C/2)) and strides over pixels; fp32 partials via shared memory.
+// ---------------------------------------------------------------- global average pool: fp16 NHWC [B,HW,C] -> fp32 [B,S,C]
+// grid = (B, S slabs of pixels), block = 256; thread t owns channel pair (t % (C/2)) and strides over its slab's pixels;
+// fp32 partials via shared memory.  out[b][s][:] holds slab s's share of the mean (already divided by HW); the consumer
+// (vec_dense_kernel) adds the S partial vectors, so the pool of a 64 x 64 x 256 map is read by 16 CTAs per image.
 __global__ void __launch_bounds__(256) avgpool_kernel(const __half* __restrict__ in, float* __restrict__ out, int HW,
                                                       int C) {
   __shared__ float2 part[256];
   const int b = blockIdx.x, c2 = C / 2, lanes = 256 / c2;
+  const int slab = blockIdx.y, nslab = gridDim.y;
+  const int per = (HW + nslab - 1) / nslab, q0 = slab * per, q1 = min(HW, q0 + per);
   const int cp = threadIdx.x % c2, pl = threadIdx.x / c2;
   float2 acc = make_float2(0.f, 0.f);
   if (pl < lanes) {
     const __half2* p = reinterpret_cast<const __half2*>(in + (long long)b * HW * C) + cp;
-    for (int q = pl; q < HW; q += lanes) {
+    for (int q = q0 + pl; q < q1; q += lanes) {
       const float2 v = __half22float2(p[(long long)q * c2]);
       acc.x += v.x; acc.y += v.y;
     }
@@ -163,8 +168,9 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const __half* __restrict__
   if (threadIdx.x < c2) {
     float2 s = make_float2(0.f, 0.f);
     for (int l = 0; l < lanes; ++l) { s.x += part[l * c2 + threadIdx.x].x; s.y += part[l * c2 + threadIdx.x].y; }
-    out[(long long)b * C + 2 * threadIdx.x] = s.x / (float)HW;
-    out[(long long)b * C + 2 * threadIdx.x + 1] = s.y / (float)HW;
+    float* o = out + ((long long)b * nslab + slab) * C;
+    o[2 * threadIdx.x] = s.x / (float)HW;
+    o[2 * threadIdx.x + 1] = s.y / (float)HW;
   }
 }
 
@@ -172,10 +178,14 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const __half* __restrict__
 // (the 1x1 convs on pooled vectors: conv_avg, conv_atten, ffm.conv1/conv2).  act: 0 none, 1 relu, 2 sigmoid.
 __global__ void __launch_bounds__(256) vec_dense_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y, int Cin,
-                                                        int Cout, int act) {
+                                                        int Cout, int act, int nparts) {
   extern __shared__ float sx[];
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < Cin; i += blockDim.x) sx[i] = x[(long long)b * Cin + i];
+  for (int i = threadIdx.x; i < Cin; i += blockDim.x) {   // x[b] = sum of nparts partial vectors (avgpool slabs)
+    float v = 0.f;
+    for (int p = 0; p < nparts; ++p) v += x[((long long)b * nparts + p) * Cin + i];
+    sx[i] = v;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int o = warp; o < Cout; o += blockDim.x >> 5) {
@@ -399,7 +409,7 @@ static void build_bisenet_layout(chb_bisenet* n) {
   }
   const int H8 = R / 2, H16 = R / 4, H32 = R / 8;
   // ---- context path (model.py:127-146)
-  bws(n, "v_avg32", B * 512 * 4);
+  bws(n, "v_avg32", B * 512 * 4 * kPoolSlabs);
   bws(n, "v_avg", B * 128 * 4);
   badd(n, "conv_avg.w", 128 * 512 * 4, CHB_F32);
   badd(n, "conv_avg.b", 128 * 4, CHB_F32);
@@ -409,7 +419,7 @@ static void build_bisenet_layout(chb_bisenet* n) {
     act16(std::string(arm) + ".feat", Hh, 128);
     add_conv(n, std::string(arm) + ".conv", Hh, 128, CHB_ACT_RELU, std::string(arm) + ".feat", CHB_F16,
              {{is32 ? "layer4.1.y" : "layer3.1.y", Ci, 9}});
-    bws(n, std::string(arm) + ".pool", B * 128 * 4);
+    bws(n, std::string(arm) + ".pool", B * 128 * 4 * kPoolSlabs);
     bws(n, std::string(arm) + ".att", B * 128 * 4);
     badd(n, std::string(arm) + ".att.w", 128 * 128 * 4, CHB_F32);
     badd(n, std::string(arm) + ".att.b", 128 * 4, CHB_F32);
@@ -421,7 +431,7 @@ static void build_bisenet_layout(chb_bisenet* n) {
   // ---- feature fusion (model.py:218-228): cat[feat_res8, feat_cp8] as two K-segments
   act16("ffm.feat", H8, 256);
   add_conv(n, "ffm.convblk", H8, 256, CHB_ACT_RELU, "ffm.feat", CHB_F16, {{"layer2.1.y", 128, 1}, {"arm16.head", 128, 1}});
-  bws(n, "ffm.pool", B * 256 * 4);
+  bws(n, "ffm.pool", B * 256 * 4 * kPoolSlabs);
   bws(n, "ffm.mid", B * 64 * 4);
   bws(n, "ffm.att", B * 256 * 4);
   badd(n, "ffm.conv1.w", 64 * 256 * 4, CHB_F32);
@@ -552,12 +562,19 @@ int chb_bisenet_forward(chb_bisenet* n, const uint8_t* img, uint8_t* mask, int o
   auto conv = [&](const std::string& nm) {
     if (rc == CHB_OK) rc = launch_conv_plan(pl[n->cid.at(nm)], CHB_IMPL_TCGEN05, st);
   };
-  auto dense = [&](const float* x, const std::string& w, const char* b, float* y, int Cin, int Cout, int act) {
-    vec_dense_kernel<<<B, 256, Cin * sizeof(float), st>>>(x, Wf(w), b ? Wf(b) : nullptr, y, Cin, Cout, act);
+  auto dense = [&](const float* x, const std::string& w, const char* b, float* y, int Cin, int Cout, int act,
+                   int nparts) {
+    vec_dense_kernel<<<B, 256, Cin * sizeof(float), st>>>(x, Wf(w), b ? Wf(b) : nullptr, y, Cin, Cout, act, nparts);
+  };
+  auto pool = [&](const __half* x, float* y, int HW, int C) {   // slabs of >= 64 pixels
+    int slabs = HW / 64;
+    slabs = slabs < 1 ? 1 : (slabs > kPoolSlabs ? kPoolSlabs : slabs);
+    avgpool_kernel<<<dim3(B, slabs), 256, 0, st>>>(x, y, HW, C);
+    return slabs;
   };
   const int R = S / 4, H8 = R / 2, H16 = R / 4, H32 = R / 8;
-  bisenet_stem_kernel<<<bgrid((long long)B * (S / 2) * (S / 2) * 4, 256), 256, 0, st>>>(img, Wf("stem.w"), Wf("stem.b"),
-                                                                                      Hp("stem"), B, S);
+  bisenet_stem_kernel<<<bgrid((long long)B * (S / 2) * (S / 2), 128), 128, 0, st>>>(img, Wf("stem.w"), Wf("stem.b"),
+                                                                                  Hp("stem"), B, S);
   maxpool3s2_kernel<<<bgrid((long long)B * R * R * 8, 256), 256, 0, st>>>(Hp("stem"), Hp("p0"), B, S / 2, 64);
   const int ch[4] = {64, 128, 256, 512};
   std::string x = "p0";
@@ -583,27 +600,27 @@ int chb_bisenet_forward(chb_bisenet* n, const uint8_t* img, uint8_t* mask, int o
     }
   }
   // context path
-  avgpool_kernel<<<B, 256, 0, st>>>(Hp("layer4.1.y"), Fp("v_avg32"), H32 * H32, 512);
-  dense(Fp("v_avg32"), "conv_avg.w", "conv_avg.b", Fp("v_avg"), 512, 128, 1);
+  int np = pool(Hp("layer4.1.y"), Fp("v_avg32"), H32 * H32, 512);
+  dense(Fp("v_avg32"), "conv_avg.w", "conv_avg.b", Fp("v_avg"), 512, 128, 1, np);
   conv("arm32.conv");
-  avgpool_kernel<<<B, 256, 0, st>>>(Hp("arm32.feat"), Fp("arm32.pool"), H32 * H32, 128);
-  dense(Fp("arm32.pool"), "arm32.att.w", "arm32.att.b", Fp("arm32.att"), 128, 128, 2);
+  np = pool(Hp("arm32.feat"), Fp("arm32.pool"), H32 * H32, 128);
+  dense(Fp("arm32.pool"), "arm32.att.w", "arm32.att.b", Fp("arm32.att"), 128, 128, 2, np);
   scale_add_up_kernel<<<bgrid((long long)B * H16 * H16 * 16, 256), 256, 0, st>>>(Hp("arm32.feat"), Fp("arm32.att"), 0.f,
                                                                                Fp("v_avg"), nullptr, Hp("arm32.sum_up"),
                                                                                B, H32, 128, 2);
   conv("conv_head32");
   conv("arm16.conv");
-  avgpool_kernel<<<B, 256, 0, st>>>(Hp("arm16.feat"), Fp("arm16.pool"), H16 * H16, 128);
-  dense(Fp("arm16.pool"), "arm16.att.w", "arm16.att.b", Fp("arm16.att"), 128, 128, 2);
+  np = pool(Hp("arm16.feat"), Fp("arm16.pool"), H16 * H16, 128);
+  dense(Fp("arm16.pool"), "arm16.att.w", "arm16.att.b", Fp("arm16.att"), 128, 128, 2, np);
   scale_add_up_kernel<<<bgrid((long long)B * H8 * H8 * 16, 256), 256, 0, st>>>(Hp("arm16.feat"), Fp("arm16.att"), 0.f,
                                                                              nullptr, Hp("arm32.head"),
                                                                              Hp("arm16.sum_up"), B, H16, 128, 2);
   conv("conv_head16");
   // feature fusion
   conv("ffm.convblk");
-  avgpool_kernel<<<B, 256, 0, st>>>(Hp("ffm.feat"), Fp("ffm.pool"), H8 * H8, 256);
-  dense(Fp("ffm.pool"), "ffm.conv1.w", nullptr, Fp("ffm.mid"), 256, 64, 1);
-  dense(Fp("ffm.mid"), "ffm.conv2.w", nullptr, Fp("ffm.att"), 64, 256, 2);
+  np = pool(Hp("ffm.feat"), Fp("ffm.pool"), H8 * H8, 256);
+  dense(Fp("ffm.pool"), "ffm.conv1.w", nullptr, Fp("ffm.mid"), 256, 64, 1, np);
+  dense(Fp("ffm.mid"), "ffm.conv2.w", nullptr, Fp("ffm.att"), 64, 256, 2, 1);
   scale_add_up_kernel<<<bgrid((long long)B * H8 * H8 * 32, 256), 256, 0, st>>>(Hp("ffm.feat"), Fp("ffm.att"), 1.f, nullptr,
                                                                              nullptr, Hp("ffm.out"), B, H8, 256, 1);
   conv("conv_out.conv");
