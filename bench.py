@@ -420,6 +420,35 @@ def run_ours(args):
                "weight_stream_floor_ms": gen.blob_bytes() / (load_peaks()["hbm_gbs"] * 1e9) * 1e3,
                "what": "SeanGeneratorB200.forward_labels(B=1, graph=True): one captured CUDA graph per call, back to "
                        "back; floor = packed weight bytes / measured HBM copy bandwidth"}
+    # ---------------- the same timed loop with the single-pass fp16 schedule ("fast" policy): what the 1e-3 costs
+    value_fast = None
+    if args.precision != "fast" and not args.no_extra_configs:
+        gen_f, errf, msf = None, None, -1.0   # collectives stay outside the try blocks (a failing rank must reach them)
+        try:
+            gen_f = SeanGeneratorB200(crop=crop, max_batch=B, device=dev, precision="fast")
+            gen_f.load_state_dict(synth.make_state_dict())
+            for i in range(3):
+                gen_f.forward_labels(labels_d, codes_d, seed=i, out=out_d)
+        except Exception as e:
+            errf = repr(e)[:200]
+        barrier()
+        if errf is None:
+            try:
+                ef0, ef1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ef0.record()
+                for i in range(args.steps):
+                    gen_f.forward_labels(labels_d, codes_d, seed=400 + i, out=out_d)
+                ef1.record()
+                torch.cuda.synchronize(dev)
+                msf = ef0.elapsed_time(ef1)
+            except Exception as e:
+                errf = repr(e)[:200]
+        barrier()
+        msf = max_over_ranks(msf)
+        failed = max_over_ranks(0.0 if errf is None else 1.0)
+        value_fast = ("error: %s" % (errf or "another rank failed")) if failed > 0 else world * B * args.steps / (msf * 1e-3)
+        del gen_f
+        torch.cuda.empty_cache()
     # ---------------- the other BASELINE.json configs, measured as stated (extra keys; the headline stays config 2)
     extra = {}
     if not args.no_extra_configs:
@@ -444,7 +473,10 @@ def run_ours(args):
                        "batch_per_gpu": B, "crop": crop, "ngf": 64, "parallelism": "image-batch shard x%d" % world,
                        "l2": "per-step working set (weights 0.53 GB + activations > 10 GB) exceeds the 126 MB L2; "
                              "no explicit flush", "outputs_finite": finite,
-                       "value_by_mask_distribution": {"blocky (headline)": value, "iid-uniform": value_iid}},
+                       "value_by_mask_distribution": {"blocky (headline)": value, "iid-uniform": value_iid},
+                       "value_by_precision_policy": {
+                           "%s (headline; max-norm <= 1e-3, see parity)" % args.precision: value,
+                           "fast (single-pass fp16 operands; max-norm 1.5-1.8e-3)": value_fast}},
             "clocks": sampler.summary() if sampler else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(labels_h.numel() + codes_h.numel() * 4),
                     "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": t_e2e / args.steps * 1e3,
