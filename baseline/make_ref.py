@@ -46,10 +46,10 @@ def staged():
 
 
 def make(force=False):
+    if staged() and not force:
+        return True          # e.g. on the GPU box: the staged copy travelled with the snapshot, /root/reference does not exist
     if not os.path.isdir(os.path.join(SRC, "sean_codes")):
         return False
-    if staged() and not force:
-        return True
     if os.path.isdir(DEST):
         shutil.rmtree(DEST)
     os.makedirs(DEST)
@@ -57,10 +57,8 @@ def make(force=False):
     for sub in SUBTREES:
         shutil.copytree(os.path.join(SRC, sub), os.path.join(DEST, sub), ignore=ignore)
     digest, n = tree_digest(DEST)
-    src_digest = hashlib.sha256()
     with open(os.path.join(DEST, "DIGEST.json"), "w") as f:
         json.dump({"source": SRC, "subtrees": SUBTREES, "files": n, "sha256": digest}, f)
-    del src_digest
     return True
 
 
