@@ -578,8 +578,11 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         bool valid = true;
         if (FAST) tg.pixel_fast(row_base + lane, b, y, x);
         else valid = tg.pixel(row_base + lane, b, y, x);
-        const int ch = p.BN >> 1;  // columns per warp-half (multiple of 8)
-        int j = chalf * ch;
+        // columns per warp-half (multiple of 8).  Fast geometry with a 32-column N tile: the first warp-half takes all
+        // 32 columns (one staged block), the second has nothing to do but hand the accumulator back.
+        const bool narrow = FAST && p.BN == 32;
+        const int ch = narrow ? (chalf == 0 ? 32 : 0) : (p.BN >> 1);
+        int j = narrow ? 0 : chalf * ch;
         const int jend = j + ch;
         const int n0 = n_tile * p.BN;
         const bool staged = FAST || (e.o_sn == 1 && (e.o_ngroup <= 0 || (e.o_ngroup % 32) == 0));

@@ -424,7 +424,8 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
     auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
     const long long ob = d.out_dtype == CHB_F16 ? 2 : 4;
     bool fast = d.TB == 1 && d.TW == 8 && d.TH == 16 && d.H % 16 == 0 && d.W % 8 == 0 && pow2(k.tiles_x) &&
-                pow2(k.tiles_y) && d.N == d.Nrows && d.BN % 64 == 0 && (d.o_sn == 1 || d.epi == CHB_EPI_MODULATE) &&
+                pow2(k.tiles_y) && d.N == d.Nrows && (d.BN % 64 == 0 || (d.BN == 32 && d.epi == CHB_EPI_PLAIN)) &&
+                (d.o_sn == 1 || d.epi == CHB_EPI_MODULATE) &&
                 (d.o_ngroup <= 0 || d.o_ngroup % 32 == 0) && (d.o_sb * ob) % 16 == 0 && (d.o_sy * ob) % 16 == 0 &&
                 (d.o_sx * ob) % 16 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0;
     if (d.epi == CHB_EPI_PLAIN && d.res)
