@@ -96,11 +96,13 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
         }
       } else {
         const uint32_t bytes = (uint32_t)p.rows * (uint32_t)sg.kc * 2u + wbytes;
-        for (int tap = 0; tap < sg.taps; ++tap) {
-          const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
-          const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;
-          for (int c = 0; c < sg.nchunk; ++c) {
-            const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;
+        // channel chunk outer, tap inner: the same accumulation order as the halo paths, so a layer gives bitwise the
+        // same result whether its tiles take this path (several small images per tile) or a halo path (one image)
+        for (int c = 0; c < sg.nchunk; ++c) {
+          const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;
+          for (int tap = 0; tap < sg.taps; ++tap) {
+            const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
+            const int dx = sg.taps == 9 ? tap % 3 - 1 : 0;
             mbar_wait(&sm.empty[stage], phase ^ 1u);
             uint8_t* sa = sm.stage_base + (size_t)stage * p.stage_bytes;
             if (elect_one()) {

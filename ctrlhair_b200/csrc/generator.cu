@@ -301,6 +301,17 @@ static chb_conv_desc base_desc(int B, int r) {
   return d;
 }
 
+// Images smaller than a 128-pixel tile (8x8 at crop 256): a PLAIN conv with shared weights batches several images into
+// one 128-row MMA tile instead of issuing half-empty MMAs.  Rows of an MMA are independent, so an image's result does
+// not depend on its tile-mates (the batch-invariance tests stay bitwise).
+static void batch_small_tiles(chb_conv_desc* d) {
+  const int px = d->TW * d->TH;
+  if (px >= 128) return;
+  int tb = 128 / px;
+  if (tb > d->B) tb = d->B;
+  d->TB = tb < 1 ? 1 : tb;
+}
+
 static void nhwc_out(chb_conv_desc* d, void* out, int dtype, int r, int C) {
   d->out = out; d->out_dtype = dtype;
   d->o_sn = 1; d->o_sx = C; d->o_sy = (int64_t)r * C; d->o_sb = (int64_t)r * r * C;
@@ -461,6 +472,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     // dx = conv_0(lrelu(ace_0(x)))   (architecture.py:73-75)
     {
       chb_conv_desc d = base_desc(B, r);
+      batch_small_tiles(&d);
       d.nseg = 1;
       const int m0 = b.split_h0 ? 2 : 1;  // [hi | lo] halves share conv_0's weights
       d.seg[0] = make_seg(ws + g->ws_h0, r, b.fin * m0, 0, b.fin * m0, 9, blobp(g, b.t_c0w));
@@ -477,6 +489,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     // out = x_s + conv_1(lrelu(ace_1(dx)))   (architecture.py:77-84); conv_s rides along as a 1x1 K-segment
     {
       chb_conv_desc d = base_desc(B, r);
+      batch_small_tiles(&d);
       int ns = 0;
       const int m1 = b.split_h1 ? 2 : 1;
       d.seg[ns] = make_seg(ws + g->ws_h1, r, b.fmid * m1, 0, b.fmid * m1, 9, blobp(g, b.t_c1w));
