@@ -202,6 +202,7 @@ SYMBOLS = [
     ("chb_poisson_blend", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("chb_poisson_coarse_inverse", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("chb_postprocess_workspace_bytes", C.c_int64, [C.c_int, C.c_int, C.c_int]),
     ("chb_postprocess_blending", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

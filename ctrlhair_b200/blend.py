@@ -119,6 +119,24 @@ def poisson_blending(source, target, mask, with_gamma=True, tol=DEFAULT_TOL, max
     return (out, stats) if return_stats else out
 
 
+def poisson_coarse_inverse(mask, device=None):
+    """The coarse level of the solver's preconditioner (a test hook): mask [B,H,256] -> float32 [B,256,256], the inverse
+    of P^T A P on 16 x 16-pixel aggregates as the solver stores it (fp16 values, un-permuted and un-scaled here)."""
+    lib = _lib.load()
+    device = _dev(device)
+    m = torch.as_tensor(mask).to(device)
+    m = (m != 0).to(torch.uint8)
+    m = (m[None] if m.dim() == 2 else m).contiguous()
+    B, H, W = m.shape
+    if W != 256:
+        raise _lib.ChbError("poisson_coarse_inverse: 256-column masks only")
+    out = torch.empty((B, 256, 256), device=device, dtype=torch.float16)
+    _launch(device, lib.chb_poisson_coarse_inverse, m.data_ptr(), out.data_ptr(), B, H)
+    # stored column (a' & 15) * 16 + (a' >> 4) holds aggregate a'
+    a = torch.arange(256, device=device)
+    return out.float()[:, :, (a & 15) * 16 + (a >> 4)] / 256.0
+
+
 def postprocess_blending(face_img, res_img, face_parsing, target_parsing, blending=True, tol=DEFAULT_TOL,
                          max_iter=DEFAULT_MAX_ITER, device=None, gamma_tables=None):
     """HairEditor.postprocess_blending (hair_editor.py:257-308): returns (image uint8 [H,W,3], res_mask_dilated

@@ -8,10 +8,12 @@
 //   * 8-bit RGB <-> HSV (cv2.cvtColor at ui/backend.py:98-101,108-125) and label map <-> one-hot
 //     (shape_branch/shape_util.py:6-20), which remove the host round trips of Backend.parse_img / output.
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 
 #include "../../include/ctrlhair_b200.h"
@@ -114,6 +116,7 @@ struct PoissonParams {
   float* stats;            // [B*3][2] = iterations, final relative residual; may be null
   const double* lut_fwd;   // [256] v ** (1/2.2) as the caller's host computes it, or null (device pow)
   const uint8_t* lut_known;// [256] uint8((v ** (1/2.2)) ** 2.2) on the caller's host, or null
+  const __half* coarse_inv;// preconditioned kernel: [B][256][256] inverse coarse operators (poisson_coarse_inverse_kernel)
   int B, H, W, R;          // R = rows per CTA
   int with_gamma, max_iter;
   double tol2;             // squared relative residual target
@@ -341,11 +344,25 @@ __global__ void __cluster_dims__(kPoiCluster, 1, 1) __launch_bounds__(kPoiThread
 constexpr int kPoi2MaxCluster = 16;
 constexpr int kPoi2Rows = 16;   // rows per thread
 
+constexpr int kPoi2Agg = 16;    // preconditioner: 16 x 16-pixel aggregates (a thread's 16-row strip lies in one)
+constexpr int kPoi2Coarse = 256;   // coarse unknowns of a 256 x 256 image
+constexpr float kPoi2InvScale = 256.f;   // the fp16 copy of A_c^-1 (entries <~ 1) is stored times 256: keeps the small
+                                         // far-field entries out of the subnormal range
+
 struct Poisson2Smem {
   double lut[256];
-  double warp_part[2][16];
-  double slots[2][2][kPoi2MaxCluster];   // [parity][value][CTA]
-  uint64_t red_bar[2];                   // one transaction barrier per parity: 16 * CL bytes of partial sums per phase
+  double warp_part[3][16];
+  double slots[2][3][kPoi2MaxCluster];   // [parity][value][CTA]
+  uint64_t red_bar[2];                   // one transaction barrier per parity: the bytes of one exchange per phase
+};
+
+// Preconditioned variant only (placed behind the three pixel buffers).
+struct Poisson2Coarse {
+  double gathered[2][kPoi2Coarse];   // [parity][aggregate]: P^T w of the whole image, every CTA receives all of it
+  double rc[kPoi2Coarse];            // P^T r, kept by recurrence in every CTA (fp64: it decays with r by 1e-11)
+  double sc[kPoi2Coarse];            // P^T s
+  float rc32[kPoi2Coarse];           // rc once more for the fp32 matvec
+  float ec[32];                      // (A_c^-1 rc) of this CTA's aggregates
 };
 
 // The address of `saddr` (a shared::cta address of this CTA) in CTA `cta` of the cluster.
@@ -404,7 +421,63 @@ __device__ __forceinline__ void poisson_cluster_sum2_async(double& a, double& b,
   a = ta; b = tb;
 }
 
-template <int W, int R, int CL>   // columns, rows per CTA, CTAs per cluster (cluster shape comes from the launch attribute)
+// The exchange of a preconditioned iteration: three cluster-wide sums AND the all-gather of the coarse restriction of
+// one vector (`wsum` = this thread's 16-row column sum; the 16 lanes that share an aggregate add up, then send the
+// aggregate's sum to every CTA) on the same transaction barrier: 8 * (3 CL + 256) bytes land per phase.
+template <int CL, int NW>
+__device__ __forceinline__ void poisson_cluster_exchange(double& a, double& b, double& c, double wsum, int agg,
+                                                         Poisson2Smem* sm, Poisson2Coarse* co, int set, uint32_t phase,
+                                                         unsigned rank) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t bar = smem_u32(&sm->red_bar[set]);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  if ((lane & 15) < CL)
+    st_async_f64(mapa_u32(smem_u32(&co->gathered[set][agg]), (uint32_t)(lane & 15)), wsum,
+                 mapa_u32(bar, (uint32_t)(lane & 15)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+    c += __shfl_down_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) { sm->warp_part[0][warp] = a; sm->warp_part[1][warp] = b; sm->warp_part[2][warp] = c; }
+  __syncthreads();
+  if (warp == 0) {
+    double v = (lane & 15) < NW ? sm->warp_part[lane >> 4][lane & 15] : 0.0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, 16);
+    const double v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 16);
+    if (lane == 0) mbar_arrive_expect_tx(&sm->red_bar[set], 8u * (3u * CL + kPoi2Coarse));
+    if (lane < 2 * CL) {
+      const int which = lane / CL, dst = lane % CL;
+      st_async_f64(mapa_u32(smem_u32(&sm->slots[set][which][rank]), (uint32_t)dst), which ? v1 : v0,
+                   mapa_u32(bar, (uint32_t)dst));
+    }
+  } else if (warp == 1) {
+    double v = lane < NW ? sm->warp_part[2][lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    v = __shfl_sync(0xffffffffu, v, 0);
+    if (lane < CL)
+      st_async_f64(mapa_u32(smem_u32(&sm->slots[set][2][rank]), (uint32_t)lane), v, mapa_u32(bar, (uint32_t)lane));
+  }
+  mbar_wait(&sm->red_bar[set], phase);
+  double ta = 0.0, tb = 0.0, tc = 0.0;
+#pragma unroll
+  for (int k = 0; k < CL; ++k) { ta += sm->slots[set][0][k]; tb += sm->slots[set][1][k]; tc += sm->slots[set][2][k]; }
+  a = ta; b = tb; c = tc;
+}
+
+// PRE: two-level additive preconditioner M^-1 = D^-1 + P A_c^-1 P^T (Jacobi + a Galerkin coarse correction on 16 x 16
+// pixel aggregates; P = piecewise constant on the aggregate's pixels of U).  A_c = P^T A P (256 x 256, one per IMAGE:
+// the three channels share U) is inverted once by poisson_coarse_inverse_kernel; a CTA keeps the fp16 rows of its own
+// aggregates in shared memory.  ~650 -> ~150 iterations at the same stopping rule; the extra per-iteration work is a
+// 16-MAC-per-thread matvec, and P^T r is maintained by recurrence from P^T w, whose all-gather rides on the dot-product
+// exchange, so an iteration still has one halo barrier and one exchange.
+//   u = M^-1 r, w = A u, g = (r,u), d = (w,u), n = (r,r); b = g/g_old, a = g/(d - b g/a_old);
+//   p = u + b p, s = w + b s, x += a p, r -= a s;   P^T s = P^T w + b P^T s, P^T r -= a P^T s.
+template <int W, int R, int CL, bool PRE>   // columns, rows per CTA, CTAs per cluster (shape from the launch attribute)
 __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * W))
     poisson_cg2_kernel(const PoissonParams p) {
   constexpr int kPoi2Threads = (R / kPoi2Rows) * W;
@@ -427,13 +500,21 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
   Poisson2Smem* sm = reinterpret_cast<Poisson2Smem*>(smem_raw);
   double* rbuf = reinterpret_cast<double*>(smem_raw + sizeof(Poisson2Smem));  // [(R + 2)][P] residual + halo ring
   double* xbuf = rbuf + (R + 2) * P;                                           // [R][W] iterate
-  double* wbuf = xbuf + R * W;                                                 // [R][W] A r
+  double* wbuf = xbuf + R * W;                                                 // [R][W] A r  (PRE: A u)
+  Poisson2Coarse* co = reinterpret_cast<Poisson2Coarse*>(wbuf + R * W);        // PRE only
+  __half* ainv = reinterpret_cast<__half*>(co + 1);                            // PRE only: [R][256] rows of A_c^-1
 
   const int tid = threadIdx.x;
   for (int i = tid; i < (R + 2) * P; i += kPoi2Threads) rbuf[i] = 0.0;
   if (tid < 256)
     sm->lut[tid] = p.with_gamma ? (p.lut_fwd ? p.lut_fwd[tid] : pow((double)tid, 1.0 / 2.2)) : (double)tid;
-  if (tid < 4 * kPoi2MaxCluster) (&sm->slots[0][0][0])[tid] = 0.0;
+  if (tid < 6 * kPoi2MaxCluster) (&sm->slots[0][0][0])[tid] = 0.0;
+  if constexpr (PRE) {
+    // rows [rank * R, rank * R + R) of this image's coarse inverse (fp16, 512 B per row, written by the launch before)
+    const uint4* g = reinterpret_cast<const uint4*>(p.coarse_inv + ((size_t)(blockIdx.x / CL / 3) * kPoi2Coarse +
+                                                                     (size_t)rank * R) * kPoi2Coarse);
+    for (int i = tid; i < R * kPoi2Coarse / 8; i += kPoi2Threads) reinterpret_cast<uint4*>(ainv)[i] = g[i];
+  }
   if (tid == 0) {
     mbar_init(&sm->red_bar[0], 1);
     mbar_init(&sm->red_bar[1], 1);
@@ -510,7 +591,19 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
   }
   double zero = 0.0;
   uint32_t red_phase[2] = {0u, 0u};
-  poisson_cluster_sum2_async<CL, kPoi2Threads / 32>(bb_local, zero, sm, 0, red_phase[0], rank);
+  const int agg = (int)rank * R + strip * kPoi2Agg + (col >> 4);   // this thread's aggregate (image-wide index)
+  if constexpr (PRE) {
+    double rsum = 0.0, zero2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kPoi2Rows; ++j) rsum += r[j];
+    poisson_cluster_exchange<CL, kPoi2Threads / 32>(bb_local, zero, zero2, rsum, agg, sm, co, 0, red_phase[0], rank);
+    if (tid < kPoi2Coarse) {
+      const double v = co->gathered[0][tid];
+      co->rc[tid] = v; co->sc[tid] = 0.0; co->rc32[tid] = (float)v;
+    }
+  } else {
+    poisson_cluster_sum2_async<CL, kPoi2Threads / 32>(bb_local, zero, sm, 0, red_phase[0], rank);
+  }
   red_phase[0] ^= 1u;
   cluster.sync();   // every CTA is done reading x0 from rbuf (own rows and halos) before r overwrites it
   const double bb = bb_local;
@@ -519,6 +612,84 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
   int it = 0, parity = 1;
   double gamma = 1.0, alpha = 1.0;
   bool first = true;
+  if constexpr (PRE) {
+    double rr = bb;   // (r, r) of the last exchange, for the statistics
+    while (true) {
+      // e = (A_c^-1 P^T r) of this thread's aggregate: 16 threads per row of the CTA's slice, 16 columns each
+      {
+        const uint4* arow = reinterpret_cast<const uint4*>(ainv + (tid >> 4) * kPoi2Coarse + (tid & 15) * 16);
+        const uint4 q0 = arow[0], q1 = arow[1];
+        const float* rv = co->rc32 + (tid & 15);
+        const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&q[k]));
+          acc0 = fmaf(f.x, rv[16 * (2 * k)], acc0);
+          acc1 = fmaf(f.y, rv[16 * (2 * k + 1)], acc1);
+        }
+        float acc = (acc0 + acc1) * (1.f / kPoi2InvScale);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((tid & 15) == 0) co->ec[tid >> 4] = acc;
+      }
+      __syncthreads();
+      const double e = (double)co->ec[strip * kPoi2Agg + (col >> 4)];
+      auto uval = [&](int j) { return ((umask >> j) & 1u) ? fma(0.25, r[j], e) : 0.0; };
+      // publish u: own pixels, and the strip-end rows into the neighbours' halos
+#pragma unroll
+      for (int j = 0; j < kPoi2Rows; ++j) rc[j * P] = uval(j);
+      if (halo_up) *halo_up = uval(0);
+      if (halo_dn) *halo_dn = uval(kPoi2Rows - 1);
+      __syncthreads();
+      cluster_arrive_release();
+      double g_l = 0.0, d_l = 0.0, n_l = 0.0, w_l = 0.0;
+      auto row = [&](int j, double up, double dn) {
+        const double c = uval(j);
+        double v = 4.0 * c - up - dn - rc[j * P - 1] - rc[j * P + 1];
+        v = ((umask >> j) & 1u) ? v : 0.0;
+        wc[j * W] = v;
+        g_l += r[j] * c;
+        d_l += c * v;
+        n_l += r[j] * r[j];
+        w_l += v;
+      };
+#pragma unroll
+      for (int j = 1; j < kPoi2Rows - 1; ++j) row(j, uval(j - 1), uval(j + 1));
+      cluster_wait_acquire();
+      row(0, rc[-P], uval(1));
+      row(kPoi2Rows - 1, uval(kPoi2Rows - 2), rc[kPoi2Rows * P]);
+      poisson_cluster_exchange<CL, kPoi2Threads / 32>(g_l, d_l, n_l, w_l, agg, sm, co, parity, red_phase[parity], rank);
+      red_phase[parity] ^= 1u;
+      const double gamma_new = g_l, delta = d_l;
+      rr = n_l;
+      if (!(rr > thresh) || it >= p.max_iter) break;
+      double beta;
+      if (first) { beta = 0.0; alpha = gamma_new / delta; first = false; }
+      else {
+        beta = gamma_new / gamma;
+        const double ga = gamma * alpha;
+        alpha = gamma_new * ga / (delta * ga - gamma_new * gamma_new);
+      }
+      gamma = gamma_new;
+      if (tid < kPoi2Coarse) {
+        const double sc = co->gathered[parity][tid] + beta * co->sc[tid];
+        const double rcv = co->rc[tid] - alpha * sc;
+        co->sc[tid] = sc; co->rc[tid] = rcv; co->rc32[tid] = (float)rcv;
+      }
+      parity ^= 1;
+#pragma unroll
+      for (int j = 0; j < kPoi2Rows; ++j) {
+        pd[j] = uval(j) + beta * pd[j];
+        s[j] = wc[j * W] + beta * s[j];
+        xc[j * W] += alpha * pd[j];
+        r[j] -= alpha * s[j];
+      }
+      ++it;
+      __syncthreads();   // rc32 of the next iteration is complete (and everybody is done with ec)
+    }
+    gamma = rr;
+  } else
   while (true) {
     // publish r: own pixels, and the strip-end rows into the neighbours' halos
 #pragma unroll
@@ -588,16 +759,197 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
   cluster.sync();
 }
 
+// The coarse operator of the preconditioner and its inverse, one 256-thread CTA per image.
+//   A_c[a][a] = 4 |a & U| - 2 #(edges of U inside a),   A_c[a][a'] = -#(edges of U between a and a'),
+// (1 on the diagonal of an aggregate without unknowns: its row and column are otherwise zero and never used).
+// A_c is symmetric positive definite and banded (the 5-point pattern of the 16 x 16 aggregate grid: half bandwidth
+// 16), so: (1) banded Cholesky A_c = L L^T, right-looking, the 16 x 16 trailing window updated by one thread per
+// element (256 steps, one barrier each); (2) thread b solves L y = e_b and L^T x = y for column b of the inverse with
+// the last 16 values in registers (the band rows are broadcast reads), keeping the lower triangle (rows >= b) in a
+// packed triangular shared-memory array; (3) the triangle is written out mirrored, so the fp16 copy is exactly
+// symmetric.  fp32 throughout: a preconditioner needs no more.
+// out layout: [image][row a][(a' & 15) * 16 + (a' >> 4)] — the order poisson_cg2_kernel<PRE>'s matvec reads.
+constexpr int kCoarseBandPitch = 20;   // floats per band row: [0] = 1 / L_ii, [d] = the d-th off-diagonal, d = 1..16
+static size_t poisson_coarse_smem_bytes() {
+  return sizeof(float) * (3 * (size_t)kPoi2Coarse * kCoarseBandPitch + (size_t)kPoi2Coarse * (kPoi2Coarse + 1) / 2);
+}
+__global__ void __launch_bounds__(256, 1)
+    poisson_coarse_inverse_kernel(const uint8_t* __restrict__ mask, int H, __half* __restrict__ out) {
+  constexpr int W = 256, N = kPoi2Coarse, LP = kCoarseBandPitch;
+  extern __shared__ __align__(16) float csm[];
+  float* Ab = csm;             // working band: Ab[i][d] = A[i][i - d]
+  float* Lf = Ab + N * LP;     // rows of L:    Lf[i][d] = L[i][i - d], Lf[i][0] = 1 / L[i][i]
+  float* Uf = Lf + N * LP;     // columns of L: Uf[i][d] = L[i + d][i], Uf[i][0] = 1 / L[i][i]
+  float* Z = Uf + N * LP;      // packed lower triangle, row i at i (i + 1) / 2
+  __shared__ int cnt[4][N];    // unknowns, inner edges, edges to the right / lower aggregate
+  const int tid = threadIdx.x;
+  const uint8_t* m = mask + (size_t)blockIdx.x * H * W;
+  for (int i = tid; i < 4 * N; i += 256) (&cnt[0][0])[i] = 0;
+  for (int i = tid; i < 3 * N * LP; i += 256) csm[i] = 0.f;
+  __syncthreads();
+  auto in_u = [&](int y, int x) {
+    return y < H && x < W && (m[y * W + x] != 0 || y == 0 || y == H - 1 || x == 0 || x == W - 1);
+  };
+  // a thread per 16-pixel row segment of an aggregate
+  for (int seg = tid; seg < 16 * N; seg += 256) {
+    const int a = seg >> 4, y = (a >> 4) * 16 + (seg & 15), x0 = (a & 15) * 16;
+    if (y >= H) continue;
+    int n = 0, inner = 0, right = 0, down = 0;
+    const bool last_row = (seg & 15) == 15;
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+      const int x = x0 + k;
+      if (!in_u(y, x)) continue;
+      ++n;
+      if (in_u(y, x + 1)) { if (k == 15) ++right; else ++inner; }
+      if (in_u(y + 1, x)) { if (last_row) ++down; else ++inner; }
+    }
+    if (n) atomicAdd(&cnt[0][a], n);
+    if (inner) atomicAdd(&cnt[1][a], inner);
+    if (right) atomicAdd(&cnt[2][a], right);
+    if (down) atomicAdd(&cnt[3][a], down);
+  }
+  __syncthreads();
+  {
+    const int i = tid;
+    Ab[i * LP] = cnt[0][i] ? (float)(4 * cnt[0][i] - 2 * cnt[1][i]) : 1.f;
+    if (i >= 1 && ((i - 1) & 15) != 15) Ab[i * LP + 1] = -(float)cnt[2][i - 1];
+    if (i >= 16) Ab[i * LP + 16] = -(float)cnt[3][i - 16];
+  }
+  __syncthreads();
+  // (1) Cholesky.  Step k reads column k of the working band (rows k + 1 .. k + 16) and the pivot; it writes only
+  // elements (i, j) with j > k, so one barrier per step orders everything.
+  {
+    const int ti = tid >> 4, tj = tid & 15;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+      const float inv = rsqrtf(fmaxf(Ab[k * LP], 1e-6f));   // (pivots are >= lambda_min(A_c) ~ 0.1: the guard never binds)
+      const int i = k + 1 + ti, j = k + 1 + tj;
+      if (i < N) {
+        const float li = Ab[i * LP + ti + 1] * inv;
+        if (tj <= ti) Ab[i * LP + (ti - tj)] -= li * (Ab[j * LP + tj + 1] * inv);
+        if (tj == 0) { Lf[i * LP + ti + 1] = li; Uf[k * LP + ti + 1] = li; }
+      }
+      if (tid == 0) { Lf[k * LP] = inv; Uf[k * LP] = inv; }
+      __syncthreads();
+    }
+  }
+  // (2) column b of the inverse
+  {
+    const int b = tid, first_blk = (b & ~31) >> 4;
+    float win[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) win[q] = 0.f;
+#pragma unroll 1
+    for (int ib = first_blk; ib < 16; ++ib) {
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii) {
+        const int i = 16 * ib + ii;
+        const float4* lr = reinterpret_cast<const float4*>(Lf + i * LP);
+        const float4 v0 = lr[0], v1 = lr[1], v2 = lr[2], v3 = lr[3], v4 = lr[4];
+        const float l[17] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w,
+                             v3.x, v3.y, v3.z, v3.w, v4.x};
+        float s0 = i == b ? 1.f : 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int d = 1; d <= 16; d += 4) {
+          s0 = fmaf(-l[d], win[(ii - d) & 15], s0);
+          s1 = fmaf(-l[d + 1], win[(ii - d - 1) & 15], s1);
+          s2 = fmaf(-l[d + 2], win[(ii - d - 2) & 15], s2);
+          s3 = fmaf(-l[d + 3], win[(ii - d - 3) & 15], s3);
+        }
+        const float y = ((s0 + s1) + (s2 + s3)) * l[0];
+        win[ii] = y;
+        if (i >= b) Z[i * (i + 1) / 2 + b] = y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) win[q] = 0.f;
+#pragma unroll 1
+    for (int ib = 15; ib >= first_blk; --ib) {
+#pragma unroll
+      for (int ii = 15; ii >= 0; --ii) {
+        const int i = 16 * ib + ii;
+        const float4* ur = reinterpret_cast<const float4*>(Uf + i * LP);
+        const float4 v0 = ur[0], v1 = ur[1], v2 = ur[2], v3 = ur[3], v4 = ur[4];
+        const float u[17] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w,
+                             v3.x, v3.y, v3.z, v3.w, v4.x};
+        float s0 = i >= b ? Z[i * (i + 1) / 2 + b] : 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int d = 1; d <= 16; d += 4) {
+          s0 = fmaf(-u[d], win[(ii + d) & 15], s0);
+          s1 = fmaf(-u[d + 1], win[(ii + d + 1) & 15], s1);
+          s2 = fmaf(-u[d + 2], win[(ii + d + 2) & 15], s2);
+          s3 = fmaf(-u[d + 3], win[(ii + d + 3) & 15], s3);
+        }
+        const float x = ((s0 + s1) + (s2 + s3)) * u[0];
+        win[ii] = x;
+        if (i >= b) Z[i * (i + 1) / 2 + b] = x;
+      }
+    }
+  }
+  __syncthreads();
+  // (3) mirrored, permuted fp16 copy: thread = position within an output row
+  {
+    const int ap = (tid >> 4) + 16 * (tid & 15);   // position tid holds column ap
+    __half* o = out + (size_t)blockIdx.x * N * N;
+#pragma unroll 4
+    for (int a = 0; a < N; ++a) {
+      const int hi = max(a, ap), lo = min(a, ap);
+      o[a * N + tid] = __float2half_rn(Z[hi * (hi + 1) / 2 + lo] * kPoi2InvScale);
+    }
+  }
+}
+
 constexpr int kPoi2W = 256, kPoi2R = 32;   // the instantiated geometry: 256 columns, H in 249..256
 // ... and the same image on 16-CTA clusters (non-portable size) of 256-thread CTAs, two CTAs per SM
 constexpr int kPoi2R16 = 16;
-static size_t poisson2_smem_bytes(int R, int W) {
-  return sizeof(Poisson2Smem) + (size_t)(R + 2) * (W + 2) * sizeof(double) + 2 * (size_t)R * W * sizeof(double);
+static size_t poisson2_smem_bytes(int R, int W, bool pre = false) {
+  return sizeof(Poisson2Smem) + (size_t)(R + 2) * (W + 2) * sizeof(double) + 2 * (size_t)R * W * sizeof(double) +
+         (pre ? sizeof(Poisson2Coarse) + (size_t)R * kPoi2Coarse * sizeof(__half) : 0);
+}
+
+// Stream-ordered scratch for the coarse inverses (128 KB per image) from a private pool per device that keeps its
+// memory between calls (the default pool would hand it back to the driver at every synchronisation).
+static cudaMemPool_t poisson_pool() {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) { pools[dev] = nullptr; cudaGetLastError(); return nullptr; }
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  return pools[dev];
 }
 static bool poisson2_fits(int R, int W) { return W == kPoi2W && R == kPoi2R; }
 
 static size_t poisson_smem_bytes(int R, int W) {
   return sizeof(PoissonSmem) + (size_t)(R + 2) * W * sizeof(double) + (size_t)R * W * sizeof(double);
+}
+
+// Launches the coarse inversion into `dst`, or into stream-ordered scratch returned through *scratch (the caller frees it
+// with cudaFreeAsync on the same stream) when dst is null.
+static cudaError_t poisson_coarse_launch(const uint8_t* mask, int B, int H, __half* dst, __half** scratch,
+                                         cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(poisson_coarse_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)poisson_coarse_smem_bytes());
+  if (e != cudaSuccess) return e;
+  if (!dst) {
+    cudaMemPool_t pool = poisson_pool();
+    if (!pool) return cudaErrorMemoryAllocation;
+    e = cudaMallocFromPoolAsync(reinterpret_cast<void**>(scratch),
+                                (size_t)B * kPoi2Coarse * kPoi2Coarse * sizeof(__half), pool, stream);
+    if (e != cudaSuccess) return e;
+    dst = *scratch;
+  }
+  poisson_coarse_inverse_kernel<<<dim3((unsigned)B), 256, poisson_coarse_smem_bytes(), stream>>>(mask, H, dst);
+  return cudaGetLastError();
 }
 
 static int poisson_launch(const uint8_t* source, const uint8_t* target, const uint8_t* mask, uint8_t* out, int B, int H,
@@ -634,18 +986,31 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
 #else
   const int force_cl16 = -1;
 #endif
-  const bool cl16 = v2 && (force_cl16 >= 0 ? force_cl16 == 1 : B * 3 <= 8);
+  // The preconditioned solver (8-CTA clusters) is the product path for 256-column images; the plain second-generation
+  // kernels stay for A/B runs of tuning builds (CHB_POISSON_PRE=0).
+#ifdef CHB_TUNING_ENV
+  static const bool no_pre = [] { const char* v = getenv("CHB_POISSON_PRE"); return v && atoi(v) == 0; }();
+#else
+  const bool no_pre = false;
+#endif
+  const bool pre = v2 && !no_pre;
+  const bool cl16 = v2 && !pre && (force_cl16 >= 0 ? force_cl16 == 1 : B * 3 <= 8);
   if (cl16) smem = poisson2_smem_bytes(kPoi2R16, W);
+  if (pre) smem = poisson2_smem_bytes(R, W, true);
   // (set on every call: the attribute is per device, and a process may drive several)
   cudaError_t e;
-  if (cl16) {
-    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (pre) {
+    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  } else if (cl16) {
+    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R16, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R16, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R16, 16, false>,
+                               cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   } else if (v2) {
-    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
+    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   } else {
     e = cudaFuncSetAttribute(poisson_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
@@ -658,6 +1023,17 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
   p.lut_fwd = lut_fwd; p.lut_known = lut_known;
   p.B = B; p.H = H; p.W = W; p.R = R;
   p.with_gamma = with_gamma ? 1 : 0; p.max_iter = max_iter; p.tol2 = tol * tol;
+  p.coarse_inv = nullptr;
+  __half* coarse = nullptr;
+  if (pre) {
+    e = poisson_coarse_launch(mask, B, H, nullptr, &coarse, stream);
+    if (e != cudaSuccess) {
+      set_error(std::string("poisson coarse inverse: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+      return CHB_ERR_CUDA;
+    }
+    p.coarse_inv = coarse;
+  }
   if (v2) {
     const int cl = cl16 ? 16 : kPoiCluster;
     const int threads = (cl16 ? kPoi2R16 : kPoi2R) / kPoi2Rows * kPoi2W;
@@ -672,8 +1048,10 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
     attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cl16 ? cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R16, 16>, p)
-             : cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster>, p);
+    e = pre    ? cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, true>, p)
+        : cl16 ? cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R16, 16, false>, p)
+               : cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, false>, p);
+    if (coarse) cudaFreeAsync(coarse, stream);
     if (e != cudaSuccess) {
       set_error(std::string("poisson_cg2 launch: ") + cudaGetErrorString(e));
       return CHB_ERR_CUDA;
@@ -806,6 +1184,23 @@ int chb_poisson_blend(const uint8_t* source, const uint8_t* target, const uint8_
                       const uint8_t* lut_known, void* stream) {
   return chb::poisson_launch(source, target, mask, out, B, H, W, with_gamma, tol, max_iter, stats, lut_fwd, lut_known,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int chb_poisson_coarse_inverse(const uint8_t* mask, uint16_t* inv_f16, int B, int H, void* stream) {
+  using namespace chb;
+  if (!mask || !inv_f16 || B <= 0 || H < 3 || H > 256) {
+    set_error("chb_poisson_coarse_inverse: bad arguments (256-column masks, 3 <= H <= 256)");
+    return CHB_ERR_ARG;
+  }
+  int rc = chb_check_device();
+  if (rc != CHB_OK) return rc;
+  cudaError_t e = poisson_coarse_launch(mask, B, H, reinterpret_cast<__half*>(inv_f16), nullptr,
+                                        reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    set_error(std::string("chb_poisson_coarse_inverse: ") + cudaGetErrorString(e));
+    return CHB_ERR_CUDA;
+  }
+  return CHB_OK;
 }
 
 int64_t chb_postprocess_workspace_bytes(int B, int H, int W) {

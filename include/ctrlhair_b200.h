@@ -390,6 +390,11 @@ int chb_blend_mask(const uint8_t* target_parsing, const uint8_t* face_parsing, u
 int chb_poisson_blend(const uint8_t* source, const uint8_t* target, const uint8_t* mask, uint8_t* out, int B, int H,
                       int W, int with_gamma, double tol, int max_iter, float* stats, const double* lut_fwd,
                       const uint8_t* lut_known, void* stream);
+/* The coarse level of chb_poisson_blend's preconditioner on its own (a test hook; the solve calls it internally for
+ * 256-column images): per image, the inverse of the Galerkin operator P^T A P of poisson_blending.py:44-70's matrix on
+ * 16 x 16-pixel aggregates.  mask uint8 [B,H,256]; inv_f16 IEEE half [B][256][256], row a, entry for aggregate a' at
+ * column (a' & 15) * 16 + (a' >> 4), scaled by 256. */
+int chb_poisson_coarse_inverse(const uint8_t* mask, uint16_t* inv_f16, int B, int H, void* stream);
 /* hair_editor.py:257-308 HairEditor.postprocess_blending in one call: face_img uint8 [B,H,W,3], res_img float
  * [B,3,H,W] (generator output), parsings uint8 [B,H,W] -> out uint8 [B,H,W,3] (+ res_mask_dilated [B,H,W], optional).
  * blending == 0: out = uint8 image of res_img only.  workspace: chb_postprocess_workspace_bytes(B,H,W) device bytes. */

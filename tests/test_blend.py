@@ -143,6 +143,56 @@ def test_poisson_256_batch_matches_oracle():
     assert np.abs(fix.astype(int) - src[0].astype(int)).max() <= 1
 
 
+def coarse_operator(mask):
+    """P^T A P of the reference's matrix (poisson_blending.py:44-70, restricted to the Laplacian rows U) for piecewise-
+    constant interpolation on 16 x 16-pixel aggregates; 1 on the diagonal of aggregates without unknowns."""
+    H, W = mask.shape
+    U = bo.unknown_set(mask)
+    idx = (np.arange(H)[:, None] // 16) * 16 + np.arange(W)[None, :] // 16
+    Ac = np.zeros((256, 256))
+    np.add.at(Ac, (idx[U], idx[U]), 4.0)
+    for dy, dx in ((0, 1), (1, 0)):
+        both = U[:H - dy, :W - dx] & U[dy:, dx:]
+        a, b = idx[:H - dy, :W - dx][both], idx[dy:, dx:][both]
+        np.add.at(Ac, (a, b), -1.0)
+        np.add.at(Ac, (b, a), -1.0)
+    empty = np.diag(Ac) == 0
+    Ac[empty, empty] = 1.0
+    return Ac
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H", [256, 250])
+def test_poisson_coarse_inverse_matches_numpy(H):
+    """The preconditioner's coarse level: banded Cholesky + 256 column solves in fp32, stored as an exactly symmetric
+    fp16 matrix.  (Its accuracy only affects the iteration count — the stopping rule is on the true residual.)"""
+    from ctrlhair_b200 import blend
+    masks = []
+    for seed in (300, 301):
+        _, _, fp, tp = face_like_case(H, 256, seed)
+        masks.append(1 - bo.blend_mask(tp, fp))
+    masks.append(np.ones((H, 256), np.uint8))          # every pixel unknown: the worst-conditioned coarse operator
+    masks.append(np.zeros((H, 256), np.uint8))         # only the border ring
+    got = blend.poisson_coarse_inverse(np.stack(masks)).cpu().numpy().astype(np.float64)
+    for i, m in enumerate(masks):
+        want = np.linalg.inv(coarse_operator(m))
+        assert np.array_equal(got[i], got[i].T)
+        # fp16 storage (2^-11 relative per entry, entries scaled by 256 before rounding) dominates the error
+        assert np.abs(got[i] - want).max() <= 1e-3 * np.abs(want).max(), (i, np.abs(got[i] - want).max())
+
+
+@pytest.mark.gpu
+def test_poisson_iteration_count_with_preconditioner():
+    """Jacobi + coarse correction on 16 x 16 aggregates: ~150 iterations where plain CG needs ~650 (CPU study in
+    tests/_poisson_precond_study.py) at the same 1e-11 stopping rule."""
+    from ctrlhair_b200 import blend
+    face, gen, fp, tp = face_like_case(256, 256, 900)
+    mask = 1 - bo.blend_mask(tp, fp)
+    _, stats = blend.poisson_blending(face, gen, mask, return_stats=True)
+    assert 50 < float(stats[..., 0].max()) < 220, stats[..., 0]
+    assert float(stats[..., 1].max()) <= 1.01e-11
+
+
 @pytest.mark.gpu
 def test_postprocess_blending_matches_oracle():
     from ctrlhair_b200 import blend
