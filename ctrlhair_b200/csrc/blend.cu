@@ -590,21 +590,21 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
     r[j] = ((umask >> j) & 1u) ? wc[j * W] - v : 0.0;
   }
   double zero = 0.0;
-  uint32_t red_phase[2] = {0u, 0u};
+  uint32_t red_phases = 0u;   // bit `set`: the phase parity of that set's transaction barrier
   const int agg = (int)rank * R + strip * kPoi2Agg + (col >> 4);   // this thread's aggregate (image-wide index)
   if constexpr (PRE) {
     double rsum = 0.0, zero2 = 0.0;
 #pragma unroll
     for (int j = 0; j < kPoi2Rows; ++j) rsum += r[j];
-    poisson_cluster_exchange<CL, kPoi2Threads / 32>(bb_local, zero, zero2, rsum, agg, sm, co, 0, red_phase[0], rank);
+    poisson_cluster_exchange<CL, kPoi2Threads / 32>(bb_local, zero, zero2, rsum, agg, sm, co, 0, red_phases & 1u, rank);
     if (tid < kPoi2Coarse) {
       const double v = co->gathered[0][tid];
       co->rc[tid] = v; co->sc[tid] = 0.0; co->rc32[tid] = (float)v;
     }
   } else {
-    poisson_cluster_sum2_async<CL, kPoi2Threads / 32>(bb_local, zero, sm, 0, red_phase[0], rank);
+    poisson_cluster_sum2_async<CL, kPoi2Threads / 32>(bb_local, zero, sm, 0, red_phases & 1u, rank);
   }
-  red_phase[0] ^= 1u;
+  red_phases ^= 1u;
   cluster.sync();   // every CTA is done reading x0 from rbuf (own rows and halos) before r overwrites it
   const double bb = bb_local;
   const double thresh = p.tol2 * bb;
@@ -620,14 +620,13 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
         const uint4* arow = reinterpret_cast<const uint4*>(ainv + (tid >> 4) * kPoi2Coarse + (tid & 15) * 16);
         const uint4 q0 = arow[0], q1 = arow[1];
         const float* rv = co->rc32 + (tid & 15);
-        const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&q[k]));
-          acc0 = fmaf(f.x, rv[16 * (2 * k)], acc0);
-          acc1 = fmaf(f.y, rv[16 * (2 * k + 1)], acc1);
-        }
+        auto mac2 = [&](uint32_t packed, int k) {   // two fp16 entries: columns (tid & 15) + 16 * (2k), + 16 * (2k + 1)
+          acc0 = fmaf(__half2float(__ushort_as_half((unsigned short)(packed & 0xffffu))), rv[16 * (2 * k)], acc0);
+          acc1 = fmaf(__half2float(__ushort_as_half((unsigned short)(packed >> 16))), rv[16 * (2 * k + 1)], acc1);
+        };
+        mac2(q0.x, 0); mac2(q0.y, 1); mac2(q0.z, 2); mac2(q0.w, 3);
+        mac2(q1.x, 4); mac2(q1.y, 5); mac2(q1.z, 6); mac2(q1.w, 7);
         float acc = (acc0 + acc1) * (1.f / kPoi2InvScale);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -659,8 +658,8 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
       cluster_wait_acquire();
       row(0, rc[-P], uval(1));
       row(kPoi2Rows - 1, uval(kPoi2Rows - 2), rc[kPoi2Rows * P]);
-      poisson_cluster_exchange<CL, kPoi2Threads / 32>(g_l, d_l, n_l, w_l, agg, sm, co, parity, red_phase[parity], rank);
-      red_phase[parity] ^= 1u;
+      poisson_cluster_exchange<CL, kPoi2Threads / 32>(g_l, d_l, n_l, w_l, agg, sm, co, parity, (red_phases >> parity) & 1u, rank);
+      red_phases ^= 1u << parity;
       const double gamma_new = g_l, delta = d_l;
       rr = n_l;
       if (!(rr > thresh) || it >= p.max_iter) break;
@@ -713,8 +712,8 @@ __global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * 
     cluster_wait_acquire();
     row(0, rc[-P], r[1]);
     row(kPoi2Rows - 1, r[kPoi2Rows - 2], rc[kPoi2Rows * P]);
-    poisson_cluster_sum2_async<CL, kPoi2Threads / 32>(g_l, d_l, sm, parity, red_phase[parity], rank);
-    red_phase[parity] ^= 1u;
+    poisson_cluster_sum2_async<CL, kPoi2Threads / 32>(g_l, d_l, sm, parity, (red_phases >> parity) & 1u, rank);
+    red_phases ^= 1u << parity;
     parity ^= 1;
     const double gamma_new = g_l, delta = d_l;
     if (!(gamma_new > thresh) || it >= p.max_iter) { gamma = gamma_new; break; }
