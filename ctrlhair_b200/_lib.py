@@ -45,6 +45,7 @@ class ConvDesc(C.Structure):
         ("noise", C.c_void_p),
         ("chan", C.c_void_p),
         ("o_split", C.c_int), ("o_lo_off", C.c_int64),
+        ("ksplit", C.c_int), ("ks_ws", C.c_void_p),
     ]
 
 
@@ -109,6 +110,7 @@ SYMBOLS = [
     ("chb_version", C.c_int, []),
     ("chb_last_error", C.c_char_p, []),
     ("chb_check_device", C.c_int, []),
+    ("chb_conv_ksplit_workspace_bytes", C.c_int64, [C.c_int]),
     ("chb_conv_run", C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     ("chb_onehot_pyramid", C.c_int,
      [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),

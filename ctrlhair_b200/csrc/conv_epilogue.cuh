@@ -13,6 +13,7 @@ struct Smem {
   uint8_t* stage_base;   // pipeline stages (A tile | weight chunks)
   uint64_t *full, *empty, *tfull, *tempty, *hfull, *hempty, *wbar;
   uint32_t* tmem_slot;
+  uint32_t* ks_flag;     // split-K: "this CTA arrived last on the current tile", broadcast to the epilogue warps
   uint8_t* stg_base;     // 8 x 4 KB epilogue staging blocks
   uint8_t* halo_base;    // halo tiles (ring of p.nhalo buffers)
   uint8_t* wstat_base;   // resident weights (weight-stationary mode)
@@ -28,7 +29,20 @@ __device__ __forceinline__ int sched_tile(const ConvKParams& p, uint32_t t) {
     return m < p.m_tiles ? n_tile * p.m_tiles + (int)m : -1;
   }
   const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-  return tile < (long long)p.m_tiles * p.n_tiles ? (int)tile : -1;
+  return tile < (long long)p.tiles_mn * p.ksplit ? (int)tile : -1;
+}
+// Split-K: a scheduled id is (split, output tile); reduces `tile` to the output tile and returns the split.
+__device__ __forceinline__ int split_of_tile(const ConvKParams& p, int& tile) {
+  if (p.ksplit <= 1) return 0;
+  const int ks = tile / p.tiles_mn;
+  tile -= ks * p.tiles_mn;
+  return ks;
+}
+// channel chunks [cb, ce) of a segment with `nchunk` chunks that split `ks` accumulates
+__device__ __forceinline__ void split_chunks(const ConvKParams& p, int ks, int nchunk, int& cb, int& ce) {
+  if (p.ksplit <= 1) { cb = 0; ce = nchunk; return; }
+  cb = nchunk * ks / p.ksplit;
+  ce = nchunk * (ks + 1) / p.ksplit;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -544,6 +558,48 @@ __device__ __forceinline__ void modulate16(const float (&g)[16], const float (&b
 // ------------------------------------------------------------------------------------------------
 // Epilogue warp role.  FAST: p.fast geometry (full 16 x 8 tiles, affine addresses, no bounds predicates).
 // ------------------------------------------------------------------------------------------------
+// Split-K combine, called by all eight epilogue warps once the tile's (partial) accumulator is complete.  Every warp
+// parks its 32 rows x [j0, j1) columns in the workspace; the CTA that counts in last adds the ksplit partials of the
+// tile in split order, writes the sum back to the same TMEM columns and returns true: the normal epilogue then runs
+// on it unchanged.  The others return false and hand the accumulator straight back.
+__device__ __forceinline__ bool ksplit_combine(const ConvKParams& p, const Smem& sm, uint32_t taddr, int tile, int ks,
+                                               int warp, int lane, int row_base, int j0, int j1) {
+  const size_t tile_elems = (size_t)128 * (size_t)p.BN;
+  float* base = p.ks_partial + (size_t)tile * (size_t)p.ksplit * tile_elems + (size_t)(row_base + lane) * (size_t)p.BN;
+  float* mine = base + (size_t)ks * tile_elems;
+  for (int j = j0; j + 8 <= j1; j += 8) {
+    float v[8];
+    tmem_ld<8>(taddr + (uint32_t)j, v);
+    tmem_ld_fence(v);
+    float4* dst = reinterpret_cast<float4*>(mine + j);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  __threadfence();   // this thread's partial is visible device-wide before the CTA counts in
+  named_bar_sync(1, 32 * kEpilogueWarps);
+  if (warp == 2 && lane == 0) {
+    const unsigned int old = atomicAdd(&p.ks_counter[tile], 1u);
+    const bool last = old == (unsigned int)p.ksplit - 1u;
+    if (last) p.ks_counter[tile] = 0u;   // ready for the next launch that uses the workspace
+    *sm.ks_flag = last ? 1u : 0u;
+  }
+  named_bar_sync(1, 32 * kEpilogueWarps);
+  if (*reinterpret_cast<volatile uint32_t*>(sm.ks_flag) == 0u) return false;
+  __threadfence();
+  for (int j = j0; j + 8 <= j1; j += 8) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < p.ksplit; ++s) {   // fixed order: the sum does not depend on which CTA came last
+      const float4* src = reinterpret_cast<const float4*>(base + (size_t)s * tile_elems + j);
+      const float4 x0 = __ldcg(src), x1 = __ldcg(src + 1);
+      a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
+      a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
+    }
+    tmem_st8(taddr + (uint32_t)j, a);
+  }
+  tmem_st_wait();
+  return true;
+}
+
 template <int EPI, int ACT, bool WSTAT, bool FAST>
 __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& sm, uint32_t tmem_base, int warp,
                                               int lane) {
@@ -571,8 +627,10 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         ro.setup(lane, q, rsh, (uint32_t)(rsy >> 2), (uint32_t)(rsx >> 2));
       }
       uint32_t it = 0;
-      for (int tile = sched_tile<WSTAT>(p, it); tile >= 0; tile = sched_tile<WSTAT>(p, ++it)) {
+      for (int sched = sched_tile<WSTAT>(p, it); sched >= 0; sched = sched_tile<WSTAT>(p, ++it)) {
         const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        int tile = sched;
+        const int ks = split_of_tile(p, tile);
         const int n_tile = FAST ? tg.set_tile_fast(p, tile) : tg.set_tile(p, tile);
         int b, y, x;
         bool valid = true;
@@ -612,7 +670,11 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
-        if (FAST) {
+        bool run = true;
+        if (!WSTAT && p.ksplit > 1) run = ksplit_combine(p, sm, taddr, tile, ks, warp, lane, row_base, j, jend);
+        if (!run) {
+          // another CTA finishes this tile
+        } else if (FAST) {
 #pragma unroll
           for (int blk = 0; blk < 4; ++blk)
             if (32 * blk < ch)

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   sm.hempty = sm.hfull + kMaxHalo;
   sm.wbar = sm.hempty + kMaxHalo;
   sm.tmem_slot = reinterpret_cast<uint32_t*>(sm.wbar + 1);
+  sm.ks_flag = sm.tmem_slot + 1;
   sm.stg_base = smem + (size_t)p.nstages * p.stage_bytes + 1024;
   sm.halo_base = sm.stg_base + kEpilogueWarps * 4096;
   sm.wstat_base = sm.halo_base + (size_t)p.nhalo * p.halo_buf_bytes;
@@ -289,6 +290,20 @@ static int validate_desc(const chb_conv_desc& d) {
                     d.N == d.Nrows && d.BN % 64 == 0,
                 "o_split needs fp16 channels-last output, N == Nrows, BN % 64 == 0 and o_lo_off % 8 == 0");
   }
+  if (d.ksplit > 1) {
+    int min_chunks = 1 << 30;
+    for (int s = 0; s < d.nseg; ++s) {
+      const int nch = d.seg[s].C / (d.seg[s].C == 32 ? 32 : 64);
+      if (nch < min_chunks) min_chunks = nch;
+    }
+    const long long tiles = (long long)((d.W + d.TW - 1) / d.TW) * ((d.H + d.TH - 1) / d.TH) *
+                            ((d.B + d.TB - 1) / d.TB) * (d.Nrows / d.BN);
+    CHB_REQUIRE(d.epi == CHB_EPI_PLAIN && d.ks_ws && d.ksplit <= 16 && d.ksplit <= min_chunks && d.BN % 16 == 0 &&
+                    tiles * (long long)sizeof(unsigned) <= (long long)kKsCounterBytes &&
+                    (reinterpret_cast<uintptr_t>(d.ks_ws) & 15) == 0,
+                "ksplit needs the PLAIN epilogue, a 16-byte aligned workspace, ksplit <= 16 and <= the channel chunks "
+                "of every segment, and at most 1024 output tiles");
+  }
 #undef CHB_REQUIRE
   return CHB_OK;
 }
@@ -336,6 +351,7 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   const int kRegion = 193 * 1024;  // 227 KB - align slack - barriers - epilogue staging
   const int wstat_min_halo = tuning_env("CHB_WSTAT_MINHALO", 2);
   if (wbytes_total + (long long)wstat_min_halo * halo_buf > kRegion || d.Nrows / d.BN > device_sm_count()) wstat_ok = false;
+  if (d.ksplit > 1) wstat_ok = false;  // resident weights and split-K answer opposite problems (many / few pixel tiles)
   k.wstat = wstat_ok ? 1 : 0;
   k.halo_any = 0;
   k.halo_bo = 0;
@@ -441,7 +457,11 @@ int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan) {
   }
   const int total = k.m_tiles * k.n_tiles;
   const int sms = device_sm_count();
-  plan->grid = total < sms ? total : sms;
+  k.ksplit = d.ksplit > 1 ? d.ksplit : 1;
+  k.tiles_mn = total;
+  k.ks_counter = reinterpret_cast<unsigned int*>(d.ks_ws);
+  k.ks_partial = d.ks_ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(d.ks_ws) + kKsCounterBytes) : nullptr;
+  plan->grid = total * k.ksplit < sms ? total * k.ksplit : sms;
   if (k.wstat) {
     int per = sms / k.n_tiles;  // CTAs per n_tile
     if (per > k.m_tiles) per = k.m_tiles;
@@ -561,6 +581,10 @@ int chb_check_device(void) {
     return CHB_ERR_ARCH;
   }
   return CHB_OK;
+}
+
+int64_t chb_conv_ksplit_workspace_bytes(int max_ctas) {
+  return max_ctas > 0 ? (int64_t)chb::ksplit_workspace_bytes(max_ctas) : 0;
 }
 
 int chb_conv_run(const chb_conv_desc* d, int impl, void* stream) {

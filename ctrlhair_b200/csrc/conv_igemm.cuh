@@ -76,8 +76,19 @@ struct ConvKParams {
   // and y and all epilogue tensors have 16-byte aligned rows, so per-tile addresses are an affine function of the
   // tile coordinates (no per-row pixel decode, no bounds predicates).
   int fast, tx_sh, ty_sh;
+  // Split-K (chb_conv_desc.ksplit > 1): tile ids run over ksplit * tiles_mn; split ks of an output tile accumulates the
+  // channel chunks [nchunk * ks / ksplit, nchunk * (ks + 1) / ksplit) of every segment, parks its fp32 accumulator in
+  // ks_partial and counts in on ks_counter[tile]; the CTA that arrives last sums the partials IN SPLIT ORDER (a fixed
+  // order: the result does not depend on which CTA that is), writes the sum back to TMEM and runs the epilogue.
+  int ksplit, tiles_mn;
+  float* ks_partial;        // [tiles_mn][ksplit][128][BN]
+  unsigned int* ks_counter; // [tiles_mn], zero between launches (the last CTA resets its tile's counter)
   EpiK e;
 };
+
+constexpr size_t kKsCounterBytes = 4096;   // head of a split-K workspace: one counter per output tile (<= 1024 tiles)
+// bytes of the split-K workspace that serves any launch with ksplit * tiles_mn <= max_ctas (BN <= 256)
+inline size_t ksplit_workspace_bytes(int max_ctas) { return kKsCounterBytes + (size_t)max_ctas * 128 * 256 * 4; }
 
 struct ConvPlan {
   ConvKParams kp;

@@ -49,18 +49,21 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
     }
   }
   for (uint32_t t = 0;; ++t) {
-    const int tile = sched_tile<WSTAT>(p, t);
+    int tile = sched_tile<WSTAT>(p, t);
     if (tile < 0) break;
+    const int ks = split_of_tile(p, tile);
     const TileOrigin o = tile_origin(p, tile);
     for (int s = 0; s < p.nseg; ++s) {
       const SegK sg = p.seg[s];
       const uint32_t wbytes = (uint32_t)p.BN * (uint32_t)sg.kc * 2u;
+      int cb, ce;   // this split's channel chunks (all of them without split-K)
+      split_chunks(p, ks, sg.nchunk, cb, ce);
       if (WSTAT || sg.halo) {
         // a 1x1 segment needs no halo: its exact 128-row tile goes into the halo ring buffer instead (29 % fewer bytes)
         const bool exact = sg.taps == 1;
         const uint32_t hbytes = (exact ? (uint32_t)p.rows : (uint32_t)((p.TW + 2) * (p.TH + 2))) * (uint32_t)sg.kc * 2u;
         const int tg = sg.taps == 9 ? p.hg : 1;  // taps per weight stage
-        for (int c = 0; c < sg.nchunk; ++c) {
+        for (int c = cb; c < ce; ++c) {
           const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;  // weight chunk (hi+lo split: both halves share it)
           mbar_wait(&sm.hempty[hs], hphase ^ 1u);
           if (elect_one()) {
@@ -98,7 +101,7 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
         const uint32_t bytes = (uint32_t)p.rows * (uint32_t)sg.kc * 2u + wbytes;
         // channel chunk outer, tap inner: the same accumulation order as the halo paths, so a layer gives bitwise the
         // same result whether its tiles take this path (several small images per tile) or a halo path (one image)
-        for (int c = 0; c < sg.nchunk; ++c) {
+        for (int c = cb; c < ce; ++c) {
           const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;
           for (int tap = 0; tap < sg.taps; ++tap) {
             const int dy = sg.taps == 9 ? tap / 3 - 1 : 0;
@@ -143,8 +146,9 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
     tc_fence_after();
   }
   for (uint32_t t = 0;; ++t) {
-    const int tile = sched_tile<WSTAT>(p, t);
+    int tile = sched_tile<WSTAT>(p, t);
     if (tile < 0) break;
+    const int ks = split_of_tile(p, tile);
     const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
     mbar_wait(&sm.tempty[acc], acc_phase ^ 1u);
     tc_fence_after();
@@ -156,6 +160,8 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
       const uint32_t wbytes = (uint32_t)p.BN * row_bytes;
       const uint32_t hiB = umma_desc_hi(row_bytes, row_bytes * 8u);
       const bool k64 = sg.kc == 64;
+      int cb, ce;
+      split_chunks(p, ks, sg.nchunk, cb, ce);
       if (WSTAT || sg.halo) {
         // tap (ky,kx): tile pixel (y,x) reads halo row (y+ky)*(TW+2) + (x+kx).  With TW == 8 every 8-row core group
         // of the UMMA operand is one tile row, (TW+2)*row_bytes apart.  The swizzle is a function of the absolute
@@ -167,7 +173,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
         const int tg = ntaps == 9 ? p.hg : 1;
         const uint32_t bstep = WSTAT ? (uint32_t)sg.nchunk_w * wbytes : wbytes;  // weight slab of the next tap
         const uint32_t row_step = hw * row_bytes;
-        for (int c = 0; c < sg.nchunk; ++c) {
+        for (int c = cb; c < ce; ++c) {
           const int cw = c >= sg.nchunk_w ? c - sg.nchunk_w : c;  // resident weight chunk of this activation chunk
           mbar_wait(&sm.hfull[hs], hphase);
           tc_fence_after();
@@ -241,7 +247,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
           }
         }
       } else {
-        const int chunks = sg.taps * sg.nchunk;
+        const int chunks = sg.taps * (ce - cb);
         for (int c = 0; c < chunks; ++c) {
           mbar_wait(&sm.full[stage], phase);
           tc_fence_after();

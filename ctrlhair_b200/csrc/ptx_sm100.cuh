@@ -518,6 +518,20 @@ __device__ __forceinline__ void tmem_ld_fence(float (&v)[N]) {
   }
 }
 
+// tcgen05.st 32x32b: the inverse of tmem_ld<8> (thread i writes 8 consecutive fp32 columns of TMEM lane base_lane + i).
+// Used by the split-K combine, which puts the summed partial accumulators back where the epilogue expects them.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]),
+               "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Named barrier `id` over `nthreads` threads (a multiple of 32) of the CTA; id 0 is __syncthreads'.
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand, rows of `row_bytes` (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B).
 // 8-row groups are `row_bytes * 8` apart (dense tile as written by a TMA box whose inner extent is row_bytes).
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_bytes) {

@@ -30,11 +30,12 @@ def default_tile(H, W):
 
 def conv_igemm(segs, N, BN, *, bias=None, bias_per_image=False, epi=EPI_PLAIN, act=ACT_NONE, out_dtype=torch.float16,
                out_layout="nhwc", res=None, res_shift=0, x=None, x_shift=0, noise=None, chan=None, tile=None,
-               impl=IMPL_TCGEN05, out=None):
+               impl=IMPL_TCGEN05, out=None, ksplit=0):
     """Implicit-GEMM conv.  segs: list of dicts {a: fp16 [B,H,W,Ca], w: fp16 [Nrows,K] | [B,Nrows,K], taps, C, ch_off}.
 
     plain:    out = act(conv + bias (+ res[b, y>>s, x>>s, :]))            -> NHWC (or NCHW) fp16/fp32
     modulate: out = act((x*a + noise*nv + c) * (1 + gamma) + beta), fp16  -> NHWC, weight rows tiled [gamma|beta] per BN
+    ksplit > 1 (plain only): that many CTAs share an output tile, each taking a slice of the channel chunks.
     """
     lib = _lib.load()
     a0 = _require_cuda(segs[0]["a"], "segs[0].a", torch.float16)
@@ -102,8 +103,23 @@ def conv_igemm(segs, N, BN, *, bias=None, bias_per_image=False, epi=EPI_PLAIN, a
             noise = _require_cuda(noise, "noise", torch.float32).contiguous()
             d.noise = noise.data_ptr()
     d.out = out.data_ptr()
+    if ksplit > 1:
+        ws = _ksplit_workspace(a0.device)
+        d.ksplit, d.ks_ws = ksplit, ws.data_ptr()
     _lib.check(lib.chb_conv_run(C.byref(d), impl, _stream_ptr()))
     return out
+
+
+_KS_WS = {}
+
+
+def _ksplit_workspace(device):
+    """One split-K workspace per device (counters zeroed once; every launch leaves them at zero)."""
+    key = (device.type, device.index)
+    if key not in _KS_WS:
+        n = _lib.load().chb_conv_ksplit_workspace_bytes(1024)
+        _KS_WS[key] = torch.zeros((n,), device=device, dtype=torch.uint8)
+    return _KS_WS[key]
 
 
 def onehot_pyramid(labels, resolutions, nclass=19):

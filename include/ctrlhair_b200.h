@@ -85,6 +85,12 @@ typedef struct {
      residual lo = fp16(v - hi) is stored at channel n + o_lo_off, so that a consumer segment with w_dup = 2 sees
      v to ~2^-22.  0 = off. */
   int o_split; int64_t o_lo_off;
+  /* Split-K for launches with few output tiles and a long K (8x8 / 16x16 convs at small batch, the 2x2 / 4x4 shape
+     layers): ksplit > 1 CTAs share one output tile, each accumulating a slice of every segment's channel chunks; the
+     partial accumulators meet in ks_ws (chb_conv_ksplit_workspace_bytes(); zero its first 4096 bytes once) and the CTA
+     that arrives last adds them in split order and runs the epilogue — deterministic, but a different fp32
+     association than ksplit = 1.  PLAIN epilogue only; 0 / 1 = off. */
+  int ksplit; void* ks_ws;
 } chb_conv_desc;
 
 enum { CHB_IMPL_TCGEN05 = 0, CHB_IMPL_SIMT_DEBUG = 1 };
@@ -93,6 +99,8 @@ enum { CHB_IMPL_TCGEN05 = 0, CHB_IMPL_SIMT_DEBUG = 1 };
 int chb_struct_size(int which);
 /* One-shot: encode tensor maps and launch. impl selects the tcgen05 kernel or the slow SIMT checker kernel. */
 int chb_conv_run(const chb_conv_desc* d, int impl, void* stream);
+/* Bytes of a split-K workspace that serves every launch with ksplit * (output tiles) <= max_ctas. */
+int64_t chb_conv_ksplit_workspace_bytes(int max_ctas);
 
 /* ------------------------------------------------------------------------------------------
  * Operator 2: label map -> one-hot pyramid (pix2pix_model.py:119-144 scatter_, and the nearest

@@ -88,7 +88,7 @@ def make_cases(device="cuda"):
     cases = []
 
     def plain_case(name, B, H, W, seg_specs, N, BN, *, out_dtype=torch.float16, act=ops.ACT_NONE, use_bias=True,
-                   use_res=False, res_shift=0, layout="nhwc", nrows=None, tile=None, seed=0):
+                   use_res=False, res_shift=0, layout="nhwc", nrows=None, tile=None, seed=0, ksplit=0):
         def run(impl):
             gen = torch.Generator().manual_seed(1000 + seed)
             rows = nrows or N
@@ -105,7 +105,7 @@ def make_cases(device="cuda"):
                 rh, rw = (H >> res_shift), (W >> res_shift)
                 res = _rand(gen, (B, rh, rw, N), 1.0, torch.float32, device)
             got = ops.conv_igemm(segs, N, BN, bias=bias, act=act, out_dtype=out_dtype, out_layout=layout, res=res,
-                                 res_shift=res_shift, tile=tile, impl=impl)
+                                 res_shift=res_shift, tile=tile, impl=impl, ksplit=ksplit)
             got = got.float()
             if layout == "nhwc":
                 got = got.permute(0, 3, 1, 2)
@@ -154,6 +154,16 @@ def make_cases(device="cuda"):
     plain_case("plain_deep_k_c1024", 1, 16, 16, [(1024, 0, 1024, 9, False)], 256, 256, out_dtype=torch.float32, seed=8)
     plain_case("plain_chan_window", 2, 16, 16, [(384, 128, 128, 9, False)], 128, 128, seed=9)
     plain_case("plain_ragged_24x20", 2, 24, 20, [(64, 0, 64, 9, False)], 64, 64, seed=10)
+    # split-K: several CTAs per output tile (halo path, per-tap path with several images per tile, two segments with a
+    # residual, a narrow N tile, more splits than CTAs can run at once is not needed: tiles * ksplit <= 148)
+    plain_case("ksplit4_deep_k_c1024_halo", 1, 16, 16, [(1024, 0, 1024, 9, False)], 256, 128, out_dtype=torch.float32,
+               seed=8, ksplit=4)
+    plain_case("ksplit3_r8_tb2_bn32", 2, 8, 8, [(1024, 0, 1024, 9, False)], 128, 32, out_dtype=torch.float32,
+               tile=(8, 8, 2), seed=21, ksplit=3)
+    plain_case("ksplit2_two_segments_res_lrelu_f16", 1, 16, 16, [(256, 0, 256, 9, False), (512, 0, 512, 1, False)], 128,
+               64, act=ops.ACT_LRELU, use_res=True, res_shift=1, seed=22, ksplit=2)
+    plain_case("ksplit8_4x4_tb8", 8, 4, 4, [(512, 0, 512, 9, False)], 256, 64, out_dtype=torch.float32, tile=(4, 4, 8),
+               seed=23, ksplit=8)
     def padded_case(name, B, H, W, C, N, BN, seed):
         def run(impl):
             gen = torch.Generator().manual_seed(3000 + seed)
