@@ -558,45 +558,86 @@ __device__ __forceinline__ void modulate16(const float (&g)[16], const float (&b
 // ------------------------------------------------------------------------------------------------
 // Epilogue warp role.  FAST: p.fast geometry (full 16 x 8 tiles, affine addresses, no bounds predicates).
 // ------------------------------------------------------------------------------------------------
+// Sum of the ksplit partial accumulators of this thread's row, columns [j0, j1), in split order (fixed: the result does
+// not depend on which CTA does it), written back to TMEM.  CW columns per step, the loads of G splits in flight at once.
+template <int CW, int G>
+__device__ __forceinline__ void ksplit_sum(const ConvKParams& p, const float* base, size_t tile_elems, uint32_t taddr,
+                                           int j0, int j1) {
+  constexpr int V = CW / 4;
+  for (int j = j0; j < j1; j += CW) {   // (j1 - j0) is a multiple of CW
+    float a[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) a[i] = 0.f;
+    for (int s0 = 0; s0 < p.ksplit; s0 += G) {
+      float4 x[G][V];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4* src = reinterpret_cast<const float4*>(base + (size_t)(s0 + g) * tile_elems) + (j >> 2) * 128;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          x[g][v] = s0 + g < p.ksplit ? __ldcg(src + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int v = 0; v < V; ++v) {   // (adding the zeros of an absent split changes nothing)
+          a[4 * v] += x[g][v].x; a[4 * v + 1] += x[g][v].y; a[4 * v + 2] += x[g][v].z; a[4 * v + 3] += x[g][v].w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CW; i += 8) {
+      const float o[8] = {a[i], a[i + 1], a[i + 2], a[i + 3], a[i + 4], a[i + 5], a[i + 6], a[i + 7]};
+      tmem_st8(taddr + (uint32_t)(j + i), o);
+    }
+  }
+}
+
 // Split-K combine, called by all eight epilogue warps once the tile's (partial) accumulator is complete.  Every warp
 // parks its 32 rows x [j0, j1) columns in the workspace; the CTA that counts in last adds the ksplit partials of the
 // tile in split order, writes the sum back to the same TMEM columns and returns true: the normal epilogue then runs
 // on it unchanged.  The others return false and hand the accumulator straight back.
 __device__ __forceinline__ bool ksplit_combine(const ConvKParams& p, const Smem& sm, uint32_t taddr, int tile, int ks,
                                                int warp, int lane, int row_base, int j0, int j1) {
+  // Layout of a partial tile: [column / 4][row][4 columns] — a warp's 32 rows of one 4-column group are 512 contiguous
+  // bytes, so the float4 stores and loads below are fully coalesced (row-major would touch 32 lines per instruction).
   const size_t tile_elems = (size_t)128 * (size_t)p.BN;
-  float* base = p.ks_partial + (size_t)tile * (size_t)p.ksplit * tile_elems + (size_t)(row_base + lane) * (size_t)p.BN;
+  float* base = p.ks_partial + (size_t)tile * (size_t)p.ksplit * tile_elems + (size_t)(row_base + lane) * 4;
   float* mine = base + (size_t)ks * tile_elems;
+  const bool tr = tile == 0 && warp == 2 && lane == 0;   // (tuning builds: time stamps of tile 0's combine)
+  if (tr) CHB_TRACE_KS(ks, 0);
   for (int j = j0; j + 8 <= j1; j += 8) {
     float v[8];
     tmem_ld<8>(taddr + (uint32_t)j, v);
     tmem_ld_fence(v);
-    float4* dst = reinterpret_cast<float4*>(mine + j);
+    float4* dst = reinterpret_cast<float4*>(mine) + (j >> 2) * 128;
     dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    dst[128] = make_float4(v[4], v[5], v[6], v[7]);
   }
-  __threadfence();   // this thread's partial is visible device-wide before the CTA counts in
+  if (tr) CHB_TRACE_KS(ks, 1);
+  fence_acq_rel_gpu();   // this thread's partial is visible device-wide before the CTA counts in
+  if (tr) CHB_TRACE_KS(ks, 2);
   named_bar_sync(1, 32 * kEpilogueWarps);
   if (warp == 2 && lane == 0) {
     const unsigned int old = atomicAdd(&p.ks_counter[tile], 1u);
     const bool last = old == (unsigned int)p.ksplit - 1u;
     if (last) p.ks_counter[tile] = 0u;   // ready for the next launch that uses the workspace
     *sm.ks_flag = last ? 1u : 0u;
+    if (tr) CHB_TRACE_KS(ks, 3);
   }
   named_bar_sync(1, 32 * kEpilogueWarps);
+  if (tr) CHB_TRACE_KS(ks, 4);
   if (*reinterpret_cast<volatile uint32_t*>(sm.ks_flag) == 0u) return false;
-  __threadfence();
-  for (int j = j0; j + 8 <= j1; j += 8) {
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < p.ksplit; ++s) {   // fixed order: the sum does not depend on which CTA came last
-      const float4* src = reinterpret_cast<const float4*>(base + (size_t)s * tile_elems + j);
-      const float4 x0 = __ldcg(src), x1 = __ldcg(src + 1);
-      a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w;
-      a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
-    }
-    tmem_st8(taddr + (uint32_t)j, a);
-  }
+  fence_acq_rel_gpu();
+  if (tr) CHB_TRACE_KS(ks, 5);
+  // The partials sit in L2 (~700 cycles away) and every load below is independent: issue the loads of a whole group
+  // of splits before the first add, and take as many columns per step as 16 float4 registers allow.
+  const int width = j1 - j0;   // 0, 16, 32, 64 or 128 columns
+  if (p.ksplit <= 2 && width % 32 == 0) ksplit_sum<32, 2>(p, base, tile_elems, taddr, j0, j1);
+  else if (p.ksplit <= 4 && width % 16 == 0) ksplit_sum<16, 4>(p, base, tile_elems, taddr, j0, j1);
+  else ksplit_sum<8, 8>(p, base, tile_elems, taddr, j0, j1);
+  if (tr) CHB_TRACE_KS(ks, 6);
   tmem_st_wait();
+  if (tr) CHB_TRACE_KS(ks, 7);
   return true;
 }
 
@@ -669,6 +710,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
+        if (it == 0 && warp == 2 && lane == 0) { CHB_TRACE_AT(5); CHB_TRACE_CTA(1); }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
         bool run = true;
         if (!WSTAT && p.ksplit > 1) run = ksplit_combine(p, sm, taddr, tile, ks, warp, lane, row_base, j, jend);
@@ -694,6 +736,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKParams& p, const Smem& 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (it == 0 && warp == 2 && lane == 0) CHB_TRACE_AT(6);
       }
     } else {
       // MODULATE: tile columns [0, BN/2) are gamma, [BN/2, BN) beta of channels c0 .. c0 + BN/2.

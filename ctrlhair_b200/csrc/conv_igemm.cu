@@ -57,6 +57,7 @@ int device_sm_count() {
 template <int EPI, int ACT, bool WSTAT, bool FAST>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) { CHB_TRACE_AT(0); CHB_TRACE_CTA(0); }
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Smem sm;
   sm.stage_base = smem;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_slot;
+  if (threadIdx.x == 0) CHB_TRACE_AT(1);
 
   if (warp == 0) {
     producer_role<WSTAT>(p, sm);
@@ -117,10 +119,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) CHB_TRACE_AT(7);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (threadIdx.x == 32) { CHB_TRACE_AT(8); CHB_TRACE_CTA(2); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -582,6 +586,18 @@ int chb_check_device(void) {
   }
   return CHB_OK;
 }
+
+#ifdef CHB_TRACE
+extern "C" int chb_debug_trace_read(unsigned long long* host16) {
+  return cudaMemcpyFromSymbol(host16, chb::chb_trace_buf, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1;
+}
+extern "C" int chb_debug_trace_ks_read(unsigned long long* host128) {
+  return cudaMemcpyFromSymbol(host128, chb::chb_trace_ks, sizeof(unsigned long long) * 128) == cudaSuccess ? 0 : -1;
+}
+extern "C" int chb_debug_trace_cta_read(unsigned long long* host480) {
+  return cudaMemcpyFromSymbol(host480, chb::chb_trace_cta, sizeof(unsigned long long) * 480) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int64_t chb_conv_ksplit_workspace_bytes(int max_ctas) {
   return max_ctas > 0 ? (int64_t)chb::ksplit_workspace_bytes(max_ctas) : 0;

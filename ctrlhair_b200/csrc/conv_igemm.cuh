@@ -81,7 +81,7 @@ struct ConvKParams {
   // ks_partial and counts in on ks_counter[tile]; the CTA that arrives last sums the partials IN SPLIT ORDER (a fixed
   // order: the result does not depend on which CTA that is), writes the sum back to TMEM and runs the epilogue.
   int ksplit, tiles_mn;
-  float* ks_partial;        // [tiles_mn][ksplit][128][BN]
+  float* ks_partial;        // [tiles_mn][ksplit][BN / 4][128 rows][4]
   unsigned int* ks_counter; // [tiles_mn], zero between launches (the last CTA resets its tile's counter)
   EpiK e;
 };
@@ -97,6 +97,26 @@ struct ConvPlan {
   int smem_bytes;
   double flops;  // tensor-core FLOPs issued (padding included)
 };
+
+#ifdef CHB_TRACE
+// Tuning builds only (tools/build_variant.py with VARIANT_FLAGS=-DCHB_TRACE): SM-clock timestamps of CTA 0's first tile,
+// read back with chb_debug_trace_read (tools/gpu_trace_small.py).
+static __device__ unsigned long long chb_trace_buf[16];   // (one copy per translation unit; conv_igemm.cu's is the live one)
+#define CHB_TRACE_AT(k) do { if (blockIdx.x == 0) chb_trace_buf[k] = clock64(); } while (0)
+static __device__ unsigned long long chb_trace_cta[3 * 160];   // per CTA: globaltimer at entry, epilogue start, exit
+__device__ __forceinline__ unsigned long long chb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CHB_TRACE_CTA(k) do { if (blockIdx.x < 160) chb_trace_cta[3 * blockIdx.x + (k)] = chb_globaltimer(); } while (0)
+static __device__ unsigned long long chb_trace_ks[16 * 8];   // split-K combine of output tile 0: [split][point]
+#define CHB_TRACE_KS(ks, k) do { chb_trace_ks[8 * (ks) + (k)] = chb_globaltimer(); } while (0)
+#else
+#define CHB_TRACE_AT(k) do { } while (0)
+#define CHB_TRACE_CTA(k) do { } while (0)
+#define CHB_TRACE_KS(ks, k) do { } while (0)
+#endif
 
 void set_error(const std::string& msg);
 int build_conv_plan(const chb_conv_desc& d, ConvPlan* plan);

@@ -51,6 +51,7 @@ __device__ __forceinline__ void producer_role(const ConvKParams& p, const Smem& 
   for (uint32_t t = 0;; ++t) {
     int tile = sched_tile<WSTAT>(p, t);
     if (tile < 0) break;
+    if (t == 0 && (threadIdx.x & 31) == 0) CHB_TRACE_AT(2);
     const int ks = split_of_tile(p, tile);
     const TileOrigin o = tile_origin(p, tile);
     for (int s = 0; s < p.nseg; ++s) {
@@ -144,6 +145,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
   if (WSTAT) {
     mbar_wait(sm.wbar, 0u);
     tc_fence_after();
+    if ((threadIdx.x & 31) == 0) CHB_TRACE_AT(9);
   }
   for (uint32_t t = 0;; ++t) {
     int tile = sched_tile<WSTAT>(p, t);
@@ -152,6 +154,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
     const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
     mbar_wait(&sm.tempty[acc], acc_phase ^ 1u);
     tc_fence_after();
+    if (t == 0 && (threadIdx.x & 31) == 0) CHB_TRACE_AT(3);
     const uint32_t d_tmem = tmem_base + acc * 256u;
     uint32_t accumulate = 0;
     for (int s = 0; s < p.nseg; ++s) {
@@ -270,6 +273,7 @@ __device__ __forceinline__ void mma_role(const ConvKParams& p, const Smem& sm, u
     }
     if (elect_one()) umma_commit(&sm.tfull[acc]);
     __syncwarp();
+    if (t == 0 && (threadIdx.x & 31) == 0) CHB_TRACE_AT(4);
   }
 }
 

@@ -71,6 +71,7 @@ struct chb_generator {
   int64_t noise_pix = 0;      // noise floats per image
   int t_fcw, t_fcb, t_imgw, t_imgb, t_fcmuw, t_fcmub, t_imgwy = -1, t_imgwylo = -1;
   int64_t ws_y = 0;  // CHB_PREC_IMG: per-tap partial sums of conv_img, fp32 [B,S,S,32]
+  int64_t ws_ks = 0; // split-K workspace (tile counters + partial accumulators) shared by the launches that split
   // workspace layout (byte offsets, sized for max_batch)
   int64_t ws_bytes = 0;
   int64_t ws_labels, ws_codes32, ws_out, ws_codes16, ws_noise, ws_mu, ws_weff, ws_x0;
@@ -236,6 +237,7 @@ static void build_layout(chb_generator* g) {
     g->debug["x_" + b.name] = {b.ws_xout, last ? CHB_F16 : CHB_F32};
   }
   g->ws_actv = g->blocks.back().ws_actv;
+  g->ws_ks = ws_alloc(g, (int64_t)ksplit_workspace_bytes(device_sm_count()));
   g->ws_hs = ws_alloc(g, m_hs);
   g->ws_h0 = ws_alloc(g, m_hin);
   if (c.precision & CHB_PREC_IMG) {
@@ -310,6 +312,43 @@ static void batch_small_tiles(chb_conv_desc* d) {
   int tb = 128 / px;
   if (tb > d->B) tb = d->B;
   d->TB = tb < 1 ? 1 : tb;
+}
+
+// A handful of images (interactive B = 1 .. 4): the 8x8 .. 32x32 PLAIN convs have fewer output tiles than the GPU has
+// SMs, and one CTA walks the whole K of its tile: 144-288 K steps of 64 at ~0.19 us = 28-55 us per launch, which is
+// what the latency of a one-image forward consisted of (tools/gpu_chain_floor.py, gpu_trace_small.py).  Split-K lets
+// 4-8 CTAs share an output tile.  The combine (partial tile through L2, two fences, a counter, the in-order sum) costs
+// ~7 us, so a launch only splits when it has >= 96 K steps and at least four ways to go; an N tile that pick_bn
+// narrowed to get more CTAs is widened again when that buys the four splits (wider MMAs, fewer reads of the A tile).
+// The partial sums are added in a fixed order (deterministic), but the fp32 association differs from an unsplit launch:
+// a one-image call and the same image inside a large batch agree to fp16 storage rounding of the activations, no longer
+// bitwise.  At production batch sizes nothing splits.
+static void split_k_few_tiles(const chb_generator* g, chb_conv_desc* d) {
+  const long long m_tiles = (long long)((d->W + d->TW - 1) / d->TW) * ((d->H + d->TH - 1) / d->TH) *
+                            ((d->B + d->TB - 1) / d->TB);
+  int min_chunks = 1 << 30, steps = 0;
+  for (int i = 0; i < d->nseg; ++i) {
+    const int nch = d->seg[i].C / (d->seg[i].C == 32 ? 32 : 64);
+    if (nch < min_chunks) min_chunks = nch;
+    steps += d->seg[i].taps * nch;
+  }
+  if (steps < 96) return;
+  const int sms = device_sm_count();
+  auto ways = [&](int bn) {
+    long long s = sms / (m_tiles * (d->Nrows / bn));
+    if (s > 8) s = 8;
+    if (s > min_chunks / 2) s = min_chunks / 2;
+    return (int)s;
+  };
+  int bn = d->BN, s = ways(bn);
+  if (s < 4 && bn < 256 && d->Nrows % (2 * bn) == 0 && ways(2 * bn) >= 4) {
+    bn *= 2;
+    s = ways(bn);
+  }
+  if (s < 4) return;
+  d->BN = bn;
+  d->ksplit = s;
+  d->ks_ws = g->ws + g->ws_ks;
 }
 
 static void nhwc_out(chb_conv_desc* d, void* out, int dtype, int r, int C) {
@@ -481,6 +520,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c0b));
       nhwc_out(&d, ws + g->ws_dx0, CHB_F32, r, b.fmid);
+      split_k_few_tiles(g, &d);
       if ((rc = push_step(steps, d, b.name + ".conv_0")) != CHB_OK) return rc;
     }
     if ((rc = modulate(2, reinterpret_cast<const float*>(ws + g->ws_dx0), r, 0, b.fmid, ws + g->ws_h1,
@@ -513,6 +553,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       const int lsplit = (last && (c.precision & CHB_PREC_IMG)) ? 1 : 0;
       nhwc_out(&d, ws + b.ws_xout, last ? CHB_F16 : CHB_F32, r, b.fout * (lsplit ? 2 : 1));
       d.o_split = lsplit; d.o_lo_off = lsplit ? b.fout : 0;
+      split_k_few_tiles(g, &d);
       if ((rc = push_step(steps, d, b.name + (b.shortcut ? ".conv_1+conv_s" : ".conv_1+res"))) != CHB_OK) return rc;
     }
     xin = reinterpret_cast<const float*>(ws + b.ws_xout);
@@ -644,6 +685,7 @@ int chb_generator_bind(chb_generator* g, const void* blob, void* workspace) {
   // mu rows 19..31 (class padding) are never written by the fc_mu GEMM and must read as zero, so that the
   // Weff columns they produce are exact zeros.
   cudaError_t err = cudaMemset(g->ws + g->ws_mu, 0, (size_t)g->n_styled * g->cfg.max_batch * 32 * g->cfg.style_len * 2);
+  if (err == cudaSuccess) err = cudaMemset(g->ws + g->ws_ks, 0, kKsCounterBytes);   // split-K tile counters start at zero
   if (err != cudaSuccess) {
     set_error(std::string("chb_generator_bind: cudaMemset failed: ") + cudaGetErrorString(err));
     return CHB_ERR_CUDA;
@@ -823,6 +865,7 @@ static void step_ranges(const chb_generator* g, const Step& s, int B, const floa
     add_br(r, d.res, ((long long)(d.B - 1) * d.r_sb + (long long)((d.H - 1) >> d.r_shift) * d.r_sy +
                       (long long)((d.W - 1) >> d.r_shift) * d.r_sx + d.N) * 4);
   if (d.noise) add_br(r, d.noise, (long long)d.B * d.W * d.H * 4);
+  if (d.ksplit > 1) add_br(w, d.ks_ws, (long long)ksplit_workspace_bytes(device_sm_count()));
 }
 
 // Captures the conv schedule into the graph being recorded on `cap` with its REAL dependencies: every step goes to a

@@ -527,6 +527,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Release / acquire fence at GPU scope (lighter than __threadfence(), which is sequentially consistent).
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // Named barrier `id` over `nthreads` threads (a multiple of 32) of the CTA; id 0 is __syncthreads'.
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

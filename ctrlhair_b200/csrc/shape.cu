@@ -342,7 +342,7 @@ struct chb_shape {
   std::vector<STensor> tensors;
   int64_t blob_bytes = 0, ws_bytes = 0;
   NetLayout enc[2], dec[2];  // 0 = hair, 1 = face
-  int64_t ws_pos, ws_in, ws_conv, ws_act, ws_feat, ws_fcout, ws_code16, ws_logit[2], ws_sums, ws_io;
+  int64_t ws_pos, ws_in, ws_conv, ws_act, ws_feat, ws_fcout, ws_code16, ws_logit[2], ws_sums, ws_io, ws_ks;
   const uint8_t* blob = nullptr;
   uint8_t* ws = nullptr;
   bool pos_ready = false;
@@ -370,8 +370,33 @@ static int64_t sws(chb_shape* z, int64_t n) {
 static int enc_cout(int i) { return 32 << i > 2048 ? 2048 : 32 << i; }
 static int dec_cout(int i) { return 32 << (6 - i) > 2048 ? 2048 : 32 << (6 - i); }
 
+// Few output tiles and a long K (the 2x2 .. 8x8 layers stream 9-151 MB of weights, the fully connected layers 17 MB):
+// pick the N tile and a split-K factor together.  A wide N tile keeps the re-reads of the activation tile low (every
+// n-tile CTA reads all of A), split-K (<= 8 CTAs per output tile, >= 2 channel chunks each) supplies the CTAs; the N
+// tile only narrows when both together stay under ~96 CTAs.
+static void few_tiles_plan(chb_conv_desc* d, int m_tiles, int nchunk, void* ks_ws) {
+  const int sms = device_sm_count();
+  const int steps = d->seg[0].taps * nchunk;   // K steps of 64 a CTA walks per tile (~0.2 us each)
+  int bn = d->BN;
+  for (;; bn /= 2) {
+    const int tiles = m_tiles * (d->Nrows / bn);
+    int s = sms / tiles;
+    if (s > 8) s = 8;
+    if (s > nchunk / 2) s = nchunk / 2;
+    if (steps < 96) s = 1;                       // the combine costs ~7 us: short K does not split ...
+    else if (s > steps / 24) s = steps / 24;     // ... and a split keeps at least 24 K steps
+    if (s < 1) s = 1;
+    const bool narrower = bn > 32 && d->Nrows % (bn / 2) == 0;
+    if (tiles * s >= 96 || !narrower) {
+      d->BN = bn;
+      if (s >= 2 && tiles <= 1024) { d->ksplit = s; d->ks_ws = ks_ws; }
+      return;
+    }
+  }
+}
+
 static chb_conv_desc conv_desc(int B, int H, int W, const void* a, int C, const void* w, const float* bias, int N, int BN,
-                               void* out) {
+                               void* out, void* ks_ws) {
   chb_conv_desc d;
   memset(&d, 0, sizeof d);
   d.B = B; d.H = H; d.W = W;
@@ -388,9 +413,6 @@ static chb_conv_desc conv_desc(int B, int H, int W, const void* a, int C, const 
     // deep layers are streamed once per N tile instead of once per image ...
     d.TB = 128 / (d.TW * d.TH);
     if (d.TB > B) d.TB = B;
-    // ... and the N tile shrinks until there are enough tiles to spread that stream over the SMs
-    const int m_tiles = ((B + d.TB - 1) / d.TB) * ((H + d.TH - 1) / d.TH) * ((W + d.TW - 1) / d.TW);
-    while (BN > 32 && N % (BN / 2) == 0 && m_tiles * (N / BN) < 96) BN /= 2;
   }
   d.nseg = 1;
   chb_conv_seg& s = d.seg[0];
@@ -400,9 +422,14 @@ static chb_conv_desc conv_desc(int B, int H, int W, const void* a, int C, const 
   d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE; d.bias = bias;
   d.out = out; d.out_dtype = CHB_F32;
   d.o_sn = 1; d.o_sx = N; d.o_sy = (int64_t)W * N; d.o_sb = (int64_t)H * W * N;
+  {
+    const int m_tiles = ((B + d.TB - 1) / d.TB) * ((H + d.TH - 1) / d.TH) * ((W + d.TW - 1) / d.TW);
+    if (m_tiles * (N / BN) < 96) few_tiles_plan(&d, m_tiles, C / (C == 32 ? 32 : 64), ks_ws);
+  }
   return d;
 }
-static chb_conv_desc fc_desc(int B, const void* a, int K, const void* w, const float* bias, int N, int BN, void* out) {
+static chb_conv_desc fc_desc(int B, const void* a, int K, const void* w, const float* bias, int N, int BN, void* out,
+                             void* ks_ws) {
   chb_conv_desc d;
   memset(&d, 0, sizeof d);
   d.B = 1; d.H = 1; d.W = B;
@@ -415,6 +442,10 @@ static chb_conv_desc fc_desc(int B, const void* a, int K, const void* w, const f
   d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE; d.bias = bias;
   d.out = out; d.out_dtype = CHB_F32;
   d.o_sn = 1; d.o_sx = N; d.o_sy = 0; d.o_sb = 0;
+  {
+    const int m_tiles = (B + d.TW - 1) / d.TW;
+    if (m_tiles * (N / BN) < 96) few_tiles_plan(&d, m_tiles, K / 64, ks_ws);
+  }
   return d;
 }
 static const void* bp(const chb_shape* z, int t) { return z->blob + z->tensors[t].offset; }
@@ -428,13 +459,13 @@ static int build_enc_plans(chb_shape* z, int net, int B, std::vector<ConvPlan>& 
     const int Hh = (S / 2) >> i, co = enc_cout(i);
     // layer i reads the space-to-depth map [B,Hh,Hh,cin] and writes fp32 [B,Hh,Hh,co]
     chb_conv_desc d = conv_desc(B, Hh, Hh, z->ws + (i == 0 ? z->ws_in : z->ws_act), cin, bp(z, z->enc[net].w[i]),
-                                bpf(z, z->enc[net].b[i]), co, co < 256 ? co : 256, z->ws + z->ws_conv);
+                                bpf(z, z->enc[net].b[i]), co, co < 256 ? co : 256, z->ws + z->ws_conv, z->ws + z->ws_ks);
     int rc = build_conv_plan(d, &plans[i]);
     if (rc != CHB_OK) return rc;
     cin = 4 * co;
   }
   chb_conv_desc f = fc_desc(B, z->ws + z->ws_feat, 8192, bp(z, z->enc[net].fcw), bpf(z, z->enc[net].fcb), kEncOut[net],
-                            kEncOut[net] < 256 ? kEncOut[net] : 256, z->ws + z->ws_fcout);
+                            kEncOut[net] < 256 ? kEncOut[net] : 256, z->ws + z->ws_fcout, z->ws + z->ws_ks);
   return build_conv_plan(f, &plans[7]);
 }
 
@@ -442,19 +473,19 @@ static int build_dec_plans(chb_shape* z, int net, int B, std::vector<ConvPlan>& 
   const int S = z->cfg.crop;
   plans.resize(9);
   chb_conv_desc f = fc_desc(B, z->ws + z->ws_code16, kDecIn[net], bp(z, z->dec[net].fcw), bpf(z, z->dec[net].fcb), 8192,
-                            256, z->ws + z->ws_fcout);
+                            256, z->ws + z->ws_fcout, z->ws + z->ws_ks);
   int rc = build_conv_plan(f, &plans[0]);
   if (rc != CHB_OK) return rc;
   int cin = 2048;
   for (int i = 0; i < 7; ++i) {
     const int r = 4 << i, co = dec_cout(i);
     chb_conv_desc d = conv_desc(B, r, r, z->ws + z->ws_act, cin, bp(z, z->dec[net].w[i]), bpf(z, z->dec[net].b[i]), co,
-                                co < 256 ? co : 256, z->ws + z->ws_conv);
+                                co < 256 ? co : 256, z->ws + z->ws_conv, z->ws + z->ws_ks);
     if ((rc = build_conv_plan(d, &plans[1 + i])) != CHB_OK) return rc;
     cin = co;
   }
   chb_conv_desc o = conv_desc(B, S, S, z->ws + z->ws_act, 32, bp(z, z->dec[net].w[7]), bpf(z, z->dec[net].b[7]),
-                              kDecOutRows[net], kDecOutRows[net], z->ws + z->ws_logit[net]);
+                              kDecOutRows[net], kDecOutRows[net], z->ws + z->ws_logit[net], z->ws + z->ws_ks);
   return build_conv_plan(o, &plans[8]);
 }
 
@@ -531,6 +562,7 @@ int chb_shape_create(const chb_shape_config* cfg, chb_shape** out) {
   z->ws_logit[1] = sws(z, B * S * S * 32 * 4);
   z->ws_sums = sws(z, B * 2 * 8 + B * 8 + B * 8);   // double moments [B][2], block counters [B], float2 constants [B]
   z->ws_io = sws(z, B * 19 * S * S * 4);
+  z->ws_ks = sws(z, (int64_t)ksplit_workspace_bytes(device_sm_count()));   // split-K counters + partial accumulators
   *out = z;
   return CHB_OK;
 }
@@ -568,7 +600,8 @@ int chb_shape_bind(chb_shape* z, const void* blob, void* workspace) {
   }
   shape_pos_kernel<<<sgrid((long long)z->cfg.crop * z->cfg.crop * kPosCh, 256), 256>>>(
       reinterpret_cast<__half*>(z->ws + z->ws_pos), z->cfg.crop);
-  cudaError_t err = cudaDeviceSynchronize();
+  cudaError_t err = cudaMemset(z->ws + z->ws_ks, 0, kKsCounterBytes);   // split-K tile counters start at zero
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();
   if (err != cudaSuccess) {
     set_error(std::string("chb_shape_bind: positional table kernel failed: ") + cudaGetErrorString(err));
     return CHB_ERR_CUDA;

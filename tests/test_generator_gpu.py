@@ -123,7 +123,10 @@ def test_full_size_batch_properties(gen256):
     for i in (0, 5):
         flat1 = synth.flatten_noise([p[i:i + 1] for p in planes])
         solo = gen256.forward_labels(labels[i:i + 1], codes[i:i + 1], noise=flat1.cuda())
-        assert torch.equal(solo[0], out[i])  # bitwise: tiles never mix images, accumulation order is fixed
+        # tiles never mix images; the one-image call splits K over more CTAs on the 8x8 .. 32x32 convs (csrc/generator.cu
+        # split_k_few_tiles): a different fp32 association, which flips the fp16 rounding of a few stored activations
+        # (measured 3.0e-4 on the tanh image; the batch-of-8 schedule itself is permutation-invariant bitwise, below)
+        assert float((solo[0] - out[i]).abs().max()) < 6e-4
     perm = torch.tensor([3, 1, 7, 0, 2, 6, 5, 4])
     flatp = synth.flatten_noise([p[perm] for p in planes])
     outp = gen256.forward_labels(labels[perm], codes[perm], noise=flatp.cuda())
