@@ -403,19 +403,26 @@ def run_ours(args):
         l1, c1 = labels_d[:1].contiguous(), codes_d[:1].contiguous()
         o1 = torch.empty((1, 3, crop, crop), dtype=torch.float32, device=dev)
         res = {}
-        for mode, use_graph in (("graph", True), ("launches", False)):
-            for i in range(5):
-                gen.forward_labels(l1, c1, seed=i, out=o1, graph=use_graph)
-            torch.cuda.synchronize(dev)
-            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_lat = 50
-            t0 = time.perf_counter()
-            ea.record()
-            for i in range(n_lat):
-                gen.forward_labels(l1, c1, seed=10 + i, out=o1, graph=use_graph)
-            eb.record()
-            torch.cuda.synchronize(dev)
-            res[mode] = {"device_ms": ea.elapsed_time(eb) / n_lat, "wall_ms": (time.perf_counter() - t0) / n_lat * 1e3}
+        # three alternating rounds, best round per mode: the first loop after the B = 64 region runs while the clocks
+        # settle from the power-capped state (it read 25 % slower than the same loop measured second)
+        for rnd in range(3):
+            for mode, use_graph in (("graph", True), ("launches", False)):
+                for i in range(5):
+                    gen.forward_labels(l1, c1, seed=i, out=o1, graph=use_graph)
+                torch.cuda.synchronize(dev)
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_lat = 50
+                t0 = time.perf_counter()
+                ea.record()
+                for i in range(n_lat):
+                    gen.forward_labels(l1, c1, seed=10 + i, out=o1, graph=use_graph)
+                eb.record()
+                torch.cuda.synchronize(dev)
+                r = {"device_ms": ea.elapsed_time(eb) / n_lat, "wall_ms": (time.perf_counter() - t0) / n_lat * 1e3}
+                rounds = res.get(mode, {}).get("rounds_ms", []) + [round(r["device_ms"], 4)]
+                if mode not in res or r["device_ms"] < res[mode]["device_ms"]:
+                    res[mode] = r
+                res[mode]["rounds_ms"] = rounds
         lat = {"batch": 1, "crop": crop, "ms": res["graph"]["device_ms"], "graph": res["graph"], "launches": res["launches"],
                "weight_stream_floor_ms": gen.blob_bytes() / (load_peaks()["hbm_gbs"] * 1e9) * 1e3,
                "what": "SeanGeneratorB200.forward_labels(B=1, graph=True): one captured CUDA graph per call, back to "
