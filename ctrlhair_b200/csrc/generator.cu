@@ -122,6 +122,16 @@ static int64_t ws_alloc(chb_generator* g, int64_t nbytes) {
   return off;
 }
 
+// Interactive batches (B <= 4) are bound by launch latency, not by MMA work: under the default policy (every h_1 split)
+// they also store h_0 as a hi+lo pair — conv_0's K doubles for ~3 % of a one-image forward, and the worst max-norm over
+// the test inputs drops from 1.0e-3 to 7.6e-4 (the large-batch schedule keeps the policy as configured).
+constexpr int kSmallBatch = 4;
+static bool small_batch_h0_split(const chb_gen_config& c, int B) {
+  unsigned all_h1 = 0;
+  for (int i = 0; i < 7; ++i) all_h1 |= CHB_PREC_H1(i);
+  return B <= kSmallBatch && (c.precision & all_h1) == all_h1;
+}
+
 static void build_layout(chb_generator* g) {
   const chb_gen_config& c = g->cfg;
   const int nf = c.ngf, L = c.style_len, B = c.max_batch;
@@ -228,7 +238,9 @@ static void build_layout(chb_generator* g) {
     const int64_t px = (int64_t)B * b.r * b.r;
     b.ws_actv = ws_alloc(g, px * 128 * b.n_ace * 2);
     m_hs = std::max<int64_t>(m_hs, px * b.fin * 2 * (b.split_hs ? 2 : 1));
+    // (interactive batches split h_0 whatever the policy says, see small_batch_h0_split: room for [hi | lo] at B <= 4)
     m_hin = std::max<int64_t>(m_hin, px * b.fin * 2 * (b.split_h0 ? 2 : 1));
+    m_hin = std::max<int64_t>(m_hin, (int64_t)std::min(B, kSmallBatch) * b.r * b.r * b.fin * 2 * 2);
     m_h1 = std::max<int64_t>(m_h1, px * b.fmid * 2 * (b.split_h1 ? 2 : 1));
     m_dx0 = std::max<int64_t>(m_dx0, px * b.fmid * 4);
     const bool last = (&b == &g->blocks.back());
@@ -507,13 +519,14 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
     if (b.shortcut) {
       if ((rc = modulate(0, xin, xin_r, b.in_shift, b.fin, ws + g->ws_hs, CHB_ACT_NONE, b.split_hs)) != CHB_OK) return rc;
     }
-    if ((rc = modulate(1, xin, xin_r, b.in_shift, b.fin, ws + g->ws_h0, CHB_ACT_LRELU, b.split_h0)) != CHB_OK) return rc;
+    const int sh0 = (b.split_h0 || small_batch_h0_split(c, B)) ? 1 : 0;
+    if ((rc = modulate(1, xin, xin_r, b.in_shift, b.fin, ws + g->ws_h0, CHB_ACT_LRELU, sh0)) != CHB_OK) return rc;
     // dx = conv_0(lrelu(ace_0(x)))   (architecture.py:73-75)
     {
       chb_conv_desc d = base_desc(B, r);
       batch_small_tiles(&d);
       d.nseg = 1;
-      const int m0 = b.split_h0 ? 2 : 1;  // [hi | lo] halves share conv_0's weights
+      const int m0 = sh0 ? 2 : 1;  // [hi | lo] halves share conv_0's weights
       d.seg[0] = make_seg(ws + g->ws_h0, r, b.fin * m0, 0, b.fin * m0, 9, blobp(g, b.t_c0w));
       d.seg[0].w_dup = m0;
       d.N = d.Nrows = b.fmid; d.BN = pick_bn(b.fmid, B, r);

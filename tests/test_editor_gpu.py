@@ -61,7 +61,9 @@ def test_gen_img_batch_equals_looped_gen_img(synthetic_sd):
     for i in range(B):
         one = ed.gen_img(codes[i:i + 1], labels[i:i + 1, None].numpy(),
                          noise=synth.flatten_noise([p[i:i + 1] for p in noise])).cpu()
-        assert torch.equal(one, batch[i]), i           # same kernels, same inputs: bitwise identical
+        # same kernels, same inputs; the split-K factor of the low-resolution convs follows the batch size, so the two
+        # schedules agree to the fp16 storage rounding of the activations, not bitwise
+        assert float((one - batch[i]).abs().max()) < 1e-3, i
     eff = codes.clone()
     eff[1, 13], eff[2, 0] = median[13], median[0]
     ref = so.generator_forward(synthetic_sd, labels, eff, noise)

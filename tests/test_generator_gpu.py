@@ -123,10 +123,12 @@ def test_full_size_batch_properties(gen256):
     for i in (0, 5):
         flat1 = synth.flatten_noise([p[i:i + 1] for p in planes])
         solo = gen256.forward_labels(labels[i:i + 1], codes[i:i + 1], noise=flat1.cuda())
-        # tiles never mix images; the one-image call splits K over more CTAs on the 8x8 .. 32x32 convs (csrc/generator.cu
-        # split_k_few_tiles): a different fp32 association, which flips the fp16 rounding of a few stored activations
-        # (measured 3.0e-4 on the tanh image; the batch-of-8 schedule itself is permutation-invariant bitwise, below)
-        assert float((solo[0] - out[i]).abs().max()) < 6e-4
+        # tiles never mix images, but the one-image call runs another schedule: split-K on the 8x8 .. 32x32 convs and the
+        # h_0 hi+lo split of interactive batches (csrc/generator.cu split_k_few_tiles, small_batch_h0_split).  The two
+        # agree to the fp16 storage rounding of the activations (the batch-of-8 schedule itself is permutation-invariant
+        # bitwise, below)
+        print("solo vs batch of 8: max |diff| %.3g" % float((solo[0] - out[i]).abs().max()))
+        assert float((solo[0] - out[i]).abs().max()) < MAX_TOL
     perm = torch.tensor([3, 1, 7, 0, 2, 6, 5, 4])
     flatp = synth.flatten_noise([p[perm] for p in planes])
     outp = gen256.forward_labels(labels[perm], codes[perm], noise=flatp.cuda())
@@ -187,7 +189,8 @@ def test_generator_512_vs_oracle(synthetic_sd):
 def test_headline_batch64_vs_oracle(synthetic_sd):
     """BASELINE.json configs[1] itself: B = 64 at 256x256.  The batch size changes the plan (fc_mu tile width, the N tile
     of the Weff GEMMs, the tile schedule of every persistent launch), so the headline schedule is compared with the
-    oracle on the first, a middle and the last image, and image-by-image with the B = 1 schedule (bitwise)."""
+    oracle on the first, a middle and the last image, and image-by-image with the B = 1 schedule (which splits K and keeps
+    h_0 as a hi+lo pair: equal to the fp16 storage rounding, not bitwise)."""
     B = 64
     g = SeanGeneratorB200(crop=256, max_batch=B)
     g.load_state_dict(synthetic_sd)
@@ -201,4 +204,5 @@ def test_headline_batch64_vs_oracle(synthetic_sd):
         l2, mx = _errs(out[i:i + 1].cpu(), ref)
         assert l2 < L2_TOL and mx < MAX_TOL, (i, l2, mx)
         solo = g.forward_labels(labels[i:i + 1].cuda(), codes[i:i + 1].cuda(), noise=synth.flatten_noise(one).cuda())
-        assert torch.equal(solo[0], out[i]), i
+        print("solo vs batch of 64: max |diff| %.3g" % float((solo[0] - out[i]).abs().max()))
+        assert float((solo[0] - out[i]).abs().max()) < MAX_TOL, i
