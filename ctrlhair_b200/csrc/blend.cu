@@ -478,8 +478,8 @@ __device__ __forceinline__ void poisson_cluster_exchange(double& a, double& b, d
 //   u = M^-1 r, w = A u, g = (r,u), d = (w,u), n = (r,r); b = g/g_old, a = g/(d - b g/a_old);
 //   p = u + b p, s = w + b s, x += a p, r -= a s;   P^T s = P^T w + b P^T s, P^T r -= a P^T s.
 template <int W, int R, int CL, bool PRE>   // columns, rows per CTA, CTAs per cluster (shape from the launch attribute)
-__global__ void __launch_bounds__((R / kPoi2Rows) * W, 512 / ((R / kPoi2Rows) * W))
-    poisson_cg2_kernel(const PoissonParams p) {
+__global__ void __launch_bounds__((R / kPoi2Rows) * W, PRE ? 1 : 512 / ((R / kPoi2Rows) * W))
+    poisson_cg2_kernel(const PoissonParams p) {   // (PRE: one CTA per SM by shared memory, so 256 threads get 255 registers)
   constexpr int kPoi2Threads = (R / kPoi2Rows) * W;
   // compile-time geometry (the reference's 256 x 256 images: 8 CTAs x 32 rows): every shared-memory offset below is
   // an immediate, which is what lets r, p and s stay in registers.  The inner loop is branch free: pixels outside U
@@ -993,23 +993,19 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
   const bool no_pre = false;
 #endif
   const bool pre = v2 && !no_pre;
-  const bool cl16 = v2 && !pre && (force_cl16 >= 0 ? force_cl16 == 1 : B * 3 <= 8);
-  if (cl16) smem = poisson2_smem_bytes(kPoi2R16, W);
-  if (pre) smem = poisson2_smem_bytes(R, W, true);
+  // 16-CTA clusters for interactive batches (see above), 8-CTA clusters otherwise; with or without the preconditioner
+  const bool cl16 = v2 && (force_cl16 >= 0 ? force_cl16 == 1 : B * 3 <= 8);
+  typedef void (*Poi2Kernel)(const PoissonParams);
+  const Poi2Kernel k2 = pre ? (cl16 ? poisson_cg2_kernel<kPoi2W, kPoi2R16, 16, true>
+                                    : poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, true>)
+                            : (cl16 ? poisson_cg2_kernel<kPoi2W, kPoi2R16, 16, false>
+                                    : poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, false>);
+  if (v2) smem = poisson2_smem_bytes(cl16 ? kPoi2R16 : R, W, pre);
   // (set on every call: the attribute is per device, and a process may drive several)
   cudaError_t e;
-  if (pre) {
-    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  } else if (cl16) {
-    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R16, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R16, 16, false>,
-                               cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  } else if (v2) {
-    e = cudaFuncSetAttribute(poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (v2) {
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && cl16) e = cudaFuncSetAttribute(k2, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   } else {
     e = cudaFuncSetAttribute(poisson_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
@@ -1047,9 +1043,7 @@ static int poisson_launch(const uint8_t* source, const uint8_t* target, const ui
     attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = pre    ? cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, true>, p)
-        : cl16 ? cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R16, 16, false>, p)
-               : cudaLaunchKernelEx(&cfg, poisson_cg2_kernel<kPoi2W, kPoi2R, kPoiCluster, false>, p);
+    e = cudaLaunchKernelEx(&cfg, k2, p);
     if (coarse) cudaFreeAsync(coarse, stream);
     if (e != cudaSuccess) {
       set_error(std::string("poisson_cg2 launch: ") + cudaGetErrorString(e));
