@@ -172,9 +172,14 @@ class BiSeNetB200(torch.nn.Module):
         self.handle, self.blob, self.workspace = h, None, None
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            self.lib.chb_bisenet_destroy(self.handle)
-            self.handle = None
+        # (at interpreter shutdown torch.nn may already be torn down: bypass nn.Module.__setattr__, never raise)
+        h = self.__dict__.get("handle")
+        if h:
+            self.__dict__["handle"] = None
+            try:
+                self.lib.chb_bisenet_destroy(h)
+            except Exception:
+                pass
 
     def _layout(self):
         name = C.create_string_buffer(96)

@@ -39,63 +39,93 @@ static inline unsigned bgrid(long long n, int block) {
 // (my_parsing_util.py:25-28), evaluated in the reference's operation order (scale, subtract, divide).  One thread = one
 // output pixel x all 64 output channels: the 7 x 7 x 3 patch is fetched and normalised once, every weight read is a
 // shared-memory broadcast (a warp reads one 16-byte word for four FMAs; rows of 21 weights are padded to 24).
+// A CTA of 128 threads takes a 16 x 8 tile of output pixels: warps 0-1 compute channels 0..31 of them, warps 2-3
+// channels 32..63 (a warp shares one channel half, so every weight read is a broadcast), and a thread owns TWO pixels
+// (rows ty and ty + 8) so that each 16-byte weight word feeds eight FMAs.  The 37 x 21 x 3 input patch
+// of the tile is normalised ONCE into shared memory (each pixel on its own would redo 147 fp32 divisions and byte loads:
+// a third of the instructions), and the FMAs go out as packed pairs (fma.rn.f32x2, two output channels per issue slot;
+// the weights sit [ky][k][co] so that a 16-byte word holds four output channels of one tap).  Each output is still the
+// same chain of 147 fp32 FMAs in the same order — bit for bit the result of the first version of this kernel (one thread
+// per pixel x 64 channels, 1.87 ms at B = 32), which is what keeps the label agreement of the parser where it was.
+__device__ __forceinline__ unsigned long long stem_pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long stem_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+constexpr int kStemTile = 8, kStemIn = 2 * kStemTile + 5, kStemPitch = 68;   // 21 input columns, rows of 63 (+5) floats
+constexpr int kStemTileH = 16, kStemInH = 2 * kStemTileH + 5;                 // 37 input rows
 __global__ void __launch_bounds__(128) bisenet_stem_kernel(const uint8_t* __restrict__ img,
                                                            const float* __restrict__ w /*[64][148]: co, (ky,kx,ci)*/,
                                                            const float* __restrict__ bias, __half* __restrict__ out,
                                                            int B, int S) {
-  __shared__ __align__(16) float sw[7 * 64 * 24];   // [ky][co][24]: 21 = 7 taps x 3 channels, zero padded
+  __shared__ __align__(16) float sw[7 * 21 * 64];            // [ky][k = kx*3+ci][co]
+  __shared__ __align__(16) float sin_[kStemInH * kStemPitch];  // normalised input patch of the tile
   __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 7 * 64 * 24; i += blockDim.x) {
-    const int ky = i / (64 * 24), r = i - ky * 64 * 24, co = r / 24, k = r - co * 24;
-    sw[i] = k < 21 ? w[co * 148 + ky * 21 + k] : 0.f;
+  for (int i = threadIdx.x; i < 7 * 21 * 64; i += blockDim.x) {
+    const int co = i & 63, r = i >> 6, ky = r / 21, k = r - ky * 21;
+    sw[i] = w[co * 148 + ky * 21 + k];
   }
   if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int So = S / 2;
+  const int So = S / 2, tiles = So / kStemTile, tiles_y = So / kStemTileH;
   const float nm[3] = {0.485f, 0.456f, 0.406f}, ns[3] = {0.229f, 0.224f, 0.225f};
-  const long long npix = (long long)B * So * So;
-  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
-       pix += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(pix % So), y = (int)((pix / So) % So), b = (int)(pix / ((long long)So * So));
-    float acc[64];
+  const int half = threadIdx.x >> 6;                 // channel half of this warp
+  const int lp = threadIdx.x & 63, ty = lp >> 3, tx = lp & 7;
+  for (long long t = blockIdx.x; t < (long long)B * tiles * tiles_y; t += gridDim.x) {
+    const int tX = (int)(t % tiles), tY = (int)((t / tiles) % tiles_y), b = (int)(t / ((long long)tiles * tiles_y));
+    const int y0 = tY * kStemTileH, x0 = tX * kStemTile;
+    __syncthreads();   // the previous tile's patch is no longer read (first pass: sw / sb are complete)
+    for (int i = threadIdx.x; i < kStemInH * kStemIn * 3; i += blockDim.x) {
+      const int c = i % 3, px = (i / 3) % kStemIn, py = i / (3 * kStemIn);
+      const int yy = 2 * y0 - 3 + py, xx = 2 * x0 - 3 + px;
+      const bool ok = yy >= 0 && yy < S && xx >= 0 && xx < S;
+      // zero padding applies to the NORMALISED image; the reference's operation order: scale, subtract, divide
+      sin_[py * kStemPitch + px * 3 + c] =
+          ok ? ((float)__ldg(img + (((long long)b * S + yy) * S + xx) * 3 + c) * (1.f / 255.f) - nm[c]) / ns[c] : 0.f;
+    }
+    __syncthreads();
+    unsigned long long acc[2][16];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = sb[j];
+    for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = stem_pk2(sb[32 * half + 2 * j], sb[32 * half + 2 * j + 1]);
+#pragma unroll 1
     for (int ky = 0; ky < 7; ++ky) {
-      const int yy = 2 * y + ky - 3;
-      float in[24];   // one kernel row: 7 taps x 3 channels (+ padding)
+      // 21 contiguous values per pixel: (kx, ci); the second pixel sits 8 output rows = 16 input rows further down
+      const float* irow = sin_ + (2 * ty + ky) * kStemPitch + 6 * tx;
+      const float4* wk = reinterpret_cast<const float4*>(sw + ky * 21 * 64 + 32 * half);
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const int xx = 2 * x + kx - 3;
-        const bool ok = yy >= 0 && yy < S && xx >= 0 && xx < S;
-        const uint8_t* p = img + (((long long)b * S + (ok ? yy : 0)) * S + (ok ? xx : 0)) * 3;
+      for (int k = 0; k < 21; ++k) {
+        const float v0 = irow[k], v1 = irow[16 * kStemPitch + k];
+        const unsigned long long vv0 = stem_pk2(v0, v0), vv1 = stem_pk2(v1, v1);
 #pragma unroll
-        for (int c = 0; c < 3; ++c)   // zero padding applies to the NORMALISED image
-          in[kx * 3 + c] = ok ? ((float)__ldg(p + c) * (1.f / 255.f) - nm[c]) / ns[c] : 0.f;
-      }
-      in[21] = in[22] = in[23] = 0.f;
-      const float4* wk = reinterpret_cast<const float4*>(sw + ky * 64 * 24);
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float a = acc[j];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const float4 wv = wk[j * 6 + q];
-          a = fmaf(in[4 * q], wv.x, a);
-          a = fmaf(in[4 * q + 1], wv.y, a);
-          a = fmaf(in[4 * q + 2], wv.z, a);
-          a = fmaf(in[4 * q + 3], wv.w, a);
+        for (int q = 0; q < 8; ++q) {
+          const float4 wv = wk[k * 16 + q];
+          const unsigned long long w01 = stem_pk2(wv.x, wv.y), w23 = stem_pk2(wv.z, wv.w);
+          acc[0][2 * q] = stem_fma2(vv0, w01, acc[0][2 * q]);
+          acc[0][2 * q + 1] = stem_fma2(vv0, w23, acc[0][2 * q + 1]);
+          acc[1][2 * q] = stem_fma2(vv1, w01, acc[1][2 * q]);
+          acc[1][2 * q + 1] = stem_fma2(vv1, w23, acc[1][2 * q + 1]);
         }
-        acc[j] = a;
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
 #pragma unroll
-    for (int v = 0; v < 8; ++v) {
-      __half2 h[4];
+    for (int pp = 0; pp < 2; ++pp) {
+      const long long pix = ((long long)b * So + (y0 + ty + 8 * pp)) * So + (x0 + tx);
+      uint4* o = reinterpret_cast<uint4*>(out + pix * 64 + 32 * half);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        h[j] = __floats2half2_rn(fmaxf(acc[8 * v + 2 * j], 0.f), fmaxf(acc[8 * v + 2 * j + 1], 0.f));
-      o[v] = *reinterpret_cast<uint4*>(h);
+      for (int v = 0; v < 4; ++v) {
+        __half2 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float lo, hi;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[pp][4 * v + j]));
+          h[j] = __floats2half2_rn(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+        }
+        o[v] = *reinterpret_cast<uint4*>(h);
+      }
     }
   }
 }
@@ -573,7 +603,7 @@ int chb_bisenet_forward(chb_bisenet* n, const uint8_t* img, uint8_t* mask, int o
     return slabs;
   };
   const int R = S / 4, H8 = R / 2, H16 = R / 4, H32 = R / 8;
-  bisenet_stem_kernel<<<bgrid((long long)B * (S / 2) * (S / 2), 128), 128, 0, st>>>(img, Wf("stem.w"), Wf("stem.b"),
+  bisenet_stem_kernel<<<bgrid((long long)B * (S / 16) * (S / 32), 1), 128, 0, st>>>(img, Wf("stem.w"), Wf("stem.b"),
                                                                                   Hp("stem"), B, S);
   maxpool3s2_kernel<<<bgrid((long long)B * R * R * 8, 256), 256, 0, st>>>(Hp("stem"), Hp("p0"), B, S / 2, 64);
   const int ch[4] = {64, 128, 256, 512};

@@ -155,9 +155,14 @@ class SolverB200:
         self._keep = None
 
     def __del__(self):
-        h, self.handle = getattr(self, "handle", None), None
+        # (at interpreter shutdown torch.nn may already be torn down: bypass nn.Module.__setattr__, never raise)
+        h = self.__dict__.get("handle")
         if h:
-            self.lib.chb_cttrain_destroy(h)
+            self.__dict__["handle"] = None
+            try:
+                self.lib.chb_cttrain_destroy(h)
+            except Exception:
+                pass
 
     # ---- state ---------------------------------------------------------------------------------------------
     def region(self, region, group):

@@ -61,10 +61,14 @@ class SeanGeneratorB200(torch.nn.Module):
         self._layout = self._read_layout()
 
     def __del__(self):
-        h = getattr(self, "handle", None)
+        # (at interpreter shutdown torch.nn may already be torn down: bypass nn.Module.__setattr__, never raise)
+        h = self.__dict__.get("handle")
         if h:
-            self.lib.chb_generator_destroy(h)
-            self.handle = None
+            self.__dict__["handle"] = None
+            try:
+                self.lib.chb_generator_destroy(h)
+            except Exception:
+                pass
 
     # ------------------------------------------------------------------ weights
     def _read_layout(self):

@@ -50,9 +50,14 @@ class ZencoderB200(torch.nn.Module):
         self.handle, self.blob, self.workspace = h, None, None
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            self.lib.chb_zencoder_destroy(self.handle)
-            self.handle = None
+        # (at interpreter shutdown torch.nn may already be torn down: bypass nn.Module.__setattr__, never raise)
+        h = self.__dict__.get("handle")
+        if h:
+            self.__dict__["handle"] = None
+            try:
+                self.lib.chb_zencoder_destroy(h)
+            except Exception:
+                pass
 
     def _layout(self):
         n = self.lib.chb_zencoder_num_tensors(self.handle)
