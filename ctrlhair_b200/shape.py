@@ -49,7 +49,7 @@ def pack_shape(sd, weight_dtype=torch.float16):
         w = w.reshape(w.shape[0], 2048, 2, 2).permute(0, 2, 3, 1).reshape(w.shape[0], 8192)
         out[p + "fc.w"] = w.contiguous().to(weight_dtype)
         out[p + "fc.b"] = torch.cat(bs, 0)
-    for net, kpad, rows in (("hair", 1088, 16), ("face", 1024, 32)):
+    for net, kpad, rows in (("hair", 1088, 32), ("face", 1024, 32)):
         p = net + "_decoder."
         w = sd["%s_decoder.in_layer.fc.weight" % net].float()       # [8192, in]
         b = sd["%s_decoder.in_layer.fc.bias" % net].float()
