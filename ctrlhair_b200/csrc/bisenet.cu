@@ -329,6 +329,34 @@ __global__ void __launch_bounds__(256) pil_resample_pass_kernel(const uint8_t* _
   }
 }
 
+// The same pass, four consecutive `inner` elements per thread (inner % 4 == 0 and 4-byte aligned rows: the y pass, whose
+// inner extent is a whole image row): one 32-bit load per tap instead of four byte loads, one 32-bit store.
+__global__ void __launch_bounds__(256) pil_resample_pass4_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                                 const int* __restrict__ bounds, const int* __restrict__ coef,
+                                                                 int ks, long long outer, int I, int O, int inner) {
+  const int inner4 = inner >> 2;
+  const long long total = outer * O * inner4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % inner4);
+    const int o = (int)((i / inner4) % O);
+    const long long q = i / ((long long)inner4 * O);
+    const int lo = __ldg(bounds + 2 * o), n = __ldg(bounds + 2 * o + 1);
+    const uint8_t* p = in + (q * I + lo) * inner + 4 * c4;
+    int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21, a3 = 1 << 21;
+    for (int k = 0; k < n; ++k) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p + (long long)k * inner));
+      const int w = __ldg(coef + o * ks + k);
+      a0 += (int)(v & 0xffu) * w;
+      a1 += (int)((v >> 8) & 0xffu) * w;
+      a2 += (int)((v >> 16) & 0xffu) * w;
+      a3 += (int)(v >> 24) * w;
+    }
+    auto clip8 = [](int a) { a >>= 22; return (uint32_t)(a < 0 ? 0 : (a > 255 ? 255 : a)); };
+    reinterpret_cast<uint32_t*>(out)[(q * O + o) * inner4 + c4] = clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16) | (clip8(a3) << 24);
+  }
+}
+
 struct BTensor {
   std::string name;
   int64_t offset, nbytes;
@@ -683,8 +711,13 @@ int chb_pil_resize_bilinear(const uint8_t* in, uint8_t* tmp, uint8_t* out, int B
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   pil_resample_pass_kernel<<<bgrid((long long)B * H * OW * C, 256), 256, 0, st>>>(in, tmp, xbounds, xcoef, xks,
                                                                                 (long long)B * H, W, OW, C);
-  pil_resample_pass_kernel<<<bgrid((long long)B * OH * OW * C, 256), 256, 0, st>>>(tmp, out, ybounds, ycoef, yks, B, H,
-                                                                                 OH, OW * C);
+  const int row = OW * C;
+  if (row % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(out)) & 3) == 0)
+    pil_resample_pass4_kernel<<<bgrid((long long)B * OH * (row / 4), 256), 256, 0, st>>>(tmp, out, ybounds, ycoef, yks, B, H,
+                                                                                       OH, row);
+  else
+    pil_resample_pass_kernel<<<bgrid((long long)B * OH * row, 256), 256, 0, st>>>(tmp, out, ybounds, ycoef, yks, B, H, OH,
+                                                                                 row);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     set_error(std::string("pil_resize launch failed: ") + cudaGetErrorString(err));
