@@ -14,7 +14,8 @@ namespace chb {
 
 constexpr int kMlpMaxLayers = 8;
 constexpr int kMlpMaxDim = 1024;
-constexpr int kMlpThreads = 256;
+constexpr int kMlpThreads = 512;
+constexpr int kMlpWarps = kMlpThreads / 32;
 
 struct MlpParams {
   chb_mlp_layer layer[kMlpMaxLayers];
@@ -35,6 +36,8 @@ __device__ __forceinline__ float mlp_act(float v, int act) {
 
 __global__ void __launch_bounds__(kMlpThreads) mlp_chain_kernel(const MlpParams p) {
   __shared__ float buf[2][kMlpMaxDim];
+  __shared__ float part[kMlpWarps * 32];   // k-sliced partial sums of a narrow layer (slices x out_dim <= 512)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     float* cur = buf[0];
     float* nxt = buf[1];
@@ -58,14 +61,29 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_chain_kernel(const MlpParams 
         }
         __syncthreads();
       }
-      for (int j = threadIdx.x; j < L.out_dim; j += kMlpThreads) {
-        // four independent accumulators and sixteen weight loads in flight: the single chain of the first version
-        // (one L2 round trip per four FMAs) made a 512-wide layer cost ~40 us
-        float a0 = L.bias ? L.bias[j] : 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      // A warp takes 32 consecutive outputs (one 128-byte weight row per k); layers narrower than 16 x 32 outputs also
+      // split K across the spare warps (the chain over k, not the FMAs, is what a small dense layer costs).  Four
+      // independent accumulators and sixteen weight loads in flight per thread.
+      const int O = L.out_dim, I = L.in_dim;
+      const int nb = (O + 31) >> 5;
+      int ks = 1;
+      while (ks * 2 * nb <= kMlpWarps) ks *= 2;
+      const bool last = l + 1 == p.nlayers;
+      auto finish = [&](int j, float acc) {
+        acc = mlp_act(acc, L.post_act);
+        if (last) p.out[(long long)b * O + j] = acc;
+        else nxt[j] = acc;
+      };
+      for (int it = warp; it < nb * ks; it += kMlpWarps) {
+        const int blk = it % nb, sl = it / nb;
+        const int j = blk * 32 + lane;
+        if (j >= O) continue;
+        const int k0 = (int)((long long)I * sl / ks), k1 = (int)((long long)I * (sl + 1) / ks);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         const float* w = L.wt + j;
-        const long long od = L.out_dim;
-        int k = 0;
-        for (; k + 16 <= L.in_dim; k += 16) {
+        const long long od = O;
+        int k = k0;
+        for (; k + 16 <= k1; k += 16) {
           float wv[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) wv[u] = __ldg(w + (k + u) * od);
@@ -77,11 +95,18 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_chain_kernel(const MlpParams 
             a3 = fmaf(cur[k + u + 3], wv[u + 3], a3);
           }
         }
-        for (; k < L.in_dim; ++k) a0 = fmaf(cur[k], __ldg(w + k * od), a0);
-        float acc = (a0 + a1) + (a2 + a3);
-        acc = mlp_act(acc, L.post_act);
-        if (l + 1 == p.nlayers) p.out[(long long)b * L.out_dim + j] = acc;
-        else nxt[j] = acc;
+        for (; k < k1; ++k) a0 = fmaf(cur[k], __ldg(w + k * od), a0);
+        const float acc = (a0 + a1) + (a2 + a3);
+        if (ks == 1) finish(j, acc + (L.bias ? L.bias[j] : 0.f));
+        else part[sl * O + j] = acc;
+      }
+      if (ks > 1) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < O; j += kMlpThreads) {
+          float acc = L.bias ? L.bias[j] : 0.f;
+          for (int sl = 0; sl < ks; ++sl) acc += part[sl * O + j];   // fixed order
+          finish(j, acc);
+        }
       }
       __syncthreads();
       float* t = cur;
