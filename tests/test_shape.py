@@ -70,6 +70,29 @@ def test_shape_cuda_matches_oracle_and_golden(shape_sd):
 
 
 @pytest.mark.gpu
+def test_shape_other_batch_size_matches_oracle(shape_sd):
+    """The plan follows the batch size (images per MMA tile, N tile and split-K factor of the 2x2 .. 8x8 layers and of
+    the fully connected layers: csrc/shape.cu few_tiles_plan): a batch of 7 against the oracle, image by image."""
+    from ctrlhair_b200.shape import ShapeGeneratorB200
+    B = 7
+    net = ShapeGeneratorB200(max_batch=B).load_state_dict(shape_sd)
+    hair, face = synth.make_shape_inputs(B)
+    hc = net.forward_hair_encoder(hair.cuda(), testing=True).cpu()
+    fc = net.forward_face_encoder(face.cuda()).cpu()
+    pick = [0, 3, 6]
+    rh = sho.forward_hair_encoder(shape_sd, hair[pick])
+    rf = sho.forward_face_encoder(shape_sd, face[pick])
+    assert float((hc[pick] - rh).norm() / rh.norm()) < 1e-3
+    assert float((fc[pick] - rf).norm() / rf.norm()) < 1e-3
+    full_h, full_f = hc.clone(), fc.clone()
+    full_h[pick], full_f[pick] = rh, rf          # decode from the oracle's codes where there are any
+    m = net.forward_decode_by_code(full_h.cuda(), full_f.cuda()).cpu()
+    ref = sho.forward_decode_by_code(shape_sd, rh, rf)
+    assert float((m[pick] - ref).abs().max()) < 1e-3
+    assert float((m[pick].argmax(1) == ref.argmax(1)).float().mean()) > 0.999
+
+
+@pytest.mark.gpu
 def test_shape_split_decoders_and_directly_change_hair_mask(shape_sd):
     """forward_hair_decoder / forward_face_decoder / forward_decoder (model.py:175-187) and the way
     Backend.directly_change_hair_mask composes them (ui/backend.py:409-420)."""
