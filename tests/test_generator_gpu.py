@@ -57,6 +57,20 @@ def test_generator_vs_oracle_and_golden_c64(synthetic_sd, gen64, kind):
         assert l2 < L2_TOL and mx < MAX_TOL, (l2, mx)
 
 
+@pytest.mark.parametrize("B", [4, 5])
+def test_generator_small_batch_policy_boundary_vs_oracle(synthetic_sd, B):
+    """B = 4 still takes the interactive schedule (extra h_0 split, split-K where it pays), B = 5 the batch schedule:
+    both against the oracle, every image."""
+    g = SeanGeneratorB200(crop=64, max_batch=B)
+    g.load_state_dict(synthetic_sd)
+    labels, codes, noise = synth.make_labels(B, 64, "iid", seed=40 + B), synth.make_codes(B, seed=50 + B), synth.make_noise(B, 64)
+    ref = so.generator_forward(synthetic_sd, labels, codes, noise)
+    out = g.forward_labels(labels.cuda(), codes.cuda(), noise=synth.flatten_noise(noise).cuda()).cpu()
+    for i in range(B):
+        l2, mx = _errs(out[i:i + 1], ref[i:i + 1])
+        assert l2 < L2_TOL and mx < MAX_TOL, (i, l2, mx)
+
+
 def test_generator_vs_reference_golden_c256_ui(gen256):
     """The B=1 UI-mode output of the unmodified reference at full size (hair_editor.py:159-179 path)."""
     g = np.load(os.path.join(GOLD, "gen_c256_b1_blocky_ui.npz"))
