@@ -534,7 +534,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--precision", default="parity", help="precision policy of SeanGeneratorB200 (parity | fast | full | shortcut)")
+    ap.add_argument("--precision", default="parity", help="precision policy of SeanGeneratorB200 (parity | fast | shortcut | h1 | full | margin)")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config3 / config4 / config5 keys")
     args = ap.parse_args()

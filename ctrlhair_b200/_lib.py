@@ -71,6 +71,10 @@ def prec_h0(i):
     return 1 << (16 + i)
 
 
+def prec_w(i):
+    return 1 << (24 + i)
+
+
 class ZencConfig(C.Structure):
     _fields_ = [("crop", C.c_int), ("label_nc", C.c_int), ("max_batch", C.c_int)]
 

@@ -42,8 +42,9 @@ struct BlockInfo {
   int fin, fout, fmid, r, level, in_shift, shortcut, styled;
   AceInfo ace[3];  // order: s, 0, 1 (s unused when !shortcut)
   int n_ace;
-  int t_shw, t_shb, t_c0w, t_c0b, t_c1w, t_c1b, t_csw, t_cswlo;
+  int t_shw, t_shb, t_c0w, t_c0b, t_c1w, t_c1b, t_csw, t_cswlo, t_c0wlo, t_c1wlo;
   int split_hs, split_h0, split_h1;  // fp16 hi+lo split of the conv_s / conv_0 / conv_1 input (chb_gen_config.precision)
+  int split_w;                       // conv_0 / conv_1 weights as hi + lo: one more K-segment a_hi * w_lo (CHB_PREC_W)
   int64_t ws_xout;  // workspace offset of the block output
   int64_t ws_actv;  // this block's mlp_shared output (own buffer: the mlp_shared launches of all blocks are independent)
 };
@@ -160,6 +161,7 @@ static void build_layout(chb_generator* g) {
     b.split_hs = (b.shortcut && (c.precision & CHB_PREC_SHORTCUT)) ? 1 : 0;
     b.split_h0 = (c.precision & CHB_PREC_H0(i)) ? 1 : 0;
     b.split_h1 = (c.precision & CHB_PREC_H1(i)) ? 1 : 0;
+    b.split_w = (c.precision & CHB_PREC_W(i)) ? 1 : 0;
     b.n_ace = b.shortcut ? 3 : 2;
     const char* an[3] = {"ace_s", "ace_0", "ace_1"};
     int actv_off = 0;
@@ -193,6 +195,8 @@ static void build_layout(chb_generator* g) {
     b.t_c1b = add_tensor(g, b.name + ".conv_1.b", (int64_t)b.fout * 4, CHB_F32);
     b.t_csw = b.shortcut ? add_tensor(g, b.name + ".conv_s.w", (int64_t)b.fout * b.fin * 2, CHB_F16) : -1;
     b.t_cswlo = b.split_hs ? add_tensor(g, b.name + ".conv_s.wlo", (int64_t)b.fout * b.fin * 2, CHB_F16) : -1;
+    b.t_c0wlo = b.split_w ? add_tensor(g, b.name + ".conv_0.wlo", (int64_t)b.fmid * 9 * b.fin * 2, CHB_F16) : -1;
+    b.t_c1wlo = b.split_w ? add_tensor(g, b.name + ".conv_1.wlo", (int64_t)b.fout * 9 * b.fmid * 2, CHB_F16) : -1;
     g->blocks.push_back(b);
   }
   g->noise_pix = noise_pix;
@@ -529,6 +533,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
       const int m0 = sh0 ? 2 : 1;  // [hi | lo] halves share conv_0's weights
       d.seg[0] = make_seg(ws + g->ws_h0, r, b.fin * m0, 0, b.fin * m0, 9, blobp(g, b.t_c0w));
       d.seg[0].w_dup = m0;
+      if (b.split_w) d.seg[d.nseg++] = make_seg(ws + g->ws_h0, r, b.fin * m0, 0, b.fin, 9, blobp(g, b.t_c0wlo));  // h_hi * w_lo
       d.N = d.Nrows = b.fmid; d.BN = pick_bn(b.fmid, B, r);
       d.epi = CHB_EPI_PLAIN; d.act = CHB_ACT_NONE;
       d.bias = reinterpret_cast<const float*>(blobp(g, b.t_c0b));
@@ -558,6 +563,7 @@ static int build_steps(chb_generator* g, int B, std::vector<Step>& steps) {
         d.res = xin; d.r_shift = b.in_shift;
         d.r_sx = b.fin; d.r_sy = (int64_t)xin_r * b.fin; d.r_sb = (int64_t)xin_r * xin_r * b.fin;
       }
+      if (b.split_w) d.seg[ns++] = make_seg(ws + g->ws_h1, r, b.fmid * m1, 0, b.fmid, 9, blobp(g, b.t_c1wlo));  // h_hi * w_lo
       d.nseg = ns;
       d.N = d.Nrows = b.fout; d.BN = pick_bn(b.fout, B, r);
       d.epi = CHB_EPI_PLAIN;

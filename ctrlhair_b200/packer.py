@@ -111,10 +111,13 @@ def pack_generator(sd, ngf=64, label_nc=19, weight_dtype=torch.float16):
             rstd = torch.rsqrt(sd[p + ".param_free_norm.running_var"].float() + BN_EPS)
             out[p + ".chan"] = torch.stack([rstd, -sd[p + ".param_free_norm.running_mean"].float() * rstd,
                                             sd[p + ".noise_var"].float() * rstd])  # planar [3][C]
-        out[name + ".conv_0.w"] = _k_major(_sn(sd, name + ".conv_0")).to(wd)
+        w0, w1 = _k_major(_sn(sd, name + ".conv_0")), _k_major(_sn(sd, name + ".conv_1"))
+        out[name + ".conv_0.w"] = w0.to(wd)
         out[name + ".conv_0.b"] = sd[name + ".conv_0.bias"].float()
-        out[name + ".conv_1.w"] = _k_major(_sn(sd, name + ".conv_1")).to(wd)
+        out[name + ".conv_1.w"] = w1.to(wd)
         out[name + ".conv_1.b"] = sd[name + ".conv_1.bias"].float()
+        out[name + ".conv_0.wlo"] = _lo(w0, wd)   # optional (CHB_PREC_W(block)): fp16 rounding residuals of the weights
+        out[name + ".conv_1.wlo"] = _lo(w1, wd)
         if fin != fout:
             ws = _k_major(_sn(sd, name + ".conv_s"))
             out[name + ".conv_s.w"] = ws.to(wd)
@@ -136,7 +139,7 @@ def pack_generator(sd, ngf=64, label_nc=19, weight_dtype=torch.float16):
     return out
 
 
-OPTIONAL = (".conv_s.wlo", "conv_img.wy", "conv_img.wylo")
+OPTIONAL = (".conv_s.wlo", ".conv_0.wlo", ".conv_1.wlo", "conv_img.wy", "conv_img.wylo")
 
 
 def is_optional(name):

@@ -148,11 +148,13 @@ typedef struct {
   unsigned precision; /* where fp16 operand rounding is compensated by an fp16 hi+lo split (0 = nowhere):
                          CHB_PREC_IMG      conv_img input and weights (generator.py:107-108)
                          CHB_PREC_SHORTCUT conv_s input and weights in every learned-shortcut block (architecture.py:86-93)
-                         CHB_PREC_H1(i) / CHB_PREC_H0(i)  the input of conv_1 / conv_0 of block i (0 = head_0 .. 6 = up_3) */
+                         CHB_PREC_H1(i) / CHB_PREC_H0(i)  the input of conv_1 / conv_0 of block i (0 = head_0 .. 6 = up_3)
+                         CHB_PREC_W(i)     the fp16 rounding residual of block i's conv_0 / conv_1 weights              */
 } chb_gen_config;
 enum { CHB_PREC_IMG = 1u, CHB_PREC_SHORTCUT = 2u };
 #define CHB_PREC_H1(i) (1u << (8 + (i)))
 #define CHB_PREC_H0(i) (1u << (16 + (i)))
+#define CHB_PREC_W(i) (1u << (24 + (i)))   /* conv_0 / conv_1 WEIGHTS of block i: one more K-segment a_hi * w_lo each */
 
 typedef struct chb_generator chb_generator;
 

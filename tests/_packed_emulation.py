@@ -64,6 +64,7 @@ def emulate(packed, labels, codes, noise_planes, ngf=64, label_nc=19, round16=Fa
         split_hs = bool(precision & PREC_SHORTCUT)
         split_h1 = bool(precision & (1 << (8 + bidx)))
         split_h0 = bool(precision & (1 << (16 + bidx)))
+        split_w = bool(round16 and (precision & (1 << (24 + bidx))))   # CHB_PREC_W: one more term h_hi * w_lo
         fin, fout = fi * ngf, fo * ngf
         r = sw * mul
         if r != prev_r:
@@ -104,8 +105,12 @@ def emulate(packed, labels, codes, noise_planes, ngf=64, label_nc=19, round16=Fa
             ai = 1
         h0 = modulate(ai, x, True, split_h0)
         dx0 = F.conv2d(h0, _unpack(packed[name + ".conv_0.w"], fin), packed[name + ".conv_0.b"], padding=1)
+        if split_w:
+            dx0 = dx0 + F.conv2d(r16(h0), _unpack(packed[name + ".conv_0.wlo"], fin), padding=1)
         h1 = modulate(ai + 1, dx0, True, split_h1)
         out = F.conv2d(h1, _unpack(packed[name + ".conv_1.w"], min(fin, fout)), packed[name + ".conv_1.b"], padding=1)
+        if split_w:
+            out = out + F.conv2d(r16(h1), _unpack(packed[name + ".conv_1.wlo"], min(fin, fout)), padding=1)
         if fin != fout:
             ws = _unpack(packed[name + ".conv_s.w"], fin, 1)
             if round16 and split_hs:  # (hs_hi + hs_lo) * ws_hi + hs_hi * ws_lo

@@ -48,7 +48,7 @@ def test_fp16_storage_forecast(synthetic_sd):
     assert errs["parity"] < 1e-3 and errs["full"] < 1e-3 and errs["full"] < errs["shortcut"], errs
 
 
-@pytest.mark.parametrize("policy", ["fast", "shortcut", "parity", "full"])
+@pytest.mark.parametrize("policy", ["fast", "shortcut", "h1", "parity", "full", "margin"])
 def test_packer_matches_library_layout(synthetic_sd, lib, policy):
     """Every tensor the library's blob layout names is produced by the packer with the right dtype and size."""
     from ctrlhair_b200.generator import PRECISION_POLICIES
@@ -70,8 +70,18 @@ def test_packer_matches_library_layout(synthetic_sd, lib, policy):
             assert off.value % 256 == 0 and off.value >= end
             end = off.value + nb.value
             seen.add(k)
-        optional = {k for k in packed if packer.is_optional(k)}
-        assert seen == (set(packed) - optional if policy == "fast" else set(packed))
+        flags = PRECISION_POLICIES[policy]
+        blocks = [b[0] for b in packer.BLOCKS]
+
+        def placed(k):   # which optional tensors this policy puts into the blob
+            if not packer.is_optional(k):
+                return True
+            if k.endswith(".conv_s.wlo"):
+                return bool(flags & _lib.PREC_SHORTCUT)
+            if k.startswith("conv_img."):
+                return bool(flags & _lib.PREC_IMG)
+            return bool(flags & _lib.prec_w(blocks.index(k.split(".")[0])))
+        assert seen == {k for k in packed if placed(k)}
         assert lib.chb_generator_blob_bytes(h) >= end
         # 267 M reference parameters -> ~534 MB of fp16 (one-hot padding 19->32 adds a little)
         assert 5.0e8 < lib.chb_generator_blob_bytes(h) < 6.0e8

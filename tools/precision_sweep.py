@@ -20,7 +20,7 @@ def errs(got, ref):
 
 
 def main():
-    policies = sys.argv[1:] or ["fast", "shortcut", "parity", "full"]
+    policies = sys.argv[1:] or ["fast", "shortcut", "h1", "parity", "full", "margin"]
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.make_state_dict()
     B = 64
