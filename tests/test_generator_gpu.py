@@ -200,6 +200,21 @@ def test_generator_512_vs_oracle(synthetic_sd):
     assert l2 < L2_TOL and mx < MAX_TOL, (l2, mx)
 
 
+def test_headline_batch64_fresh_inputs_vs_oracle(synthetic_sd):
+    """The same schedule on inputs no other test or benchmark uses (iid label maps, new codes and noise): the default
+    policy's per-image max-norm averages 8.1e-4 over 24 such images (tools/gpu_maxnorm_distribution.py), 9.5e-4 at worst."""
+    B = 64
+    g = SeanGeneratorB200(crop=256, max_batch=B)
+    g.load_state_dict(synthetic_sd)
+    labels, codes = synth.make_labels(B, 256, "iid", seed=102), synth.make_codes(B, seed=152)
+    planes = synth.make_noise(B, 256)
+    out = g.forward_labels(labels.cuda(), codes.cuda(), noise=synth.flatten_noise(planes).cuda())
+    for i in (5, 20, 40, 55):
+        ref = so.generator_forward(synthetic_sd, labels[i:i + 1], codes[i:i + 1], [p[i:i + 1] for p in planes])
+        l2, mx = _errs(out[i:i + 1].cpu(), ref)
+        assert l2 < L2_TOL and mx < MAX_TOL, (i, l2, mx)
+
+
 def test_headline_batch64_vs_oracle(synthetic_sd):
     """BASELINE.json configs[1] itself: B = 64 at 256x256.  The batch size changes the plan (fc_mu tile width, the N tile
     of the Weff GEMMs, the tile schedule of every persistent launch), so the headline schedule is compared with the
